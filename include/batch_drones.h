@@ -1,0 +1,165 @@
+/* batch_drones.h — C-ABI of the B200-native batched drone-step library.
+ *
+ * The reference (khuzema-h/marl-gym-pybullet-drones) is pure Python and has no
+ * FFI for this path; the interface the path sits behind is
+ *   - Gymnasium `reset/step` of the aviaries
+ *       gym_pybullet_drones/envs/BaseAviary.py:220-255 (reset), :259-383 (step)
+ *   - the VecEnv protocol the MAPPO rollout calls
+ *       safe_control_gym/envs/env_wrappers/vectorized_env/subproc_vec_env.py:51-73,186-207
+ * This header is what a ctypes binding placed under those two protocols binds
+ * (see INTEGRATION.md for the stub).  Each entry point names the reference
+ * code it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; every *_dev pointer is CALLER-OWNED DEVICE memory,
+ *     every *_host pointer is host memory; the library owns only the drone state
+ *     inside the handle.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     All device entry points are stream-ordered, never synchronise, and are
+ *     CUDA-graph capturable; bd_step_host() synchronises `stream` before returning.
+ *   - "Real" = float when cfg.precision == BD_F32, double when BD_F64.
+ *   - return 0 on success, a negative BD_E* code otherwise (never exit());
+ *     bd_last_error() returns the message of the calling thread's last failure.
+ *   - one handle per GPU; a handle is not thread-safe.
+ *
+ * Shapes: N = n_envs, M = n_drones, A = 4 (RPM) or 1 (ONE_D_RPM),
+ *   B = ctrl_freq/2 (BaseRLAviary.py:66), D = 12 + B*A (+11 for the spiral task).
+ */
+#ifndef BATCH_DRONES_H_
+#define BATCH_DRONES_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BD_VERSION 1
+
+enum { BD_TASK_HOVER = 0, BD_TASK_MULTIHOVER = 1, BD_TASK_SPIRAL = 2 };
+enum { BD_ACT_RPM = 0, BD_ACT_ONE_D_RPM = 1 };
+enum { BD_MODEL_CF2X = 0, BD_MODEL_CF2P = 1, BD_MODEL_RACE = 2 };
+enum { BD_F32 = 0, BD_F64 = 1 };
+enum { BD_AERO_GND = 1, BD_AERO_DRAG = 2, BD_AERO_DW = 4 };
+enum { BD_INTEGRATOR_QUAT = 0, BD_INTEGRATOR_EULER = 1 };
+enum { BD_RESET_FIXED = 0, BD_RESET_JITTER_PHILOX = 1, BD_RESET_JITTER_BUFFER = 2 };
+
+enum {
+  BD_OK = 0,
+  BD_EINVAL = -1,   /* bad argument / unsupported configuration */
+  BD_ECUDA = -2,    /* a CUDA runtime call failed                */
+  BD_ENOMEM = -3    /* device or host allocation failed          */
+};
+
+/* Everything BaseAviary.__init__ / BaseRLAviary.__init__ / the task __init__
+ * take or derive (BaseAviary.py:74-128, BaseRLAviary.py:66-67, HoverAviary.py:51-52,
+ * MultiHoverAviary.py:58-72, SpiralAviary.py:39-56).  Airframe numbers are the
+ * URDF <properties> (cf2x.urdf:5,11-12) parsed by the host language. */
+typedef struct bd_config {
+  int32_t struct_size;      /* = sizeof(bd_config), ABI guard                         */
+  int32_t device;           /* CUDA device ordinal                                    */
+  int32_t n_envs;           /* N                                                      */
+  int32_t n_drones;         /* M (1..128); BD_TASK_HOVER requires 1                   */
+  int32_t task;             /* BD_TASK_*                                              */
+  int32_t act_type;         /* BD_ACT_*                                               */
+  int32_t drone_model;      /* BD_MODEL_* (torque mixing, BaseAviary.py:846-854)      */
+  int32_t precision;        /* BD_F32 fast mode | BD_F64 parity mode                  */
+  int32_t aero_flags;       /* BD_AERO_* bits on top of DYN                           */
+  int32_t integrator;       /* BD_INTEGRATOR_QUAT (BaseAviary.py:879-892) or _EULER
+                               (safe_control_gym/.../base_aviary.py:499-508)          */
+  int32_t pyb_freq;         /* BaseAviary.py:78                                       */
+  int32_t ctrl_freq;        /* BaseAviary.py:77; pyb_freq % ctrl_freq must be 0       */
+  int32_t auto_reset;       /* 1: SubprocVecEnv semantics (subproc_vec_env.py:195-206) */
+  int32_t reset_mode;       /* BD_RESET_*; JITTER_* = MultiHoverAviary.py:83-102      */
+  int32_t action_is_f32;    /* BD_F64 only: actions are float (numpy computes
+                               1+0.05*a in float32 then), else double                 */
+  int32_t keep_ang_vel;     /* 1: keep world angular velocity for bd_get_state        */
+  uint64_t seed;            /* Philox key for BD_RESET_JITTER_PHILOX                  */
+  double episode_len_sec;   /* 8 (hover, multihover) / 12 (spiral)                    */
+  /* airframe */
+  double mass, arm, kf, km, ixx, iyy, izz, g;
+  double thrust2weight, gnd_eff_coeff, prop_radius, drag_coeff_xy, drag_coeff_z;
+  double dw_coeff_1, dw_coeff_2, dw_coeff_3;
+  double prop_xy[8];        /* x0,y0,...,x3,y3 body-frame propeller offsets            */
+  /* spiral task (SpiralAviary.py:33-45) */
+  double spiral_radius, spiral_period, height_rate, target_center[3];
+} bd_config;
+
+typedef struct bd_handle bd_handle;
+
+/* Replaces BaseAviary.__init__ + _housekeeping (BaseAviary.py:74-216, 451-505):
+ * allocates the SoA drone state on cfg->device and puts every env in its
+ * reset state with the default initial poses (BaseAviary.py:194-203; spiral
+ * ring SpiralAviary.py:47-53). */
+int bd_create(const bd_config* cfg, bd_handle** out);
+
+/* Replaces BaseAviary.close / SubprocVecEnv.close. */
+void bd_destroy(bd_handle* h);
+
+/* INIT_XYZS / INIT_RPYS (BaseAviary.py:194-207).  Host arrays of doubles,
+ * (M,3) when per_env == 0, (N,M,3) when per_env == 1; rpy_host may be NULL
+ * (zeros).  Like the constructor (BaseAviary.py:212-214; MultiHoverAviary.py:72)
+ * it also puts EVERY env into its reset state at exactly these poses (no
+ * jitter, step counters zeroed, action history kept).  Synchronises. */
+int bd_set_init_poses(bd_handle* h, const double* xyz_host, const double* rpy_host, int per_env);
+
+/* Jitter draws for BD_RESET_JITTER_BUFFER: (N,M,3) Real in [-0.25,0.25), the
+ * stand-in for np.random.uniform at MultiHoverAviary.py:83.  Copied (stream
+ * ordered) into the handle; each env consumes its row at its next reset. */
+int bd_set_jitter(bd_handle* h, const void* jitter_dev, void* stream);
+
+/* Replaces env.reset() on every env with env_mask_dev[e] != 0 (all envs when
+ * NULL): MultiHoverAviary.py:75-110 + BaseAviary.py:220-255.  Writes the reset
+ * observation rows (float32, (N,M,D)) of those envs when obs_dev != NULL. */
+int bd_reset(bd_handle* h, const uint8_t* env_mask_dev, float* obs_dev, void* stream);
+
+/* Replaces one VecEnv.step(): BaseRLAviary._preprocessAction (BaseRLAviary.py:160-239),
+ * BaseAviary.step's substep loop with _dynamics/_integrateQ (BaseAviary.py:343-374,
+ * 815-892), _computeObs/_computeReward/_computeTerminated/_computeTruncated of the
+ * task, the step-counter advance (:382) and, with auto_reset, the worker's
+ * reset-on-done (subproc_vec_env.py:195-206).  ONE kernel launch.
+ *   actions_dev      (N,M,A) float (double when BD_F64 && !action_is_f32)
+ *   obs_dev          (N,M,D) float; for envs that were auto-reset this is the RESET obs
+ *   reward_dev       (N) Real
+ *   terminated_dev   (N) uint8, truncated_dev (N) uint8
+ *   terminal_obs_dev (N,M,D) float or NULL; rows are written only for envs that
+ *                    finished in this step (info['terminal_observation'])       */
+int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_dev,
+            uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev,
+            void* stream);
+
+/* Same as bd_step with HOST buffers: copies the actions up, steps, copies
+ * obs/reward/flags (and terminal obs when not NULL) back and synchronises
+ * `stream`.  Buffers should be page-locked for full PCIe rate. */
+int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                 uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
+                 void* stream);
+
+/* Replaces BaseAviary._getDroneStateVector (BaseAviary.py:541-561) for every
+ * drone: state20_dev (N,M,20) Real = [pos3 quat4 rpy3 vel3 ang_v3 last_rpm4];
+ * ang_v is NaN unless cfg.keep_ang_vel.  Optional: body rates `self.rpy_rates`
+ * (N,M,3) Real and the per-env step counter (N) int32. */
+int bd_get_state(bd_handle* h, void* state20_dev, void* rates_dev, int32_t* step_counter_dev,
+                 void* stream);
+
+/* Inject a state (parity tests, curriculum starts): kin13_dev (N,M,13) Real =
+ * [pos3 quat4(xyzw) vel3 body_rates3]; optional targets_dev (N,M,3) Real
+ * (TARGET_POS) and step_counter_dev (N) int32.  Quaternions are taken as given. */
+int bd_set_state(bd_handle* h, const void* kin13_dev, const void* targets_dev,
+                 const int32_t* step_counter_dev, void* stream);
+
+/* TARGET_POS of every drone, (N,M,3) Real (MultiHoverAviary.py:72,106). */
+int bd_get_targets(bd_handle* h, void* targets_dev, void* stream);
+
+int bd_obs_dim(const bd_handle* h);              /* D                                 */
+int bd_act_dim(const bd_handle* h);              /* A                                 */
+int bd_action_buffer_size(const bd_handle* h);   /* B                                 */
+int bd_substeps(const bd_handle* h);             /* PYB_STEPS_PER_CTRL                */
+int64_t bd_launch_count(const bd_handle* h);     /* kernels launched by this handle   */
+const char* bd_last_error(void);
+int bd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BATCH_DRONES_H_ */

@@ -1,0 +1,107 @@
+"""ctypes binding of `libbatchdrones.so` (the C-ABI in `include/batch_drones.h`).
+
+There is no fallback: if the shared library has not been built, or the CUDA
+runtime reports an error, the calls raise.  Build with
+`python -m marl_gym_pybullet_drones_b200.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbatchdrones.so")
+
+BD_TASK = {"hover": 0, "multihover": 1, "spiral": 2}
+BD_ACT = {"rpm": 0, "one_d_rpm": 1}
+BD_MODEL = {"cf2x": 0, "cf2p": 1, "racer": 2}
+BD_PRECISION = {"fp32": 0, "fp64": 1}
+BD_INTEGRATOR = {"quat": 0, "euler": 1}
+BD_RESET = {"fixed": 0, "jitter_philox": 1, "jitter_buffer": 2}
+
+EXPORTS = (
+    "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
+    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_obs_dim", "bd_act_dim",
+    "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
+)
+
+
+class BdConfig(C.Structure):
+    """Mirror of `struct bd_config` (include/batch_drones.h)."""
+
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32),
+        ("n_envs", C.c_int32), ("n_drones", C.c_int32),
+        ("task", C.c_int32), ("act_type", C.c_int32), ("drone_model", C.c_int32),
+        ("precision", C.c_int32), ("aero_flags", C.c_int32), ("integrator", C.c_int32),
+        ("pyb_freq", C.c_int32), ("ctrl_freq", C.c_int32),
+        ("auto_reset", C.c_int32), ("reset_mode", C.c_int32),
+        ("action_is_f32", C.c_int32), ("keep_ang_vel", C.c_int32),
+        ("seed", C.c_uint64),
+        ("episode_len_sec", C.c_double),
+        ("mass", C.c_double), ("arm", C.c_double), ("kf", C.c_double), ("km", C.c_double),
+        ("ixx", C.c_double), ("iyy", C.c_double), ("izz", C.c_double), ("g", C.c_double),
+        ("thrust2weight", C.c_double), ("gnd_eff_coeff", C.c_double), ("prop_radius", C.c_double),
+        ("drag_coeff_xy", C.c_double), ("drag_coeff_z", C.c_double),
+        ("dw_coeff_1", C.c_double), ("dw_coeff_2", C.c_double), ("dw_coeff_3", C.c_double),
+        ("prop_xy", C.c_double * 8),
+        ("spiral_radius", C.c_double), ("spiral_period", C.c_double), ("height_rate", C.c_double),
+        ("target_center", C.c_double * 3),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the library once and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`python -m marl_gym_pybullet_drones_b200.build` (needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, u8p, f32p, dp = C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(C.c_double)
+    lib.bd_create.argtypes = [C.POINTER(BdConfig), C.POINTER(vp)]
+    lib.bd_create.restype = C.c_int
+    lib.bd_destroy.argtypes = [vp]
+    lib.bd_destroy.restype = None
+    lib.bd_set_init_poses.argtypes = [vp, dp, dp, C.c_int]
+    lib.bd_set_init_poses.restype = C.c_int
+    lib.bd_set_jitter.argtypes = [vp, vp, vp]
+    lib.bd_set_jitter.restype = C.c_int
+    lib.bd_reset.argtypes = [vp, u8p, f32p, vp]
+    lib.bd_reset.restype = C.c_int
+    lib.bd_step.argtypes = [vp, vp, f32p, vp, u8p, u8p, f32p, vp]
+    lib.bd_step.restype = C.c_int
+    lib.bd_step_host.argtypes = [vp, vp, f32p, vp, u8p, u8p, f32p, vp]
+    lib.bd_step_host.restype = C.c_int
+    lib.bd_get_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.bd_get_state.restype = C.c_int
+    lib.bd_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.bd_set_state.restype = C.c_int
+    lib.bd_get_targets.argtypes = [vp, vp, vp]
+    lib.bd_get_targets.restype = C.c_int
+    for name in ("bd_obs_dim", "bd_act_dim", "bd_action_buffer_size", "bd_substeps"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = C.c_int
+    lib.bd_launch_count.argtypes = [vp]
+    lib.bd_launch_count.restype = C.c_int64
+    lib.bd_last_error.argtypes = []
+    lib.bd_last_error.restype = C.c_char_p
+    lib.bd_version.argtypes = []
+    lib.bd_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().bd_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what} failed ({rc}): {msg}")

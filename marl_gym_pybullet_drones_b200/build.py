@@ -1,0 +1,56 @@
+"""Build `libbatchdrones.so` in-tree with nvcc for sm_100a.
+
+    python -m marl_gym_pybullet_drones_b200.build [--force]
+
+The library is a plain C-ABI shared object (no torch, no pybind): it travels
+with the source tree and is loaded through ctypes (`_native.py`).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = [os.path.join(CSRC, "bd_kernels.cu"), os.path.join(CSRC, "bd_api.cu")]
+HEADERS = [os.path.join(CSRC, "bd_params.h"),
+           os.path.join(os.path.dirname(_HERE), "include", "batch_drones.h")]
+OUT = os.path.join(_HERE, "libbatchdrones.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def find_nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; cannot build the CUDA extension")
+    return cand
+
+
+def up_to_date() -> bool:
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(p) <= t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

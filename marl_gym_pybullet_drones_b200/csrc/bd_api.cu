@@ -1,0 +1,440 @@
+// C-ABI of the batched drone-step library (include/batch_drones.h).
+// Host-side only: argument checking, device allocations, kernel-parameter
+// blocks and stream-ordered launches.  No CPU compute path exists here; if CUDA
+// is unavailable every call fails with BD_ECUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/batch_drones.h"
+#include "bd_params.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define BD_CUDA(expr)                                                                 \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      return fail(BD_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                  __FILE__, __LINE__);                                                \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    target = dev;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != target) cudaSetDevice(prev);
+  }
+  int target = -1;
+};
+
+}  // namespace
+
+struct bd_handle {
+  bd_config cfg;
+  int S = 0, A = 0, B = 0, D = 0, Ds = 0, E = 0;
+  long long n_total = 0;
+  size_t real = 4;
+  bd::LaunchSpec spec{};
+  // device allocations
+  void *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s4 = nullptr;
+  float* hist = nullptr;
+  int2* envc = nullptr;
+  void* init_xyz = nullptr;
+  void* init_rpy = nullptr;
+  int init_env_stride = 0;
+  void* jitter = nullptr;
+  // staging for bd_step_host
+  void* h_actions = nullptr;
+  float* h_obs = nullptr;
+  void* h_reward = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr;
+  float* h_tobs = nullptr;
+  int64_t launches = 0;
+  int reset_epoch = 0;
+  bd::Params<float> pf{};
+  bd::Params<double> pd{};
+};
+
+namespace {
+
+template <typename R>
+void fill_params(const bd_handle* h, bd::Params<R>& P) {
+  const bd_config& c = h->cfg;
+  using R4 = typename bd::V4<R>::type;
+  P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D; P.Ds = h->Ds;
+  P.E = h->E; P.n_total = h->n_total;
+  P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
+  P.hist = h->hist; P.envc = h->envc;
+  P.init_xyz = (const R*)h->init_xyz; P.init_rpy = (const R*)h->init_rpy;
+  P.init_env_stride = h->init_env_stride;
+  P.jitter = (const R*)h->jitter;
+  P.actions = nullptr; P.obs = nullptr; P.reward = nullptr; P.terminated = nullptr;
+  P.truncated = nullptr; P.terminal_obs = nullptr; P.reset_mask = nullptr;
+  // derived constants exactly as BaseAviary.py:117-118 computes them, in double,
+  // then narrowed once to the kernel's precision
+  const double gravity = c.g * c.mass;
+  const double hover_rpm = sqrt(gravity / (4 * c.kf));
+  const double max_rpm = sqrt((c.thrust2weight * gravity) / (4 * c.kf));
+  const double max_thrust = 4 * c.kf * max_rpm * max_rpm;
+  const double gnd_h_clip =
+      0.25 * c.prop_radius * sqrt((15 * max_rpm * max_rpm * c.kf * c.gnd_eff_coeff) / max_thrust);
+  P.dt = (R)(1.0 / c.pyb_freq);
+  P.hover_rpm = (R)hover_rpm;
+  P.kf = (R)c.kf; P.km = (R)c.km;
+  P.arm = (R)(c.drone_model == BD_MODEL_CF2P ? c.arm : c.arm / sqrt(2.0));
+  P.inv_m = (R)(1.0 / c.mass);
+  P.gravity = (R)gravity;
+  P.jx = (R)c.ixx; P.jy = (R)c.iyy; P.jz = (R)c.izz;
+  P.ijx = (R)(1.0 / c.ixx); P.ijy = (R)(1.0 / c.iyy); P.ijz = (R)(1.0 / c.izz);
+  P.gnd_coeff = (R)c.gnd_eff_coeff; P.prop_radius = (R)c.prop_radius; P.gnd_h_clip = (R)gnd_h_clip;
+  P.drag_xy = (R)c.drag_coeff_xy; P.drag_z = (R)c.drag_coeff_z;
+  P.dw1 = (R)c.dw_coeff_1; P.dw2 = (R)c.dw_coeff_2; P.dw3 = (R)c.dw_coeff_3;
+  for (int k = 0; k < 4; ++k) { P.prop_x[k] = (R)c.prop_xy[2 * k]; P.prop_y[k] = (R)c.prop_xy[2 * k + 1]; }
+  P.sp_R = (R)c.spiral_radius;
+  P.sp_omega = (R)(c.spiral_period != 0.0 ? 2 * 3.14159265358979323846 / c.spiral_period : 0.0);
+  P.sp_vz = (R)c.height_rate; P.sp_cx = (R)c.target_center[0]; P.sp_cy = (R)c.target_center[1];
+  P.pyb_freq = (double)c.pyb_freq; P.episode_len = c.episode_len_sec;
+  P.model = c.drone_model; P.aero = c.aero_flags; P.integrator = c.integrator;
+  P.auto_reset = c.auto_reset; P.reset_mode = c.reset_mode; P.action_is_f32 = c.action_is_f32;
+  P.keep_angv = c.keep_ang_vel;
+  P.seed = c.seed;
+  P.reset_epoch = 0;
+}
+
+void refresh_params(bd_handle* h) {
+  if (h->cfg.precision == BD_F64) fill_params<double>(h, h->pd);
+  else fill_params<float>(h, h->pf);
+}
+
+void* params_ptr(bd_handle* h) { return h->cfg.precision == BD_F64 ? (void*)&h->pd : (void*)&h->pf; }
+
+template <typename F>
+void with_params(bd_handle* h, F&& f) {
+  if (h->cfg.precision == BD_F64) f(h->pd); else f(h->pf);
+}
+
+int upload_table(bd_handle* h, const double* src, size_t count, void** dst) {
+  std::vector<unsigned char> tmp(count * h->real);
+  if (h->real == 8) {
+    memcpy(tmp.data(), src, count * 8);
+  } else {
+    float* f = reinterpret_cast<float*>(tmp.data());
+    for (size_t i = 0; i < count; ++i) f[i] = (float)src[i];
+  }
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  BD_CUDA(cudaMalloc(dst, count * h->real));
+  BD_CUDA(cudaMemcpy(*dst, tmp.data(), count * h->real, cudaMemcpyHostToDevice));
+  return BD_OK;
+}
+
+int default_init_tables(bd_handle* h) {
+  const bd_config& c = h->cfg;
+  const int M = c.n_drones;
+  std::vector<double> xyz(M * 3), rpy(M * 3, 0.0);
+  for (int i = 0; i < M; ++i) {
+    if (c.task == BD_TASK_SPIRAL) {            // SpiralAviary.py:47-53
+      const double ang = 2 * 3.14159265358979323846 * i / M;
+      xyz[i * 3 + 0] = c.spiral_radius * cos(ang);
+      xyz[i * 3 + 1] = c.spiral_radius * sin(ang);
+      xyz[i * 3 + 2] = 0.3;
+    } else {                                   // BaseAviary.py:194-197 (collision cyl h=.025, offset 0)
+      xyz[i * 3 + 0] = i * 4 * c.arm;
+      xyz[i * 3 + 1] = i * 4 * c.arm;
+      xyz[i * 3 + 2] = 0.025 / 2 - 0.0 + .1;
+    }
+  }
+  h->init_env_stride = 0;
+  int rc = upload_table(h, xyz.data(), xyz.size(), &h->init_xyz);
+  if (rc) return rc;
+  return upload_table(h, rpy.data(), rpy.size(), &h->init_rpy);
+}
+
+int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  with_params(h, [&](auto& P) {
+    auto Q = P;
+    Q.reset_mask = mask;
+    Q.obs = obs;
+    if (force_fixed) Q.reset_mode = BD_RESET_FIXED;
+    Q.reset_epoch = ++h->reset_epoch;
+    e = bd::launch_reset(h->spec, &Q, st);
+  });
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "reset kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+void free_all(bd_handle* h) {
+  cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
+  cudaFree(h->hist); cudaFree(h->envc); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
+  cudaFree(h->jitter);
+  cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
+  cudaFree(h->h_trunc); cudaFree(h->h_tobs);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bd_version(void) { return BD_VERSION; }
+const char* bd_last_error(void) { return g_err; }
+
+int bd_create(const bd_config* cfg, bd_handle** out) {
+  if (!cfg || !out) return fail(BD_EINVAL, "bd_create: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(bd_config))
+    return fail(BD_EINVAL, "bd_create: struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(bd_config));
+  if (cfg->n_envs < 1) return fail(BD_EINVAL, "bd_create: n_envs must be >= 1");
+  if (cfg->n_drones < 1 || cfg->n_drones > bd::kMaxDrones)
+    return fail(BD_EINVAL, "bd_create: n_drones must be in [1,%d]", bd::kMaxDrones);
+  if (cfg->task < 0 || cfg->task > 2) return fail(BD_EINVAL, "bd_create: unknown task %d", cfg->task);
+  if (cfg->task == BD_TASK_HOVER && cfg->n_drones != 1)
+    return fail(BD_EINVAL, "bd_create: the hover task is single-drone (HoverAviary.py:54)");
+  if (cfg->act_type != BD_ACT_RPM && cfg->act_type != BD_ACT_ONE_D_RPM)
+    return fail(BD_EINVAL, "bd_create: only RPM and ONE_D_RPM actions are stepped on the GPU");
+  if (cfg->drone_model < 0 || cfg->drone_model > 2) return fail(BD_EINVAL, "bd_create: unknown drone_model");
+  if (cfg->precision != BD_F32 && cfg->precision != BD_F64) return fail(BD_EINVAL, "bd_create: unknown precision");
+  if (cfg->pyb_freq <= 0 || cfg->ctrl_freq <= 0 || cfg->pyb_freq % cfg->ctrl_freq != 0)
+    return fail(BD_EINVAL, "[ERROR] in BaseAviary.__init__(), pyb_freq is not divisible by env_freq.");
+  if (cfg->ctrl_freq / 2 < 1) return fail(BD_EINVAL, "bd_create: ctrl_freq must be >= 2 (action buffer)");
+  if (cfg->aero_flags & ~7) return fail(BD_EINVAL, "bd_create: unknown aero flag");
+  if (cfg->integrator != BD_INTEGRATOR_QUAT && cfg->integrator != BD_INTEGRATOR_EULER)
+    return fail(BD_EINVAL, "bd_create: unknown integrator");
+  if (cfg->reset_mode < 0 || cfg->reset_mode > 2) return fail(BD_EINVAL, "bd_create: unknown reset_mode");
+  if (!(cfg->mass > 0) || !(cfg->kf > 0) || !(cfg->ixx > 0) || !(cfg->iyy > 0) || !(cfg->izz > 0))
+    return fail(BD_EINVAL, "bd_create: airframe constants must be positive");
+
+  int ndev = 0;
+  BD_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(BD_EINVAL, "bd_create: device %d out of range (%d visible)", cfg->device, ndev);
+  DeviceGuard guard(cfg->device);
+  if (!guard.ok) return fail(BD_ECUDA, "bd_create: cannot select device %d", cfg->device);
+
+  bd_handle* h = new (std::nothrow) bd_handle();
+  if (!h) return fail(BD_ENOMEM, "bd_create: out of host memory");
+  h->cfg = *cfg;
+  h->S = cfg->pyb_freq / cfg->ctrl_freq;
+  h->A = cfg->act_type == BD_ACT_RPM ? 4 : 1;
+  h->B = cfg->ctrl_freq / 2;
+  h->D = 12 + h->B * h->A + (cfg->task == BD_TASK_SPIRAL ? 11 : 0);
+  h->Ds = (h->D + 3) & ~3;
+  h->E = bd::kBlock / cfg->n_drones;
+  h->n_total = (long long)cfg->n_envs * cfg->n_drones;
+  h->real = cfg->precision == BD_F64 ? 8 : 4;
+  h->spec.task = cfg->task;
+  h->spec.act_a = h->A;
+  h->spec.precision = cfg->precision;
+  h->spec.device = cfg->device;
+  h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel) ? 1 : 0;
+
+  const size_t smem = bd::step_smem_bytes(cfg->precision, h->Ds);
+  cudaDeviceProp prop;
+  cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
+  if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
+  if (smem > prop.sharedMemPerBlockOptin) {
+    delete h;
+    return fail(BD_EINVAL, "bd_create: observation tile needs %zu B of shared memory (> %zu)", smem,
+                (size_t)prop.sharedMemPerBlockOptin);
+  }
+
+  const size_t plane = (size_t)h->n_total * 4 * h->real;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  alloc(&h->s0, plane); alloc(&h->s1, plane); alloc(&h->s2, plane); alloc(&h->s3, plane);
+  if (cfg->keep_ang_vel) alloc(&h->s4, plane);
+  alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
+  alloc((void**)&h->envc, (size_t)cfg->n_envs * sizeof(int2));
+  if (e != cudaSuccess) {
+    free_all(h); delete h;
+    return fail(e == cudaErrorMemoryAllocation ? BD_ENOMEM : BD_ECUDA, "bd_create: device allocation failed: %s",
+                cudaGetErrorString(e));
+  }
+  int rc = default_init_tables(h);
+  if (rc) { free_all(h); delete h; return rc; }
+  refresh_params(h);
+  rc = do_reset(h, nullptr, nullptr, /*force_fixed=*/1, nullptr);   // __init__: no jitter (MultiHoverAviary.py:72)
+  if (rc == BD_OK) {
+    cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) rc = fail(BD_ECUDA, "bd_create: initial reset failed: %s", cudaGetErrorString(se));
+  }
+  if (rc) { free_all(h); delete h; return rc; }
+  *out = h;
+  return BD_OK;
+}
+
+void bd_destroy(bd_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h->cfg.device);
+  free_all(h);
+  delete h;
+}
+
+int bd_set_init_poses(bd_handle* h, const double* xyz_host, const double* rpy_host, int per_env) {
+  if (!h || !xyz_host) return fail(BD_EINVAL, "bd_set_init_poses: null argument");
+  DeviceGuard guard(h->cfg.device);
+  BD_CUDA(cudaDeviceSynchronize());
+  const size_t count = (size_t)(per_env ? h->cfg.n_envs : 1) * h->cfg.n_drones * 3;
+  int rc = upload_table(h, xyz_host, count, &h->init_xyz);
+  if (rc) return rc;
+  if (rpy_host) {
+    rc = upload_table(h, rpy_host, count, &h->init_rpy);
+  } else {
+    std::vector<double> z(count, 0.0);
+    rc = upload_table(h, z.data(), count, &h->init_rpy);
+  }
+  if (rc) return rc;
+  h->init_env_stride = per_env ? h->cfg.n_drones * 3 : 0;
+  refresh_params(h);
+  // like BaseAviary.__init__ -> _housekeeping: every env starts at the given poses, un-jittered
+  rc = do_reset(h, nullptr, nullptr, /*force_fixed=*/1, nullptr);
+  if (rc) return rc;
+  BD_CUDA(cudaDeviceSynchronize());
+  return BD_OK;
+}
+
+int bd_set_jitter(bd_handle* h, const void* jitter_dev, void* stream) {
+  if (!h || !jitter_dev) return fail(BD_EINVAL, "bd_set_jitter: null argument");
+  DeviceGuard guard(h->cfg.device);
+  const size_t bytes = (size_t)h->n_total * 3 * h->real;
+  if (!h->jitter) {
+    BD_CUDA(cudaMalloc(&h->jitter, bytes));
+    refresh_params(h);
+  }
+  BD_CUDA(cudaMemcpyAsync(h->jitter, jitter_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return BD_OK;
+}
+
+int bd_reset(bd_handle* h, const uint8_t* env_mask_dev, float* obs_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_reset: null handle");
+  if (h->cfg.reset_mode == BD_RESET_JITTER_BUFFER && h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter)
+    return fail(BD_EINVAL, "bd_reset: BD_RESET_JITTER_BUFFER needs bd_set_jitter() first");
+  DeviceGuard guard(h->cfg.device);
+  return do_reset(h, env_mask_dev, obs_dev, 0, (cudaStream_t)stream);
+}
+
+int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_dev,
+            uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_step: null handle");
+  if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev)
+    return fail(BD_EINVAL, "bd_step: actions, obs, reward, terminated and truncated are required");
+  if (((uintptr_t)obs_dev & 15) || ((uintptr_t)actions_dev & 15))
+    return fail(BD_EINVAL, "bd_step: actions and obs must be 16-byte aligned");
+  if (h->cfg.auto_reset && h->cfg.reset_mode == BD_RESET_JITTER_BUFFER &&
+      h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter)
+    return fail(BD_EINVAL, "bd_step: BD_RESET_JITTER_BUFFER needs bd_set_jitter() first");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = cudaSuccess;
+  with_params(h, [&](auto& P) {
+    P.actions = actions_dev;
+    P.obs = obs_dev;
+    P.reward = (decltype(P.reward))reward_dev;
+    P.terminated = terminated_dev;
+    P.truncated = truncated_dev;
+    P.terminal_obs = terminal_obs_dev;
+    e = bd::launch_step(h->spec, &P, (cudaStream_t)stream);
+  });
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                 uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
+                 void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_step_host: null handle");
+  if (!actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host)
+    return fail(BD_EINVAL, "bd_step_host: actions, obs, reward, terminated and truncated are required");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t act_elem = (h->cfg.precision == BD_F64 && !h->cfg.action_is_f32) ? 8 : 4;
+  const size_t act_bytes = (size_t)h->n_total * h->A * act_elem;
+  const size_t obs_bytes = (size_t)h->n_total * h->D * sizeof(float);
+  const size_t n = (size_t)h->cfg.n_envs;
+  if (!h->h_actions) {
+    BD_CUDA(cudaMalloc(&h->h_actions, act_bytes));
+    BD_CUDA(cudaMalloc((void**)&h->h_obs, obs_bytes));
+    BD_CUDA(cudaMalloc(&h->h_reward, n * h->real));
+    BD_CUDA(cudaMalloc((void**)&h->h_term, n));
+    BD_CUDA(cudaMalloc((void**)&h->h_trunc, n));
+  }
+  if (terminal_obs_host && !h->h_tobs) {
+    BD_CUDA(cudaMalloc((void**)&h->h_tobs, obs_bytes));
+    BD_CUDA(cudaMemsetAsync(h->h_tobs, 0, obs_bytes, st));
+  }
+  BD_CUDA(cudaMemcpyAsync(h->h_actions, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
+  int rc = bd_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_term, h->h_trunc,
+                   terminal_obs_host ? h->h_tobs : nullptr, stream);
+  if (rc) return rc;
+  BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  BD_CUDA(cudaMemcpyAsync(reward_host, h->h_reward, n * h->real, cudaMemcpyDeviceToHost, st));
+  BD_CUDA(cudaMemcpyAsync(terminated_host, h->h_term, n, cudaMemcpyDeviceToHost, st));
+  BD_CUDA(cudaMemcpyAsync(truncated_host, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
+  if (terminal_obs_host)
+    BD_CUDA(cudaMemcpyAsync(terminal_obs_host, h->h_tobs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  BD_CUDA(cudaStreamSynchronize(st));
+  return BD_OK;
+}
+
+int bd_get_state(bd_handle* h, void* state20_dev, void* rates_dev, int32_t* step_counter_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_get_state: null handle");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_get_state(h->cfg.precision, params_ptr(h), state20_dev, rates_dev,
+                                       step_counter_dev, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "get_state kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_set_state(bd_handle* h, const void* kin13_dev, const void* targets_dev,
+                 const int32_t* step_counter_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_set_state: null handle");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_set_state(h->cfg.precision, params_ptr(h), kin13_dev, targets_dev,
+                                       step_counter_dev, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "set_state kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_get_targets(bd_handle* h, void* targets_dev, void* stream) {
+  if (!h || !targets_dev) return fail(BD_EINVAL, "bd_get_targets: null argument");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_get_targets(h->cfg.precision, params_ptr(h), targets_dev, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "get_targets kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_obs_dim(const bd_handle* h) { return h ? h->D : BD_EINVAL; }
+int bd_act_dim(const bd_handle* h) { return h ? h->A : BD_EINVAL; }
+int bd_action_buffer_size(const bd_handle* h) { return h ? h->B : BD_EINVAL; }
+int bd_substeps(const bd_handle* h) { return h ? h->S : BD_EINVAL; }
+int64_t bd_launch_count(const bd_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Internal kernel-parameter block shared by bd_kernels.cu and bd_api.cu.
+// Not part of the public ABI (that is include/batch_drones.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bd {
+
+constexpr int kBlock = 128;        // threads per CTA; one thread per drone
+constexpr int kMaxDrones = 128;    // M <= kBlock (an env never straddles CTAs)
+constexpr int kMaxJitterTries = 64;
+
+template <typename Real> struct V4;
+template <> struct V4<float>  { using type = float4;  };
+template <> struct V4<double> { using type = double4; };
+
+// Device-resident SoA drone state (see DESIGN.md "HBM layout").
+//   s0[g] = (px, py, pz, qx)   s1[g] = (qy, qz, qw, vx)
+//   s2[g] = (vy, vz, wx, wy)   s3[g] = (wz, tx, ty, tz)      t = TARGET_POS
+//   s4[g] = (avx, avy, avz, -) world angular velocity, only with keep_ang_vel
+//   hist[slot][g][A]           float action ring, B slots (survives reset,
+//                              BaseRLAviary.py:153-154,187)
+//   envc[e] = (step_counter since reset, total steps)  -> ring head = total % B
+template <typename Real>
+struct Params {
+  int N, M, S, A, B, D, Ds, E;
+  long long n_total;
+  typename V4<Real>::type *s0, *s1, *s2, *s3, *s4;
+  float* hist;
+  int2* envc;
+  const Real* init_xyz;
+  const Real* init_rpy;
+  int init_env_stride;            // 0 (shared (M,3) table) or M*3
+  const Real* jitter;             // (N,M,3) or nullptr
+  // per-call I/O
+  const void* actions;
+  float* obs;
+  Real* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  float* terminal_obs;
+  const uint8_t* reset_mask;
+  // constants
+  Real dt, hover_rpm, kf, km, arm, inv_m, gravity;
+  Real jx, jy, jz, ijx, ijy, ijz;
+  Real gnd_coeff, prop_radius, gnd_h_clip, drag_xy, drag_z, dw1, dw2, dw3;
+  Real prop_x[4], prop_y[4];
+  Real sp_R, sp_omega, sp_vz, sp_cx, sp_cy;
+  double pyb_freq, episode_len;
+  int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
+  int reset_epoch;                // >=1 for explicit bd_reset calls (Philox stream id), 0 in-step
+  unsigned long long seed;
+};
+
+struct LaunchSpec {
+  int task, act_a, precision, generic, device;
+};
+
+// implemented in bd_kernels.cu
+cudaError_t launch_step(const LaunchSpec& ls, const void* params, cudaStream_t st);
+cudaError_t launch_reset(const LaunchSpec& ls, const void* params, cudaStream_t st);
+cudaError_t launch_get_state(int precision, const void* params, void* state20, void* rates,
+                             int32_t* step_counter, cudaStream_t st);
+cudaError_t launch_set_state(int precision, const void* params, const void* kin13,
+                             const void* targets, const int32_t* step_counter, cudaStream_t st);
+cudaError_t launch_get_targets(int precision, const void* params, void* targets, cudaStream_t st);
+size_t step_smem_bytes(int precision, int Ds);
+
+}  // namespace bd
