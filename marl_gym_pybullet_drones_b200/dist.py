@@ -1,0 +1,89 @@
+"""Multi-GPU plumbing: one process per GPU, environments sharded, no data-path collective.
+
+The reference parallelises by spreading env objects over worker processes with
+`np.array_split` (`subproc_vec_env.py:28,53`).  Here every rank owns a contiguous
+env slice resident in its own GPU's HBM for the whole run; stepping needs no
+communication.  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used
+only for what genuinely crosses ranks: episode-statistics reduction and the
+trainer's gradient all-reduce.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_envs(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """(start, count) of this rank's contiguous env slice — np.array_split's partition."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(total_envs, world_size)
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
+def init_distributed(backend: str | None = None) -> Tuple[int, int, int]:
+    """Initialise from the torchrun environment; returns (rank, local_rank, world_size)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def reduce_episode_stats(return_sum: torch.Tensor, length_sum: torch.Tensor, episodes: torch.Tensor):
+    """Global mean episode return / length from per-rank sums (one small all-reduce).
+
+    Replaces reading `VecRecordEpisodeStatistics.return_queue/length_queue`
+    (`record_episode_statistics.py:162-164`, consumed at `mappo/mappo.py:1186-1226`) when
+    the envs live on several GPUs."""
+    packed = torch.stack([return_sum.double().sum(), length_sum.double().sum(), episodes.double().sum()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    n = packed[2].clamp_min(1.0)
+    return (packed[0] / n).item(), (packed[1] / n).item(), int(packed[2].item())
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20) -> int:
+    """Average gradients across ranks with bucketed all-reduces (the MAPPO nets are
+    0.2-0.4 M fp32 parameters, i.e. normally ONE bucket; latency-bound, not bandwidth-bound).
+    Returns the number of collectives issued."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    calls, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal calls, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+        calls += 1
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return calls

@@ -180,14 +180,19 @@ class OracleAviary:
             self.vel[i] = self._store_vel[i]
             self.ang_v[i] = self._store_angv[i]
 
-    def reset(self, jitter=None):
+    def reset(self, jitter=None, fixed=False):
         """MultiHoverAviary.py:75-110 then BaseAviary.py:220-255.
 
         `jitter`: optional iterable of (M,3) arrays standing in for the successive
         `np.random.uniform(-0.25, 0.25, (M, 3))` draws (MultiHoverAviary.py:83,101);
         default = process-global `np.random`, as in the reference.
+        `fixed=True` (test injection, the counterpart of BD_RESET_FIXED): skip the
+        jitter / clip / rejection block and reset at INIT_XYZS as they are.
         """
-        if self.task == "multihover":
+        if self.task == "multihover" and fixed:
+            self.TARGET_POS = self.INIT_XYZS + np.array([[0, 0, 1 / (i + 1)] for i in range(self.NUM_DRONES)])
+            self.termination_reasons = []
+        elif self.task == "multihover":
             if not hasattr(self, "ORIGINAL_INIT_XYZS"):
                 self.ORIGINAL_INIT_XYZS = self.INIT_XYZS.copy()
             draws = iter(jitter) if jitter is not None else (
@@ -448,13 +453,13 @@ class OracleAviary:
         pass
 
 
-def step_env_autoreset(env, action, jitter=None):
+def step_env_autoreset(env, action, **reset_kwargs):
     """subproc_vec_env.py:188-207: 5-tuple -> (ob, reward, done, info) with auto-reset."""
     ob, reward, terminated, truncated, info = env.step(action)
     done = terminated or truncated
     if done:
         end_obs, end_info = np.array(ob, copy=True), dict(info)
-        ob, info = env.reset(jitter) if jitter is not None else env.reset()
+        ob, info = env.reset(**reset_kwargs)
         info = dict(info)
         info["terminal_observation"] = end_obs
         info["terminal_info"] = end_info
@@ -464,15 +469,16 @@ def step_env_autoreset(env, action, jitter=None):
 class OracleVecEnv:
     """Sequential stand-in for SubprocVecEnv.step/reset (subproc_vec_env.py:51-73)."""
 
-    def __init__(self, envs):
+    def __init__(self, envs, **reset_kwargs):
         self.envs = list(envs)
         self.num_envs = len(self.envs)
+        self.reset_kwargs = reset_kwargs
 
     def reset(self):
-        res = [e.reset() for e in self.envs]
+        res = [e.reset(**self.reset_kwargs) for e in self.envs]
         return np.stack([r[0] for r in res]), {"n": [r[1] for r in res]}
 
     def step(self, actions):
-        res = [step_env_autoreset(e, a) for e, a in zip(self.envs, actions)]
+        res = [step_env_autoreset(e, a, **self.reset_kwargs) for e, a in zip(self.envs, actions)]
         obs, rews, dones, infos = zip(*res)
         return np.stack(obs), np.stack(rews), np.stack(dones), {"n": infos}

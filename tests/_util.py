@@ -27,11 +27,7 @@ def oracle_from_cfg(cfg, init_xyzs, init_rpys, aero=0, integrator="quat"):
     task = c.pop("task")
     env = OracleAviary(task=task, initial_xyzs=init_xyzs, initial_rpys=init_rpys, aero=aero,
                        integrator=integrator, **c)
-    if task == "multihover":
-        env.ORIGINAL_INIT_XYZS = env.INIT_XYZS.copy()
-        env.reset(jitter=[np.zeros((env.NUM_DRONES, 3))])
-    else:
-        env.reset()
+    env.reset(fixed=True)
     return env
 
 

@@ -1,0 +1,373 @@
+"""GPU parity: the CUDA step kernels (through the C-ABI) against the reference golden
+trajectories and the fp64 oracle.
+
+Stated tolerances (BASELINE.json north_star):
+  fp64 mode : state/reward <= 1e-9 relative (|a-b| / max(|b|,1)) at EVERY step of the whole horizon
+              (up to 580 control steps = 2900 substeps); terminated/truncated identical.
+  fp32 mode : <= 1e-5 relative for one control step from an identical state;
+              free-running <= 1e-3 over a 242-step episode horizon (<= 1e-2 over 580 steps);
+              terminated/truncated identical on the golden cases.
+  obs       : float32 storage -> compared at 2.5e-7 relative in fp64 mode.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import batch_from_cfg, golden_names, load_golden, oracle_from_cfg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9
+OBS_F32_TOL = 2.5e-7
+
+
+def _action_dtype(A, precision):
+    return torch.float32 if (precision == "fp32" or A.dtype == np.float32) else torch.float64
+
+
+def _dev(a, dtype, n=1):
+    return torch.as_tensor(a).to("cuda", dtype)[None].expand(n, -1, -1).contiguous()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp64_matches_reference_golden(name):
+    cfg, g = load_golden(name)
+    A = g["actions"]
+    adt = _action_dtype(A, "fp64")
+    N = 3   # replicate the env: also checks that tiles do not interfere
+    env = batch_from_cfg(cfg, g["init_xyzs"], g["init_rpys"], num_envs=N, precision="fp64", action_dtype=adt,
+                         keep_ang_vel=True)
+    obs0 = env.reset_device().cpu().numpy()
+    assert rel_err(obs0[N - 1], g["obs0"]) <= OBS_F32_TOL
+    for t in range(A.shape[0]):
+        r = env.step_device(_dev(A[t], adt, N))
+        st, rates = env.get_state(with_rates=True)
+        st, rates = st.cpu().numpy(), rates.cpu().numpy()
+        for e in (0, N - 1):
+            assert rel_err(st[e][:, :16], g["states"][t][:, :16]) <= FP64_TOL, (name, t)
+            assert rel_err(rates[e], g["rpy_rates"][t]) <= FP64_TOL, (name, t)
+            if t > 0:   # last_clipped_action = rpm (fp32-rounded action history in fp64-action cases)
+                assert rel_err(st[e][:, 16:20], g["states"][t][:, 16:20]) <= 1e-7, (name, t)
+        assert rel_err(r.obs.cpu().numpy()[N - 1], g["obs"][t]) <= OBS_F32_TOL, (name, t)
+        assert rel_err(r.reward.cpu().numpy(), np.full(N, g["reward"][t])) <= FP64_TOL, (name, t)
+        assert r.terminated.cpu().numpy().tolist() == [bool(g["terminated"][t])] * N, (name, t)
+        assert r.truncated.cpu().numpy().tolist() == [bool(g["truncated"][t])] * N, (name, t)
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_free_running_matches_reference_golden(name):
+    cfg, g = load_golden(name)
+    A = g["actions"]
+    env = batch_from_cfg(cfg, g["init_xyzs"], g["init_rpys"], num_envs=2, precision="fp32")
+    env.reset_device()
+    worst = 0.0
+    for t in range(A.shape[0]):
+        r = env.step_device(_dev(A[t], torch.float32, 2))
+        err = rel_err(r.obs.cpu().numpy()[1][:, :12], g["obs"][t][:, :12])
+        worst = max(worst, err)
+        assert err <= (1e-3 if t < 250 else 1e-2), (name, t, err)
+        assert rel_err(r.reward.cpu().numpy()[1], g["reward"][t]) <= 1e-3, (name, t)
+        assert bool(r.terminated[1]) == bool(g["terminated"][t]) and bool(r.truncated[1]) == bool(g["truncated"][t])
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["multihover2_gauss_f32", "hover_rpm_tilted", "spiral5_gauss_f32",
+                                  "multihover4_cf2p", "multihover2_racer_1d"])
+def test_fp32_single_step_error_from_identical_state(name):
+    """<= 1e-5 relative per control step when both start from the same (golden) state."""
+    cfg, g = load_golden(name)
+    A = g["actions"]
+    env = batch_from_cfg(cfg, g["init_xyzs"], g["init_rpys"], num_envs=1, precision="fp32", keep_ang_vel=True)
+    env.reset_device()
+    S = cfg["pyb_freq"] // cfg["ctrl_freq"]
+    T = min(A.shape[0], 60)
+    for t in range(T):
+        if t > 0:
+            kin = np.concatenate([g["states"][t - 1][:, 0:7], g["states"][t - 1][:, 10:13], g["rpy_rates"][t - 1]],
+                                 axis=1)[None]
+            env.set_state(torch.as_tensor(kin), step_counter=torch.tensor([t * S], dtype=torch.int32))
+        env.step_device(_dev(A[t], torch.float32))
+        st = env.get_state().cpu().numpy()[0]
+        ref = g["states"][t]
+        # quaternion sign is canonical in both; compare pos, quat, rpy, vel, ang_v
+        assert rel_err(st[:, :16], ref[:, :16]) <= 1e-5, (name, t, rel_err(st[:, :16], ref[:, :16]))
+    env.close()
+
+
+def _run_pair(cfg, xyz, rpy, actions, precision, physics="dyn", aero=0, integrator="quat", tol=FP64_TOL,
+              obs_tol=OBS_F32_TOL):
+    """Step N envs (distinct actions) on GPU and N oracles on CPU; compare every step."""
+    T, N = actions.shape[0], actions.shape[1]
+    adt = torch.float32 if actions.dtype == np.float32 else torch.float64
+    if precision == "fp32":
+        adt = torch.float32
+    env = batch_from_cfg(cfg, xyz, rpy, num_envs=N, precision=precision, physics=physics, action_dtype=adt,
+                         keep_ang_vel=True, integrator=integrator)
+    env.reset_device()
+    oracles = [oracle_from_cfg(cfg, xyz, rpy, aero=aero, integrator=integrator) for _ in range(N)]
+    for t in range(T):
+        r = env.step_device(torch.as_tensor(actions[t]).to("cuda", adt))
+        st = env.get_state().cpu().numpy()
+        obs, rew = r.obs.cpu().numpy(), r.reward.cpu().numpy()
+        for e, o in enumerate(oracles):
+            oo, orr, ote, otr, _ = o.step(actions[t, e])
+            ost = np.array([o.state_vector(i) for i in range(o.NUM_DRONES)])
+            assert rel_err(st[e][:, :16], ost[:, :16]) <= tol, (t, e, rel_err(st[e][:, :16], ost[:, :16]))
+            assert rel_err(obs[e], np.asarray(oo, dtype=np.float64)) <= max(obs_tol, tol), (t, e)
+            assert rel_err(rew[e], orr) <= tol, (t, e)
+            assert bool(r.terminated[e]) == bool(ote) and bool(r.truncated[e]) == bool(otr), (t, e)
+    env.close()
+
+
+SPIRAL5 = dict(task="spiral", drone_model="cf2x", num_drones=5, pyb_freq=240, ctrl_freq=48, act="rpm")
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", FP64_TOL), ("fp32", 2e-4)])
+@pytest.mark.parametrize("physics,aero", [("dyn_gnd", 1), ("dyn_drag", 2), ("dyn_dw", 4), ("dyn_gnd_drag_dw", 7)])
+def test_aero_terms_match_oracle_cfg3(precision, tol, physics, aero):
+    """BASELINE configs[2]: Spiral, 5 drones, ground effect + drag + downwash (O(M^2)), 240/48 Hz."""
+    rng = np.random.default_rng(3)
+    M, N, T = 5, 6, 30
+    # ring start lowered / stacked so that every term is active: two drones share (x,y) at different heights
+    xyz = np.array([[0.4 * np.cos(2 * np.pi * i / M), 0.4 * np.sin(2 * np.pi * i / M), 0.05 + 0.05 * i]
+                    for i in range(M)])
+    xyz[3, :2] = xyz[0, :2] + [0.01, -0.02]
+    xyz[3, 2] = 0.45
+    actions = (0.2 * rng.standard_normal((T, N, M, 4))).astype(np.float32)
+    _run_pair(SPIRAL5, xyz, np.zeros((M, 3)), actions, precision, physics=physics, aero=aero, tol=tol,
+              obs_tol=OBS_F32_TOL if precision == "fp64" else tol)
+
+
+def test_downwash_stacked_pair_fp64():
+    """examples/downwash.py layout moved inside the wake: lower drone is pushed down."""
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=2, pyb_freq=240, ctrl_freq=48, act="rpm")
+    xyz = np.array([[0.0, 0.0, 1.0], [0.02, 0.01, 0.5]])
+    actions = np.zeros((20, 2, 2, 4), dtype=np.float32)
+    actions[:, 1] = 0.1
+    _run_pair(cfg, xyz, np.zeros((2, 3)), actions, "fp64", physics="dyn_dw", aero=4)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", FP64_TOL), ("fp32", 2e-4)])
+def test_euler_integrator_variant(precision, tol):
+    """safe_control_gym base_aviary.py:499-508: rpy += dt*w, quat = fromEuler(rpy), rates stored un-rotated."""
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=2, pyb_freq=240, ctrl_freq=30, act="rpm")
+    rng = np.random.default_rng(5)
+    actions = (0.2 * rng.standard_normal((25, 3, 2, 4))).astype(np.float32)
+    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.7]])
+    _run_pair(cfg, xyz, np.array([[0.1, -0.2, 0.3], [0.0, 0.0, 0.0]]), actions, precision, integrator="euler",
+              tol=tol, obs_tol=OBS_F32_TOL if precision == "fp64" else tol)
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (1, 300), (3, 43), (5, 26), (7, 19), (16, 9), (100, 3), (128, 2)])
+def test_ragged_shapes_fp64(M, N):
+    """Envs never straddle CTAs: E = 128 // M envs per CTA, partially filled last CTA, M up to 128."""
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    rng = np.random.default_rng(M * 1000 + N)
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[i % side, i // side, 0.5 + 0.01 * i] for i in range(M)], dtype=np.float64)
+    T = 3
+    actions = (0.3 * rng.standard_normal((T, N, M, 4))).astype(np.float32)
+    adt = torch.float32
+    env = batch_from_cfg(cfg, xyz, np.zeros((M, 3)), num_envs=N, precision="fp64", action_dtype=adt, keep_ang_vel=True)
+    env.reset_device()
+    check = sorted(set([0, N // 2, N - 1]))
+    oracles = {e: oracle_from_cfg(cfg, xyz, np.zeros((M, 3))) for e in check}
+    for t in range(T):
+        r = env.step_device(torch.as_tensor(actions[t]).to("cuda", adt))
+        obs, rew = r.obs.cpu().numpy(), r.reward.cpu().numpy()
+        for e, o in oracles.items():
+            oo, orr, ote, otr, _ = o.step(actions[t, e])
+            assert rel_err(obs[e], np.asarray(oo, dtype=np.float64)) <= OBS_F32_TOL, (t, e)
+            assert rel_err(rew[e], orr) <= FP64_TOL
+            assert bool(r.terminated[e]) == bool(ote)
+    env.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_autoreset_matches_vec_oracle_with_injected_jitter(precision):
+    """subproc_vec_env.py:188-207 + MultiHoverAviary.py:75-110 with the same uniform draws on both sides."""
+    from oracle.aviary_oracle import OracleAviary, step_env_autoreset
+    M, N, T = 2, 6, 90
+    xyz = np.array([[0.0, 0.0, 0.2], [1.0, 0.0, 0.3]])
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    rng = np.random.default_rng(11)
+    env = batch_from_cfg(cfg, xyz, None, num_envs=N, precision=precision, action_dtype=torch.float32,
+                         auto_reset=True, reset_mode="jitter_buffer")
+    oracles = [OracleAviary(task="multihover", num_drones=M, initial_xyzs=xyz) for _ in range(N)]
+    j0 = rng.uniform(-0.25, 0.25, (N, M, 3))
+    env.set_jitter(torch.as_tensor(j0))
+    obs = env.reset_device().cpu().numpy()
+    for e, o in enumerate(oracles):
+        oo, _ = o.reset(jitter=[j0[e]])
+        assert rel_err(obs[e], np.asarray(oo, dtype=np.float64)) <= OBS_F32_TOL
+    tol = FP64_TOL if precision == "fp64" else 1e-3
+    n_done = 0
+    for t in range(T):
+        a = (rng.uniform(-1, 1, (N, M, 4)) - 0.6).astype(np.float32)   # descending: crashes -> resets
+        jit = rng.uniform(-0.25, 0.25, (N, M, 3))
+        env.set_jitter(torch.as_tensor(jit))
+        r = env.step_device(torch.as_tensor(a, device="cuda"), want_terminal_obs=True)
+        obs, rew = r.obs.cpu().numpy(), r.reward.cpu().numpy()
+        tob = r.terminal_obs.cpu().numpy()
+        for e, o in enumerate(oracles):
+            oo, orr, od, info = step_env_autoreset(o, a[e], jitter=[jit[e]])
+            assert bool(r.done[e]) == bool(od), (t, e)
+            assert rel_err(rew[e], orr) <= tol
+            assert rel_err(obs[e], np.asarray(oo, dtype=np.float64)) <= max(tol, OBS_F32_TOL), (t, e)
+            if od:
+                n_done += 1
+                assert rel_err(tob[e], np.asarray(info["terminal_observation"], dtype=np.float64)) <= max(tol, OBS_F32_TOL)
+        tg = env.get_targets().cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert rel_err(tg[e], o.TARGET_POS) <= (FP64_TOL if precision == "fp64" else 1e-6)
+    assert n_done >= 5
+    env.close()
+
+
+def test_autoreset_fixed_mode_hover_and_spiral():
+    from oracle.aviary_oracle import OracleAviary, step_env_autoreset
+    for task, M, cf, T in (("hover", 1, 30, 30), ("spiral", 3, 48, 70)):
+        cfg = dict(task=task, drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=cf, act="rpm")
+        N = 4
+        env = batch_from_cfg(cfg, None if task == "spiral" else np.array([[0.0, 0.0, 0.5]]), None, num_envs=N,
+                             precision="fp64", action_dtype=torch.float32, auto_reset=True, reset_mode="fixed")
+        oracles = [OracleAviary(task=task, num_drones=M, ctrl_freq=cf,
+                                initial_xyzs=None if task == "spiral" else [[0, 0, 0.5]]) for _ in range(N)]
+        env.reset_device()
+        [o.reset() for o in oracles]
+        rng = np.random.default_rng(1)
+        dones = 0
+        for t in range(T):
+            a = (rng.uniform(-1, 1, (N, M, 4)) + (0.9 if task == "hover" else -0.8)).astype(np.float32)
+            r = env.step_device(torch.as_tensor(a, device="cuda"), want_terminal_obs=True)
+            obs = r.obs.cpu().numpy()
+            for e, o in enumerate(oracles):
+                oo, orr, od, info = step_env_autoreset(o, a[e])
+                assert bool(r.done[e]) == bool(od), (task, t, e)
+                assert rel_err(obs[e], np.asarray(oo, dtype=np.float64)) <= OBS_F32_TOL, (task, t, e)
+                assert rel_err(r.reward[e].item(), orr) <= FP64_TOL
+                dones += int(od)
+        assert dones >= 2, task
+        env.close()
+
+
+def test_philox_jitter_reset_properties():
+    """On-device MultiHoverAviary.reset (:83-106): bounds, clipping, separation, targets, determinism."""
+    M, N = 4, 513
+    grid = np.array([[0.0, 0.0, 0.15], [1.0, 0.0, 0.5], [0.0, 1.0, 0.95], [1.0, 1.0, 0.5]])
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+
+    def fresh(seed):
+        e = batch_from_cfg(cfg, grid, None, num_envs=N, precision="fp32", auto_reset=True,
+                           reset_mode="jitter_philox", seed=seed)
+        return e, e.reset_device().cpu().numpy()
+    e1, o1 = fresh(7)
+    e2, o2 = fresh(7)
+    e3, o3 = fresh(8)
+    assert np.array_equal(o1, o2) and not np.array_equal(o1, o3)
+    pos = o1[:, :, 0:3].astype(np.float64)
+    d = pos - grid[None]
+    assert np.all(np.abs(d[..., :2]) <= 0.25 + 1e-6)
+    assert pos[..., 2].min() >= 0.1 - 1e-7 and pos[..., 2].max() <= 1.0 + 1e-7
+    assert (pos[:, 0, 2] == np.float32(0.1)).any() and (pos[:, 2, 2] == np.float32(1.0)).any()   # clip is active
+    dist = np.linalg.norm(pos[:, :, None, :] - pos[:, None, :, :], axis=-1) + 10 * np.eye(M)[None]
+    assert dist.min() >= 0.5
+    assert len(np.unique(pos[:, 0, 0])) > N // 2          # per-env streams differ
+    tg = e1.get_targets().cpu().numpy()
+    want = pos + np.array([[0, 0, 1 / (i + 1)] for i in range(M)])[None]
+    assert np.allclose(tg, want, atol=1e-6)
+    # a second explicit reset draws new positions; the action history is untouched (zeros)
+    o1b = e1.reset_device().cpu().numpy()
+    assert not np.array_equal(o1b[:, :, :3], o1[:, :, :3]) and np.all(o1b[:, :, 12:] == 0)
+    for e in (e1, e2, e3):
+        e.close()
+
+
+def test_reset_mask_and_history_survives_reset():
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=2, pyb_freq=240, ctrl_freq=30, act="rpm")
+    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5]])
+    env = batch_from_cfg(cfg, xyz, None, num_envs=5, precision="fp32")
+    env.reset_device()
+    a = torch.full((5, 2, 4), 0.25, device="cuda")
+    for _ in range(3):
+        r = env.step_device(a)
+    mask = torch.tensor([0, 1, 0, 0, 1], dtype=torch.uint8, device="cuda")
+    out = r.obs.clone()
+    env.reset_device(env_mask=mask, out=out)
+    st, sc = env.get_state(with_step_counter=True)
+    assert sc.cpu().tolist() == [24, 0, 24, 24, 0]
+    o = out.cpu().numpy()
+    assert np.allclose(o[1, :, :3], xyz) and np.all(o[1, :, 6:12] == 0)
+    assert np.array_equal(o[0], r.obs.cpu().numpy()[0])                  # unmasked rows untouched
+    assert np.all(o[1, :, -12:] == 0.25) and np.all(o[1, :, 12:-12] == 0)  # BaseRLAviary.py:153-154,187
+    assert np.all(st.cpu().numpy()[1, :, 16:20] == 0)                    # last_clipped_action zeroed (:468)
+    env.close()
+
+
+def test_host_step_equals_device_step():
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=3, pyb_freq=240, ctrl_freq=30, act="rpm")
+    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5]])
+    rng = np.random.default_rng(0)
+    envs = [batch_from_cfg(cfg, xyz, None, num_envs=37, precision="fp32") for _ in range(2)]
+    for e in envs:
+        e.reset_device()
+    for t in range(6):
+        a = rng.uniform(-1, 1, (37, 3, 4)).astype(np.float32)
+        d = envs[0].step_device(torch.as_tensor(a, device="cuda"))
+        h = envs[1].step_host(a)
+        assert np.array_equal(d.obs.cpu().numpy(), h["obs"])
+        assert np.array_equal(d.reward.cpu().numpy(), h["reward"])
+        assert np.array_equal(d.terminated.cpu().numpy(), h["terminated"])
+    assert envs[0].launch_count == envs[1].launch_count
+    for e in envs:
+        e.close()
+
+
+def test_full_size_cfg4_properties():
+    """BASELINE configs[3] at full single-GPU size (65,536 envs x 4 drones): size-independent properties."""
+    M, N = 4, 65536
+    grid = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5], [1.0, 1.0, 0.5]])
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    env = batch_from_cfg(cfg, grid, None, num_envs=N, precision="fp32", auto_reset=False)
+    ref = oracle_from_cfg(cfg, grid, None)
+    env.reset_device()
+    rng = np.random.default_rng(4)
+    prev_obs = None
+    for t in range(4):
+        a1 = (0.5 * rng.standard_normal((M, 4))).astype(np.float32)
+        a = torch.as_tensor(a1, device="cuda")[None].expand(N, -1, -1).contiguous()
+        r = env.step_device(a)
+        obs = r.obs
+        # (1) every env received the same action -> every env must be bit-identical (tiling / indexing)
+        assert torch.equal(obs, obs[0:1].expand_as(obs))
+        assert torch.equal(r.reward, r.reward[0:1].expand_as(r.reward))
+        # (2) ... and equal to the oracle within the fp32 tolerance
+        oo, orr, _, _, _ = ref.step(a1)
+        assert rel_err(obs[N - 1].cpu().numpy(), np.asarray(oo, dtype=np.float64)) <= 1e-4
+        # (3) history shift: obs_t[12+4:] == obs_{t-1}[12+8:] shifted by one action
+        if prev_obs is not None:
+            assert torch.equal(obs[:, :, 12:12 + 56], prev_obs[:, :, 16:16 + 56])
+        assert torch.equal(obs[:, :, -4:], a)
+        prev_obs = obs
+    st = env.get_state()
+    qn = torch.linalg.vector_norm(st[:, :, 3:7], dim=-1)
+    assert float((qn - 1).abs().max()) <= 3e-7
+    # (4) determinism with distinct actions: two aviaries, same inputs -> identical bits
+    env2 = batch_from_cfg(cfg, grid, None, num_envs=N, precision="fp32", auto_reset=False)
+    env.reset_device()
+    env2.reset_device()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.rand((3, N, M, 4), generator=g, device="cuda") * 2 - 1
+    for t in range(3):
+        ra, rb = env.step_device(acts[t]), env2.step_device(acts[t])
+        assert torch.equal(ra.obs, rb.obs) and torch.equal(ra.reward, rb.reward)
+    # (5) checksum of per-env rewards is invariant to the env order (permute actions <-> permuted rewards)
+    perm = torch.randperm(N, device="cuda", generator=g)
+    env.reset_device()
+    env2.reset_device()
+    ra, rb = env.step_device(acts[0]), env2.step_device(acts[0][perm].contiguous())
+    # (the action-history columns differ: the two aviaries have different pasts)
+    assert torch.equal(ra.reward[perm], rb.reward) and torch.equal(ra.obs[perm][..., :12], rb.obs[..., :12])
+    env.close()
+    env2.close()
