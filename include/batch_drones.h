@@ -151,6 +151,11 @@ int bd_set_state(bd_handle* h, const void* kin13_dev, const void* targets_dev,
 /* TARGET_POS of every drone, (N,M,3) Real (MultiHoverAviary.py:72,106). */
 int bd_get_targets(bd_handle* h, void* targets_dev, void* stream);
 
+/* BD_F64 handles only: switch between float32 and float64 action input (see
+ * bd_config.action_is_f32).  numpy evaluates HOVER_RPM*(1+0.05*a) partly in float32
+ * when the policy hands float32 actions to the reference (BaseRLAviary.py:192). */
+int bd_set_action_f32(bd_handle* h, int is_f32);
+
 int bd_obs_dim(const bd_handle* h);              /* D                                 */
 int bd_act_dim(const bd_handle* h);              /* A                                 */
 int bd_action_buffer_size(const bd_handle* h);   /* B                                 */

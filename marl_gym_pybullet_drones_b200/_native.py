@@ -21,7 +21,7 @@ BD_RESET = {"fixed": 0, "jitter_philox": 1, "jitter_buffer": 2}
 
 EXPORTS = (
     "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
-    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_obs_dim", "bd_act_dim",
+    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
 )
 
@@ -88,6 +88,8 @@ def load():
     lib.bd_set_state.restype = C.c_int
     lib.bd_get_targets.argtypes = [vp, vp, vp]
     lib.bd_get_targets.restype = C.c_int
+    lib.bd_set_action_f32.argtypes = [vp, C.c_int]
+    lib.bd_set_action_f32.restype = C.c_int
     for name in ("bd_obs_dim", "bd_act_dim", "bd_action_buffer_size", "bd_substeps"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = C.c_int

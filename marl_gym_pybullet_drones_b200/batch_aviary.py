@@ -264,6 +264,8 @@ class BatchAviary:
         """One control step for all envs.  `actions`: (N,M,A) CUDA tensor of `action_dtype`."""
         self._check_open()
         N, M = self.num_envs, self.NUM_DRONES
+        if self.precision == "fp64" and actions.dtype in (torch.float32, torch.float64):
+            self._set_action_dtype(actions.dtype)
         if actions.device != self.device or actions.dtype != self.action_dtype or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=self.action_dtype).contiguous()
         if actions.numel() != N * M * self.ACTION_DIM:
@@ -296,6 +298,13 @@ class BatchAviary:
         """
         self._check_open()
         N, M = self.num_envs, self.NUM_DRONES
+        actions = np.asarray(actions)
+        if self.precision == "fp64" and actions.dtype in (np.float32, np.float64):
+            want = torch.float32 if actions.dtype == np.float32 else torch.float64
+            if want != self.action_dtype:
+                self._set_action_dtype(want)
+                if hasattr(self, "_host_bufs"):
+                    del self._host_bufs
         np_act = np.float32 if self.action_dtype == torch.float32 else np.float64
         if out is None:
             if not hasattr(self, "_host_bufs"):
@@ -321,6 +330,15 @@ class BatchAviary:
                     terminated=out["terminated"].numpy().view(np.bool_),
                     truncated=out["truncated"].numpy().view(np.bool_),
                     terminal_obs=tob.numpy() if tob is not None else None)
+
+    def _set_action_dtype(self, dtype):
+        """fp64 mode: follow the dtype of the actions handed in, like numpy does in the reference
+        (float32 actions -> `1 + 0.05*a` is evaluated in float32, BaseRLAviary.py:192)."""
+        if dtype == self.action_dtype:
+            return
+        torch.cuda.current_stream(self.device).synchronize()
+        _native.check(self._lib.bd_set_action_f32(self._h, int(dtype == torch.float32)), "bd_set_action_f32")
+        self.action_dtype = dtype
 
     # ------------------------------------------------------------ state access
     def get_state(self, with_rates: bool = False, with_step_counter: bool = False):

@@ -431,6 +431,20 @@ int bd_get_targets(bd_handle* h, void* targets_dev, void* stream) {
   return BD_OK;
 }
 
+int bd_set_action_f32(bd_handle* h, int is_f32) {
+  if (!h) return fail(BD_EINVAL, "bd_set_action_f32: null handle");
+  if (h->cfg.precision == BD_F32 && !is_f32)
+    return fail(BD_EINVAL, "bd_set_action_f32: BD_F32 handles take float actions only");
+  h->cfg.action_is_f32 = is_f32 ? 1 : 0;
+  if (h->h_actions) {   // staging buffer of bd_step_host is sized for the action element type
+    DeviceGuard guard(h->cfg.device);
+    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term); cudaFree(h->h_trunc);
+    h->h_actions = nullptr; h->h_obs = nullptr; h->h_reward = nullptr; h->h_term = nullptr; h->h_trunc = nullptr;
+  }
+  refresh_params(h);
+  return BD_OK;
+}
+
 int bd_obs_dim(const bd_handle* h) { return h ? h->D : BD_EINVAL; }
 int bd_act_dim(const bd_handle* h) { return h ? h->A : BD_EINVAL; }
 int bd_action_buffer_size(const bd_handle* h) { return h ? h->B : BD_EINVAL; }

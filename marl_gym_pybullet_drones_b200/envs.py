@@ -64,7 +64,12 @@ class _SingleAviary(Env):
     def step(self, action):
         """BaseAviary.step (:259-383): 5-tuple, no auto-reset."""
         action = np.asarray(action)
-        a = torch.as_tensor(action.reshape(1, self.NUM_DRONES, -1)).to(self._batch.device, self._batch.action_dtype)
+        if action.dtype not in (np.float32, np.float64):
+            action = action.astype(np.float64)
+        if self._batch.precision == "fp32":
+            action = action.astype(np.float32)
+        # the action's own dtype is kept: numpy computes the rpm partly in float32 for float32 actions
+        a = torch.as_tensor(np.ascontiguousarray(action.reshape(1, self.NUM_DRONES, -1))).to(self._batch.device)
         res = self._batch.step_device(a)
         obs = res.obs[0].cpu().numpy()
         reward = float(res.reward[0].item())

@@ -361,7 +361,9 @@ def test_full_size_cfg4_properties():
     acts = torch.rand((3, N, M, 4), generator=g, device="cuda") * 2 - 1
     for t in range(3):
         ra, rb = env.step_device(acts[t]), env2.step_device(acts[t])
-        assert torch.equal(ra.obs, rb.obs) and torch.equal(ra.reward, rb.reward)
+        # (older action-history columns differ: `env` has a longer past than `env2`)
+        assert torch.equal(ra.obs[..., :12], rb.obs[..., :12]) and torch.equal(ra.reward, rb.reward)
+        assert torch.equal(ra.obs[..., -4 * (t + 1):], rb.obs[..., -4 * (t + 1):])
     # (5) checksum of per-env rewards is invariant to the env order (permute actions <-> permuted rewards)
     perm = torch.randperm(N, device="cuda", generator=g)
     env.reset_device()
