@@ -53,14 +53,15 @@ struct DeviceGuard {
 
 struct bd_handle {
   bd_config cfg;
-  int S = 0, A = 0, B = 0, D = 0, Ds = 0, E = 0;
+  int S = 0, A = 0, B = 0, D = 0, E = 0;
   long long n_total = 0;
   size_t real = 4;
   bd::LaunchSpec spec{};
   // device allocations
   void *s0 = nullptr, *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s4 = nullptr;
   float* hist = nullptr;
-  int2* envc = nullptr;
+  int* stepc = nullptr;
+  int* gsteps = nullptr;
   void* init_xyz = nullptr;
   void* init_rpy = nullptr;
   int init_env_stride = 0;
@@ -83,10 +84,10 @@ template <typename R>
 void fill_params(const bd_handle* h, bd::Params<R>& P) {
   const bd_config& c = h->cfg;
   using R4 = typename bd::V4<R>::type;
-  P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D; P.Ds = h->Ds;
+  P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
   P.E = h->E; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
-  P.hist = h->hist; P.envc = h->envc;
+  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps;
   P.init_xyz = (const R*)h->init_xyz; P.init_rpy = (const R*)h->init_rpy;
   P.init_env_stride = h->init_env_stride;
   P.jitter = (const R*)h->jitter;
@@ -116,11 +117,18 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.sp_omega = (R)(c.spiral_period != 0.0 ? 2 * 3.14159265358979323846 / c.spiral_period : 0.0);
   P.sp_vz = (R)c.height_rate; P.sp_cx = (R)c.target_center[0]; P.sp_cy = (R)c.target_center[1];
   P.pyb_freq = (double)c.pyb_freq; P.episode_len = c.episode_len_sec;
+  {  // integer form of `step_counter / PYB_FREQ > EPISODE_LEN_SEC` (MultiHoverAviary.py:268), same fp64 division
+    long long k = (long long)(c.episode_len_sec * c.pyb_freq) - 2;
+    if (k < 0) k = 0;
+    while (!((double)k / (double)c.pyb_freq > c.episode_len_sec)) ++k;
+    P.trunc_counter = (int)k;
+  }
   P.model = c.drone_model; P.aero = c.aero_flags; P.integrator = c.integrator;
   P.auto_reset = c.auto_reset; P.reset_mode = c.reset_mode; P.action_is_f32 = c.action_is_f32;
   P.keep_angv = c.keep_ang_vel;
   P.seed = c.seed;
   P.reset_epoch = 0;
+  { const char* dbg = getenv("BD_DEBUG_SKIP"); P.debug_skip = dbg ? atoi(dbg) : 0; }
 }
 
 void refresh_params(bd_handle* h) {
@@ -188,7 +196,7 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
 
 void free_all(bd_handle* h) {
   cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
-  cudaFree(h->hist); cudaFree(h->envc); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
+  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
@@ -240,7 +248,6 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   h->A = cfg->act_type == BD_ACT_RPM ? 4 : 1;
   h->B = cfg->ctrl_freq / 2;
   h->D = 12 + h->B * h->A + (cfg->task == BD_TASK_SPIRAL ? 11 : 0);
-  h->Ds = (h->D + 3) & ~3;
   h->E = bd::kBlock / cfg->n_drones;
   h->n_total = (long long)cfg->n_envs * cfg->n_drones;
   h->real = cfg->precision == BD_F64 ? 8 : 4;
@@ -249,14 +256,25 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   h->spec.precision = cfg->precision;
   h->spec.device = cfg->device;
   h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel) ? 1 : 0;
+  {
+    // kernel selection: the fast tile kernel covers the throughput configurations
+    // (float, plain DYN, M a power of two <= 32); everything else runs the two-role CTA
+    // kernel.  BD_STEP_IMPL=cta forces the latter (A/B measurements, tests).
+    const int m = cfg->n_drones;
+    const bool pow2 = (m & (m - 1)) == 0 && m <= 32;
+    const char* force = getenv("BD_STEP_IMPL");
+    h->spec.impl = (cfg->precision == BD_F32 && !h->spec.generic && pow2) ? 1 : 0;
+    if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
+  }
 
-  const size_t smem = bd::step_smem_bytes(cfg->precision, h->Ds);
+  const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D);
   cudaDeviceProp prop;
   cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
+  if (h->spec.impl == 1 && (size_t)bd::kBlock * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
   if (smem > prop.sharedMemPerBlockOptin) {
     delete h;
-    return fail(BD_EINVAL, "bd_create: observation tile needs %zu B of shared memory (> %zu)", smem,
+    return fail(BD_EINVAL, "bd_create: the history staging tile needs %zu B of shared memory (> %zu)", smem,
                 (size_t)prop.sharedMemPerBlockOptin);
   }
 
@@ -269,7 +287,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   alloc(&h->s0, plane); alloc(&h->s1, plane); alloc(&h->s2, plane); alloc(&h->s3, plane);
   if (cfg->keep_ang_vel) alloc(&h->s4, plane);
   alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
-  alloc((void**)&h->envc, (size_t)cfg->n_envs * sizeof(int2));
+  alloc((void**)&h->stepc, (size_t)cfg->n_envs * sizeof(int));
+  alloc((void**)&h->gsteps, 2 * sizeof(int));
   if (e != cudaSuccess) {
     free_all(h); delete h;
     return fail(e == cudaErrorMemoryAllocation ? BD_ENOMEM : BD_ECUDA, "bd_create: device allocation failed: %s",

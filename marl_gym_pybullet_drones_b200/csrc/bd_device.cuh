@@ -1,0 +1,422 @@
+// Device-side building blocks shared by the step kernels (bd_kernels.cu):
+// Bullet's closed-form quaternion helpers, the two arithmetic flavours of the explicit
+// dynamics, the reset logic and the per-task observation / reward / termination terms.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "bd_params.h"
+
+namespace bd {
+
+enum { TASK_HOVER = 0, TASK_MULTIHOVER = 1, TASK_SPIRAL = 2 };
+enum { MODEL_CF2X = 0, MODEL_CF2P = 1, MODEL_RACE = 2 };
+enum { AERO_GND = 1, AERO_DRAG = 2, AERO_DW = 4 };
+enum { RESET_FIXED = 0, RESET_PHILOX = 1, RESET_BUFFER = 2 };
+
+// ---------------------------------------------------------------- small maths
+__device__ __forceinline__ float  sqrt_(float x)  { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float  exp_(float x)  { return expf(x); }
+__device__ __forceinline__ double exp_(double x) { return exp(x); }
+__device__ __forceinline__ float  atan2_(float y, float x)  { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float  asin_(float x)  { return asinf(x); }
+__device__ __forceinline__ double asin_(double x) { return asin(x); }
+__device__ __forceinline__ void sincos_(float x, float* s, float* c)  { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ float  abs_(float x)  { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+
+__device__ __forceinline__ float4  make4(float a, float b, float c, float d)   { return make_float4(a, b, c, d); }
+__device__ __forceinline__ double4 make4(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------- Philox
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float  u01(uint32_t a, uint32_t, float)  { return (a >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b, double) {
+  return ((a >> 5) * 67108864.0 + (b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------- Bullet closed-form helpers
+// btMatrix3x3::setRotation == pybullet getMatrixFromQuaternion (BaseAviary.py:836)
+template <typename R>
+__device__ __forceinline__ void quat_to_mat(R x, R y, R z, R w, R m[9]) {
+  const R d = x * x + y * y + z * z + w * w;
+  const R s = R(2) / d;
+  const R xs = x * s, ys = y * s, zs = z * s;
+  const R wx = w * xs, wy = w * ys, wz = w * zs;
+  const R xx = x * xs, xy = x * ys, xz = x * zs;
+  const R yy = y * ys, yz = y * zs, zz = z * zs;
+  m[0] = R(1) - (yy + zz); m[1] = xy - wz;          m[2] = xz + wy;
+  m[3] = xy + wz;          m[4] = R(1) - (xx + zz); m[5] = yz - wx;
+  m[6] = xz - wy;          m[7] = yz + wx;          m[8] = R(1) - (xx + yy);
+}
+
+// btMatrix3x3::getRotation (what getBasePositionAndOrientation returns, :517)
+template <typename R>
+__device__ __forceinline__ void mat_to_quat(const R m[9], R& x, R& y, R& z, R& w) {
+  const R trace = m[0] + m[4] + m[8];
+  if (trace > R(0)) {
+    R s = sqrt_(trace + R(1));
+    w = s * R(0.5);
+    s = R(0.5) / s;
+    x = (m[7] - m[5]) * s;
+    y = (m[2] - m[6]) * s;
+    z = (m[3] - m[1]) * s;
+  } else {
+    const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+    if (i == 0) {
+      R s = sqrt_(m[0] - m[4] - m[8] + R(1));
+      x = s * R(0.5); s = R(0.5) / s;
+      w = (m[7] - m[5]) * s; y = (m[3] + m[1]) * s; z = (m[6] + m[2]) * s;
+    } else if (i == 1) {
+      R s = sqrt_(m[4] - m[8] - m[0] + R(1));
+      y = s * R(0.5); s = R(0.5) / s;
+      w = (m[2] - m[6]) * s; z = (m[7] + m[5]) * s; x = (m[1] + m[3]) * s;
+    } else {
+      R s = sqrt_(m[8] - m[0] - m[4] + R(1));
+      z = s * R(0.5); s = R(0.5) / s;
+      w = (m[3] - m[1]) * s; x = (m[2] + m[6]) * s; y = (m[5] + m[7]) * s;
+    }
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void bullet_roundtrip(R& x, R& y, R& z, R& w) {
+  R m[9];
+  quat_to_mat(x, y, z, w, m);
+  mat_to_quat(m, x, y, z, w);
+}
+
+// Same map as bullet_roundtrip for float throughput: q/|q| with Bullet's sign rule
+// (trace > 0 <=> 4w^2 > 1 -> w >= 0; else the largest diagonal's component >= 0).
+__device__ __forceinline__ void fast_canonical(float& x, float& y, float& z, float& w) {
+  const float rn = rsqrtf(fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w))));
+  x *= rn; y *= rn; z *= rn; w *= rn;
+  bool neg;
+  if (w * w > 0.25f) {
+    neg = w < 0.0f;
+  } else {
+    const float xx = x * x, yy = y * y, zz = z * z;   // m00 < m11 <=> xx < yy
+    const int i = xx < yy ? (yy < zz ? 2 : 1) : (xx < zz ? 2 : 0);
+    neg = (i == 0 ? x : (i == 1 ? y : z)) < 0.0f;
+  }
+  if (neg) { x = -x; y = -y; z = -z; w = -w; }
+}
+
+// pybullet getEulerFromQuaternion (:518) incl. its gimbal branches
+template <typename R>
+__device__ __forceinline__ void quat_to_euler(R x, R y, R z, R w, R& roll, R& pitch, R& yaw) {
+  const R sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
+  const R sarg = R(-2) * (x * z - w * y);
+  const R half_pi = R(0.5 * 3.14159265358979323846);
+  if (sarg <= R(-0.99999)) {
+    roll = R(0); pitch = -half_pi; yaw = R(2) * atan2_(x, -y);
+  } else if (sarg >= R(0.99999)) {
+    roll = R(0); pitch = half_pi; yaw = R(2) * atan2_(-x, y);
+  } else {
+    roll = atan2_(R(2) * (y * z + w * x), squ - sqx - sqy + sqz);
+    pitch = asin_(sarg);
+    yaw = atan2_(R(2) * (x * y + w * z), squ + sqx - sqy - sqz);
+  }
+}
+
+// pybullet getQuaternionFromEuler (:488), normalised
+template <typename R>
+__device__ __forceinline__ void euler_to_quat(R roll, R pitch, R yaw, R& x, R& y, R& z, R& w) {
+  R sp, cp, st, ct, ss, cs;
+  sincos_(roll / R(2), &sp, &cp);
+  sincos_(pitch / R(2), &st, &ct);
+  sincos_(yaw / R(2), &ss, &cs);
+  x = sp * ct * cs - cp * st * ss;
+  y = cp * st * cs + sp * ct * ss;
+  z = cp * ct * ss - sp * st * cs;
+  w = cp * ct * cs + sp * st * ss;
+  const R n = sqrt_(x * x + y * y + z * z + w * w);
+  x /= n; y /= n; z /= n; w /= n;
+}
+
+// BaseAviary._integrateQ (:879-892): q <- cos(th) q + sin(th)/|w| Lambda(w) q
+template <typename R>
+__device__ __forceinline__ void integrate_q_exact(R& x, R& y, R& z, R& w, R p, R q, R r, R dt) {
+  const R n = sqrt_(p * p + q * q + r * r);
+  if (n <= R(1e-8)) return;                       // np.isclose(norm, 0): atol 1e-8
+  R s, c;
+  sincos_(n * dt / R(2), &s, &c);
+  const R k = R(2) / n * R(0.5) * s;
+  const R nx = c * x + k * (r * y - q * z + p * w);
+  const R ny = c * y + k * (-r * x + p * z + q * w);
+  const R nz = c * z + k * (q * x - p * y + r * w);
+  const R nw = c * w + k * (-p * x - q * y - r * z);
+  x = nx; y = ny; z = nz; w = nw;
+}
+
+// float fast path: cos(th) and sin(th)/|w| = (dt/2) sinc(th) as polynomials in th^2
+__device__ __forceinline__ void integrate_q_fast(float& x, float& y, float& z, float& w,
+                                                 float p, float q, float r, float half_dt) {
+  const float n2 = fmaf(p, p, fmaf(q, q, r * r));
+  const float u = n2 * half_dt * half_dt;         // th^2
+  float c, k;
+  if (u <= 0.25f) {
+    c = fmaf(u, fmaf(u, fmaf(u, fmaf(u, 2.4801587e-5f, -1.3888889e-3f), 4.1666668e-2f), -0.5f), 1.0f);
+    k = half_dt * fmaf(u, fmaf(u, fmaf(u, fmaf(u, 2.7557319e-6f, -1.9841270e-4f), 8.3333338e-3f),
+                                    -1.6666667e-1f), 1.0f);
+  } else {
+    const float n = sqrtf(n2);
+    float s;
+    sincosf(n * half_dt, &s, &c);
+    k = s / n;
+  }
+  const float nx = fmaf(k, fmaf(r, y, fmaf(-q, z, p * w)), c * x);
+  const float ny = fmaf(k, fmaf(-r, x, fmaf(p, z, q * w)), c * y);
+  const float nz = fmaf(k, fmaf(q, x, fmaf(-p, y, r * w)), c * z);
+  const float nw = fmaf(k, -fmaf(p, x, fmaf(q, y, r * z)), c * w);
+  x = nx; y = ny; z = nz; w = nw;
+}
+
+// --------------------------------------------------------------- reset logic
+template <typename R>
+struct Drone {
+  R px, py, pz, qx, qy, qz, qw, vx, vy, vz, wx, wy, wz, tx, ty, tz;
+};
+
+// INIT pose of (env, drone) -> freshly reset drone (BaseAviary._housekeeping :451-505
+// + kinematic refresh :509-519) and its 12 kinematic observation entries.
+template <typename R, int TASK>
+__device__ __forceinline__ void reset_drone(const Params<R>& P, int env, int drone, const R* cand,
+                                            Drone<R>& d, float kin[12]) {
+  const long long ib = (long long)env * P.init_env_stride + drone * 3;
+  R ix = P.init_xyz[ib], iy = P.init_xyz[ib + 1], iz = P.init_xyz[ib + 2];
+  if (TASK == TASK_MULTIHOVER && cand != nullptr) { ix = cand[0]; iy = cand[1]; iz = cand[2]; }
+  d.px = ix; d.py = iy; d.pz = iz;
+  euler_to_quat(P.init_rpy[ib], P.init_rpy[ib + 1], P.init_rpy[ib + 2], d.qx, d.qy, d.qz, d.qw);
+  bullet_roundtrip(d.qx, d.qy, d.qz, d.qw);
+  d.vx = d.vy = d.vz = R(0);
+  d.wx = d.wy = d.wz = R(0);
+  if (TASK == TASK_HOVER) { d.tx = R(0); d.ty = R(0); d.tz = R(1); }                 // HoverAviary.py:51
+  else if (TASK == TASK_MULTIHOVER) { d.tx = ix; d.ty = iy; d.tz = iz + R(1) / R(drone + 1); }  // :72,106
+  else { d.tx = d.ty = d.tz = R(0); }
+  R roll, pitch, yaw;
+  quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
+  kin[0] = (float)d.px; kin[1] = (float)d.py; kin[2] = (float)d.pz;
+  kin[3] = (float)roll; kin[4] = (float)pitch; kin[5] = (float)yaw;
+  kin[6] = kin[7] = kin[8] = kin[9] = kin[10] = kin[11] = 0.0f;
+}
+
+// MultiHoverAviary.reset (:83-102) for one env, run by its leader thread:
+// ORIGINAL_INIT_XYZS + U(-0.25,0.25)^3, z clipped to [0.1,1], redraw until every
+// pair is >= 0.5 m apart.  `cand` = shared-memory rows of this env's M drones.
+// The reference loops forever when no draw can succeed; here kMaxJitterTries
+// draws, then the un-jittered layout (documented deviation).
+template <typename R>
+__device__ void sample_jitter(const Params<R>& P, int env, int total_steps, int epoch, R* cand) {
+  const int M = P.M;
+  const long long ib = (long long)env * P.init_env_stride;
+  for (int attempt = 0; attempt <= kMaxJitterTries; ++attempt) {
+    const bool last = attempt == kMaxJitterTries;
+    for (int i = 0; i < M; ++i) {
+      R j[3] = {R(0), R(0), R(0)};
+      if (!last) {
+        if (P.reset_mode == RESET_BUFFER && P.jitter != nullptr) {
+          const long long jb = ((long long)env * M + i) * 3;
+          j[0] = P.jitter[jb]; j[1] = P.jitter[jb + 1]; j[2] = P.jitter[jb + 2];
+        } else {
+          uint32_t c[4] = {(uint32_t)env, (uint32_t)total_steps, (uint32_t)(attempt * M + i), (uint32_t)epoch << 1};
+          uint32_t c2[4] = {c[0], c[1], c[2], c[3] | 1u};
+          philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+          philox4x32_10(c2, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+          j[0] = R(-0.25) + R(0.5) * u01(c[0], c[1], R(0));
+          j[1] = R(-0.25) + R(0.5) * u01(c[2], c[3], R(0));
+          j[2] = R(-0.25) + R(0.5) * u01(c2[0], c2[1], R(0));
+        }
+      }
+      R z = P.init_xyz[ib + i * 3 + 2] + j[2];
+      z = z < R(0.1) ? R(0.1) : (z > R(1.0) ? R(1.0) : z);
+      cand[i * 3 + 0] = P.init_xyz[ib + i * 3 + 0] + j[0];
+      cand[i * 3 + 1] = P.init_xyz[ib + i * 3 + 1] + j[1];
+      cand[i * 3 + 2] = z;
+    }
+    if (last || P.reset_mode == RESET_BUFFER) return;
+    bool ok = true;
+    for (int a = 0; a < M && ok; ++a)
+      for (int b = a + 1; b < M; ++b) {
+        const R dx = cand[a * 3] - cand[b * 3], dy = cand[a * 3 + 1] - cand[b * 3 + 1],
+                dz = cand[a * 3 + 2] - cand[b * 3 + 2];
+        if (sqrt_(dx * dx + dy * dy + dz * dz) < R(0.5)) { ok = false; break; }
+      }
+    if (ok) return;
+  }
+}
+
+// --------------------------------------------------------------- task maths
+template <typename R>
+__device__ __forceinline__ void spiral_reference(const Params<R>& P, int step_counter, int drone,
+                                                 R ref_p[3], R ref_v[3], R& sphi, R& cphi) {
+  const R t = (R)((double)step_counter / P.pyb_freq);                            // SpiralAviary.py:84
+  const R phase = P.sp_omega * t + R(2) * R(3.14159265358979323846) * R(drone) / R(P.M);
+  sincos_(phase, &sphi, &cphi);
+  ref_p[0] = P.sp_cx + P.sp_R * cphi;
+  ref_p[1] = P.sp_cy + P.sp_R * sphi;
+  ref_p[2] = R(0.3) + P.sp_vz * t;
+  ref_v[0] = -P.sp_R * P.sp_omega * sphi;
+  ref_v[1] = P.sp_R * P.sp_omega * cphi;
+  ref_v[2] = P.sp_vz;
+}
+
+}  // namespace bd
+
+namespace bd {
+
+// ---------------------------------------------------------------------------
+// Fast float flavour of S substeps (BaseAviary.py:343-374 with _dynamics :815-877).
+// `onep[k]` = fl32(1 + 0.05 a_k) per motor, i.e. rpm_k / HOVER_RPM as numpy rounds it.
+//   rpm_k = H (1 + s_k)  =>  rpm_k^2 = H^2 (1 + u_k),  u_k = s_k (2 + s_k).  With
+//   4 KF H^2 = m g (BaseAviary.py:118) the hover terms cancel analytically, which
+//   removes the float32 cancellation in thrust - gravity and in the torque mixes:
+//   thrust/m = g (1 + e), e = sum(u)/4;  f_k = (m g / 4)(1 + u_k);  KM rpm_k^2 = KM H^2 (1 + u_k)
+// Per substep only the rotation's third column is formed; the full matrix once, for the
+// world angular velocity R_old w_new (:873) of the last substep.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<float>& d, const float onep[4],
+                                              float& avx, float& avy, float& avz) {
+  const float dt = P.dt;
+  float u[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float sk = onep[k] - 1.0f;                  // exact (Sterbenz)
+    u[k] = sk * (2.0f + sk);
+  }
+  const float qf = 0.25f * P.gravity;                   // KF H^2
+  const float qm = P.km * (P.hover_rpm * P.hover_rpm);  // KM H^2
+  float tz = qm * ((-u[0] + u[1]) + (-u[2] + u[3]));
+  float tx, ty;
+  if (P.model == 0) { tx = -qf * ((u[0] + u[1]) - (u[2] + u[3])) * P.arm; ty = qf * ((-u[0] + u[1]) + (u[2] - u[3])) * P.arm; }
+  else if (P.model == 1) { tx = qf * (u[1] - u[3]) * P.arm; ty = qf * (-u[0] + u[2]) * P.arm; }
+  else { tx = qf * ((u[0] + u[1]) - (u[2] + u[3])) * P.arm; ty = qf * ((-u[0] + u[1]) + (u[2] - u[3])) * P.arm; tz = -tz; }
+  const float kx = dt * P.ijx * tx, ky = dt * P.ijy * ty, kz = dt * P.ijz * tz;
+  const float gx = dt * P.ijx * (P.jz - P.jy), gy = dt * P.ijy * (P.jx - P.jz), gz = dt * P.ijz * (P.jy - P.jx);
+  const float e4 = 0.25f * ((u[0] + u[1]) + (u[2] + u[3]));
+  const float cg = dt * P.gravity * P.inv_m;            // dt g
+  const float c1 = cg * (1.0f + e4), c2 = cg * e4, c3 = -2.0f * cg;
+  const float half_dt = 0.5f * dt;
+#pragma unroll 1
+  for (int s = 0; s < P.S; ++s) {
+    const float x = d.qx, y = d.qy, z = d.qz, w = d.qw;   // unit, canonical
+    const float xxyy = fmaf(x, x, y * y);
+    const float r02 = 2.0f * fmaf(x, z, w * y), r12 = 2.0f * fmaf(y, z, -w * x),
+                r22 = fmaf(-2.0f, xxyy, 1.0f);
+    // a = g [(1+e) R[:,2] - e_z];  (1+e) r22 - 1 = e r22 - 2 (x^2 + y^2)
+    d.vx = fmaf(c1, r02, d.vx);
+    d.vy = fmaf(c1, r12, d.vy);
+    d.vz = fmaf(c2, r22, fmaf(c3, xxyy, d.vz));
+    const float owx = d.wx, owy = d.wy, owz = d.wz;
+    d.wx = fmaf(-gx, owy * owz, owx + kx);
+    d.wy = fmaf(-gy, owz * owx, owy + ky);
+    d.wz = fmaf(-gz, owx * owy, owz + kz);
+    d.px = fmaf(dt, d.vx, d.px);
+    d.py = fmaf(dt, d.vy, d.py);
+    d.pz = fmaf(dt, d.vz, d.pz);
+    if (s == P.S - 1) {
+      const float r00 = fmaf(-2.0f, fmaf(y, y, z * z), 1.0f), r01 = 2.0f * fmaf(x, y, -w * z);
+      const float r10 = 2.0f * fmaf(x, y, w * z), r11 = fmaf(-2.0f, fmaf(x, x, z * z), 1.0f);
+      const float r20 = 2.0f * fmaf(x, z, -w * y), r21 = 2.0f * fmaf(y, z, w * x);
+      avx = fmaf(r00, d.wx, fmaf(r01, d.wy, r02 * d.wz));
+      avy = fmaf(r10, d.wx, fmaf(r11, d.wy, r12 * d.wz));
+      avz = fmaf(r20, d.wx, fmaf(r21, d.wy, r22 * d.wz));
+    }
+    integrate_q_fast(d.qx, d.qy, d.qz, d.qw, d.wx, d.wy, d.wz, half_dt);
+    fast_canonical(d.qx, d.qy, d.qz, d.qw);
+  }
+}
+
+// Spiral env's 11 extra observation entries (SpiralAviary.py:120-146)
+template <typename R>
+__device__ __forceinline__ void spiral_extras(float* ext, const Drone<R>& d, const R rp[3], const R rv[3],
+                                              R sphi, R cphi) {
+  // SpiralAviary.py:130: "vel" = state[3:6] = quaternion x,y,z (reference quirk)
+  ext[0] = (float)(rp[0] - d.px); ext[1] = (float)(rp[1] - d.py); ext[2] = (float)(rp[2] - d.pz);
+  ext[3] = (float)(rv[0] - d.qx); ext[4] = (float)(rv[1] - d.qy); ext[5] = (float)(rv[2] - d.qz);
+  ext[6] = (float)sphi; ext[7] = (float)cphi;
+  ext[8] = (float)rv[0]; ext[9] = (float)rv[1]; ext[10] = (float)rv[2];
+}
+
+// Per-drone reward contribution and termination/truncation condition bits of the task
+// (bit0: terminated condition, bit1: truncated condition), plus the spiral extras.
+//   HoverAviary.py:77-117, MultiHoverAviary.py:128-241, SpiralAviary.py:150-191
+template <typename R, int TASK>
+__device__ __forceinline__ void task_terms(const Params<R>& P, const Drone<R>& d, R roll, R pitch,
+                                           int step_counter, int drone, float* ext, R& contrib, int& flags) {
+  contrib = R(0);
+  flags = 0;
+  if (TASK == 0) {
+    const R ex = d.tx - d.px, ey = d.ty - d.py, ez = d.tz - d.pz;
+    const R dist = sqrt_(ex * ex + ey * ey + ez * ez);
+    const R d2 = dist * dist;
+    const R r = R(2) - d2 * d2;                                                  // HoverAviary.py:78
+    contrib = r > R(0) ? r : R(0);
+    if (dist < R(.0001)) flags |= 1;                                             // :93
+    if (abs_(d.px) > R(1.5) || abs_(d.py) > R(1.5) || d.pz > R(2.0) ||
+        abs_(roll) > R(.4) || abs_(pitch) > R(.4)) flags |= 2;                   // :109-111
+  } else if (TASK == 1) {
+    const R ex = d.px - d.tx, ey = d.py - d.ty;
+    const R err_xy = sqrt_(ex * ex + ey * ey);
+    const R err_z = d.pz - d.tz;
+    const R vel_z = d.vz;
+    const R r_xy = R(1) / (R(1) + err_xy);
+    const R r_z = exp_(R(-7.5) * abs_(err_z));
+    const R r_vel = abs_(err_z) < R(0.2) ? R(-1.5) * (vel_z * vel_z) : R(0);
+    const R bonus = (err_xy < R(0.03) && abs_(err_z) < R(0.03) && abs_(vel_z) < R(0.03)) ? R(0.5) : R(0);
+    contrib = ((r_xy + r_z) + r_vel) + bonus;                                    // MultiHoverAviary.py:173-179
+    if (d.pz < R(0.03)) flags |= 1;                                              // :226
+    if (abs_(roll) > R(1.2) || abs_(pitch) > R(1.2)) flags |= 1;                 // :231
+    if (abs_(d.px) > R(3.0) || abs_(d.py) > R(3.0)) flags |= 1;                  // :236
+  } else {
+    R rp[3], rv[3], sphi, cphi;
+    spiral_reference(P, step_counter, drone, rp, rv, sphi, cphi);
+    spiral_extras(ext, d, rp, rv, sphi, cphi);
+    const R dpx = d.px - rp[0], dpy = d.py - rp[1], dpz = d.pz - rp[2];
+    const R npos = sqrt_(dpx * dpx + dpy * dpy + dpz * dpz);
+    const R dvx = d.qx - rv[0], dvy = d.qy - rv[1], dvz = d.qz - rv[2];           // :156 (same quirk)
+    const R nvel = sqrt_(dvx * dvx + dvy * dvy + dvz * dvz);
+    const R r_pos = exp_(R(-4.0) * (npos * npos));
+    const R r_vel = exp_(R(-2.0) * (nvel * nvel));
+    R r_tan = R(0);
+    const R rx = d.px - P.sp_cx, ry = d.py - P.sp_cy;
+    const R nr = sqrt_(rx * rx + ry * ry);
+    if (nr > R(1e-3)) {
+      const R tgx = -(ry / nr), tgy = rx / nr;
+      const R nv = sqrt_(d.qx * d.qx + d.qy * d.qy);
+      if (nv > R(1e-3)) {
+        const R dot = (d.qx / nv) * tgx + (d.qy / nv) * tgy;
+        r_tan = dot > R(0) ? dot : R(0);
+      }
+    }
+    contrib = (R(1.0) * r_pos + R(2.0) * r_vel) + R(1.0) * r_tan;               // :179
+    if (d.pz < R(0.05) || d.pz > R(3.0)) flags |= 1;                             // :188-190
+  }
+}
+
+}  // namespace bd

@@ -20,14 +20,16 @@ template <> struct V4<double> { using type = double4; };
 //   s4[g] = (avx, avy, avz, -) world angular velocity, only with keep_ang_vel
 //   hist[slot][g][A]           float action ring, B slots (survives reset,
 //                              BaseRLAviary.py:153-154,187)
-//   envc[e] = (step_counter since reset, total steps)  -> ring head = total % B
+//   stepc[e]                   step_counter since the env's last reset (BaseAviary.py:382,460)
+//   gsteps[0] = total control steps taken (ring head = total % B, Philox stream), gsteps[1] = CTA ticket
 template <typename Real>
 struct Params {
-  int N, M, S, A, B, D, Ds, E;
+  int N, M, S, A, B, D, E;
   long long n_total;
   typename V4<Real>::type *s0, *s1, *s2, *s3, *s4;
   float* hist;
-  int2* envc;
+  int* stepc;
+  int* gsteps;
   const Real* init_xyz;
   const Real* init_rpy;
   int init_env_stride;            // 0 (shared (M,3) table) or M*3
@@ -47,13 +49,16 @@ struct Params {
   Real prop_x[4], prop_y[4];
   Real sp_R, sp_omega, sp_vz, sp_cx, sp_cy;
   double pyb_freq, episode_len;
+  int trunc_counter;              // smallest step_counter with step_counter / pyb_freq > episode_len (fp64)
   int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
+  int debug_skip;                 // profiling aid (env BD_DEBUG_SKIP): bit0 skip copy role, bit1 skip physics role
   int reset_epoch;                // >=1 for explicit bd_reset calls (Philox stream id), 0 in-step
   unsigned long long seed;
 };
 
 struct LaunchSpec {
   int task, act_a, precision, generic, device;
+  int impl;        // 0: two-role CTA kernel (any config), 1: fast tile kernel (bd_step_tile.cuh)
 };
 
 // implemented in bd_kernels.cu
@@ -64,6 +69,6 @@ cudaError_t launch_get_state(int precision, const void* params, void* state20, v
 cudaError_t launch_set_state(int precision, const void* params, const void* kin13,
                              const void* targets, const int32_t* step_counter, cudaStream_t st);
 cudaError_t launch_get_targets(int precision, const void* params, void* targets, cudaStream_t st);
-size_t step_smem_bytes(int precision, int Ds);
+size_t step_smem_bytes(int precision, int A, int B, int D);
 
 }  // namespace bd

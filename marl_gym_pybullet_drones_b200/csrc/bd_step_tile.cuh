@@ -1,0 +1,281 @@
+// Fast step kernel (float, plain DYN, M in {1,2,4,8,16,32}): one CTA per tile of 128 drones.
+//
+// Measured facts that shape it (scripts/microbench/*.cu, profiles/README.md):
+//   * observation rows must leave the SM as complete, contiguous rows: 16-byte or
+//     partial-sector row pieces write at 1.6-1.9 TB/s, whole rows at 5-6 TB/s;
+//   * the memory skeleton of a step (read 4 state planes + action + 14 ring planes, write
+//     state, one ring slot and whole rows) runs at 0.85-0.96 of the measured HBM peak with
+//     exactly this shape — 128 rows per CTA, every load issued before anything is consumed,
+//     a row-major shared-memory tile — and slower with 32-row tiles or persistent CTAs;
+//   * shared memory, not registers, bounds occupancy: the 128 x D tile must be the ONLY
+//     shared memory of the CTA for 6 CTAs (24 warps) to fit on an SM.
+//
+// Per CTA: (1) 4 state planes, action and step counter with 128-bit coalesced loads, then
+// the B-1 ring planes with cp.async (no registers) straight into the thread's own row of
+// the tile; (2) S substeps in registers while the history lands; (3) kinematic part, task
+// terms and the new action complete the row; per-env reward / termination reductions and
+// the MultiHover re-spawn rule use warp shuffles (envs are lane groups, M | 32), so there
+// is no reduction scratch; (4) one __syncthreads, then the 128 finished rows (36 864 B for
+// D = 72) leave as ONE TMA bulk store issued by thread 0; state planes and the ring slot
+// are plain 128-bit stores.
+// The global step count (ring head, Philox stream id) lives in device memory and is
+// advanced by the last CTA to finish, so the launch is CUDA-graph replayable.
+#pragma once
+#include "bd_device.cuh"
+
+namespace bd {
+
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(ssrc));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+template <int A>
+struct TileIn {
+  float4 s0, s1, s2, s3;
+  float4 act;   // A == 1: only .x is used
+  int stepc;
+};
+
+template <int A>
+__device__ __forceinline__ void load_inputs(const Params<float>& P, long long g, int log2m, TileIn<A>& in) {
+  if (g < P.n_total) {
+    in.s0 = P.s0[g]; in.s1 = P.s1[g]; in.s2 = P.s2[g]; in.s3 = P.s3[g];
+    if constexpr (A == 4) in.act = reinterpret_cast<const float4*>(P.actions)[g];
+    else in.act = make_float4(reinterpret_cast<const float*>(P.actions)[g], 0.f, 0.f, 0.f);
+    in.stepc = P.stepc[g >> log2m];
+  } else {
+    in.s0 = in.s1 = in.s2 = in.s3 = in.act = make_float4(0.f, 0.f, 0.f, 0.f);
+    in.s1.z = 1.0f;
+    in.stepc = 0;
+  }
+}
+
+// action history of one tile, oldest -> second newest (BaseRLAviary.py:317-318):
+// ring slots head+1 .. head-1  ->  columns 12 .. 12+(B-1)A of my row of the tile.
+// Two straight runs (slots head+1..B-1, then 0..head-1) so the loop body is one LDGSTS
+// plus two pointer bumps.
+template <int A, bool VEC>
+__device__ __forceinline__ void issue_history(const Params<float>& P, long long g, int head, float* myrow) {
+  if (g < P.n_total) {
+    float* dst = myrow + 12;
+    const size_t plane = (size_t)P.n_total * A;
+    const float* src = P.hist + (size_t)g * A + (size_t)(head + 1) * plane;
+    const int n1 = P.B - 1 - head;   // slots head+1 .. B-1
+#pragma unroll 2
+    for (int j = 0; j < n1; ++j) {
+      if constexpr (VEC) cp_async<16>(dst, src);
+      else {
+#pragma unroll
+        for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
+      }
+      dst += A; src += plane;
+    }
+    src = P.hist + (size_t)g * A;    // slots 0 .. head-1
+#pragma unroll 2
+    for (int j = 0; j < head; ++j) {
+      if constexpr (VEC) cp_async<16>(dst, src);
+      else {
+#pragma unroll
+        for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
+      }
+      dst += A; src += plane;
+    }
+  }
+  cp_async_commit();
+}
+
+template <int TASK, int A, bool VEC>
+__global__ void __launch_bounds__(kBlock, 6)
+step_kernel_tile(const __grid_constant__ Params<float> P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int M = P.M, B = P.B, D = P.D;
+  const int log2m = 31 - __clz(M);
+  constexpr bool vec = VEC;   // A == 4 and D % 4 == 0: 128-bit row accesses
+  float* tile_s = reinterpret_cast<float*>(smem_raw);   // [kBlock][D] row-major, dense
+  float* myrow = tile_s + (size_t)tid * D;
+  const int drone = lane & (M - 1);
+  const int group_base = lane & ~(M - 1);
+  const long long g0 = (long long)blockIdx.x * kBlock;
+  const long long g = g0 + tid;
+  const bool active = g < P.n_total;
+  const int env = (int)(g >> log2m);
+  const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
+
+  // ---- 1. every load of the tile is issued before anything is consumed ------------------------
+  TileIn<A> cur;
+  load_inputs<A>(P, g, log2m, cur);
+  const int total = P.gsteps[0];   // uniform address; only the last CTA to finish modifies it, after every read
+  const int head = total % B;   // ring slot overwritten by this step's action
+  issue_history<A, VEC>(P, g, head, myrow);
+  const int stepc = cur.stepc;
+
+  Drone<float> d;
+  d.px = cur.s0.x; d.py = cur.s0.y; d.pz = cur.s0.z; d.qx = cur.s0.w;
+  d.qy = cur.s1.x; d.qz = cur.s1.y; d.qw = cur.s1.z; d.vx = cur.s1.w;
+  d.vy = cur.s2.x; d.vz = cur.s2.y; d.wx = cur.s2.z; d.wy = cur.s2.w;
+  d.wz = cur.s3.x; d.tx = cur.s3.y; d.ty = cur.s3.z; d.tz = cur.s3.w;
+  float onep[4];
+  if constexpr (A == 4) {
+    // numpy evaluates 1 + 0.05*a in float32 for float32 actions (two roundings, BaseRLAviary.py:192)
+    onep[0] = __fadd_rn(1.0f, __fmul_rn(0.05f, cur.act.x));
+    onep[1] = __fadd_rn(1.0f, __fmul_rn(0.05f, cur.act.y));
+    onep[2] = __fadd_rn(1.0f, __fmul_rn(0.05f, cur.act.z));
+    onep[3] = __fadd_rn(1.0f, __fmul_rn(0.05f, cur.act.w));
+  } else {
+    onep[0] = onep[1] = onep[2] = onep[3] = __fadd_rn(1.0f, __fmul_rn(0.05f, cur.act.x));   // :225
+  }
+
+  // ---- 2. S substeps in registers while the history lands --------------------------------------
+  float avx = 0.f, avy = 0.f, avz = 0.f;
+  if (!(P.debug_skip & 4)) fast_substeps(P, d, onep, avx, avy, avz);
+  float roll, pitch, yaw;
+  quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
+
+  // ---- 3. complete my observation row ------------------------------------------------------------
+  cp_async_wait_all();
+  float contrib = 0.f;
+  int flags = 0;
+  if (active) {
+    if (vec) {
+      float4* r4 = reinterpret_cast<float4*>(myrow);
+      r4[0] = make_float4(d.px, d.py, d.pz, roll);
+      r4[1] = make_float4(pitch, yaw, d.vx, d.vy);
+      r4[2] = make_float4(d.vz, avx, avy, avz);
+    } else {
+      myrow[0] = d.px; myrow[1] = d.py; myrow[2] = d.pz; myrow[3] = roll; myrow[4] = pitch; myrow[5] = yaw;
+      myrow[6] = d.vx; myrow[7] = d.vy; myrow[8] = d.vz; myrow[9] = avx; myrow[10] = avy; myrow[11] = avz;
+    }
+    task_terms<float, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
+    // newest history entry: tail of the row and ring slot `head`
+    if constexpr (A == 4) {
+      if (vec) *reinterpret_cast<float4*>(myrow + 12 + (B - 1) * 4) = cur.act;
+      else { float* o = myrow + 12 + (B - 1) * 4; o[0] = cur.act.x; o[1] = cur.act.y; o[2] = cur.act.z; o[3] = cur.act.w; }
+      *reinterpret_cast<float4*>(P.hist + ((size_t)head * P.n_total + g) * 4) = cur.act;
+    } else {
+      myrow[12 + B - 1] = cur.act.x;
+      P.hist[(size_t)head * P.n_total + g] = cur.act.x;
+    }
+  }
+
+  // ---- per-env reduction with shuffles (envs are lane groups of M) --------------------------------
+#pragma unroll 1
+  for (int o = M >> 1; o > 0; o >>= 1) {
+    contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+  }
+  const float reward = (TASK == TASK_HOVER) ? contrib : contrib / (float)M;
+  const bool time_up = stepc >= P.trunc_counter;   // step_counter/PYB_FREQ > EPISODE_LEN_SEC, pre-increment (:379,:382)
+  const bool terminated = (flags & 1) != 0;
+  const bool truncated = ((flags & 2) != 0) || time_up;
+  const bool done_reset = active && (terminated || truncated) && P.auto_reset;
+  if (active && drone == 0) {
+    P.reward[env] = reward;
+    P.terminated[env] = terminated ? 1 : 0;
+    P.truncated[env] = truncated ? 1 : 0;
+    P.stepc[env] = done_reset ? 0 : stepc + P.S;
+  }
+
+  // ---- reset-on-done (subproc_vec_env.py:195-206), rare -------------------------------------------
+  if (__any_sync(0xffffffffu, done_reset)) {
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (jit) {   // MultiHoverAviary.py:83-102, every lane draws its own drone's jitter
+      const long long ib = (long long)env * P.init_env_stride + drone * 3;
+      bool retry = done_reset;
+#pragma unroll 1
+      for (int attempt = 0; attempt <= kMaxJitterTries; ++attempt) {
+        const bool last = attempt == kMaxJitterTries;
+        if (retry) {
+          float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+          if (!last) {
+            if (P.reset_mode == RESET_BUFFER && P.jitter != nullptr) {
+              j0 = P.jitter[g * 3]; j1 = P.jitter[g * 3 + 1]; j2 = P.jitter[g * 3 + 2];
+            } else {
+              uint32_t c[4] = {(uint32_t)env, (uint32_t)total, (uint32_t)(attempt * M + drone), 0u};
+              uint32_t c2[4] = {c[0], c[1], c[2], 1u};
+              philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+              philox4x32_10(c2, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+              j0 = -0.25f + 0.5f * u01(c[0], c[1], 0.f);
+              j1 = -0.25f + 0.5f * u01(c[2], c[3], 0.f);
+              j2 = -0.25f + 0.5f * u01(c2[0], c2[1], 0.f);
+            }
+          }
+          cx = P.init_xyz[ib] + j0;
+          cy = P.init_xyz[ib + 1] + j1;
+          cz = P.init_xyz[ib + 2] + j2;
+          cz = cz < 0.1f ? 0.1f : (cz > 1.0f ? 1.0f : cz);
+        }
+        int bad = 0;
+#pragma unroll 1
+        for (int o = 1; o < M; ++o) {
+          const int src = group_base | ((lane + o) & (M - 1));
+          const float ox = __shfl_sync(0xffffffffu, cx, src), oy = __shfl_sync(0xffffffffu, cy, src),
+                      oz = __shfl_sync(0xffffffffu, cz, src);
+          const float dx = cx - ox, dy = cy - oy, dz = cz - oz;
+          bad |= (sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
+        }
+#pragma unroll 1
+        for (int o = M >> 1; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        if (last || P.reset_mode == RESET_BUFFER) bad = 0;
+        retry = retry && (bad != 0);
+        if (!__any_sync(0xffffffffu, retry)) break;
+      }
+    }
+    if (done_reset) {
+      if (P.terminal_obs != nullptr) {
+        float* to = P.terminal_obs + (size_t)g * D;
+        for (int k = 0; k < D; ++k) to[k] = myrow[k];
+      }
+      const float cand[3] = {cx, cy, cz};
+      float kin[12];
+      reset_drone<float, TASK>(P, env, drone, jit ? cand : nullptr, d, kin);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) myrow[k] = kin[k];
+      if (TASK == TASK_SPIRAL) {   // reset obs is evaluated at step_counter = 0
+        float rp[3], rv[3], sphi, cphi;
+        spiral_reference(P, 0, drone, rp, rv, sphi, cphi);
+        spiral_extras(myrow + 12 + B * A, d, rp, rv, sphi, cphi);
+      }
+    }
+  }
+
+  // ---- 4. the finished rows leave as one TMA bulk store; state planes as 128-bit stores ------------
+  const long long left = P.n_total - g0;
+  const int rows = (int)(left < (long long)kBlock ? left : (long long)kBlock);
+  const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+  float* gobs = P.obs + (size_t)g0 * D;
+  const bool bulk = (bytes & 15u) == 0;
+  if (bulk) fence_proxy_async_smem();    // my generic-proxy writes -> visible to the async proxy
+  __syncthreads();
+  if (bulk) {
+    if (tid == 0) bulk_store_s2g(gobs, tile_s, bytes);
+  } else {                               // ragged last tile whose byte count is not a multiple of 16
+    for (int i = tid; i < rows * D; i += kBlock) gobs[i] = tile_s[i];
+  }
+  if (active) {
+    P.s0[g] = make_float4(d.px, d.py, d.pz, d.qx);
+    P.s1[g] = make_float4(d.qy, d.qz, d.qw, d.vx);
+    P.s2[g] = make_float4(d.vy, d.vz, d.wx, d.wy);
+    P.s3[g] = make_float4(d.wz, d.tx, d.ty, d.tz);
+  }
+  // ---- advance the global step count: last CTA out.  Every thread of this CTA consumed
+  // gsteps[0] (ring addresses) before the __syncthreads above, so the ticket needs no fence:
+  // a __threadfence here would hold the CTA — and its shared memory — until all of its stores
+  // have drained (measured: ~half of the CTA's lifetime).  Kernel completion publishes the data.
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
+    if (ticket == gridDim.x - 1) {
+      P.gsteps[1] = 0;
+      P.gsteps[0] = total + 1;
+    }
+    if (bulk) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
+  }
+}
+
+}  // namespace bd
