@@ -73,6 +73,8 @@ struct bd_handle {
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float* h_tobs = nullptr;
   int64_t launches = 0;
+  long long total_steps = 0;   // host mirror of gsteps[0]
+  bool graph_mode = false;     // a step was captured into a CUDA graph: the device counter is authoritative
   int reset_epoch = 0;
   bd::Params<float> pf{};
   bd::Params<double> pd{};
@@ -128,6 +130,8 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.keep_angv = c.keep_ang_vel;
   P.seed = c.seed;
   P.reset_epoch = 0;
+  P.total_wrap = h->B * ((1 << 30) / h->B);
+  P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
   { const char* dbg = getenv("BD_DEBUG_SKIP"); P.debug_skip = dbg ? atoi(dbg) : 0; }
 }
 
@@ -136,7 +140,12 @@ void refresh_params(bd_handle* h) {
   else fill_params<float>(h, h->pf);
 }
 
-void* params_ptr(bd_handle* h) { return h->cfg.precision == BD_F64 ? (void*)&h->pd : (void*)&h->pf; }
+void* params_ptr(bd_handle* h) {
+  const int ht = h->graph_mode ? -1 : (int)h->total_steps;
+  h->pd.host_total = ht;
+  h->pf.host_total = ht;
+  return h->cfg.precision == BD_F64 ? (void*)&h->pd : (void*)&h->pf;
+}
 
 template <typename F>
 void with_params(bd_handle* h, F&& f) {
@@ -183,6 +192,7 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
   cudaError_t e = cudaSuccess;
   with_params(h, [&](auto& P) {
     auto Q = P;
+    Q.host_total = h->graph_mode ? -1 : (int)h->total_steps;
     Q.reset_mask = mask;
     Q.obs = obs;
     if (force_fixed) Q.reset_mode = BD_RESET_FIXED;
@@ -265,6 +275,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     const char* force = getenv("BD_STEP_IMPL");
     h->spec.impl = (cfg->precision == BD_F32 && !h->spec.generic && pow2) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
+    const char* pdl = getenv("BD_PDL");
+    h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
   }
 
   const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D);
@@ -368,8 +380,16 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
       h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter)
     return fail(BD_EINVAL, "bd_step: BD_RESET_JITTER_BUFFER needs bd_set_jitter() first");
   DeviceGuard guard(h->cfg.device);
+  if (!h->graph_mode) {
+    // Captured launches are replayed with frozen parameters, so from the first capture on
+    // the ring head comes from the device-resident counter (kept current by every launch).
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+      h->graph_mode = true;
+  }
   cudaError_t e = cudaSuccess;
   with_params(h, [&](auto& P) {
+    P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
     P.actions = actions_dev;
     P.obs = obs_dev;
     P.reward = (decltype(P.reward))reward_dev;
@@ -379,6 +399,8 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
     e = bd::launch_step(h->spec, &P, (cudaStream_t)stream);
   });
   h->launches++;
+  h->total_steps++;
+  if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) h->total_steps = 0;
   if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
   return BD_OK;
 }

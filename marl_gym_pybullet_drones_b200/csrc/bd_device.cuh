@@ -324,7 +324,7 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
   const float half_dt = 0.5f * dt;
 #pragma unroll 1
   for (int s = 0; s < P.S; ++s) {
-    const float x = d.qx, y = d.qy, z = d.qz, w = d.qw;   // unit, canonical
+    const float x = d.qx, y = d.qy, z = d.qz, w = d.qw;   // unit up to rounding
     const float xxyy = fmaf(x, x, y * y);
     const float r02 = 2.0f * fmaf(x, z, w * y), r12 = 2.0f * fmaf(y, z, -w * x),
                 r22 = fmaf(-2.0f, xxyy, 1.0f);
@@ -348,8 +348,12 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
       avz = fmaf(r20, d.wx, fmaf(r21, d.wy, r22 * d.wz));
     }
     integrate_q_fast(d.qx, d.qy, d.qz, d.qw, d.wx, d.wy, d.wz, half_dt);
-    fast_canonical(d.qx, d.qy, d.qz, d.qw);
   }
+  // Bullet's per-substep round trip (normalise + sign rule, :509-519) commutes with the
+  // quaternion step, which is linear in q and norm-preserving: canon(step(canon(q))) ==
+  // canon(step(q)).  Applying it once per control step gives the same quaternion up to float
+  // rounding (|q|^2 drifts by ~1e-7 over 8 substeps) and saves ~10 % of the instructions.
+  fast_canonical(d.qx, d.qy, d.qz, d.qw);
 }
 
 // Spiral env's 11 extra observation entries (SpiralAviary.py:120-146)

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kBlock, Bounds<R, GENERIC>::kMinBlocks)
 step_kernel(const __grid_constant__ Params<R> P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_total;
-  if (threadIdx.x == 0) s_total = *reinterpret_cast<const volatile int*>(P.gsteps);
+  if (threadIdx.x == 0) s_total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
   __syncthreads();
   const int total = s_total;
   const int head = total % P.B;   // ring slot overwritten by this step's action
@@ -449,7 +449,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
     if (ticket == gridDim.x - 1) {   // every CTA has read gsteps[0] before taking its ticket
       P.gsteps[1] = 0;
-      P.gsteps[0] = total + 1;
+      P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
     }
   }
 }
@@ -469,7 +469,7 @@ reset_kernel(const __grid_constant__ Params<R> P) {
   const int env = blockIdx.x * E + env_l;
   const bool active = (env_l < E) && (env < P.N) && (P.reset_mask == nullptr || P.reset_mask[env] != 0);
   const long long g = (long long)env * M + drone;
-  const int total = P.gsteps[0];
+  const int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
   const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
   if (jit) {
     if (active && drone == 0) sample_jitter(P, env, total, P.reset_epoch, spos + (size_t)tid * 3);
@@ -512,7 +512,7 @@ __global__ void get_state_kernel(const __grid_constant__ Params<R> P, R* state20
   const int env = (int)(g / P.M);
   const R4 a0 = P.s0[g], a1 = P.s1[g], a2 = P.s2[g], a3 = P.s3[g];
   const int stepc = P.stepc[env];
-  const int head = P.gsteps[0] % P.B;
+  const int head = (P.host_total >= 0 ? P.host_total : P.gsteps[0]) % P.B;
   if (state20 != nullptr) {
     R* o = state20 + g * 20;
     o[0] = a0.x; o[1] = a0.y; o[2] = a0.z;
@@ -616,8 +616,17 @@ static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& 
     cfgd[dv] = smem;
   }
   const int grid = (int)((P.n_total + kBlock - 1) / kBlock);
-  kern<<<grid, kBlock, smem, st>>>(P);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ls.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, P);
 }
 
 template <typename R, int TASK, int A>

@@ -52,12 +52,16 @@ struct Params {
   int trunc_counter;              // smallest step_counter with step_counter / pyb_freq > episode_len (fp64)
   int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
   int debug_skip;                 // profiling aid (env BD_DEBUG_SKIP): bit0 skip copy role, bit1 skip physics role
+  int host_total;                 // >= 0: total control steps so far, tracked by the host (ring head with no
+                                  // memory latency); -1: read gsteps[0] (CUDA-graph capture / replay)
+  int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
   int reset_epoch;                // >=1 for explicit bd_reset calls (Philox stream id), 0 in-step
   unsigned long long seed;
 };
 
 struct LaunchSpec {
   int task, act_a, precision, generic, device;
+  int pdl;         // launch the fast kernel with programmatic stream serialization
   int impl;        // 0: two-role CTA kernel (any config), 1: fast tile kernel (bd_step_tile.cuh)
 };
 

@@ -25,9 +25,14 @@
 
 namespace bd {
 
+// Observation rows are written once and never read back by the simulator: mark them evict-first
+// in L2 so that they do not push out the persistent state / ring planes of the next step.
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(ssrc));
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes)
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(s),
+               "r"(bytes), "l"(policy)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
@@ -56,39 +61,44 @@ __device__ __forceinline__ void load_inputs(const Params<float>& P, long long g,
   }
 }
 
-// action history of one tile, oldest -> second newest (BaseRLAviary.py:317-318):
-// ring slots head+1 .. head-1  ->  columns 12 .. 12+(B-1)A of my row of the tile.
-// Two straight runs (slots head+1..B-1, then 0..head-1) so the loop body is one LDGSTS
-// plus two pointer bumps.
+// action history of one tile, oldest -> second newest (BaseRLAviary.py:317-318): time-ordered
+// entries j in [j0, j1) of B-1, entry j = ring slot (head+1+j) % B -> columns 12+jA.. of my row.
 template <int A, bool VEC>
-__device__ __forceinline__ void issue_history(const Params<float>& P, long long g, int head, float* myrow) {
-  if (g < P.n_total) {
-    float* dst = myrow + 12;
-    const size_t plane = (size_t)P.n_total * A;
-    const float* src = P.hist + (size_t)g * A + (size_t)(head + 1) * plane;
-    const int n1 = P.B - 1 - head;   // slots head+1 .. B-1
+__device__ __forceinline__ void history_run(float*& dst, const float* src, size_t plane, int n) {
 #pragma unroll 2
-    for (int j = 0; j < n1; ++j) {
-      if constexpr (VEC) cp_async<16>(dst, src);
-      else {
+  for (int j = 0; j < n; ++j) {
+    if constexpr (VEC) cp_async<16>(dst, src);
+    else {
 #pragma unroll
-        for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
-      }
-      dst += A; src += plane;
+      for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
     }
-    src = P.hist + (size_t)g * A;    // slots 0 .. head-1
-#pragma unroll 2
-    for (int j = 0; j < head; ++j) {
-      if constexpr (VEC) cp_async<16>(dst, src);
-      else {
-#pragma unroll
-        for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
-      }
-      dst += A; src += plane;
+    dst += A;
+    src += plane;
+  }
+}
+
+template <int A, bool VEC>
+__device__ __forceinline__ void issue_history(const Params<float>& P, long long g, int head, float* myrow,
+                                              int j0, int j1) {
+  if (g < P.n_total) {
+    const size_t plane = (size_t)P.n_total * A;
+    const float* base = P.hist + (size_t)g * A;
+    float* dst = myrow + 12 + j0 * A;
+    // entries j0..j1-1 = slots head+1+j0 .. ; split at the ring wrap into two straight runs
+    const int s0 = head + 1 + j0;            // may be >= B
+    const int n = j1 - j0;
+    if (s0 >= P.B) {
+      history_run<A, VEC>(dst, base + (size_t)(s0 - P.B) * plane, plane, n);
+    } else {
+      const int n1 = min(n, P.B - s0);
+      history_run<A, VEC>(dst, base + (size_t)s0 * plane, plane, n1);
+      history_run<A, VEC>(dst, base, plane, n - n1);
     }
   }
-  cp_async_commit();
 }
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 template <int TASK, int A, bool VEC>
 __global__ void __launch_bounds__(kBlock, 6)
@@ -109,11 +119,28 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
 
   // ---- 1. every load of the tile is issued before anything is consumed ------------------------
+  // Programmatic dependent launch: this grid may become resident while the previous kernel of
+  // the stream is still in its last wave.  Before griddepcontrol.wait only data that no earlier
+  // kernel can be writing is touched: the ring planes except the one the previous step wrote
+  // (its slot `head-1`, time index B-2).  68 % of the step's reads are in flight before the
+  // previous kernel has even finished.
+  pdl_launch_dependents();
+  int total, head;
+  if (P.host_total >= 0) {
+    total = P.host_total;
+    head = total % B;   // ring slot overwritten by this step's action
+    issue_history<A, VEC>(P, g, head, myrow, 0, B - 2);
+    pdl_wait();
+  } else {              // CUDA-graph mode: the step count is read from device memory
+    pdl_wait();
+    total = P.gsteps[0];   // only the last CTA to finish modifies it, after every read
+    head = total % B;
+    issue_history<A, VEC>(P, g, head, myrow, 0, B - 2);
+  }
   TileIn<A> cur;
   load_inputs<A>(P, g, log2m, cur);
-  const int total = P.gsteps[0];   // uniform address; only the last CTA to finish modifies it, after every read
-  const int head = total % B;   // ring slot overwritten by this step's action
-  issue_history<A, VEC>(P, g, head, myrow);
+  issue_history<A, VEC>(P, g, head, myrow, B - 2, B - 1);
+  cp_async_commit();
   const int stepc = cur.stepc;
 
   Drone<float> d;
@@ -272,7 +299,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
     if (ticket == gridDim.x - 1) {
       P.gsteps[1] = 0;
-      P.gsteps[0] = total + 1;
+      P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
     }
     if (bulk) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
   }
