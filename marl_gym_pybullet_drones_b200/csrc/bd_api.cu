@@ -132,7 +132,6 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.reset_epoch = 0;
   P.total_wrap = h->B * ((1 << 30) / h->B);
   P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
-  { const char* dbg = getenv("BD_DEBUG_SKIP"); P.debug_skip = dbg ? atoi(dbg) : 0; }
 }
 
 void refresh_params(bd_handle* h) {

@@ -423,4 +423,59 @@ __device__ __forceinline__ void task_terms(const Params<R>& P, const Drone<R>& d
   }
 }
 
+// ------------------------------------------------ async copies: TMA bulk store, cp.async history, PDL
+// Observation rows are written once and never read back by the simulator: mark them evict-first
+// in L2 so that they do not push out the persistent state / ring planes of the next step.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(ssrc));
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(s),
+               "r"(bytes), "l"(policy)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// action history of one tile, oldest -> second newest (BaseRLAviary.py:317-318): time-ordered
+// entries j in [j0, j1) of B-1, entry j = ring slot (head+1+j) % B -> columns 12+jA.. of my row.
+template <int A, bool VEC>
+__device__ __forceinline__ void history_run(float*& dst, const float* src, size_t plane, int n) {
+#pragma unroll 2
+  for (int j = 0; j < n; ++j) {
+    if constexpr (VEC) cp_async<16>(dst, src);
+    else {
+#pragma unroll
+      for (int k = 0; k < A; ++k) cp_async<4>(dst + k, src + k);
+    }
+    dst += A;
+    src += plane;
+  }
+}
+
+template <typename R, int A, bool VEC>
+__device__ __forceinline__ void issue_history(const Params<R>& P, long long g, int head, float* myrow,
+                                              int j0, int j1) {
+  if (g < P.n_total) {
+    const size_t plane = (size_t)P.n_total * A;
+    const float* base = P.hist + (size_t)g * A;
+    float* dst = myrow + 12 + j0 * A;
+    // entries j0..j1-1 = slots head+1+j0 .. ; split at the ring wrap into two straight runs
+    const int s0 = head + 1 + j0;            // may be >= B
+    const int n = j1 - j0;
+    if (s0 >= P.B) {
+      history_run<A, VEC>(dst, base + (size_t)(s0 - P.B) * plane, plane, n);
+    } else {
+      const int n1 = min(n, P.B - s0);
+      history_run<A, VEC>(dst, base + (size_t)s0 * plane, plane, n1);
+      history_run<A, VEC>(dst, base, plane, n - n1);
+    }
+  }
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 }  // namespace bd

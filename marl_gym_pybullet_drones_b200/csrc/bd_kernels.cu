@@ -40,103 +40,48 @@ template <typename R, bool GENERIC> struct Bounds { static constexpr int kMinBlo
 template <> struct Bounds<float, false> { static constexpr int kMinBlocks = 6; };
 template <> struct Bounds<float, true> { static constexpr int kMinBlocks = 3; };
 
-constexpr int kCopyPad = kBlock + 1;   // plane stride (in elements) of the copy role's staging tile
-
-// -------------------------------------------------------------------------
-// copy role: action-history ring -> observation rows  (BaseRLAviary.py:317-318)
-//
-// obs[g][12 + j*A + k] = hist[(head+1+j) % B][g][k],  j = 0..B-2   (oldest -> second newest)
-//
-// 68 % of a step's HBM traffic, independent of the physics.  The ring planes are read
-// with fully coalesced loads (lane = drone), staged in shared memory and written out with
-// lane = consecutive 16-byte chunk of a row, so both sides move whole 32-byte sectors.
-// -------------------------------------------------------------------------
-template <typename R, int A>
-__device__ __forceinline__ void copy_role(const Params<R>& P, int blk, int head, unsigned char* smem_raw) {
-  const int tid = threadIdx.x;
-  const int B = P.B, D = P.D;
-  const long long g0 = (long long)blk * P.E * P.M;
-  const long long left = P.n_total - g0;
-  const int rows = (int)(left < (long long)P.E * P.M ? left : (long long)P.E * P.M);
-  const int nslots = B - 1;
-  if (A == 4 && (D & 3) == 0) {
-    float4* sp = reinterpret_cast<float4*>(smem_raw);            // [nslots][kCopyPad]
-    const size_t plane = (size_t)P.n_total;                      // in float4 units
-    if (tid < rows) {
-      const float4* hb = reinterpret_cast<const float4*>(P.hist) + g0 + tid;
-      int slot = head;
-      int j = 0;
-      for (; j + 7 <= nslots; j += 7) {                          // 7 independent 128-bit loads in flight
-        float4 v[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          slot = (slot + 1 == B) ? 0 : slot + 1;
-          v[k] = __ldcs(hb + (size_t)slot * plane);
-        }
-#pragma unroll
-        for (int k = 0; k < 7; ++k) sp[(j + k) * kCopyPad + tid] = v[k];
-      }
-      for (; j < nslots; ++j) {
-        slot = (slot + 1 == B) ? 0 : slot + 1;
-        sp[j * kCopyPad + tid] = __ldcs(hb + (size_t)slot * plane);
-      }
-    }
-    __syncthreads();
-    const int nch = rows * nslots;
-    int row = tid / nslots, c = tid - row * nslots;
-    const int drow = kBlock / nslots, dc = kBlock - drow * nslots;
-    float* ob = P.obs + (size_t)g0 * D + 12;
-    for (int q = tid; q < nch; q += kBlock) {
-      __stcs(reinterpret_cast<float4*>(ob + (size_t)row * D) + c, sp[c * kCopyPad + row]);
-      row += drow; c += dc;
-      if (c >= nslots) { c -= nslots; ++row; }
-    }
-  } else {
-    float* sp = reinterpret_cast<float*>(smem_raw);              // [nslots*A][kCopyPad]
-    const int ncols = nslots * A;
-    if (tid < rows) {
-      int slot = head;
-      for (int j = 0; j < nslots; ++j) {
-        slot = (slot + 1 == B) ? 0 : slot + 1;
-        const float* hp = P.hist + ((size_t)slot * P.n_total + g0 + tid) * A;
-#pragma unroll
-        for (int k = 0; k < A; ++k) sp[(j * A + k) * kCopyPad + tid] = hp[k];
-      }
-    }
-    __syncthreads();
-    const int n = rows * ncols;
-    float* ob = P.obs + (size_t)g0 * D + 12;
-    for (int q = tid; q < n; q += kBlock) {
-      const int row = q / ncols, c = q - row * ncols;
-      ob[(size_t)row * D + c] = sp[c * kCopyPad + row];
-    }
-  }
-}
-
-// -------------------------------------------------------------------------
-// physics role: one thread per drone, E = 128/M whole environments per CTA
-// -------------------------------------------------------------------------
+// =========================================================================
+//                     generic step kernel (any configuration)
+// =========================================================================
+// Same shape as the fast kernel (bd_step_tile.cuh): one CTA per tile of E = 128/M whole
+// environments, every load issued up front (ring planes with cp.async into the thread's row of
+// a dense row-major shared-memory tile), the finished rows leave as one contiguous block.
+// Differences: any M <= 128 (per-env reductions through shared memory instead of shuffles),
+// double or float, the exact arithmetic flavour, ground effect / drag / downwash (positions of
+// the env's drones staged in shared memory per substep), Euler-angle integrator, optional
+// world angular velocity plane.
 template <typename R, int TASK, int A, bool GENERIC>
-__device__ __forceinline__ void physics_role(const Params<R>& P, int blk, int head, int total,
-                                             unsigned char* smem_raw) {
+__global__ void __launch_bounds__(kBlock, Bounds<R, GENERIC>::kMinBlocks)
+step_kernel(const __grid_constant__ Params<R> P) {
   using R4 = typename V4<R>::type;
   constexpr bool FAST = (sizeof(R) == 4) && !GENERIC;
-  R* sred = reinterpret_cast<R*>(smem_raw);                               // [kBlock]
-  R* spos = sred + kBlock;                                                // [kBlock][3]
-  int* sflag = reinterpret_cast<int*>(spos + 3 * kBlock);                 // [kBlock]
-  int* sdone = sflag + kBlock;                                            // [kBlock]
-
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int M = P.M, E = P.E, B = P.B, D = P.D;
+  float* tile_s = reinterpret_cast<float*>(smem_raw);                         // [kBlock][D] dense
+  R* sred = reinterpret_cast<R*>(smem_raw + (((size_t)kBlock * D * 4 + 15) & ~(size_t)15));   // [kBlock]
+  R* spos = sred + kBlock;                                                    // [kBlock][3]
+  int* sflag = reinterpret_cast<int*>(spos + 3 * kBlock);                     // [kBlock]
+  int* sdone = sflag + kBlock;                                                // [kBlock]
+  float* myrow = tile_s + (size_t)tid * D;
+  const bool vec = (A == 4) && ((D & 3) == 0);
+
   const int env_l = tid / M;
   const int drone = tid - env_l * M;
-  const int env = blk * E + env_l;
+  const int env = blockIdx.x * E + env_l;
   const bool active = (env_l < E) && (env < P.N);
-  const long long g = (long long)env * M + drone;
-  float* grow = P.obs + (size_t)g * D;
-  const bool vec = (D & 3) == 0;
+  const long long g0 = (long long)blockIdx.x * E * M;
+  const long long g = g0 + tid;
 
-  // ---- 1. state + action + step counter (independent loads, issued back to back) ----------
+  // ---- 1. every load of the tile is issued before anything is consumed ----------------------
+  const int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
+  const int head = total % B;   // ring slot overwritten by this step's action
+  if (active) {
+    if (vec) issue_history<R, A, (A == 4)>(P, g, head, myrow, 0, B - 1);
+    else issue_history<R, A, false>(P, g, head, myrow, 0, B - 1);
+  }
+  cp_async_commit();
+
   Drone<R> d;
   R rpm[4];
   float af[4] = {0.f, 0.f, 0.f, 0.f};
@@ -183,19 +128,11 @@ __device__ __forceinline__ void physics_role(const Params<R>& P, int blk, int he
         else { rpm[0] = rpm[1] = rpm[2] = rpm[3] = r; onep[0] = onep[1] = onep[2] = onep[3] = s; }
       }
     }
-    // newest history entry: ring slot `head` (the stale slot, not read by the copy role)
-    // and the tail of the observation row
+    // newest history entry: ring slot `head` (the stale slot) and the tail of the row
     float* hp = P.hist + ((size_t)head * P.n_total + g) * A;
-    float* newest = grow + 12 + (B - 1) * A;
-    if constexpr (A == 4) {
-      const float4 v = make_float4(af[0], af[1], af[2], af[3]);
-      *reinterpret_cast<float4*>(hp) = v;
-      if (vec) *reinterpret_cast<float4*>(newest) = v;
-      else { newest[0] = v.x; newest[1] = v.y; newest[2] = v.z; newest[3] = v.w; }
-    } else {
-      hp[0] = af[0];
-      newest[0] = af[0];
-    }
+    float* newest = myrow + 12 + (B - 1) * A;
+#pragma unroll
+    for (int k = 0; k < A; ++k) { hp[k] = af[k]; newest[k] = af[k]; }
     if (GENERIC && (P.aero & AERO_DRAG) && stepc > 0) {
       // last_clipped_action (BaseAviary.py:372,468): previous step's rpm, zero after a reset
       const int prev = head == 0 ? B - 1 : head - 1;
@@ -325,25 +262,19 @@ __device__ __forceinline__ void physics_role(const Params<R>& P, int blk, int he
     }
   }
 
-  // ---- 3. observation row (kinematic part), reward terms, flags ----------------
+  // ---- 3. complete my observation row, reward terms, flags ---------------------
   R roll, pitch, yaw;
   quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
   R contrib = R(0);
   int flags = 0;   // bit0: terminated condition, bit1: truncated condition (hover bounds)
+  cp_async_wait_all();
   if (active) {
     // [pos rpy vel ang_v] (BaseRLAviary.py:314-315)
-    if (vec) {
-      float4* r4 = reinterpret_cast<float4*>(grow);
-      r4[0] = make_float4((float)d.px, (float)d.py, (float)d.pz, (float)roll);
-      r4[1] = make_float4((float)pitch, (float)yaw, (float)d.vx, (float)d.vy);
-      r4[2] = make_float4((float)d.vz, (float)avx, (float)avy, (float)avz);
-    } else {
-      grow[0] = (float)d.px; grow[1] = (float)d.py; grow[2] = (float)d.pz;
-      grow[3] = (float)roll; grow[4] = (float)pitch; grow[5] = (float)yaw;
-      grow[6] = (float)d.vx; grow[7] = (float)d.vy; grow[8] = (float)d.vz;
-      grow[9] = (float)avx; grow[10] = (float)avy; grow[11] = (float)avz;
-    }
-    task_terms<R, TASK>(P, d, roll, pitch, stepc, drone, grow + 12 + B * A, contrib, flags);
+    myrow[0] = (float)d.px; myrow[1] = (float)d.py; myrow[2] = (float)d.pz;
+    myrow[3] = (float)roll; myrow[4] = (float)pitch; myrow[5] = (float)yaw;
+    myrow[6] = (float)d.vx; myrow[7] = (float)d.vy; myrow[8] = (float)d.vz;
+    myrow[9] = (float)avx; myrow[10] = (float)avy; myrow[11] = (float)avz;
+    task_terms<R, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
   }
   sred[tid] = contrib;
   sflag[tid] = flags;
@@ -379,40 +310,34 @@ __device__ __forceinline__ void physics_role(const Params<R>& P, int blk, int he
     if (my_reset) {
       if (P.terminal_obs != nullptr) {   // info['terminal_observation']: the full last row of the episode
         float* to = P.terminal_obs + (size_t)g * D;
-        to[0] = (float)d.px; to[1] = (float)d.py; to[2] = (float)d.pz;
-        to[3] = (float)roll; to[4] = (float)pitch; to[5] = (float)yaw;
-        to[6] = (float)d.vx; to[7] = (float)d.vy; to[8] = (float)d.vz;
-        to[9] = (float)avx; to[10] = (float)avy; to[11] = (float)avz;
-        int slot = head;
-        for (int j = 0; j < B - 1; ++j) {
-          slot = (slot + 1 == B) ? 0 : slot + 1;
-          const float* hp = P.hist + ((size_t)slot * P.n_total + g) * A;
-          for (int k = 0; k < A; ++k) to[12 + j * A + k] = hp[k];
-        }
-        for (int k = 0; k < A; ++k) to[12 + (B - 1) * A + k] = af[k];
-        for (int k = 12 + B * A; k < D; ++k) to[k] = grow[k];   // spiral extras written above by this thread
+        for (int k = 0; k < D; ++k) to[k] = myrow[k];
       }
       float kin[12];
       reset_drone<R, TASK>(P, env, drone, jit ? spos + (size_t)tid * 3 : nullptr, d, kin);
-      if (vec) {
-        float4* r4 = reinterpret_cast<float4*>(grow);
-        r4[0] = make_float4(kin[0], kin[1], kin[2], kin[3]);
-        r4[1] = make_float4(kin[4], kin[5], kin[6], kin[7]);
-        r4[2] = make_float4(kin[8], kin[9], kin[10], kin[11]);
-      } else {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) grow[k] = kin[k];
-      }
+      for (int k = 0; k < 12; ++k) myrow[k] = kin[k];
       avx = avy = avz = R(0);
       if (TASK == TASK_SPIRAL) {   // reset obs is evaluated at step_counter = 0
         R rp[3], rv[3], sphi, cphi;
         spiral_reference(P, 0, drone, rp, rv, sphi, cphi);
-        spiral_extras(grow + 12 + B * A, d, rp, rv, sphi, cphi);
+        spiral_extras(myrow + 12 + B * A, d, rp, rv, sphi, cphi);
       }
     }
   }
 
-  // ---- 6. state planes ------------------------------------------------------------
+  // ---- 6. the finished rows leave as one contiguous block; state planes -------------------
+  const long long left = P.n_total - g0;
+  const int rows = (int)(left < (long long)E * M ? left : (long long)E * M);
+  const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+  float* gobs = P.obs + (size_t)g0 * D;
+  const bool bulk = ((bytes & 15u) == 0) && ((((size_t)g0 * D * 4) & 15) == 0);
+  if (bulk) fence_proxy_async_smem();
+  __syncthreads();
+  if (bulk) {
+    if (tid == 0) bulk_store_s2g(gobs, tile_s, bytes);
+  } else {
+    for (int i = tid; i < rows * D; i += kBlock) gobs[i] = tile_s[i];
+  }
   if (active) {
     P.s0[g] = make4(d.px, d.py, d.pz, d.qx);
     P.s1[g] = make4(d.qy, d.qz, d.qw, d.vx);
@@ -420,37 +345,15 @@ __device__ __forceinline__ void physics_role(const Params<R>& P, int blk, int he
     P.s3[g] = make4(d.wz, d.tx, d.ty, d.tz);
     if (GENERIC && P.keep_angv) P.s4[g] = make4(avx, avy, avz, R(0));
   }
-}
-
-// =========================================================================
-//                                step kernel
-// =========================================================================
-// grid = 2 x ceil(N / E) CTAs: even CTAs run the physics role, odd CTAs the copy role for
-// the same 128-drone row range.  The two roles touch disjoint bytes (the copy role never
-// reads ring slot `head`, which the physics role overwrites), so they need no ordering;
-// interleaving them in block order puts bandwidth-bound and issue-bound CTAs on every SM
-// at the same time.  The global step count (ring head, Philox stream) lives in device
-// memory so that a captured CUDA graph can be replayed: every CTA reads it on entry, the
-// last CTA to leave increments it.
-template <typename R, int TASK, int A, bool GENERIC>
-__global__ void __launch_bounds__(kBlock, Bounds<R, GENERIC>::kMinBlocks)
-step_kernel(const __grid_constant__ Params<R> P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_total;
-  if (threadIdx.x == 0) s_total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
-  __syncthreads();
-  const int total = s_total;
-  const int head = total % P.B;   // ring slot overwritten by this step's action
-  const int blk = blockIdx.x >> 1;
-  if (blockIdx.x & 1) { if (!(P.debug_skip & 1)) copy_role<R, A>(P, blk, head, smem_raw); }
-  else { if (!(P.debug_skip & 2)) physics_role<R, TASK, A, GENERIC>(P, blk, head, total, smem_raw); }
-  __syncthreads();
-  if (threadIdx.x == 0) {   // no fence: the value was consumed long ago; kernel completion publishes the data
+  // advance the device-resident step count: last CTA out (every thread consumed `total` before
+  // the barrier above; no fence, see bd_step_tile.cuh)
+  if (tid == 0) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
-    if (ticket == gridDim.x - 1) {   // every CTA has read gsteps[0] before taking its ticket
+    if (ticket == gridDim.x - 1) {
       P.gsteps[1] = 0;
       P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
     }
+    if (bulk) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
   }
 }
 
@@ -573,11 +476,10 @@ __global__ void get_targets_kernel(const __grid_constant__ Params<R> P, R* targe
 //                              host-side dispatch
 // =========================================================================
 size_t step_smem_bytes(int precision, int A, int B, int D) {
+  (void)A; (void)B;
   const size_t real = precision ? 8 : 4;
-  const size_t physics = (size_t)kBlock * real * 4 + (size_t)kBlock * 8;
-  const size_t copy = (A == 4 && (D & 3) == 0) ? (size_t)(B - 1) * kCopyPad * 16
-                                               : (size_t)(B - 1) * A * kCopyPad * 4;
-  return physics > copy ? physics : copy;
+  const size_t tile = ((size_t)kBlock * D * 4 + 15) & ~(size_t)15;
+  return tile + (size_t)kBlock * real * 4 + (size_t)kBlock * 8;
 }
 
 template <typename R, int TASK, int A, bool GENERIC>
@@ -590,7 +492,7 @@ static cudaError_t launch_step_t(const Params<R>& P, int device, cudaStream_t st
     if (e != cudaSuccess) return e;
     configured[device & 63] = smem;
   }
-  const int grid = 2 * ((P.N + P.E - 1) / P.E);   // even CTAs: physics role, odd CTAs: copy role
+  const int grid = (P.N + P.E - 1) / P.E;
   kern<<<grid, kBlock, smem, st>>>(P);
   return cudaGetLastError();
 }

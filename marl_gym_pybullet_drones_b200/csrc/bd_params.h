@@ -51,7 +51,6 @@ struct Params {
   double pyb_freq, episode_len;
   int trunc_counter;              // smallest step_counter with step_counter / pyb_freq > episode_len (fp64)
   int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
-  int debug_skip;                 // profiling aid (env BD_DEBUG_SKIP): bit0 skip copy role, bit1 skip physics role
   int host_total;                 // >= 0: total control steps so far, tracked by the host (ring head with no
                                   // memory latency); -1: read gsteps[0] (CUDA-graph capture / replay)
   int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
