@@ -19,13 +19,14 @@ __all__ = [
     "ActionType", "DroneModel", "ImageType", "ObservationType", "Physics",
     "DroneConstants", "drone_constants", "parse_urdf",
     "BatchAviary", "StepResult", "HoverAviary", "MultiHoverAviary", "SpiralFormationAviary",
-    "BatchVecEnv", "VecRecordEpisodeStatistics", "make_vec_envs",
+    "BatchVecEnv", "VecRecordEpisodeStatistics", "make_vec_envs", "DeviceMAPPO",
 ]
 
 _LAZY = {
     "BatchAviary": ".batch_aviary", "StepResult": ".batch_aviary",
     "HoverAviary": ".envs", "MultiHoverAviary": ".envs", "SpiralFormationAviary": ".envs",
     "BatchVecEnv": ".vec_env", "VecRecordEpisodeStatistics": ".vec_env", "make_vec_envs": ".vec_env",
+    "DeviceMAPPO": ".mappo",
 }
 
 

@@ -1,0 +1,303 @@
+"""MAPPO with the whole rollout and update on the GPU.
+
+The reference trainer (`gym_pybullet_drones/mappo/mappo.py:619-1184`, `agent.py:339-423,602-772`,
+`buffer.py:428-614`) crosses the host/device boundary twice per env step, runs GAE as a Python
+triple loop in numpy and updates on 32-sample minibatches.  Here the envs live in a
+`BatchAviary`; observations are written by the step kernel directly into the rollout buffer
+slot they belong to, actions are sampled on the device and handed to the kernel without a copy,
+GAE is a backwards scan over T device tensors, and the update uses large minibatches.
+
+What is kept from the reference (and where it is switchable):
+  * CTDE: one actor shared by all agents (`share_actor_weights`), tanh MLP obs_dim -> hidden ->
+    hidden -> act_dim, state-independent `logstd = -0.5`, diagonal Gaussian whose log-prob is
+    summed over action dims (`agent.py:87-130`, `distributions.py:9-21`); centralised critic on the
+    concatenated local observations of the env's agents (`agent.py:164-223`, `mappo.py:583-617`);
+  * the env's scalar reward is broadcast to every agent, mask = 1 - done (`mappo.py:758-772`);
+  * `rollout_values="zeros"` reproduces the reference's rollout, which stores v = 0
+    (`agent.py:413`), so GAE degenerates to lambda-returns; `"critic"` evaluates the critic
+    during the rollout (textbook GAE);
+  * advantages normalised over the whole buffer with (adv-mean)/(std+1e-8) (`buffer.py:666-695`);
+  * clipped-ratio policy loss + entropy bonus, update skipped when the minibatch
+    approx_kl > 1.5 target_kl (`agent.py:602-641,731`); critic loss 0.5 (V - mean_agents(ret))^2
+    (`agent.py:643-700`); two Adam optimisers; no gradient clipping (`config.py:32` is unused);
+  * truncation is not bootstrapped (the envs never emit 'TimeLimit.truncated', `mappo.py:827,845`).
+
+Multi-GPU: every rank owns its env shard; gradients are averaged with one bucketed all-reduce
+per optimiser step (`dist.allreduce_gradients`), episode statistics with one small all-reduce.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .batch_aviary import BatchAviary, StepResult
+from .dist import allreduce_gradients, reduce_episode_stats
+
+MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-217 overrides
+    "hidden_dim": 256,
+    "activation": "tanh",
+    "gamma": 0.99,
+    "use_gae": True,
+    "gae_lambda": 0.95,
+    "clip_param": 0.2,
+    "target_kl": 0.01,
+    "entropy_coef": 0.005,
+    "opt_epochs": 10,
+    "mini_batch_size": 32,        # in ENV-steps (each sample carries all M agents), as in the reference
+    "actor_lr": 3e-4,
+    "critic_lr": 1e-3,
+    "rollout_steps": 256,
+    "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
+    "use_clipped_value": False,
+}
+
+
+class MLP(nn.Module):
+    """`safe_control_gym/math_and_models/neural_networks.py:18-53` (default nn.Linear init)."""
+
+    def __init__(self, input_dim, output_dim, hidden_dims, act="tanh"):
+        super().__init__()
+        dims = [input_dim] + list(hidden_dims) + [output_dim]
+        self.fcs = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(len(dims) - 1)])
+        self.act = getattr(torch, act)
+
+    def forward(self, x):
+        for fc in self.fcs[:-1]:
+            x = self.act(fc(x))
+        return self.fcs[-1](x)
+
+
+class ActorCritic(nn.Module):
+    """Shared actor + centralised critic (`mappo/agent.py:225-337`)."""
+
+    def __init__(self, obs_dim, act_dim, num_agents, hidden_dim=256, activation="tanh"):
+        super().__init__()
+        self.obs_dim, self.act_dim, self.num_agents = obs_dim, act_dim, num_agents
+        self.actor = MLP(obs_dim, act_dim, [hidden_dim, hidden_dim], activation)
+        self.logstd = nn.Parameter(-0.5 * torch.ones(act_dim))
+        self.critic = MLP(num_agents * obs_dim, 1, [hidden_dim, hidden_dim], activation)
+
+    def actor_parameters(self):
+        return list(self.actor.parameters()) + [self.logstd]
+
+    def dist(self, obs):
+        return torch.distributions.Normal(self.actor(obs), self.logstd.exp())
+
+    def logp(self, obs, act):
+        return self.dist(obs).log_prob(act).sum(-1, keepdim=True)
+
+    def value(self, global_obs):
+        return self.critic(global_obs)
+
+
+class DeviceMAPPO:
+    """On-device MAPPO around a `BatchAviary` (`MAPPO.learn/train_step`, `mappo/mappo.py:289-1184`)."""
+
+    def __init__(self, env: BatchAviary, seed: int = 0, **kwargs):
+        self.cfg = dict(MAPPO_CONFIG)
+        self.cfg.update(kwargs)
+        self.env = env
+        self.device = env.device
+        if env.action_dtype != torch.float32:
+            raise ValueError("DeviceMAPPO drives fp32 aviaries")
+        self.N, self.M, self.D, self.A = env.num_envs, env.NUM_DRONES, env.OBS_DIM, env.ACTION_DIM
+        self.T = int(self.cfg["rollout_steps"])
+        torch.manual_seed(seed)   # same initial weights on every rank
+        self.ac = ActorCritic(self.D, self.A, self.M, self.cfg["hidden_dim"], self.cfg["activation"]).to(self.device)
+        self.actor_opt = torch.optim.Adam(self.ac.actor_parameters(), lr=self.cfg["actor_lr"])
+        self.critic_opt = torch.optim.Adam(self.ac.critic.parameters(), lr=self.cfg["critic_lr"])
+        self.gen = torch.Generator(device=self.device)
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.gen.manual_seed(seed * 1000003 + rank)
+        T, N, M, D, A = self.T, self.N, self.M, self.D, self.A
+        dev = self.device
+        # rollout storage; the step kernel writes obs[t+1] in place
+        self.obs = torch.zeros((T + 1, N, M, D), device=dev)
+        self.act = torch.zeros((T, N, M, A), device=dev)
+        self.logp = torch.zeros((T, N, M, 1), device=dev)
+        self.val = torch.zeros((T + 1, N, 1), device=dev)
+        self.rew = torch.zeros((T, N), device=dev)
+        self.term = torch.zeros((T, N), dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros((T, N), dtype=torch.uint8, device=dev)
+        self.ret = torch.zeros((T, N, 1), device=dev)
+        self.adv = torch.zeros((T, N, 1), device=dev)
+        # episode statistics (VecRecordEpisodeStatistics semantics, record_episode_statistics.py:144-171)
+        self.ep_return = torch.zeros(N, device=dev)
+        self.ep_length = torch.zeros(N, device=dev)
+        self.done_return_sum = torch.zeros((), device=dev, dtype=torch.float64)
+        self.done_length_sum = torch.zeros((), device=dev, dtype=torch.float64)
+        self.done_count = torch.zeros((), device=dev, dtype=torch.float64)
+        self.total_env_steps = 0
+        self._reset_done = False
+
+    # ------------------------------------------------------------------ rollout
+    def reset(self):
+        self.env.reset_device(out=self.obs[0])
+        self.ep_return.zero_()
+        self.ep_length.zero_()
+        self._reset_done = True
+
+    @torch.no_grad()
+    def collect_rollout(self):
+        """T env steps for all N envs; no host synchronisation inside the loop."""
+        if not self._reset_done:
+            self.reset()
+        elif self.total_env_steps > 0:
+            self.obs[0].copy_(self.obs[self.T])   # the rollout continues where the previous one stopped
+        T, N, M = self.T, self.N, self.M
+        std = self.ac.logstd.exp()
+        use_critic = self.cfg["rollout_values"] == "critic"
+        for t in range(T):
+            obs_t = self.obs[t]
+            mean = self.ac.actor(obs_t.view(N * M, self.D)).view(N, M, self.A)
+            noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
+            act = mean + std * noise                                  # unclipped Gaussian (agent.py:399-400)
+            self.act[t] = act
+            self.logp[t] = (-0.5 * noise.pow(2) - self.ac.logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
+            if use_critic:
+                self.val[t] = self.ac.value(obs_t.view(N, M * self.D))
+            out = StepResult(self.obs[t + 1], self.rew[t], self.term[t].view(torch.bool),
+                             self.trunc[t].view(torch.bool), None)
+            self.env.step_device(self.act[t], out=out)
+            done = (self.term[t] | self.trunc[t]).bool()
+            self.ep_return += self.rew[t]
+            self.ep_length += 1
+            self.done_return_sum += (self.ep_return * done).sum()
+            self.done_length_sum += (self.ep_length * done).sum()
+            self.done_count += done.sum()
+            self.ep_return.masked_fill_(done, 0.0)
+            self.ep_length.masked_fill_(done, 0.0)
+        # bootstrap value of the last observation (`last_val`, mappo.py:1049-1157)
+        self.val[T] = self.ac.value(self.obs[T].view(N, M * self.D))
+        if not use_critic:
+            self.val[:T].zero_()                                       # agent.py:413: v stored as zeros
+        self.total_env_steps += T * N
+
+    @torch.no_grad()
+    def compute_returns(self):
+        """GAE / returns as a backwards scan (`buffer.py:561-614`), per env (reward is shared by the agents)."""
+        g, lam = self.cfg["gamma"], self.cfg["gae_lambda"]
+        mask = 1.0 - (self.term | self.trunc).float().unsqueeze(-1)   # (T,N,1)
+        ret = self.val[self.T].clone()
+        adv = torch.zeros_like(ret)
+        for t in reversed(range(self.T)):
+            r = self.rew[t].unsqueeze(-1)
+            ret = r + g * mask[t] * ret
+            if self.cfg["use_gae"]:
+                td = r + g * mask[t] * self.val[t + 1] - self.val[t]
+                adv = adv * lam * g * mask[t] + td
+            else:
+                adv = ret - self.val[t]
+            self.ret[t] = ret
+            self.adv[t] = adv
+        mean, std = self.adv.mean(), self.adv.std()
+        if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            stats = torch.stack([self.adv.sum(), self.adv.pow(2).sum(),
+                                 torch.tensor(float(self.adv.numel()), device=self.device)])
+            torch.distributed.all_reduce(stats)
+            mean = stats[0] / stats[2]
+            std = (stats[1] / stats[2] - mean * mean).clamp_min(0).sqrt()
+        self.adv_n = (self.adv - mean) / (std + 1e-8)                   # buffer.py:666-695
+
+    # ------------------------------------------------------------------- update
+    def update(self) -> Dict[str, float]:
+        """`MAPPOAgent.update` (agent.py:702-772) on device tensors."""
+        cfg = self.cfg
+        T, N, M, D, A = self.T, self.N, self.M, self.D, self.A
+        n = T * N
+        obs = self.obs[:T].reshape(n, M, D)
+        act = self.act.reshape(n, M, A)
+        logp_old = self.logp.reshape(n, M, 1)
+        adv = self.adv_n.reshape(n, 1, 1).expand(n, M, 1)             # reward/advantage tiled to every agent
+        ret = self.ret.reshape(n, 1)                                  # = mean over agents of identical returns
+        mb = min(int(cfg["mini_batch_size"]), n)
+        num_mb = n // mb
+        stats = torch.zeros(5, device=self.device)
+        for _ in range(int(cfg["opt_epochs"])):
+            perm = torch.randperm(n, device=self.device, generator=self.gen)
+            for i in range(num_mb):
+                idx = perm[i * mb:(i + 1) * mb]
+                o, a = obs[idx].reshape(mb * M, D), act[idx].reshape(mb * M, A)
+                lp_old, ad = logp_old[idx].reshape(mb * M, 1), adv[idx].reshape(mb * M, 1)
+                dist = self.ac.dist(o)
+                lp = dist.log_prob(a).sum(-1, keepdim=True)
+                ratio = torch.exp(lp - lp_old)
+                clip_adv = torch.clamp(ratio, 1 - cfg["clip_param"], 1 + cfg["clip_param"]) * ad
+                policy_loss = -torch.min(ratio * ad, clip_adv).mean()
+                entropy_loss = -dist.entropy().sum(-1).mean()
+                approx_kl = (lp_old - lp).mean().detach()
+                self.actor_opt.zero_grad(set_to_none=True)
+                (policy_loss + cfg["entropy_coef"] * entropy_loss).backward()
+                allreduce_gradients(self.ac.actor_parameters())
+                # KL gate (agent.py:731): the optimiser step (Adam moments included) is skipped entirely
+                # when the minibatch violates the constraint; one scalar read-back per minibatch
+                if cfg["target_kl"] <= 0 or approx_kl.item() <= 1.5 * cfg["target_kl"]:
+                    self.actor_opt.step()
+                v = self.ac.value(obs[idx].reshape(mb, M * D))
+                value_loss = 0.5 * (v - ret[idx]).pow(2).mean()
+                self.critic_opt.zero_grad(set_to_none=True)
+                value_loss.backward()
+                allreduce_gradients(self.ac.critic.parameters())
+                self.critic_opt.step()
+                stats += torch.stack([policy_loss.detach(), value_loss.detach(), entropy_loss.detach(), approx_kl,
+                                      torch.ones((), device=self.device)])
+        s = (stats[:4] / stats[4]).tolist()
+        return {"policy_loss": s[0], "value_loss": s[1], "entropy_loss": s[2], "approx_kl": s[3]}
+
+    # --------------------------------------------------------------------- loop
+    def pop_episode_stats(self):
+        """Mean return / length of the episodes finished since the last call (all ranks)."""
+        out = reduce_episode_stats(self.done_return_sum, self.done_length_sum, self.done_count)
+        self.done_return_sum.zero_()
+        self.done_length_sum.zero_()
+        self.done_count.zero_()
+        return out
+
+    def train_step(self) -> Dict[str, float]:
+        t0 = time.time()
+        self.collect_rollout()
+        self.compute_returns()
+        res = self.update()
+        mean_r, mean_l, n_ep = self.pop_episode_stats()
+        torch.cuda.synchronize(self.device)
+        res.update(ep_return=mean_r, ep_length=mean_l, episodes=n_ep, total_env_steps=self.total_env_steps,
+                   step_time=time.time() - t0)
+        return res
+
+    def learn(self, max_env_steps: int, log=None):
+        history = []
+        while self.total_env_steps < max_env_steps:
+            res = self.train_step()
+            history.append(res)
+            if log is not None:
+                log(res)
+        return history
+
+    @torch.no_grad()
+    def select_action(self, obs: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
+        """`MAPPO.select_action` (mappo.py:272-287): mean action for evaluation."""
+        mean = self.ac.actor(obs.reshape(-1, self.D)).view(*obs.shape[:-1], self.A)
+        if deterministic:
+            return mean
+        return mean + self.ac.logstd.exp() * torch.randn(mean.shape, device=mean.device, generator=self.gen)
+
+    def state_dict(self):
+        return {"agent": {"ac": self.ac.state_dict(), "actor_opt": self.actor_opt.state_dict(),
+                          "critic_opt": self.critic_opt.state_dict()},
+                "total_steps": self.total_env_steps}
+
+    def load_state_dict(self, sd):
+        self.ac.load_state_dict(sd["agent"]["ac"])
+        self.actor_opt.load_state_dict(sd["agent"]["actor_opt"])
+        self.critic_opt.load_state_dict(sd["agent"]["critic_opt"])
+        self.total_env_steps = int(sd.get("total_steps", 0))
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.device))

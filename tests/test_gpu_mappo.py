@@ -1,0 +1,67 @@
+"""On-device MAPPO: GAE scan equals the reference's per-sequence numpy loop, the loop
+learns, checkpoints round-trip.  GPU only (the envs are CUDA kernels)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_returns(rews, vals, masks, last_val, gamma, lam):
+    """`mappo/buffer.py:561-614` (_compute_single_agent_returns) with terminal_vals = 0, use_gae=True."""
+    T = len(rews)
+    rets, advs = np.zeros(T), np.zeros(T)
+    ext = np.concatenate([vals, [last_val]])
+    ret, adv = last_val, 0.0
+    for i in reversed(range(T)):
+        ret = rews[i] + gamma * masks[i] * ret
+        td = rews[i] + gamma * masks[i] * ext[i + 1] - vals[i]
+        adv = adv * lam * gamma * masks[i] + td
+        rets[i], advs[i] = ret, adv
+    return rets, advs
+
+
+@pytest.mark.parametrize("rollout_values", ["zeros", "critic"])
+def test_gae_scan_matches_reference_loop(rollout_values):
+    from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
+    env = BatchAviary(task="multihover", num_envs=16, num_drones=2,
+                      initial_xyzs=np.array([[0.0, 0.0, 0.2], [1.0, 0.0, 0.2]]))
+    algo = DeviceMAPPO(env, rollout_steps=48, hidden_dim=32, rollout_values=rollout_values, seed=3)
+    algo.collect_rollout()
+    algo.compute_returns()
+    rew, val = algo.rew.cpu().numpy().astype(np.float64), algo.val.cpu().numpy().astype(np.float64)[..., 0]
+    mask = 1.0 - (algo.term | algo.trunc).cpu().numpy().astype(np.float64)
+    assert (mask == 0).any()                       # crashes happened: the mask path is exercised
+    if rollout_values == "zeros":
+        assert np.all(val[:-1] == 0)               # agent.py:413
+    for e in range(16):
+        rets, advs = _ref_returns(rew[:, e], val[:-1, e], mask[:, e], val[-1, e], 0.99, 0.95)
+        assert np.allclose(algo.ret.cpu().numpy()[:, e, 0], rets, rtol=2e-5, atol=2e-5)
+        assert np.allclose(algo.adv.cpu().numpy()[:, e, 0], advs, rtol=2e-5, atol=2e-5)
+    a = algo.adv.cpu().numpy()
+    assert np.allclose(algo.adv_n.cpu().numpy(), (a - a.mean()) / (a.std(ddof=1) + 1e-8), atol=1e-4)
+    env.close()
+
+
+def test_hover_learns_and_checkpoint_roundtrip(tmp_path):
+    from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
+    torch.manual_seed(0)
+    env = BatchAviary(task="hover", num_envs=1024, act="one_d_rpm", seed=1)
+    algo = DeviceMAPPO(env, rollout_steps=121, hidden_dim=64, mini_batch_size=8192, opt_epochs=4,
+                       rollout_values="critic", actor_lr=1e-3, target_kl=0.05, seed=0)
+    first = algo.train_step()
+    assert first["episodes"] == 0 or np.isfinite(first["ep_return"])
+    hist = algo.learn(max_env_steps=algo.total_env_steps + 14 * 121 * 1024)
+    rets = [h["ep_return"] for h in hist if h["episodes"] > 0]
+    assert len(rets) >= 4
+    # random policy hovers around z0: ~1.38/step; a learnt policy climbs towards z=1 (2/step)
+    assert np.mean(rets[-2:]) > np.mean(rets[:2]) + 10.0, rets
+    assert all(np.isfinite(list(h.values())).all() for h in hist)
+    p = tmp_path / "model_latest.pt"
+    algo.save(p)
+    algo2 = DeviceMAPPO(env, rollout_steps=121, hidden_dim=64, seed=5)
+    algo2.load(p)
+    o = algo.obs[0]
+    assert torch.equal(algo.select_action(o), algo2.select_action(o))
+    assert algo2.total_env_steps == algo.total_env_steps
+    env.close()
