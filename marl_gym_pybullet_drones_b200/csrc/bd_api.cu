@@ -272,7 +272,10 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     const int m = cfg->n_drones;
     const bool pow2 = (m & (m - 1)) == 0 && m <= 32;
     const char* force = getenv("BD_STEP_IMPL");
-    h->spec.impl = (cfg->precision == BD_F32 && !h->spec.generic && pow2) ? 1 : 0;
+    // the fast kernel also carries downwash alone (shuffle exchange inside the env's lane group)
+    const bool fast_aero = cfg->aero_flags == 0 || cfg->aero_flags == BD_AERO_DW;
+    const bool plain = fast_aero && cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
+    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;

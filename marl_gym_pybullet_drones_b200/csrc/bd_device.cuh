@@ -300,8 +300,12 @@ namespace bd {
 // Per substep only the rotation's third column is formed; the full matrix once, for the
 // world angular velocity R_old w_new (:873) of the last substep.
 // ---------------------------------------------------------------------------
+// DW: pairwise downwash (BaseAviary.py:798-804) for envs that are lane groups of M (M | 32): the
+// substep-start positions of the group's other drones arrive by warp shuffle (Jacobi snapshot,
+// no shared memory, no barrier); the body-z force enters as F R[:,2] / m.
+template <bool DW>
 __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<float>& d, const float onep[4],
-                                              float& avx, float& avy, float& avz) {
+                                              float& avx, float& avy, float& avz, int lane = 0) {
   const float dt = P.dt;
   float u[4];
 #pragma unroll
@@ -328,10 +332,32 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
     const float xxyy = fmaf(x, x, y * y);
     const float r02 = 2.0f * fmaf(x, z, w * y), r12 = 2.0f * fmaf(y, z, -w * x),
                 r22 = fmaf(-2.0f, xxyy, 1.0f);
-    // a = g [(1+e) R[:,2] - e_z];  (1+e) r22 - 1 = e r22 - 2 (x^2 + y^2)
-    d.vx = fmaf(c1, r02, d.vx);
-    d.vy = fmaf(c1, r12, d.vy);
-    d.vz = fmaf(c2, r22, fmaf(c3, xxyy, d.vz));
+    float c1s = c1, c2s = c2;
+    if constexpr (DW) {
+      const int M = P.M, base = lane & ~(M - 1);
+      float fdw = 0.f;
+#pragma unroll 1
+      for (int o = 1; o < M; ++o) {
+        const int src = base | ((lane + o) & (M - 1));
+        const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
+                    oz = __shfl_sync(0xffffffffu, d.pz, src);
+        const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
+        const float dxy2 = fmaf(dx, dx, dy * dy);
+        const float ratio = __fdividef(P.prop_radius, 4.0f * dz);
+        const float alpha = P.dw1 * ratio * ratio;
+        const float beta = fmaf(P.dw2, dz, P.dw3);
+        const float q2 = __fdividef(dxy2, beta * beta);
+        const float f = -alpha * __expf(-0.5f * q2);
+        if (dz > 0.f && dxy2 < 100.f) fdw += f;                 // :801 (delta_xy < 10)
+      }
+      const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
+      c1s += k;
+      c2s += k;
+    }
+    // a = g [(1+e) R[:,2] - e_z] (+ F_dw R[:,2] / m);  (1+e) r22 - 1 = e r22 - 2 (x^2 + y^2)
+    d.vx = fmaf(c1s, r02, d.vx);
+    d.vy = fmaf(c1s, r12, d.vy);
+    d.vz = fmaf(c2s, r22, fmaf(c3, xxyy, d.vz));
     const float owx = d.wx, owy = d.wy, owz = d.wz;
     d.wx = fmaf(-gx, owy * owz, owx + kx);
     d.wy = fmaf(-gy, owz * owx, owy + ky);

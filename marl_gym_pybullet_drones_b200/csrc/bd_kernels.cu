@@ -155,7 +155,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   R avx = R(0), avy = R(0), avz = R(0);   // world angular velocity R_old * w_new (:873)
 
   if constexpr (FAST) {
-    fast_substeps(P, d, onep, avx, avy, avz);
+    fast_substeps<false>(P, d, onep, avx, avy, avz);
   } else {
 #pragma unroll 1
     for (int s = 0; s < P.S; ++s) {
@@ -508,9 +508,11 @@ template <int TASK, int A>
 static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
   const size_t smem = (size_t)kBlock * P.D * 4;   // the [128][D] observation tile and nothing else
   const bool vecrow = (A == 4) && (P.D % 4 == 0);
-  auto kern = vecrow ? step_kernel_tile<TASK, A, (A == 4)> : step_kernel_tile<TASK, A, false>;
-  static size_t configured[2][64] = {{0}};
-  size_t* const cfgd = configured[vecrow ? 1 : 0];
+  const bool dw = (P.aero & AERO_DW) != 0;
+  auto kern = vecrow ? (dw ? step_kernel_tile<TASK, A, (A == 4), true> : step_kernel_tile<TASK, A, (A == 4), false>)
+                     : (dw ? step_kernel_tile<TASK, A, false, true> : step_kernel_tile<TASK, A, false, false>);
+  static size_t configured[4][64] = {{0}};
+  size_t* const cfgd = configured[(vecrow ? 1 : 0) + (dw ? 2 : 0)];
   const int dv = ls.device & 63;
   if (smem > cfgd[dv]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

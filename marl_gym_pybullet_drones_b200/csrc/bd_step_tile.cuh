@@ -1,4 +1,4 @@
-// Fast step kernel (float, plain DYN, M in {1,2,4,8,16,32}): one CTA per tile of 128 drones.
+// Fast step kernel (float, DYN with optional downwash, M in {1,2,4,8,16,32}): one CTA per tile of 128 drones.
 //
 // Measured facts that shape it (scripts/microbench/*.cu, profiles/README.md):
 //   * observation rows must leave the SM as complete, contiguous rows: 16-byte or
@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_inputs(const Params<float>& P, long long g,
   }
 }
 
-template <int TASK, int A, bool VEC>
+template <int TASK, int A, bool VEC, bool DW>
 __global__ void __launch_bounds__(kBlock, 6)
 step_kernel_tile(const __grid_constant__ Params<float> P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -107,7 +107,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
 
   // ---- 2. S substeps in registers while the history lands --------------------------------------
   float avx = 0.f, avy = 0.f, avz = 0.f;
-  fast_substeps(P, d, onep, avx, avy, avz);
+  fast_substeps<DW>(P, d, onep, avx, avy, avz, lane);
   float roll, pitch, yaw;
   quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
 
