@@ -164,6 +164,28 @@ int64_t bd_launch_count(const bd_handle* h);     /* kernels launched by this han
 const char* bd_last_error(void);
 int bd_version(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused actor forward on the tensor cores (the caller of the step).
+ * Replaces the batched branch of MAPPOActorCritic.step (mappo/agent.py:389-415): shared actor
+ * MLP obs_dim -> hidden -> hidden -> act_dim with tanh (safe_control_gym/math_and_models/
+ * neural_networks.py:18-53), Gaussian sample with state-independent logstd and its summed
+ * log-probability (distributions.py:9-21), in one tcgen05/TMEM kernel (bf16 operands, fp32
+ * accumulation).  hidden in {64,128,256}, act_dim <= 4.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bd_actor bd_actor;
+int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor** out);
+void bd_actor_destroy(bd_actor* a);
+/* fp32 device pointers in torch.nn.Linear layout: w1 (hidden,obs_dim), w2 (hidden,hidden),
+ * w3 (act_dim,hidden), biases, logstd (act_dim).  Repacked (stream ordered) to bf16 UMMA tiles. */
+int bd_actor_set_weights(bd_actor* a, const float* w1, const float* b1, const float* w2, const float* b2,
+                         const float* w3, const float* b3, const float* logstd, void* stream);
+/* obs_dev (rows,obs_dim) float -> act_dev (rows,act_dim), logp_dev (rows), optional mean_dev.
+ * noise_dev (rows,act_dim) standard normals, or NULL: Philox4x32-10(seed; row, offset). */
+int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const float* noise_dev, uint64_t seed,
+                     uint64_t offset, float* act_dev, float* logp_dev, float* mean_dev, void* stream);
+int64_t bd_actor_launch_count(const bd_actor* a);
+const char* bd_actor_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ EXPORTS = (
     "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
     "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
+    "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_launch_count",
+    "bd_actor_last_error",
 )
 
 
@@ -99,6 +101,18 @@ def load():
     lib.bd_last_error.restype = C.c_char_p
     lib.bd_version.argtypes = []
     lib.bd_version.restype = C.c_int
+    lib.bd_actor_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.bd_actor_create.restype = C.c_int
+    lib.bd_actor_destroy.argtypes = [vp]
+    lib.bd_actor_destroy.restype = None
+    lib.bd_actor_set_weights.argtypes = [vp] + [vp] * 7 + [vp]
+    lib.bd_actor_set_weights.restype = C.c_int
+    lib.bd_actor_forward.argtypes = [vp, vp, C.c_int64, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp]
+    lib.bd_actor_forward.restype = C.c_int
+    lib.bd_actor_launch_count.argtypes = [vp]
+    lib.bd_actor_launch_count.restype = C.c_int64
+    lib.bd_actor_last_error.argtypes = []
+    lib.bd_actor_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -1,0 +1,415 @@
+// Fused actor forward on 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces the batched branch of `MAPPOActorCritic.step` (reference
+// gym_pybullet_drones/mappo/agent.py:389-415): for every drone row
+//     mean = W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3        (MLP, neural_networks.py:18-53)
+//     act  = mean + exp(logstd) * eps,  eps ~ N(0, I)        (dist.sample, agent.py:399-400)
+//     logp = sum_k [-eps_k^2/2 - logstd_k - log(2 pi)/2]     (Normal.log_prob summed, distributions.py:12-21)
+// in ONE kernel: observations are read once (fp32 -> bf16 in registers), the three GEMMs run
+// as tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M = 128 rows per CTA, N = hidden, K = 16 per
+// instruction, issued by one thread), activations never leave the SM: TMEM -> registers
+// (tcgen05.ld) -> +bias, tanh.approx -> bf16 -> shared memory in the canonical K-major UMMA
+// layout -> next layer's A operand.
+//
+// Shared memory (hidden = 256, obs_dim = 72 -> K1 = 80): region A 64 KB holds {X tile 20 KB,
+// W1 40 KB} during layer 1 and the 128 x 256 bf16 activation tile afterwards; W2 (128 KB) and W3
+// (8 KB, N padded to 16) stay resident for the CTA's lifetime (persistent grid, one CTA per SM);
+// W1 is re-read from L2 per tile (40 KB).  TMEM: 256 columns (128 lanes x 256 fp32) reused by the
+// three layers.  Operand layout: 8 x 8 bf16 core matrices (128 B), LBO = 128 B between the two
+// K-halves of an instruction, SBO = (K/8) * 128 B between 8-row groups, no swizzle.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "../../include/batch_drones.h"
+
+namespace {
+
+constexpr int kRows = 128;   // UMMA M
+constexpr int kNOut = 16;    // layer-3 N (act_dim padded; UMMA needs N % 16 == 0 at M = 128)
+
+thread_local char g_actor_err[256] = "";
+int afail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_actor_err, sizeof(g_actor_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128 (InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// element (r, k) of a [rows x K] K-major operand tile, in bf16 elements
+__host__ __device__ __forceinline__ size_t canon_off(int r, int k, int K) {
+  return (size_t)(r >> 3) * (K >> 3) * 64 + (size_t)(k >> 3) * 64 + (size_t)(r & 7) * 8 + (k & 7);
+}
+
+struct ActorDev {
+  const __nv_bfloat16 *w1, *w2, *w3;   // canonical layouts: [HID x K1], [HID x HID], [16 x HID]
+  const float *b1, *b2, *b3, *logstd;  // b3 / logstd padded to 16
+  int obs_dim, K1, act_dim;
+};
+
+// TMEM accumulator row -> +bias, tanh -> bf16 activation tile (next layer's A operand)
+template <int HID>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* __restrict__ bias, __nv_bfloat16* sH, int row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < HID; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_row + (uint32_t)c0, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = tanh_fast(__uint_as_float(v[q * 8 + j]) + bias[c0 + q * 8 + j]);
+      uint4 pk;
+      pk.x = pack_bf16(h[0], h[1]); pk.y = pack_bf16(h[2], h[3]); pk.z = pack_bf16(h[4], h[5]); pk.w = pack_bf16(h[6], h[7]);
+      *reinterpret_cast<uint4*>(sH + canon_off(row, c0 + q * 8, HID)) = pk;
+    }
+  }
+}
+
+template <int HID>
+__global__ void __launch_bounds__(kRows, 1)
+actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
+                     unsigned long long seed, unsigned long long offset, float* __restrict__ act, float* __restrict__ logp,
+                     float* __restrict__ mean_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int K1 = W.K1;
+  const size_t actb = (size_t)kRows * HID * 2, l1b = (size_t)(kRows + HID) * K1 * 2;
+  const size_t regA = ((actb > l1b ? actb : l1b) + 127) & ~(size_t)127;   // same formula on the host
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);               // X tile, later activations
+  __nv_bfloat16* sW1 = sA + (size_t)kRows * K1;                             // inside region A
+  __nv_bfloat16* sW2 = reinterpret_cast<__nv_bfloat16*>(smem + regA);
+  __nv_bfloat16* sW3 = sW2 + (size_t)HID * HID;
+  float* sB1 = reinterpret_cast<float*>(sW3 + (size_t)kNOut * HID);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;        // [16]
+  float* sLs = sB3 + kNOut;      // [16]
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // ---- one-time: resident weights, barrier, tensor memory ------------------------------------
+  for (int i = tid; i < HID * HID / 8; i += kRows) reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(W.w2)[i];
+  for (int i = tid; i < kNOut * HID / 8; i += kRows) reinterpret_cast<uint4*>(sW3)[i] = reinterpret_cast<const uint4*>(W.w3)[i];
+  for (int i = tid; i < HID; i += kRows) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd[tid]; }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // my warp's 32 TMEM lanes
+  const uint32_t bar = smem_u32(&mbar);
+  uint32_t parity = 0;
+  const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+
+  const long long n_tiles = (rows + kRows - 1) / kRows;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row_g = tile * kRows + tid;
+    const bool valid = row_g < rows;
+    // ---- X tile: my row, fp32 -> bf16, canonical K-major layout; W1 from L2 -----------------------
+    {
+      const float* src = obs + (size_t)row_g * W.obs_dim;
+      const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
+      for (int k0 = 0; k0 < K1; k0 += 8) {
+        float x[8];
+        if (vec4 && valid && k0 + 8 <= W.obs_dim) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src + k0)), b = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (valid && k0 + j < W.obs_dim) ? __ldg(src + k0 + j) : 0.0f;
+        }
+        uint4 pk;
+        pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]); pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+        *reinterpret_cast<uint4*>(sA + canon_off(tid, k0, K1)) = pk;
+      }
+      for (int i = tid; i < HID * K1 / 8; i += kRows) reinterpret_cast<uint4*>(sW1)[i] = reinterpret_cast<const uint4*>(W.w1)[i];
+    }
+    proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();   // my tcgen05.ld of the previous tile are complete (wait::ld) and ordered
+    __syncthreads();
+    // ---- layer 1: acc[128 x HID] = X W1^T ---------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sbo = (uint32_t)(K1 / 8) * 128u;
+      for (int s = 0; s < K1 / 16; ++s)
+        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW1 + s * 256, 128, sbo), umma_idesc(HID), s > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity); parity ^= 1;
+    tc_fence_after();
+    epilogue_hidden<HID>(tmem_row, sB1, sA, tid);          // overwrites X / W1 (layer-1 MMAs are complete)
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2: acc = H1 W2^T ---------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sbo = (uint32_t)(HID / 8) * 128u;
+      for (int s = 0; s < HID / 16; ++s)
+        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW2 + s * 256, 128, sbo), umma_idesc(HID), s > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity); parity ^= 1;
+    tc_fence_after();
+    epilogue_hidden<HID>(tmem_row, sB2, sA, tid);          // H2 over H1 (layer-2 MMAs are complete)
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 3: acc[128 x 16] = H2 W3^T -------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sbo = (uint32_t)(HID / 8) * 128u;
+      for (int s = 0; s < HID / 16; ++s)
+        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW3 + s * 256, 128, sbo), umma_idesc(kNOut), s > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity); parity ^= 1;
+    tc_fence_after();
+    // ---- epilogue: Gaussian sample + log-prob ----------------------------------------------------------
+    uint32_t v[16];
+    tmem_ld16(tmem_row, v);
+    if (valid) {
+      float eps[4] = {0.f, 0.f, 0.f, 0.f};
+      if (noise != nullptr) {
+        for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
+      } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
+        uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+        const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.28318530718f * u1, &s0, &c0);
+        __sincosf(6.28318530718f * u3, &s1, &c1);
+        eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+      }
+      float lp = 0.f;
+      for (int k = 0; k < W.act_dim; ++k) {
+        const float m = __uint_as_float(v[k]) + sB3[k];
+        const float ls = sLs[k];
+        act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
+        if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
+        lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+      }
+      logp[row_g] = lp;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+}
+
+// fp32 [n x k] row-major (torch nn.Linear weight) -> bf16 canonical K-major [n_pad x k_pad], zero padded
+__global__ void pack_weight_kernel(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pad * k_pad) return;
+  const int r = idx / k_pad, c = idx - r * k_pad;
+  const float v = (r < n && c < k) ? w[(size_t)r * k + c] : 0.0f;
+  out[canon_off(r, c, k_pad)] = __float2bfloat16(v);
+}
+__global__ void pad_vector_kernel(const float* __restrict__ v, int n, int n_pad, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) out[i] = i < n ? v[i] : 0.0f;
+}
+
+}  // namespace
+
+struct bd_actor {
+  int device, obs_dim, hidden, act_dim, K1, sm_count;
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *logstd = nullptr;
+  size_t smem = 0;
+  int64_t launches = 0;
+};
+
+extern "C" {
+
+const char* bd_actor_last_error(void) { return g_actor_err; }
+
+int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor** out) {
+  if (!out) return afail(BD_EINVAL, "bd_actor_create: null out");
+  *out = nullptr;
+  if (hidden != 256 && hidden != 128 && hidden != 64) return afail(BD_EINVAL, "bd_actor_create: hidden must be 64, 128 or 256");
+  if (act_dim < 1 || act_dim > 4) return afail(BD_EINVAL, "bd_actor_create: act_dim must be in [1,4]");
+  if (obs_dim < 1) return afail(BD_EINVAL, "bd_actor_create: obs_dim must be positive");
+  const int K1 = (obs_dim + 15) & ~15;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess)
+    return afail(BD_ECUDA, "bd_actor_create: cannot select device %d", device);
+  bd_actor* a = new (std::nothrow) bd_actor();
+  if (!a) return afail(BD_ENOMEM, "bd_actor_create: out of host memory");
+  a->device = device; a->obs_dim = obs_dim; a->hidden = hidden; a->act_dim = act_dim; a->K1 = K1;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  a->sm_count = prop.multiProcessorCount;
+  const size_t actb = (size_t)kRows * hidden * 2, l1b = (size_t)(kRows + hidden) * K1 * 2;
+  const size_t regA = ((actb > l1b ? actb : l1b) + 127) & ~(size_t)127;
+  a->smem = regA + (size_t)hidden * hidden * 2 + (size_t)kNOut * hidden * 2 + (size_t)(2 * hidden + 2 * kNOut) * 4;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); };
+  alloc((void**)&a->w1, (size_t)hidden * K1 * 2);
+  alloc((void**)&a->w2, (size_t)hidden * hidden * 2);
+  alloc((void**)&a->w3, (size_t)kNOut * hidden * 2);
+  alloc((void**)&a->b1, hidden * 4); alloc((void**)&a->b2, hidden * 4);
+  alloc((void**)&a->b3, kNOut * 4); alloc((void**)&a->logstd, kNOut * 4);
+  if (a->smem > prop.sharedMemPerBlockOptin) {
+    cudaFree(a->w1); cudaFree(a->w2); cudaFree(a->w3); cudaFree(a->b1); cudaFree(a->b2); cudaFree(a->b3); cudaFree(a->logstd);
+    const size_t need = a->smem;
+    delete a;
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return afail(BD_EINVAL, "bd_actor_create: obs_dim %d with hidden %d needs %zu B of shared memory (> %zu)", obs_dim, hidden,
+                 need, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  if (e == cudaSuccess) {
+    if (hidden == 256) e = cudaFuncSetAttribute(actor_forward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+    else if (hidden == 128) e = cudaFuncSetAttribute(actor_forward_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+    else e = cudaFuncSetAttribute(actor_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+  }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    cudaFree(a->w1); cudaFree(a->w2); cudaFree(a->w3); cudaFree(a->b1); cudaFree(a->b2); cudaFree(a->b3); cudaFree(a->logstd);
+    delete a;
+    return afail(BD_ECUDA, "bd_actor_create: %s", cudaGetErrorString(e));
+  }
+  *out = a;
+  return BD_OK;
+}
+
+void bd_actor_destroy(bd_actor* a) {
+  if (!a) return;
+  cudaFree(a->w1); cudaFree(a->w2); cudaFree(a->w3); cudaFree(a->b1); cudaFree(a->b2); cudaFree(a->b3); cudaFree(a->logstd);
+  delete a;
+}
+
+int bd_actor_set_weights(bd_actor* a, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                         const float* b3, const float* logstd, void* stream) {
+  if (!a || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !logstd) return afail(BD_EINVAL, "bd_actor_set_weights: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = a->hidden;
+  auto grid = [](int n) { return (n + 255) / 256; };
+  pack_weight_kernel<<<grid(H * a->K1), 256, 0, st>>>(w1, H, a->obs_dim, H, a->K1, a->w1);
+  pack_weight_kernel<<<grid(H * H), 256, 0, st>>>(w2, H, H, H, H, a->w2);
+  pack_weight_kernel<<<grid(kNOut * H), 256, 0, st>>>(w3, a->act_dim, H, kNOut, H, a->w3);
+  pad_vector_kernel<<<grid(H), 256, 0, st>>>(b1, H, H, a->b1);
+  pad_vector_kernel<<<grid(H), 256, 0, st>>>(b2, H, H, a->b2);
+  pad_vector_kernel<<<1, 32, 0, st>>>(b3, a->act_dim, kNOut, a->b3);
+  pad_vector_kernel<<<1, 32, 0, st>>>(logstd, a->act_dim, kNOut, a->logstd);
+  a->launches += 7;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_set_weights: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const float* noise_dev, uint64_t seed, uint64_t offset,
+                     float* act_dev, float* logp_dev, float* mean_dev, void* stream) {
+  if (!a || !obs_dev || !act_dev || !logp_dev) return afail(BD_EINVAL, "bd_actor_forward: obs, act and logp are required");
+  if (rows <= 0) return BD_OK;
+  ActorDev W{a->w1, a->w2, a->w3, a->b1, a->b2, a->b3, a->logstd, a->obs_dim, a->K1, a->act_dim};
+  const long long n_tiles = (rows + kRows - 1) / kRows;
+  const int grid = (int)(n_tiles < a->sm_count ? n_tiles : a->sm_count);   // persistent: one CTA per SM
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->hidden == 256) actor_forward_kernel<256><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  else if (a->hidden == 128) actor_forward_kernel<128><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  else actor_forward_kernel<64><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  a->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_forward: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int64_t bd_actor_launch_count(const bd_actor* a) { return a ? a->launches : 0; }
+
+}  // extern "C"
