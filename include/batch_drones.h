@@ -74,6 +74,8 @@ typedef struct bd_config {
   int32_t action_is_f32;    /* BD_F64 only: actions are float (numpy computes
                                1+0.05*a in float32 then), else double                 */
   int32_t keep_ang_vel;     /* 1: keep world angular velocity for bd_get_state        */
+  int32_t track_episodes;   /* 1: accumulate episode returns/lengths (bd_episode_stats) */
+  int32_t reserved0;        /* must be 0                                              */
   uint64_t seed;            /* Philox key for BD_RESET_JITTER_PHILOX                  */
   double episode_len_sec;   /* 8 (hover, multihover) / 12 (spiral)                    */
   /* airframe */
@@ -150,6 +152,12 @@ int bd_set_state(bd_handle* h, const void* kin13_dev, const void* targets_dev,
 
 /* TARGET_POS of every drone, (N,M,3) Real (MultiHoverAviary.py:72,106). */
 int bd_get_targets(bd_handle* h, void* targets_dev, void* stream);
+
+/* Replaces VecRecordEpisodeStatistics (record_episode_statistics.py:144-171) for envs that live
+ * on the device: stats3_dev[0..2] = sum of returns, sum of lengths and number of the episodes that
+ * finished since the last reset of the accumulators (per-step return = the env's scalar reward).
+ * stats3_dev may be NULL (reset only).  Stream ordered.  Needs cfg.track_episodes = 1. */
+int bd_episode_stats(bd_handle* h, double* stats3_dev, int reset, void* stream);
 
 /* BD_F64 handles only: switch between float32 and float64 action input (see
  * bd_config.action_is_f32).  numpy evaluates HOVER_RPM*(1+0.05*a) partly in float32

@@ -21,7 +21,7 @@ BD_RESET = {"fixed": 0, "jitter_philox": 1, "jitter_buffer": 2}
 
 EXPORTS = (
     "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
-    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
+    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_episode_stats", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
     "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_launch_count",
     "bd_actor_last_error",
@@ -39,6 +39,7 @@ class BdConfig(C.Structure):
         ("pyb_freq", C.c_int32), ("ctrl_freq", C.c_int32),
         ("auto_reset", C.c_int32), ("reset_mode", C.c_int32),
         ("action_is_f32", C.c_int32), ("keep_ang_vel", C.c_int32),
+        ("track_episodes", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64),
         ("episode_len_sec", C.c_double),
         ("mass", C.c_double), ("arm", C.c_double), ("kf", C.c_double), ("km", C.c_double),
@@ -90,6 +91,8 @@ def load():
     lib.bd_set_state.restype = C.c_int
     lib.bd_get_targets.argtypes = [vp, vp, vp]
     lib.bd_get_targets.restype = C.c_int
+    lib.bd_episode_stats.argtypes = [vp, vp, C.c_int, vp]
+    lib.bd_episode_stats.restype = C.c_int
     lib.bd_set_action_f32.argtypes = [vp, C.c_int]
     lib.bd_set_action_f32.restype = C.c_int
     for name in ("bd_obs_dim", "bd_act_dim", "bd_action_buffer_size", "bd_substeps"):

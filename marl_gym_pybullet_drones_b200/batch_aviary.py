@@ -72,6 +72,7 @@ class BatchAviary:
                  reset_mode: Optional[str] = None,
                  integrator: str = "quat",
                  keep_ang_vel: bool = False,
+                 track_episode_stats: bool = False,
                  action_dtype=None,
                  seed: int = 0,
                  spiral_radius: float = 0.4,
@@ -163,6 +164,7 @@ class BatchAviary:
         cfg.reset_mode = _native.BD_RESET[reset_mode]
         cfg.action_is_f32 = int(action_dtype == torch.float32)
         cfg.keep_ang_vel = int(keep_ang_vel)
+        cfg.track_episodes = int(track_episode_stats)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.episode_len_sec = float(self.EPISODE_LEN_SEC)
         cfg.mass, cfg.arm, cfg.kf, cfg.km = k.M, k.L, k.KF, k.KM
@@ -385,6 +387,16 @@ class BatchAviary:
         t = torch.empty((self.num_envs, self.NUM_DRONES, 3), dtype=self.real_dtype, device=self.device)
         _native.check(self._lib.bd_get_targets(self._h, C.c_void_p(t.data_ptr()), self._stream()), "bd_get_targets")
         return t
+
+    def episode_stats(self, reset: bool = True) -> torch.Tensor:
+        """Device tensor [sum of returns, sum of lengths, count] of the episodes finished since the
+        accumulators were last reset (`VecRecordEpisodeStatistics` on the device; no host sync).
+        Needs `track_episode_stats=True` at construction."""
+        self._check_open()
+        out = torch.empty(3, dtype=torch.float64, device=self.device)
+        _native.check(self._lib.bd_episode_stats(self._h, C.c_void_p(out.data_ptr()), int(reset), self._stream()),
+                      "bd_episode_stats")
+        return out
 
     def set_jitter(self, jitter: torch.Tensor):
         """Jitter draws in [-0.25,0.25) consumed by the next reset of each env (reset_mode='jitter_buffer')."""

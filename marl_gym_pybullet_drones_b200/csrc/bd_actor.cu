@@ -31,6 +31,7 @@
 namespace {
 
 constexpr int kRows = 128;   // UMMA M
+constexpr int kThreads = 256; // 8 warps: warp w owns TMEM lanes 32*(w%4).. and the column half w/4 in the epilogues
 constexpr int kNOut = 16;    // layer-3 N (act_dim padded; UMMA needs N % 16 == 0 at M = 128)
 
 thread_local char g_actor_err[256] = "";
@@ -132,27 +133,56 @@ struct ActorDev {
   int obs_dim, K1, act_dim;
 };
 
-// TMEM accumulator row -> +bias, tanh -> bf16 activation tile (next layer's A operand)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <int HID>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* __restrict__ bias, __nv_bfloat16* sH, int row) {
+__device__ __forceinline__ void hidden_chunk(const uint32_t v[32], int c0, const float* __restrict__ bias, __nv_bfloat16* sH, int row) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = tanh_fast(__uint_as_float(v[q * 8 + j]) + bias[c0 + q * 8 + j]);
+    uint4 pk;
+    pk.x = pack_bf16(h[0], h[1]); pk.y = pack_bf16(h[2], h[3]); pk.z = pack_bf16(h[4], h[5]); pk.w = pack_bf16(h[6], h[7]);
+    *reinterpret_cast<uint4*>(sH + canon_off(row, c0 + q * 8, HID)) = pk;
+  }
+}
+
+// TMEM accumulator row -> +bias, tanh -> bf16 activation tile (next layer's A operand).  The TMEM
+// read of the next 32 columns is in flight while the current 32 go through the SFU (tanh.approx)
+// and the bf16 pack: the two are the epilogue's bottlenecks (64 B/clk TMEM read, 16 tanh/clk).
+template <int HID>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* __restrict__ bias, __nv_bfloat16* sH, int row,
+                                                int cbeg, int cend) {
+  uint32_t va[32], vb[32];
+  tmem_ld32_nowait(tmem_row + (uint32_t)cbeg, va);
+  tmem_wait_ld();
 #pragma unroll 1
-  for (int c0 = 0; c0 < HID; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_row + (uint32_t)c0, v);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float h[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = tanh_fast(__uint_as_float(v[q * 8 + j]) + bias[c0 + q * 8 + j]);
-      uint4 pk;
-      pk.x = pack_bf16(h[0], h[1]); pk.y = pack_bf16(h[2], h[3]); pk.z = pack_bf16(h[4], h[5]); pk.w = pack_bf16(h[6], h[7]);
-      *reinterpret_cast<uint4*>(sH + canon_off(row, c0 + q * 8, HID)) = pk;
-    }
+  for (int c0 = cbeg; c0 < cend; c0 += 64) {
+    const bool more1 = c0 + 32 < cend;
+    if (more1) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 32), vb);
+    hidden_chunk<HID>(va, c0, bias, sH, row);
+    tmem_wait_ld();
+    if (!more1) break;
+    const bool more2 = c0 + 64 < cend;
+    if (more2) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 64), va);
+    hidden_chunk<HID>(vb, c0 + 32, bias, sH, row);
+    tmem_wait_ld();
   }
 }
 
 template <int HID>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
                      unsigned long long seed, unsigned long long offset, float* __restrict__ act, float* __restrict__ logp,
                      float* __restrict__ mean_out) {
@@ -172,10 +202,14 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (kRows - 1);      // my row of the tile = my TMEM lane
+  const int half = tid >> 7;              // which half of the columns I handle in the epilogues
+  constexpr int kHalfCols = (HID / 2 + 31) / 32 * 32 > HID ? HID : (HID / 2 + 31) / 32 * 32;
+  const int cbeg = half == 0 ? 0 : kHalfCols, cend = half == 0 ? kHalfCols : HID;
   // ---- one-time: resident weights, barrier, tensor memory ------------------------------------
-  for (int i = tid; i < HID * HID / 8; i += kRows) reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(W.w2)[i];
-  for (int i = tid; i < kNOut * HID / 8; i += kRows) reinterpret_cast<uint4*>(sW3)[i] = reinterpret_cast<const uint4*>(W.w3)[i];
-  for (int i = tid; i < HID; i += kRows) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  for (int i = tid; i < HID * HID / 8; i += kThreads) reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(W.w2)[i];
+  for (int i = tid; i < kNOut * HID / 8; i += kThreads) reinterpret_cast<uint4*>(sW3)[i] = reinterpret_cast<const uint4*>(W.w3)[i];
+  for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
   if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd[tid]; }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -189,34 +223,70 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // my warp's 32 TMEM lanes
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // my warp's 32 TMEM lanes
   const uint32_t bar = smem_u32(&mbar);
   uint32_t parity = 0;
   const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
 
-  const long long n_tiles = (rows + kRows - 1) / kRows;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row_g = tile * kRows + tid;
-    const bool valid = row_g < rows;
-    // ---- X tile: my row, fp32 -> bf16, canonical K-major layout; W1 from L2 -----------------------
-    {
-      const float* src = obs + (size_t)row_g * W.obs_dim;
-      const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
-      for (int k0 = 0; k0 < K1; k0 += 8) {
-        float x[8];
-        if (vec4 && valid && k0 + 8 <= W.obs_dim) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src + k0)), b = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
-          x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-        } else {
+  // W1 never changes: each thread keeps its share of the packed tile in registers (<= 16 x 128 bit) and
+  // re-deposits it after the activation tile has overwritten the staging region.  The next tile's
+  // observation chunks are prefetched into registers while the current tile is in the tensor core
+  // (one CTA per SM leaves 255 registers per thread).
+  constexpr int kMaxW1 = 16, kMaxX = 8;
+  const int w1_chunks = HID * K1 / 8;
+  uint4 w1r[kMaxW1];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (valid && k0 + j < W.obs_dim) ? __ldg(src + k0 + j) : 0.0f;
+  for (int i = 0; i < kMaxW1; ++i) {
+    const int idx = i * kThreads + tid;
+    w1r[i] = idx < w1_chunks ? reinterpret_cast<const uint4*>(W.w1)[idx] : make_uint4(0, 0, 0, 0);
+  }
+  const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
+  // raw fp32 chunks stay in registers until the next tile starts: converting right after the load
+  // would stall on the global latency that the prefetch is meant to hide
+  auto load_x = [&](long long tile, float4 (&xa)[kMaxX], float4 (&xb)[kMaxX]) {
+    const long long rg = tile * kRows + row;
+    const bool ok = rg < rows;
+    const float* src = obs + (size_t)rg * W.obs_dim;
+#pragma unroll
+    for (int c = 0; c < kMaxX; ++c) {
+      const int k0 = half * 8 + c * 16;      // the two threads of a row take alternate 8-column chunks
+      xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 < K1 && ok) {
+        if (vec4 && k0 + 8 <= W.obs_dim) {
+          xa[c] = __ldg(reinterpret_cast<const float4*>(src + k0));
+          xb[c] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+        } else {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (k0 + j < W.obs_dim) ? __ldg(src + k0 + j) : 0.0f;
+          xa[c] = make_float4(x[0], x[1], x[2], x[3]);
+          xb[c] = make_float4(x[4], x[5], x[6], x[7]);
         }
-        uint4 pk;
-        pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]); pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
-        *reinterpret_cast<uint4*>(sA + canon_off(tid, k0, K1)) = pk;
       }
-      for (int i = tid; i < HID * K1 / 8; i += kRows) reinterpret_cast<uint4*>(sW1)[i] = reinterpret_cast<const uint4*>(W.w1)[i];
     }
+  };
+
+  const long long n_tiles = (rows + kRows - 1) / kRows;
+  float4 xa[kMaxX], xb[kMaxX];
+  if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x, xa, xb);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row_g = tile * kRows + row;
+    const bool valid = row_g < rows;
+    // ---- X tile (prefetched; fp32 -> bf16, canonical K-major layout) and W1 from registers --------
+#pragma unroll
+    for (int c = 0; c < kMaxX; ++c) {
+      const int k0 = half * 8 + c * 16;
+      if (k0 < K1)
+        *reinterpret_cast<uint4*>(sA + canon_off(row, k0, K1)) =
+            make_uint4(pack_bf16(xa[c].x, xa[c].y), pack_bf16(xa[c].z, xa[c].w), pack_bf16(xb[c].x, xb[c].y), pack_bf16(xb[c].z, xb[c].w));
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxW1; ++i) {
+      const int idx = i * kThreads + tid;
+      if (idx < w1_chunks) reinterpret_cast<uint4*>(sW1)[idx] = w1r[i];
+    }
+    if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x, xa, xb);   // in flight during the three layers
     proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();   // my tcgen05.ld of the previous tile are complete (wait::ld) and ordered
     __syncthreads();
@@ -230,7 +300,7 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
     }
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-    epilogue_hidden<HID>(tmem_row, sB1, sA, tid);          // overwrites X / W1 (layer-1 MMAs are complete)
+    epilogue_hidden<HID>(tmem_row, sB1, sA, row, cbeg, cend);   // overwrites X / W1 (layer-1 MMAs are complete)
     proxy_fence();
     tc_fence_before();
     __syncthreads();
@@ -244,7 +314,7 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
     }
     mbar_wait(bar, parity); parity ^= 1;
     tc_fence_after();
-    epilogue_hidden<HID>(tmem_row, sB2, sA, tid);          // H2 over H1 (layer-2 MMAs are complete)
+    epilogue_hidden<HID>(tmem_row, sB2, sA, row, cbeg, cend);   // H2 over H1 (layer-2 MMAs are complete)
     proxy_fence();
     tc_fence_before();
     __syncthreads();
@@ -260,8 +330,8 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
     tc_fence_after();
     // ---- epilogue: Gaussian sample + log-prob ----------------------------------------------------------
     uint32_t v[16];
-    tmem_ld16(tmem_row, v);
-    if (valid) {
+    if (half == 0) tmem_ld16(tmem_row, v);   // warp-uniform: warps 0-3 finish the rows
+    if (valid && half == 0) {
       float eps[4] = {0.f, 0.f, 0.f, 0.f};
       if (noise != nullptr) {
         for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
@@ -401,9 +471,9 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
   const long long n_tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(n_tiles < a->sm_count ? n_tiles : a->sm_count);   // persistent: one CTA per SM
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->hidden == 256) actor_forward_kernel<256><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
-  else if (a->hidden == 128) actor_forward_kernel<128><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
-  else actor_forward_kernel<64><<<grid, kRows, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  if (a->hidden == 256) actor_forward_kernel<256><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  else if (a->hidden == 128) actor_forward_kernel<128><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  else actor_forward_kernel<64><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
   a->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_forward: %s", cudaGetErrorString(e));

@@ -62,6 +62,8 @@ struct bd_handle {
   float* hist = nullptr;
   int* stepc = nullptr;
   int* gsteps = nullptr;
+  float* ep_ret = nullptr;
+  double* ep_acc = nullptr;
   void* init_xyz = nullptr;
   void* init_rpy = nullptr;
   int init_env_stride = 0;
@@ -89,7 +91,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
   P.E = h->E; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
-  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps;
+  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
   P.init_xyz = (const R*)h->init_xyz; P.init_rpy = (const R*)h->init_rpy;
   P.init_env_stride = h->init_env_stride;
   P.jitter = (const R*)h->jitter;
@@ -205,7 +207,7 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
 
 void free_all(bd_handle* h) {
   cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
-  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
+  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
@@ -303,6 +305,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
   alloc((void**)&h->stepc, (size_t)cfg->n_envs * sizeof(int));
   alloc((void**)&h->gsteps, 2 * sizeof(int));
+  if (cfg->track_episodes) alloc((void**)&h->ep_ret, (size_t)cfg->n_envs * sizeof(float));
+  alloc((void**)&h->ep_acc, 3 * sizeof(double));
   if (e != cudaSuccess) {
     free_all(h); delete h;
     return fail(e == cudaErrorMemoryAllocation ? BD_ENOMEM : BD_ECUDA, "bd_create: device allocation failed: %s",
@@ -485,6 +489,16 @@ int bd_set_action_f32(bd_handle* h, int is_f32) {
     h->h_actions = nullptr; h->h_obs = nullptr; h->h_reward = nullptr; h->h_term = nullptr; h->h_trunc = nullptr;
   }
   refresh_params(h);
+  return BD_OK;
+}
+
+int bd_episode_stats(bd_handle* h, double* stats3_dev, int reset, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_episode_stats: null handle");
+  if (!h->ep_ret) return fail(BD_EINVAL, "bd_episode_stats: the handle was created with track_episodes = 0");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_episode_stats(h->ep_acc, stats3_dev, reset, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "episode_stats kernel launch failed: %s", cudaGetErrorString(e));
   return BD_OK;
 }
 

@@ -88,6 +88,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   float onep[4] = {1.f, 1.f, 1.f, 1.f};   // fl32(1 + 0.05 a) per motor (float actions)
   R last_rpm[4] = {R(0), R(0), R(0), R(0)};
   int stepc = 0;
+  float ep_in = 0.f;
   if (active) {
     const R4 a0 = P.s0[g], a1 = P.s1[g], a2 = P.s2[g], a3 = P.s3[g];
     bool from_double = false;
@@ -107,6 +108,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
       }
     }
     stepc = P.stepc[env];
+    if (P.ep_ret != nullptr) ep_in = P.ep_ret[env];
     d.px = a0.x; d.py = a0.y; d.pz = a0.z; d.qx = a0.w;
     d.qy = a1.x; d.qz = a1.y; d.qw = a1.z; d.vx = a1.w;
     d.vy = a2.x; d.vz = a2.y; d.wx = a2.z; d.wy = a2.w;
@@ -296,6 +298,17 @@ step_kernel(const __grid_constant__ Params<R> P) {
     done_reset = ((terminated || truncated) && P.auto_reset) ? 1 : 0;
     P.stepc[env] = done_reset ? 0 : stepc + P.S;
     sdone[env_l] = done_reset;
+    // episode statistics on the device (record_episode_statistics.py:144-171)
+    if (P.ep_ret != nullptr) {
+      float ep = ep_in + (float)reward;
+      if (terminated || truncated) {
+        atomicAdd(P.ep_acc + 0, (double)ep);
+        atomicAdd(P.ep_acc + 1, (double)(stepc / P.S + 1));
+        atomicAdd(P.ep_acc + 2, 1.0);
+        ep = 0.f;
+      }
+      P.ep_ret[env] = ep;
+    }
   }
   const int any_reset = __syncthreads_or(done_reset);
 
@@ -387,7 +400,7 @@ reset_kernel(const __grid_constant__ Params<R> P) {
   P.s2[g] = make4(d.vy, d.vz, d.wx, d.wy);
   P.s3[g] = make4(d.wz, d.tx, d.ty, d.tz);
   if (P.keep_angv) P.s4[g] = make4(R(0), R(0), R(0), R(0));
-  if (drone == 0) P.stepc[env] = 0;   // the ring head (total steps) is untouched by a reset
+  if (drone == 0) { P.stepc[env] = 0; if (P.ep_ret != nullptr) P.ep_ret[env] = 0.f; }   // the ring head (total steps) is untouched by a reset
   if (P.obs != nullptr) {
     float* row = P.obs + (size_t)g * P.D;
     for (int k = 0; k < 12; ++k) row[k] = kin[k];
@@ -599,6 +612,17 @@ cudaError_t launch_set_state(int precision, const void* p, const void* kin13, co
     const auto& P = *static_cast<const Params<float>*>(p);
     set_state_kernel<float><<<flat_grid(P), 256, 0, st>>>(P, (const float*)kin13, (const float*)targets, step_counter);
   }
+  return cudaGetLastError();
+}
+
+__global__ void episode_stats_kernel(double* acc, double* out3, int reset) {
+  if (threadIdx.x < 3) {
+    if (out3 != nullptr) out3[threadIdx.x] = acc[threadIdx.x];
+    if (reset) acc[threadIdx.x] = 0.0;
+  }
+}
+cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st) {
+  episode_stats_kernel<<<1, 32, 0, st>>>(ep_acc, out3, reset);
   return cudaGetLastError();
 }
 

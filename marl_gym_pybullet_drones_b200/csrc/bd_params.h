@@ -30,6 +30,8 @@ struct Params {
   float* hist;
   int* stepc;
   int* gsteps;
+  float* ep_ret;                  // running episode return per env (VecRecordEpisodeStatistics, :144-171)
+  double* ep_acc;                 // [3] sums over finished episodes: return, length, count
   const Real* init_xyz;
   const Real* init_rpy;
   int init_env_stride;            // 0 (shared (M,3) table) or M*3
@@ -72,6 +74,7 @@ cudaError_t launch_get_state(int precision, const void* params, void* state20, v
 cudaError_t launch_set_state(int precision, const void* params, const void* kin13,
                              const void* targets, const int32_t* step_counter, cudaStream_t st);
 cudaError_t launch_get_targets(int precision, const void* params, void* targets, cudaStream_t st);
+cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st);
 size_t step_smem_bytes(int precision, int A, int B, int D);
 
 }  // namespace bd

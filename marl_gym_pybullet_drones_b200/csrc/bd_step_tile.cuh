@@ -30,6 +30,7 @@ struct TileIn {
   float4 s0, s1, s2, s3;
   float4 act;   // A == 1: only .x is used
   int stepc;
+  float ep_ret;
 };
 
 template <int A>
@@ -39,10 +40,12 @@ __device__ __forceinline__ void load_inputs(const Params<float>& P, long long g,
     if constexpr (A == 4) in.act = reinterpret_cast<const float4*>(P.actions)[g];
     else in.act = make_float4(reinterpret_cast<const float*>(P.actions)[g], 0.f, 0.f, 0.f);
     in.stepc = P.stepc[g >> log2m];
+    in.ep_ret = P.ep_ret != nullptr ? P.ep_ret[g >> log2m] : 0.f;
   } else {
     in.s0 = in.s1 = in.s2 = in.s3 = in.act = make_float4(0.f, 0.f, 0.f, 0.f);
     in.s1.z = 1.0f;
     in.stepc = 0;
+    in.ep_ret = 0.f;
   }
 }
 
@@ -153,6 +156,17 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     P.terminated[env] = terminated ? 1 : 0;
     P.truncated[env] = truncated ? 1 : 0;
     P.stepc[env] = done_reset ? 0 : stepc + P.S;
+    // episode statistics on the device (record_episode_statistics.py:144-171)
+    if (P.ep_ret != nullptr) {
+      float ep = cur.ep_ret + reward;   // loaded up front with the other inputs
+      if (terminated || truncated) {
+        atomicAdd(P.ep_acc + 0, (double)ep);
+        atomicAdd(P.ep_acc + 1, (double)(stepc / P.S + 1));
+        atomicAdd(P.ep_acc + 2, 1.0);
+        ep = 0.f;
+      }
+      P.ep_ret[env] = ep;
+    }
   }
 
   // ---- reset-on-done (subproc_vec_env.py:195-206), rare -------------------------------------------

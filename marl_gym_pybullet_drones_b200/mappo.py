@@ -53,6 +53,7 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_steps": 256,
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
+    "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
 }
 
 
@@ -104,6 +105,8 @@ class DeviceMAPPO:
         self.device = env.device
         if env.action_dtype != torch.float32:
             raise ValueError("DeviceMAPPO drives fp32 aviaries")
+        if not env._cfg.track_episodes:
+            raise ValueError("DeviceMAPPO needs BatchAviary(..., track_episode_stats=True)")
         self.N, self.M, self.D, self.A = env.num_envs, env.NUM_DRONES, env.OBS_DIM, env.ACTION_DIM
         self.T = int(self.cfg["rollout_steps"])
         torch.manual_seed(seed)   # same initial weights on every rank
@@ -126,19 +129,24 @@ class DeviceMAPPO:
         self.ret = torch.zeros((T, N, 1), device=dev)
         self.adv = torch.zeros((T, N, 1), device=dev)
         # episode statistics (VecRecordEpisodeStatistics semantics, record_episode_statistics.py:144-171)
-        self.ep_return = torch.zeros(N, device=dev)
-        self.ep_length = torch.zeros(N, device=dev)
-        self.done_return_sum = torch.zeros((), device=dev, dtype=torch.float64)
-        self.done_length_sum = torch.zeros((), device=dev, dtype=torch.float64)
-        self.done_count = torch.zeros((), device=dev, dtype=torch.float64)
+        # (the step kernel accumulates them: BatchAviary.episode_stats)
         self.total_env_steps = 0
         self._reset_done = False
+        self.fused = None
+        if self.cfg["fused_actor"] and self.cfg["activation"] == "tanh":
+            from ._native import NativeError
+            from .actor import FusedActor
+            try:
+                self.fused = FusedActor(self.D, int(self.cfg["hidden_dim"]), self.A, device=self.device)
+            except NativeError:
+                self.fused = None   # shape outside the fused kernel's envelope: torch path
+        self._fused_seed = seed * 7919 + rank
+        self._fused_stale = True
 
     # ------------------------------------------------------------------ rollout
     def reset(self):
         self.env.reset_device(out=self.obs[0])
-        self.ep_return.zero_()
-        self.ep_length.zero_()
+        self.env.episode_stats(reset=True)
         self._reset_done = True
 
     @torch.no_grad()
@@ -151,26 +159,25 @@ class DeviceMAPPO:
         T, N, M = self.T, self.N, self.M
         std = self.ac.logstd.exp()
         use_critic = self.cfg["rollout_values"] == "critic"
+        if self.fused is not None and self._fused_stale:
+            self.fused.set_weights(self.ac.actor, self.ac.logstd)     # bf16 tensor-core tiles of the current policy
+            self._fused_stale = False
         for t in range(T):
             obs_t = self.obs[t]
-            mean = self.ac.actor(obs_t.view(N * M, self.D)).view(N, M, self.A)
-            noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
-            act = mean + std * noise                                  # unclipped Gaussian (agent.py:399-400)
-            self.act[t] = act
-            self.logp[t] = (-0.5 * noise.pow(2) - self.ac.logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
+            if self.fused is not None:
+                # one kernel: MLP on tcgen05, Gaussian sample (Philox), summed log-prob; writes act[t], logp[t]
+                self.fused.forward(obs_t.view(N * M, self.D), seed=self._fused_seed,
+                                   out_act=self.act[t].view(N * M, self.A), out_logp=self.logp[t].view(N * M))
+            else:
+                mean = self.ac.actor(obs_t.view(N * M, self.D)).view(N, M, self.A)
+                noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
+                self.act[t] = mean + std * noise                      # unclipped Gaussian (agent.py:399-400)
+                self.logp[t] = (-0.5 * noise.pow(2) - self.ac.logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
             if use_critic:
                 self.val[t] = self.ac.value(obs_t.view(N, M * self.D))
             out = StepResult(self.obs[t + 1], self.rew[t], self.term[t].view(torch.bool),
                              self.trunc[t].view(torch.bool), None)
-            self.env.step_device(self.act[t], out=out)
-            done = (self.term[t] | self.trunc[t]).bool()
-            self.ep_return += self.rew[t]
-            self.ep_length += 1
-            self.done_return_sum += (self.ep_return * done).sum()
-            self.done_length_sum += (self.ep_length * done).sum()
-            self.done_count += done.sum()
-            self.ep_return.masked_fill_(done, 0.0)
-            self.ep_length.masked_fill_(done, 0.0)
+            self.env.step_device(self.act[t], out=out)   # episode statistics are kept by the step kernel
         # bootstrap value of the last observation (`last_val`, mappo.py:1049-1157)
         self.val[T] = self.ac.value(self.obs[T].view(N, M * self.D))
         if not use_critic:
@@ -245,17 +252,15 @@ class DeviceMAPPO:
                 self.critic_opt.step()
                 stats += torch.stack([policy_loss.detach(), value_loss.detach(), entropy_loss.detach(), approx_kl,
                                       torch.ones((), device=self.device)])
+        self._fused_stale = True
         s = (stats[:4] / stats[4]).tolist()
         return {"policy_loss": s[0], "value_loss": s[1], "entropy_loss": s[2], "approx_kl": s[3]}
 
     # --------------------------------------------------------------------- loop
     def pop_episode_stats(self):
         """Mean return / length of the episodes finished since the last call (all ranks)."""
-        out = reduce_episode_stats(self.done_return_sum, self.done_length_sum, self.done_count)
-        self.done_return_sum.zero_()
-        self.done_length_sum.zero_()
-        self.done_count.zero_()
-        return out
+        s = self.env.episode_stats(reset=True)
+        return reduce_episode_stats(s[0], s[1], s[2])
 
     def train_step(self) -> Dict[str, float]:
         t0 = time.time()
@@ -295,6 +300,7 @@ class DeviceMAPPO:
         self.actor_opt.load_state_dict(sd["agent"]["actor_opt"])
         self.critic_opt.load_state_dict(sd["agent"]["critic_opt"])
         self.total_env_steps = int(sd.get("total_steps", 0))
+        self._fused_stale = True
 
     def save(self, path):
         torch.save(self.state_dict(), path)

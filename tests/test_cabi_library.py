@@ -54,7 +54,7 @@ def test_config_struct_layout_matches_header(lib):
         for part in decl.split(","):
             names.append(re.sub(r"\[.*\]", "", part).strip())
     assert names == [f[0] for f in _native.BdConfig._fields_]
-    assert C.sizeof(_native.BdConfig) == 320
+    assert C.sizeof(_native.BdConfig) == 328
 
 
 def test_create_rejects_bad_configs_with_messages(lib):

@@ -115,3 +115,37 @@ def test_multi_device_handles_are_independent():
     b.close()
     with pytest.raises(RuntimeError):
         a.step_device(act)
+
+
+@pytest.mark.parametrize("M,physics", [(4, "dyn"), (3, "dyn")])   # fast tile kernel / generic kernel
+def test_device_episode_statistics_match_host_bookkeeping(M, physics):
+    """bd_episode_stats == VecRecordEpisodeStatistics semantics (record_episode_statistics.py:144-171)."""
+    from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
+    N, T = 300, 120
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[float(i % side), float(i // side), 0.3] for i in range(M)])
+    env = BatchAviary(task="multihover", num_envs=N, num_drones=M, initial_xyzs=xyz, physics=physics, seed=4,
+                      track_episode_stats=True)
+    env.reset_device()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ep_r, ep_l = np.zeros(N), np.zeros(N)
+    rets, lens = [], []
+    for t in range(T):
+        a = torch.rand((N, M, 4), generator=g, device="cuda") * 2 - 1.4
+        r = env.step_device(a)
+        rew, done = r.reward.cpu().numpy().astype(np.float64), r.done.cpu().numpy()
+        ep_r += rew
+        ep_l += 1
+        for e in np.nonzero(done)[0]:
+            rets.append(ep_r[e]); lens.append(ep_l[e])
+            ep_r[e] = 0; ep_l[e] = 0
+        if t == 59:
+            s = env.episode_stats(reset=True).cpu().numpy()
+            assert s[2] == len(rets) and s[1] == sum(lens) and abs(s[0] - sum(rets)) <= 1e-3 * max(1.0, abs(sum(rets)))
+            rets, lens = [], []
+    s = env.episode_stats(reset=False).cpu().numpy()
+    assert len(rets) > 50 and s[2] == len(rets) and s[1] == sum(lens)
+    assert abs(s[0] - sum(rets)) <= 1e-3 * max(1.0, abs(sum(rets)))
+    assert np.array_equal(env.episode_stats(reset=True).cpu().numpy(), s)      # reset=False left them in place
+    assert env.episode_stats().cpu().numpy().tolist() == [0.0, 0.0, 0.0]
+    env.close()

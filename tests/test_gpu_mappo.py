@@ -24,7 +24,7 @@ def _ref_returns(rews, vals, masks, last_val, gamma, lam):
 @pytest.mark.parametrize("rollout_values", ["zeros", "critic"])
 def test_gae_scan_matches_reference_loop(rollout_values):
     from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
-    env = BatchAviary(task="multihover", num_envs=16, num_drones=2,
+    env = BatchAviary(task="multihover", num_envs=16, num_drones=2, track_episode_stats=True,
                       initial_xyzs=np.array([[0.0, 0.0, 0.2], [1.0, 0.0, 0.2]]))
     algo = DeviceMAPPO(env, rollout_steps=48, hidden_dim=32, rollout_values=rollout_values, seed=3)
     algo.collect_rollout()
@@ -46,9 +46,10 @@ def test_gae_scan_matches_reference_loop(rollout_values):
 def test_hover_learns_and_checkpoint_roundtrip(tmp_path):
     from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
     torch.manual_seed(0)
-    env = BatchAviary(task="hover", num_envs=1024, act="one_d_rpm", seed=1)
+    env = BatchAviary(task="hover", num_envs=1024, act="one_d_rpm", seed=1, track_episode_stats=True)
     algo = DeviceMAPPO(env, rollout_steps=121, hidden_dim=64, mini_batch_size=8192, opt_epochs=4,
                        rollout_values="critic", actor_lr=1e-3, target_kl=0.05, seed=0)
+    assert algo.fused is not None          # the rollout policy runs on the tcgen05 kernel
     first = algo.train_step()
     assert first["episodes"] == 0 or np.isfinite(first["ep_return"])
     hist = algo.learn(max_env_steps=algo.total_env_steps + 14 * 121 * 1024)
@@ -57,6 +58,7 @@ def test_hover_learns_and_checkpoint_roundtrip(tmp_path):
     # random policy hovers around z0: ~1.38/step; a learnt policy climbs towards z=1 (2/step)
     assert np.mean(rets[-2:]) > np.mean(rets[:2]) + 10.0, rets
     assert all(np.isfinite(list(h.values())).all() for h in hist)
+    assert algo.fused.launch_count > 15 * 121
     p = tmp_path / "model_latest.pt"
     algo.save(p)
     algo2 = DeviceMAPPO(env, rollout_steps=121, hidden_dim=64, seed=5)
@@ -64,4 +66,24 @@ def test_hover_learns_and_checkpoint_roundtrip(tmp_path):
     o = algo.obs[0]
     assert torch.equal(algo.select_action(o), algo2.select_action(o))
     assert algo2.total_env_steps == algo.total_env_steps
+    env.close()
+
+
+def test_fused_and_torch_rollouts_agree_statistically():
+    """Same policy, fused (bf16 tensor cores, Philox) vs torch (fp32, torch RNG) rollouts: the stored
+    log-probs are self-consistent with the fp32 actor to bf16 accuracy (PPO ratio ~ 1 before any update)."""
+    from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
+    grid = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5], [1.0, 1.0, 0.5]])
+    env = BatchAviary(task="multihover", num_envs=512, num_drones=4, initial_xyzs=grid, seed=2,
+                      track_episode_stats=True)
+    algo = DeviceMAPPO(env, rollout_steps=16, hidden_dim=256, seed=1)
+    assert algo.fused is not None
+    algo.collect_rollout()
+    T, N, M, D, A = algo.T, algo.N, algo.M, algo.D, algo.A
+    with torch.no_grad():
+        lp = algo.ac.logp(algo.obs[:T].reshape(-1, D), algo.act.reshape(-1, A))
+    ratio = torch.exp(lp - algo.logp.reshape(-1, 1))
+    assert abs(ratio.mean().item() - 1.0) < 5e-3 and (ratio - 1).abs().max().item() < 0.15
+    eps = (algo.act.reshape(-1, A) - algo.ac.actor(algo.obs[:T].reshape(-1, D)).detach()) / algo.ac.logstd.exp().detach()
+    assert abs(eps.mean().item()) < 2e-2 and abs(eps.std().item() - 1.0) < 2e-2
     env.close()
