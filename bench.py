@@ -320,7 +320,7 @@ def run_ours(args):
                 "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "bd::step_kernel<float,MULTIHOVER,4,false>",
+                         "kernel": "bd::step_kernel_tile<MULTIHOVER,4,4,false>",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "algorithmic_bytes_per_drone_substep": bytes_per_drone_step / S,
                          "kernel_ms": kernel_ms},

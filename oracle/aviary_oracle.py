@@ -38,6 +38,7 @@ from collections import deque
 import numpy as np
 
 from . import bullet_math as bm
+from .dsl_pid import DSLPIDOracle
 
 AERO_GND, AERO_DRAG, AERO_DW = 1, 2, 4
 
@@ -99,7 +100,8 @@ class OracleAviary:
     """One environment: M drones, explicit dynamics, KIN observation, RPM/ONE_D_RPM action.
 
     task: 'hover' (HoverAviary), 'multihover' (MultiHoverAviary), 'spiral'
-    (SpiralFormationAviary).  `act`: 'rpm' | 'one_d_rpm'.
+    (SpiralFormationAviary).  `act`: 'rpm' | 'one_d_rpm' | 'pid' | 'vel' | 'one_d_pid'
+    (the last three through `oracle/dsl_pid.py`, BaseRLAviary.py:73-78,193-235).
     """
 
     def __init__(self, task="multihover", drone_model="cf2x", num_drones=1,
@@ -142,7 +144,13 @@ class OracleAviary:
         self.INIT_XYZS = np.array(initial_xyzs, dtype=np.float64).reshape(M, 3)
         self.INIT_RPYS = (np.zeros((M, 3)) if initial_rpys is None
                           else np.array(initial_rpys, dtype=np.float64).reshape(M, 3))
-        self.A = 4 if act == "rpm" else 1                                     # BaseRLAviary.py:141-146
+        self.A = {"rpm": 4, "vel": 4, "pid": 3, "one_d_rpm": 1, "one_d_pid": 1}[act]   # BaseRLAviary.py:141-146
+        if act in ("pid", "vel", "one_d_pid"):                                # BaseRLAviary.py:73-78
+            if drone_model not in ("cf2x", "cf2p"):
+                raise ValueError("[ERROR] in BaseRLAviary.__init()__, no controller is available for the specified drone_model")
+            self.ctrl = [DSLPIDOracle() for _ in range(M)]
+        if act == "vel":                                                      # BaseRLAviary.py:94-95
+            self.SPEED_LIMIT = 0.03 * self.P.MAX_SPEED_KMH * (1000 / 3600)
         self.action_buffer = deque(maxlen=self.ACTION_BUFFER_SIZE)
         for _ in range(self.ACTION_BUFFER_SIZE):                              # BaseRLAviary.py:153-154
             self.action_buffer.append(np.zeros((M, self.A)))
@@ -217,16 +225,44 @@ class OracleAviary:
         return self._compute_obs(), self._compute_info()
 
     # ------------------------------------------------------------------- step
+    def _calculate_next_step(self, current_position, destination, step_size=1):
+        """BaseAviary.py:1108-1150."""
+        direction = destination - current_position
+        distance = np.linalg.norm(direction)
+        if distance <= step_size:
+            return destination
+        return current_position + (direction / distance) * step_size
+
     def _preprocess_action(self, action):
-        """BaseRLAviary.py:160-239 (RPM and ONE_D_RPM branches; no clipping)."""
+        """BaseRLAviary.py:160-239 (no clipping in the RPM branches)."""
         self.action_buffer.append(action)
         rpm = np.zeros((self.NUM_DRONES, 4))
         for k in range(action.shape[0]):
             target = action[k, :]
             if self.ACT == "rpm":
                 rpm[k, :] = np.array(self.P.HOVER_RPM * (1 + 0.05 * target))           # :192
-            else:
+            elif self.ACT == "one_d_rpm":
                 rpm[k, :] = np.repeat(self.P.HOVER_RPM * (1 + 0.05 * target), 4)        # :225
+            elif self.ACT == "pid":                                                     # :193-206
+                state = self.state_vector(k)
+                next_pos = self._calculate_next_step(state[0:3], target, 1)
+                rpm[k, :] = self.ctrl[k].compute_control(self.CTRL_TIMESTEP, state[0:3], state[3:7],
+                                                         state[10:13], target_pos=next_pos)
+            elif self.ACT == "vel":                                                     # :207-222
+                state = self.state_vector(k)
+                if np.linalg.norm(target[0:3]) != 0:
+                    v_unit_vector = target[0:3] / np.linalg.norm(target[0:3])
+                else:
+                    v_unit_vector = np.zeros(3)
+                rpm[k, :] = self.ctrl[k].compute_control(
+                    self.CTRL_TIMESTEP, state[0:3], state[3:7], state[10:13], target_pos=state[0:3],
+                    target_rpy=np.array([0, 0, state[9]]),
+                    target_vel=self.SPEED_LIMIT * np.abs(target[3]) * v_unit_vector)
+            else:                                                                       # one_d_pid, :226-235
+                state = self.state_vector(k)
+                rpm[k, :] = self.ctrl[k].compute_control(
+                    self.CTRL_TIMESTEP, state[0:3], state[3:7], state[10:13],
+                    target_pos=state[0:3] + 0.1 * np.array([0, 0, target[0]]))
         return rpm
 
     def step(self, action):

@@ -9,9 +9,32 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 AERO = {"gnd": 1, "drag": 2, "dw": 4}
 
 
-def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("aero"))
+CONTROLLER_CASES = ("spiral3_vel", "spiral3_vel_f32", "multihover2_vel_cf2p", "multihover2_pid", "hover_one_d_pid")
+
+
+def golden_names(controller=False):
+    """Golden trajectories; `controller=True` selects the PID / VEL / ONE_D_PID cases instead."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                   if not os.path.basename(p).startswith("aero"))
+    return [n for n in names if (n in CONTROLLER_CASES) == controller]
+
+
+def oracle_inject(env, states, rpy_rates, ctrl_state=None):
+    """Put an OracleAviary into the state of a golden row: states (M,20), body rates (M,3) — the
+    dynamics integrate `rpy_rates`, the state vector only carries R*rates (BaseAviary.py:873) —
+    and ctrl_state (M,9)."""
+    for i in range(env.NUM_DRONES):
+        env._store_pos[i] = tuple(states[i, 0:3])
+        env._store_quat[i] = tuple(states[i, 3:7])
+        env._store_vel[i] = tuple(states[i, 10:13])
+        env._store_angv[i] = tuple(states[i, 13:16])
+        if ctrl_state is not None:
+            env.ctrl[i].integral_pos_e = ctrl_state[i, 0:3].copy()
+            env.ctrl[i].integral_rpy_e = ctrl_state[i, 3:6].copy()
+            env.ctrl[i].last_rpy = ctrl_state[i, 6:9].copy()
+    env.last_clipped_action = states[:, 16:20].copy()
+    env.rpy_rates = np.array(rpy_rates, dtype=np.float64).copy()
+    env._refresh_kinematics()
 
 
 def load_golden(name):

@@ -43,7 +43,9 @@ def _make_env(c, task, **kw):
     return env
 
 
-def rollout(c, task, actions, np_seed=None, **kw):
+def rollout(c, task, actions, np_seed=None, reset_at=(), **kw):
+    """`reset_at`: step indices before which `env.reset()` is called again on the SAME env object
+    (the controllers of the PID action types are not reset by it, BaseRLAviary.py:73-78)."""
     env = _make_env(c, task, **kw)
     if np_seed is not None:
         np.random.seed(np_seed)
@@ -55,16 +57,31 @@ def rollout(c, task, actions, np_seed=None, **kw):
                obs=[], reward=[], terminated=[], truncated=[], states=[], rpy_rates=[])
     if hasattr(env, "TARGET_POS"):
         out["target_pos"] = np.array(env.TARGET_POS, dtype=np.float64).reshape(-1, 3)
+    has_ctrl = hasattr(env, "ctrl")
+    if has_ctrl:
+        out["ctrl_state"] = []
+    if len(reset_at):
+        out["reset_at"] = np.array(reset_at, dtype=np.int64)
+        out["reset_obs"], out["reset_init_xyzs"] = [], []
     for t in range(T):
+        if t in reset_at:
+            ro, _ = env.reset()
+            out["reset_obs"].append(np.asarray(ro, dtype=np.float64))
+            out["reset_init_xyzs"].append(np.array(env.INIT_XYZS, dtype=np.float64))
         o, r, te, tr, _ = env.step(actions[t])
+        if has_ctrl:
+            out["ctrl_state"].append(np.array([np.concatenate([k.integral_pos_e, k.integral_rpy_e, k.last_rpy])
+                                               for k in env.ctrl]))
         out["obs"].append(np.asarray(o, dtype=np.float64))
         out["reward"].append(float(r))
         out["terminated"].append(bool(te))
         out["truncated"].append(bool(tr))
         out["states"].append(np.array([env._getDroneStateVector(i) for i in range(M)]))
         out["rpy_rates"].append(env.rpy_rates.copy())
-    for k in ("obs", "reward", "terminated", "truncated", "states", "rpy_rates"):
-        out[k] = np.array(out[k])
+    for k in ("obs", "reward", "terminated", "truncated", "states", "rpy_rates", "ctrl_state", "reset_obs",
+              "reset_init_xyzs"):
+        if k in out:
+            out[k] = np.array(out[k])
     env.close()
     return out
 
@@ -76,6 +93,42 @@ def save(name, cfg, data):
           f"term@{int(np.argmax(data['terminated'])) if data['terminated'].any() else None} "
           f"trunc@{int(np.argmax(data['truncated'])) if data['truncated'].any() else None} "
           f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def controller_cases(c):
+    """ActionType.PID / VEL / ONE_D_PID: DSLPIDControl inside _preprocessAction (BaseRLAviary.py:193-235)."""
+    rng = np.random.default_rng
+    # Spiral's default action type is VEL (SpiralAviary.py:32), M=3 default, 240/48; fp64 actions
+    cfg = dict(task="spiral", drone_model="cf2x", num_drones=3, pyb_freq=240, ctrl_freq=48, act="vel")
+    kw = {k: v for k, v in cfg.items() if k != "task"}
+    a = rng(21).uniform(-1, 1, (160, 3, 4))
+    a[40:44] = 0.0                                   # zero direction: v_unit_vector = 0 branch (:210-213)
+    save("spiral3_vel", cfg, rollout(c, "spiral", a, reset_at=(96,), **kw))
+    # same with float32 actions (numpy keeps the unit vector and the speed factor in float32)
+    a = rng(22).uniform(-1, 1, (64, 3, 4)).astype(np.float32)
+    save("spiral3_vel_f32", cfg, rollout(c, "spiral", a, **kw))
+    # MultiHover M=2 on CF2P with VEL, 240/30, jittered spawn, two resets on the same env object
+    cfg = dict(task="multihover", drone_model="cf2p", num_drones=2, pyb_freq=240, ctrl_freq=30, act="vel",
+               initial_xyzs=[[0, 0, .5], [1.2, 0, .6]])
+    a = rng(23).uniform(-1, 1, (120, 2, 4))
+    save("multihover2_vel_cf2p", cfg, rollout(c, "multihover", a, np_seed=4, reset_at=(50, 90), drone_model="cf2p",
+                                              num_drones=2, pyb_freq=240, ctrl_freq=30, act="vel",
+                                              initial_xyzs=np.array(cfg["initial_xyzs"])))
+    # PID waypoint targets (A=3): near (< 1 m: target itself) and far (> 1 m: unit step) destinations
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=2, pyb_freq=240, ctrl_freq=30, act="pid",
+               initial_xyzs=[[0, 0, .5], [1.0, 0, .5]])
+    a = np.zeros((150, 2, 3))
+    a[:, 0] = [0.3, 0.2, 1.0]
+    a[:, 1] = [1.0, -0.4, 0.8]
+    a[60:] = rng(24).uniform(-1, 1, (90, 2, 3)) * [2.5, 2.5, 1.0] + [0, 0, 1.2]
+    save("multihover2_pid", cfg, rollout(c, "multihover", a, np_seed=6, reset_at=(100,), drone_model="cf2x",
+                                         num_drones=2, pyb_freq=240, ctrl_freq=30, act="pid",
+                                         initial_xyzs=np.array(cfg["initial_xyzs"])))
+    # HoverAviary with ONE_D_PID (A=1), float32 actions
+    cfg = dict(task="hover", drone_model="cf2x", pyb_freq=240, ctrl_freq=30, act="one_d_pid")
+    a = rng(25).uniform(-1, 1, (120, 1, 1)).astype(np.float32)
+    a[:30] = 1.0
+    save("hover_one_d_pid", cfg, rollout(c, "hover", a, **{k: v for k, v in cfg.items() if k != "task"}))
 
 
 def aero_samples(c):
@@ -185,6 +238,7 @@ def main():
     a += (0.004 * rng(12).standard_normal((580, 5, 4))).astype(np.float32)
     save("spiral5_long", cfg3, rollout(c, "spiral", a, **kw3))
 
+    controller_cases(c)
     aero_samples(c)
 
 
