@@ -22,7 +22,7 @@
  *     bd_last_error() returns the message of the calling thread's last failure.
  *   - one handle per GPU; a handle is not thread-safe.
  *
- * Shapes: N = n_envs, M = n_drones, A = 4 (RPM) or 1 (ONE_D_RPM),
+ * Shapes: N = n_envs, M = n_drones, A = 4 (RPM, VEL), 3 (PID) or 1 (ONE_D_RPM, ONE_D_PID),
  *   B = ctrl_freq/2 (BaseRLAviary.py:66), D = 12 + B*A (+11 for the spiral task).
  */
 #ifndef BATCH_DRONES_H_
@@ -37,7 +37,9 @@ extern "C" {
 #define BD_VERSION 1
 
 enum { BD_TASK_HOVER = 0, BD_TASK_MULTIHOVER = 1, BD_TASK_SPIRAL = 2 };
-enum { BD_ACT_RPM = 0, BD_ACT_ONE_D_RPM = 1 };
+/* ActionType (utils/enums.py:35-41).  PID / VEL / ONE_D_PID run the reference's DSLPIDControl
+ * (control/DSLPIDControl.py:82-246) inside the step kernel, one controller per drone. */
+enum { BD_ACT_RPM = 0, BD_ACT_ONE_D_RPM = 1, BD_ACT_PID = 2, BD_ACT_VEL = 3, BD_ACT_ONE_D_PID = 4 };
 enum { BD_MODEL_CF2X = 0, BD_MODEL_CF2P = 1, BD_MODEL_RACE = 2 };
 enum { BD_F32 = 0, BD_F64 = 1 };
 enum { BD_AERO_GND = 1, BD_AERO_DRAG = 2, BD_AERO_DW = 4 };
@@ -75,7 +77,9 @@ typedef struct bd_config {
                                1+0.05*a in float32 then), else double                 */
   int32_t keep_ang_vel;     /* 1: keep world angular velocity for bd_get_state        */
   int32_t track_episodes;   /* 1: accumulate episode returns/lengths (bd_episode_stats) */
-  int32_t reserved0;        /* must be 0                                              */
+  int32_t ctrl_reset_on_reset; /* PID action types: 1 = an env reset also clears its drones' controller
+                               memory; 0 = reference behaviour, the controllers are built once in
+                               BaseRLAviary.__init__ (:73-78) and never reset by env.reset()   */
   uint64_t seed;            /* Philox key for BD_RESET_JITTER_PHILOX                  */
   double episode_len_sec;   /* 8 (hover, multihover) / 12 (spiral)                    */
   /* airframe */
@@ -85,6 +89,10 @@ typedef struct bd_config {
   double prop_xy[8];        /* x0,y0,...,x3,y3 body-frame propeller offsets            */
   /* spiral task (SpiralAviary.py:33-45) */
   double spiral_radius, spiral_period, height_rate, target_center[3];
+  /* PID action types: the controller is always DSLPIDControl(DroneModel.CF2X)
+   * (BaseRLAviary.py:76), so its mass / kf are CF2X's (BaseControl.py:35-37), not the env's */
+  double ctrl_mass, ctrl_kf;
+  double speed_limit;       /* VEL: 0.03 * MAX_SPEED_KMH * 1000/3600 (BaseRLAviary.py:95)     */
 } bd_config;
 
 typedef struct bd_handle bd_handle;
@@ -158,6 +166,13 @@ int bd_get_targets(bd_handle* h, void* targets_dev, void* stream);
  * finished since the last reset of the accumulators (per-step return = the env's scalar reward).
  * stats3_dev may be NULL (reset only).  Stream ordered.  Needs cfg.track_episodes = 1. */
 int bd_episode_stats(bd_handle* h, double* stats3_dev, int reset, void* stream);
+
+/* DSL PID controller memory of every drone, (N,M,9) Real =
+ * [integral_pos_e(3), integral_rpy_e(3), last_rpy(3)] (DSLPIDControl.py:64-79).
+ * bd_set_controller_state(NULL) zeroes it = `ctrl[k].reset()` on every drone.
+ * BD_EINVAL for the RPM action types. */
+int bd_get_controller_state(bd_handle* h, void* ctrl9_dev, void* stream);
+int bd_set_controller_state(bd_handle* h, const void* ctrl9_dev, void* stream);
 
 /* BD_F64 handles only: switch between float32 and float64 action input (see
  * bd_config.action_is_f32).  numpy evaluates HOVER_RPM*(1+0.05*a) partly in float32

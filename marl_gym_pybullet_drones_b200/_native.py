@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbatchdrones.so")
 
 BD_TASK = {"hover": 0, "multihover": 1, "spiral": 2}
-BD_ACT = {"rpm": 0, "one_d_rpm": 1}
+BD_ACT = {"rpm": 0, "one_d_rpm": 1, "pid": 2, "vel": 3, "one_d_pid": 4}
 BD_MODEL = {"cf2x": 0, "cf2p": 1, "racer": 2}
 BD_PRECISION = {"fp32": 0, "fp64": 1}
 BD_INTEGRATOR = {"quat": 0, "euler": 1}
@@ -21,7 +21,8 @@ BD_RESET = {"fixed": 0, "jitter_philox": 1, "jitter_buffer": 2}
 
 EXPORTS = (
     "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
-    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_episode_stats", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
+    "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_episode_stats",
+    "bd_get_controller_state", "bd_set_controller_state", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
     "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_launch_count",
     "bd_actor_last_error",
@@ -39,7 +40,7 @@ class BdConfig(C.Structure):
         ("pyb_freq", C.c_int32), ("ctrl_freq", C.c_int32),
         ("auto_reset", C.c_int32), ("reset_mode", C.c_int32),
         ("action_is_f32", C.c_int32), ("keep_ang_vel", C.c_int32),
-        ("track_episodes", C.c_int32), ("reserved0", C.c_int32),
+        ("track_episodes", C.c_int32), ("ctrl_reset_on_reset", C.c_int32),
         ("seed", C.c_uint64),
         ("episode_len_sec", C.c_double),
         ("mass", C.c_double), ("arm", C.c_double), ("kf", C.c_double), ("km", C.c_double),
@@ -50,6 +51,7 @@ class BdConfig(C.Structure):
         ("prop_xy", C.c_double * 8),
         ("spiral_radius", C.c_double), ("spiral_period", C.c_double), ("height_rate", C.c_double),
         ("target_center", C.c_double * 3),
+        ("ctrl_mass", C.c_double), ("ctrl_kf", C.c_double), ("speed_limit", C.c_double),
     ]
 
 
@@ -93,6 +95,10 @@ def load():
     lib.bd_get_targets.restype = C.c_int
     lib.bd_episode_stats.argtypes = [vp, vp, C.c_int, vp]
     lib.bd_episode_stats.restype = C.c_int
+    lib.bd_get_controller_state.argtypes = [vp, vp, vp]
+    lib.bd_get_controller_state.restype = C.c_int
+    lib.bd_set_controller_state.argtypes = [vp, vp, vp]
+    lib.bd_set_controller_state.restype = C.c_int
     lib.bd_set_action_f32.argtypes = [vp, C.c_int]
     lib.bd_set_action_f32.restype = C.c_int
     for name in ("bd_obs_dim", "bd_act_dim", "bd_action_buffer_size", "bd_substeps"):

@@ -73,6 +73,7 @@ class BatchAviary:
                  integrator: str = "quat",
                  keep_ang_vel: bool = False,
                  track_episode_stats: bool = False,
+                 reset_controllers: bool = False,
                  action_dtype=None,
                  seed: int = 0,
                  spiral_radius: float = 0.4,
@@ -89,8 +90,9 @@ class BatchAviary:
             raise NotImplementedError("GUI / video recording need PyBullet's renderer (out of scope)")
         if obs != ObservationType.KIN:
             raise NotImplementedError("only ObservationType.KIN is produced by the GPU path")
-        if act not in (ActionType.RPM, ActionType.ONE_D_RPM):
-            raise NotImplementedError(f"{act}: only ActionType.RPM and ONE_D_RPM are stepped on the GPU")
+        if act in (ActionType.PID, ActionType.VEL, ActionType.ONE_D_PID) and drone_model not in (
+                DroneModel.CF2X, DroneModel.CF2P):   # BaseRLAviary.py:73-78
+            raise ValueError("[ERROR] in BaseRLAviary.__init()__, no controller is available for the specified drone_model")
         if pyb_freq % ctrl_freq != 0:   # BaseAviary.py:79-80
             raise ValueError('[ERROR] in BaseAviary.__init__(), pyb_freq is not divisible by env_freq.')
         if precision not in _native.BD_PRECISION:
@@ -165,6 +167,14 @@ class BatchAviary:
         cfg.action_is_f32 = int(action_dtype == torch.float32)
         cfg.keep_ang_vel = int(keep_ang_vel)
         cfg.track_episodes = int(track_episode_stats)
+        # DSL PID in the loop (ActionType.PID / VEL / ONE_D_PID): the reference always builds
+        # DSLPIDControl(DroneModel.CF2X) (BaseRLAviary.py:76) and never resets it with the env
+        cfg.ctrl_reset_on_reset = int(reset_controllers)
+        kc: DroneConstants = drone_constants(DroneModel.CF2X)
+        cfg.ctrl_mass, cfg.ctrl_kf = kc.M, kc.KF
+        if act == ActionType.VEL:
+            self.SPEED_LIMIT = 0.03 * k.MAX_SPEED_KMH * (1000 / 3600)             # BaseRLAviary.py:94-95
+        cfg.speed_limit = float(getattr(self, "SPEED_LIMIT", 0.0))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.episode_len_sec = float(self.EPISODE_LEN_SEC)
         cfg.mass, cfg.arm, cfg.kf, cfg.km = k.M, k.L, k.KF, k.KM
@@ -387,6 +397,28 @@ class BatchAviary:
         t = torch.empty((self.num_envs, self.NUM_DRONES, 3), dtype=self.real_dtype, device=self.device)
         _native.check(self._lib.bd_get_targets(self._h, C.c_void_p(t.data_ptr()), self._stream()), "bd_get_targets")
         return t
+
+    def get_controller_state(self) -> torch.Tensor:
+        """DSL PID memory of every drone, (N,M,9) = [integral_pos_e, integral_rpy_e, last_rpy]
+        (DSLPIDControl.py:64-79); PID / VEL / ONE_D_PID action types only."""
+        self._check_open()
+        t = torch.empty((self.num_envs, self.NUM_DRONES, 9), dtype=self.real_dtype, device=self.device)
+        _native.check(self._lib.bd_get_controller_state(self._h, C.c_void_p(t.data_ptr()), self._stream()),
+                      "bd_get_controller_state")
+        return t
+
+    def set_controller_state(self, ctrl=None):
+        """Overwrite the DSL PID memory ((N,M,9)); `None` zeroes it = `ctrl[k].reset()` on every drone."""
+        self._check_open()
+        ptr = None
+        if ctrl is not None:
+            c = torch.as_tensor(ctrl).to(device=self.device, dtype=self.real_dtype).contiguous()
+            if tuple(c.shape) != (self.num_envs, self.NUM_DRONES, 9):
+                raise ValueError("ctrl must have shape (N,M,9)")
+            ptr = C.c_void_p(c.data_ptr())
+        _native.check(self._lib.bd_set_controller_state(self._h, ptr, self._stream()), "bd_set_controller_state")
+        if ctrl is not None:
+            torch.cuda.current_stream(self.device).synchronize()   # `c` may be a temporary
 
     def episode_stats(self, reset: bool = True) -> torch.Tensor:
         """Device tensor [sum of returns, sum of lengths, count] of the episodes finished since the

@@ -64,6 +64,7 @@ struct bd_handle {
   int* gsteps = nullptr;
   float* ep_ret = nullptr;
   double* ep_acc = nullptr;
+  void* ctrl = nullptr;        // DSL PID memory + commanded rpm, PID action types only
   void* init_xyz = nullptr;
   void* init_rpy = nullptr;
   int init_env_stride = 0;
@@ -92,6 +93,12 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.E = h->E; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
   P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
+  P.ctrl = (R*)h->ctrl;
+  P.act_type = c.act_type; P.ctrl_reset = c.ctrl_reset_on_reset;
+  P.ctrl_dt = (R)(1.0 / c.ctrl_freq);                      // CTRL_TIMESTEP (BaseAviary.py:83)
+  P.ctrl_gravity = (R)(c.g * c.ctrl_mass);                 // BaseControl.py:35
+  P.ctrl_4kf = (R)(4 * c.ctrl_kf);                         // DSLPIDControl.py:187
+  P.speed_limit = (R)c.speed_limit; P.speed_limit_f = (float)c.speed_limit;
   P.init_xyz = (const R*)h->init_xyz; P.init_rpy = (const R*)h->init_rpy;
   P.init_env_stride = h->init_env_stride;
   P.jitter = (const R*)h->jitter;
@@ -207,7 +214,8 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
 
 void free_all(bd_handle* h) {
   cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
-  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->init_xyz); cudaFree(h->init_rpy);
+  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
+  cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
@@ -231,8 +239,13 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (cfg->task < 0 || cfg->task > 2) return fail(BD_EINVAL, "bd_create: unknown task %d", cfg->task);
   if (cfg->task == BD_TASK_HOVER && cfg->n_drones != 1)
     return fail(BD_EINVAL, "bd_create: the hover task is single-drone (HoverAviary.py:54)");
-  if (cfg->act_type != BD_ACT_RPM && cfg->act_type != BD_ACT_ONE_D_RPM)
-    return fail(BD_EINVAL, "bd_create: only RPM and ONE_D_RPM actions are stepped on the GPU");
+  if (cfg->act_type < BD_ACT_RPM || cfg->act_type > BD_ACT_ONE_D_PID)
+    return fail(BD_EINVAL, "bd_create: unknown act_type %d", cfg->act_type);
+  const bool pid_act = cfg->act_type >= BD_ACT_PID;
+  if (pid_act && cfg->drone_model == BD_MODEL_RACE)
+    return fail(BD_EINVAL, "[ERROR] in BaseRLAviary.__init()__, no controller is available for the specified drone_model");
+  if (pid_act && (!(cfg->ctrl_mass > 0) || !(cfg->ctrl_kf > 0) || cfg->speed_limit < 0))
+    return fail(BD_EINVAL, "bd_create: PID action types need ctrl_mass > 0, ctrl_kf > 0, speed_limit >= 0");
   if (cfg->drone_model < 0 || cfg->drone_model > 2) return fail(BD_EINVAL, "bd_create: unknown drone_model");
   if (cfg->precision != BD_F32 && cfg->precision != BD_F64) return fail(BD_EINVAL, "bd_create: unknown precision");
   if (cfg->pyb_freq <= 0 || cfg->ctrl_freq <= 0 || cfg->pyb_freq % cfg->ctrl_freq != 0)
@@ -256,7 +269,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (!h) return fail(BD_ENOMEM, "bd_create: out of host memory");
   h->cfg = *cfg;
   h->S = cfg->pyb_freq / cfg->ctrl_freq;
-  h->A = cfg->act_type == BD_ACT_RPM ? 4 : 1;
+  h->A = (cfg->act_type == BD_ACT_RPM || cfg->act_type == BD_ACT_VEL) ? 4 : (cfg->act_type == BD_ACT_PID ? 3 : 1);
   h->B = cfg->ctrl_freq / 2;
   h->D = 12 + h->B * h->A + (cfg->task == BD_TASK_SPIRAL ? 11 : 0);
   h->E = bd::kBlock / cfg->n_drones;
@@ -266,7 +279,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   h->spec.act_a = h->A;
   h->spec.precision = cfg->precision;
   h->spec.device = cfg->device;
-  h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel) ? 1 : 0;
+  h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel || pid_act) ? 1 : 0;
   {
     // kernel selection: the fast tile kernel covers the throughput configurations
     // (float, plain DYN, M a power of two <= 32); everything else runs the two-role CTA
@@ -277,7 +290,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     // the fast kernel also carries downwash alone (shuffle exchange inside the env's lane group)
     const bool fast_aero = cfg->aero_flags == 0 || cfg->aero_flags == BD_AERO_DW;
     const bool plain = fast_aero && cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
-    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2) ? 1 : 0;
+    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
@@ -307,6 +320,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   alloc((void**)&h->gsteps, 2 * sizeof(int));
   if (cfg->track_episodes) alloc((void**)&h->ep_ret, (size_t)cfg->n_envs * sizeof(float));
   alloc((void**)&h->ep_acc, 3 * sizeof(double));
+  if (pid_act) alloc(&h->ctrl, (size_t)bd::kCtrlPlanesHost * h->n_total * h->real);   // zeros: DSLPIDControl.reset()
   if (e != cudaSuccess) {
     free_all(h); delete h;
     return fail(e == cudaErrorMemoryAllocation ? BD_ENOMEM : BD_ECUDA, "bd_create: device allocation failed: %s",
@@ -475,6 +489,26 @@ int bd_get_targets(bd_handle* h, void* targets_dev, void* stream) {
   cudaError_t e = bd::launch_get_targets(h->cfg.precision, params_ptr(h), targets_dev, (cudaStream_t)stream);
   h->launches++;
   if (e != cudaSuccess) return fail(BD_ECUDA, "get_targets kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_get_controller_state(bd_handle* h, void* ctrl9_dev, void* stream) {
+  if (!h || !ctrl9_dev) return fail(BD_EINVAL, "bd_get_controller_state: null argument");
+  if (!h->ctrl) return fail(BD_EINVAL, "bd_get_controller_state: the action type has no controller");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_ctrl_state(h->cfg.precision, params_ptr(h), ctrl9_dev, nullptr, 0, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "ctrl_state kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_set_controller_state(bd_handle* h, const void* ctrl9_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_set_controller_state: null handle");
+  if (!h->ctrl) return fail(BD_EINVAL, "bd_set_controller_state: the action type has no controller");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_ctrl_state(h->cfg.precision, params_ptr(h), nullptr, ctrl9_dev, 1, (cudaStream_t)stream);
+  h->launches++;
+  if (e != cudaSuccess) return fail(BD_ECUDA, "ctrl_state kernel launch failed: %s", cudaGetErrorString(e));
   return BD_OK;
 }
 

@@ -449,6 +449,117 @@ __device__ __forceinline__ void task_terms(const Params<R>& P, const Drone<R>& d
   }
 }
 
+// ------------------------------------------------ DSL PID controller (ActionType.PID / VEL / ONE_D_PID)
+// BaseRLAviary._preprocessAction (:193-235) turns these actions into motor RPMs through one
+// DSLPIDControl per drone (control/DSLPIDControl.py:82-246).  The controller is always built for
+// CF2X (BaseRLAviary.py:76): CF2X gains, mixer, mass and kf whatever airframe the env flies.
+// Its memory — integral position error, integral attitude error, last rpy — is 9 numbers per
+// drone, kept in plane-major device memory (ctrl[k * n_total + g]); planes 9..12 hold the
+// commanded RPMs (`last_clipped_action`, BaseAviary.py:372, read by the drag model and bd_get_state).
+enum { ACT_RPM = 0, ACT_ONE_D_RPM = 1, ACT_PID = 2, ACT_VEL = 3, ACT_ONE_D_PID = 4 };
+constexpr int kCtrlPlanes = 13;
+
+template <typename R>
+__device__ __forceinline__ R clip_(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// target position / yaw / velocity from the raw action (BaseRLAviary.py:193-235).
+// `af` = the action as float (always valid), `ad` = the action as double when the caller passed
+// doubles (`from_double`); numpy keeps float32 actions in float32 through the VEL unit-vector
+// and speed arithmetic (norm = sqrt(sdot): float products summed in double, rounded to float).
+template <typename R>
+__device__ __forceinline__ void pid_targets(const Params<R>& P, const Drone<R>& d, R yaw, const float af[4],
+                                            const double ad[4], bool from_double, R tp[3], R& tyaw, R tv[3]) {
+  tp[0] = d.px; tp[1] = d.py; tp[2] = d.pz;
+  tv[0] = tv[1] = tv[2] = R(0);
+  tyaw = R(0);
+  if (P.act_type == ACT_PID) {                      // :193-206 with _calculateNextStep (BaseAviary.py:1108-1150)
+    R dest[3], dir[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { dest[k] = from_double ? (R)ad[k] : (R)af[k]; }
+    dir[0] = dest[0] - d.px; dir[1] = dest[1] - d.py; dir[2] = dest[2] - d.pz;
+    const R dist = sqrt_(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    if (dist <= R(1)) { tp[0] = dest[0]; tp[1] = dest[1]; tp[2] = dest[2]; }
+    else { tp[0] = d.px + dir[0] / dist; tp[1] = d.py + dir[1] / dist; tp[2] = d.pz + dir[2] / dist; }
+  } else if (P.act_type == ACT_VEL) {               // :207-222
+    tyaw = yaw;                                     // keep current yaw
+    if (from_double) {
+      const double n = sqrt(ad[0] * ad[0] + ad[1] * ad[1] + ad[2] * ad[2]);
+      const double sp = (double)P.speed_limit * fabs(ad[3]);
+      if (n != 0.0) { tv[0] = (R)(sp * (ad[0] / n)); tv[1] = (R)(sp * (ad[1] / n)); tv[2] = (R)(sp * (ad[2] / n)); }
+    } else {
+      const float p0 = __fmul_rn(af[0], af[0]), p1 = __fmul_rn(af[1], af[1]), p2 = __fmul_rn(af[2], af[2]);
+      const float n = __fsqrt_rn((float)(((double)p0 + (double)p1) + (double)p2));
+      const float sp = __fmul_rn(P.speed_limit_f, fabsf(af[3]));
+      if (n != 0.f) {
+        tv[0] = (R)__fmul_rn(sp, __fdiv_rn(af[0], n));
+        tv[1] = (R)__fmul_rn(sp, __fdiv_rn(af[1], n));
+        tv[2] = (R)__fmul_rn(sp, __fdiv_rn(af[2], n));
+      }
+    }
+  } else {                                          // ONE_D_PID :226-235
+    const R a0 = from_double ? (R)ad[0] : (R)af[0];
+    tp[2] = d.pz + R(0.1) * a0;
+  }
+}
+
+// DSLPIDControl.computeControl (:82-139): position loop -> thrust and target attitude,
+// attitude loop -> PWM -> RPM.  c[0..2] integral_pos_e, c[3..5] integral_rpy_e, c[6..8] last_rpy.
+// The scipy round trip of the target attitude (matrix -> 'XYZ' Euler -> quaternion -> matrix,
+// :159-160,201-203) is the identity on an orthonormal matrix and is not performed.
+template <typename R>
+__device__ __forceinline__ void dsl_pid(const Params<R>& P, const Drone<R>& d, R roll, R pitch, R yaw,
+                                        const R tp[3], R tyaw, const R tv[3], R c[9], R rpm[4]) {
+  const R dt = P.ctrl_dt;
+  R m[9];
+  quat_to_mat(d.qx, d.qy, d.qz, d.qw, m);
+  // ---- _dslPIDPositionControl (:143-197)
+  const R pe[3] = {tp[0] - d.px, tp[1] - d.py, tp[2] - d.pz};
+  const R ve[3] = {tv[0] - d.vx, tv[1] - d.vy, tv[2] - d.vz};
+  c[0] = clip_(c[0] + pe[0] * dt, R(-2), R(2));
+  c[1] = clip_(c[1] + pe[1] * dt, R(-2), R(2));
+  c[2] = clip_(clip_(c[2] + pe[2] * dt, R(-2), R(2)), R(-0.15), R(0.15));
+  R tt[3];
+  tt[0] = (R(0.4) * pe[0] + R(0.05) * c[0]) + R(0.2) * ve[0];
+  tt[1] = (R(0.4) * pe[1] + R(0.05) * c[1]) + R(0.2) * ve[1];
+  tt[2] = ((R(1.25) * pe[2] + R(0.05) * c[2]) + R(0.5) * ve[2]) + P.ctrl_gravity;
+  R scalar = (tt[0] * m[2] + tt[1] * m[5]) + tt[2] * m[8];
+  scalar = scalar > R(0) ? scalar : R(0);
+  const R thrust = (sqrt_(scalar / P.ctrl_4kf) - R(4070.3)) / R(0.2685);
+  const R tn = sqrt_((tt[0] * tt[0] + tt[1] * tt[1]) + tt[2] * tt[2]);
+  const R z[3] = {tt[0] / tn, tt[1] / tn, tt[2] / tn};
+  R sy, cy;
+  sincos_(tyaw, &sy, &cy);
+  // y = z x x_c / |.|, x_c = (cos yaw, sin yaw, 0);  x = y x z
+  R y[3] = {-z[2] * sy, z[2] * cy, z[0] * sy - z[1] * cy};
+  const R yn = sqrt_((y[0] * y[0] + y[1] * y[1]) + y[2] * y[2]);
+  y[0] /= yn; y[1] /= yn; y[2] /= yn;
+  const R x[3] = {y[1] * z[2] - y[2] * z[1], y[2] * z[0] - y[0] * z[2], y[0] * z[1] - y[1] * z[0]};
+  // ---- _dslPIDAttitudeControl (:201-246): rot_e from Rt^T Rc - Rc^T Rt, Rt = [x y z]
+  const R c0[3] = {m[0], m[3], m[6]}, c1[3] = {m[1], m[4], m[7]}, c2[3] = {m[2], m[5], m[8]};
+  auto dot3 = [](const R a[3], const R b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; };
+  const R re[3] = {dot3(z, c1) - dot3(y, c2), dot3(x, c2) - dot3(z, c0), dot3(y, c0) - dot3(x, c1)};
+  const R rpy[3] = {roll, pitch, yaw};
+  R tq[3];
+  const R ptor[3] = {R(70000), R(70000), R(60000)}, dtor[3] = {R(20000), R(20000), R(12000)};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const R rate_e = R(0) - (rpy[k] - c[6 + k]) / dt;
+    c[6 + k] = rpy[k];
+    R ir = clip_(c[3 + k] - re[k] * dt, R(-1500), R(1500));
+    if (k < 2) ir = clip_(ir, R(-1), R(1));
+    c[3 + k] = ir;
+    const R itor = k == 2 ? R(500) : R(0);
+    tq[k] = clip_((-(ptor[k] * re[k]) + dtor[k] * rate_e) + itor * ir, R(-3200), R(3200));
+  }
+  // CF2X mixer (:48-53), PWM clip (:241), PWM -> RPM (:242)
+  const R mix[4][3] = {{R(-.5), R(-.5), R(-1)}, {R(-.5), R(.5), R(1)}, {R(.5), R(.5), R(-1)}, {R(.5), R(-.5), R(1)}};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const R pwm = clip_(thrust + ((mix[k][0] * tq[0] + mix[k][1] * tq[1]) + mix[k][2] * tq[2]), R(20000), R(65535));
+    rpm[k] = R(0.2685) * pwm + R(4070.3);
+  }
+}
+
 // ------------------------------------------------ async copies: TMA bulk store, cp.async history, PDL
 // Observation rows are written once and never read back by the simulator: mark them evict-first
 // in L2 so that they do not push out the persistent state / ring planes of the next step.

@@ -83,7 +83,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   cp_async_commit();
 
   Drone<R> d;
-  R rpm[4];
+  R rpm[4] = {R(0), R(0), R(0), R(0)};
   float af[4] = {0.f, 0.f, 0.f, 0.f};
   float onep[4] = {1.f, 1.f, 1.f, 1.f};   // fl32(1 + 0.05 a) per motor (float actions)
   R last_rpm[4] = {R(0), R(0), R(0), R(0)};
@@ -104,7 +104,8 @@ step_kernel(const __grid_constant__ Params<R> P) {
         const float4 v = *reinterpret_cast<const float4*>(ap);
         af[0] = v.x; af[1] = v.y; af[2] = v.z; af[3] = v.w;
       } else {
-        af[0] = ap[0];
+#pragma unroll
+        for (int k = 0; k < A; ++k) af[k] = ap[k];
       }
     }
     stepc = P.stepc[env];
@@ -113,21 +114,49 @@ step_kernel(const __grid_constant__ Params<R> P) {
     d.qy = a1.x; d.qz = a1.y; d.qw = a1.z; d.vx = a1.w;
     d.vy = a2.x; d.vz = a2.y; d.wx = a2.z; d.wy = a2.w;
     d.wz = a3.x; d.tx = a3.y; d.ty = a3.z; d.tz = a3.w;
+    bool pid = false;
+    if constexpr (GENERIC) pid = P.act_type >= ACT_PID;
     if (from_double) {
 #pragma unroll
-      for (int k = 0; k < A; ++k) {
-        af[k] = (float)ad[k];
-        const R r = P.hover_rpm * (R(1) + R(0.05) * (R)ad[k]);               // BaseRLAviary.py:192
-        if constexpr (A == 4) rpm[k] = r; else rpm[0] = rpm[1] = rpm[2] = rpm[3] = r;
+      for (int k = 0; k < A; ++k) af[k] = (float)ad[k];
+    }
+    if (pid) {
+      if constexpr (GENERIC) {
+        // DSL PID in the loop (BaseRLAviary.py:193-235): state at the start of the step -> rpm
+        R roll0, pitch0, yaw0;
+        quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll0, pitch0, yaw0);
+        R tp[3], tv[3], tyaw, c[9];
+        pid_targets(P, d, yaw0, af, ad, from_double, tp, tyaw, tv);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = P.ctrl[(size_t)k * P.n_total + g];
+        if ((P.aero & AERO_DRAG) && stepc > 0) {   // last_clipped_action (BaseAviary.py:372,468)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) last_rpm[k] = P.ctrl[(size_t)(9 + k) * P.n_total + g];
+        }
+        dsl_pid(P, d, roll0, pitch0, yaw0, tp, tyaw, tv, c, rpm);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P.ctrl[(size_t)k * P.n_total + g] = c[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) P.ctrl[(size_t)(9 + k) * P.n_total + g] = rpm[k];
+      }
+    } else if (from_double) {
+      if constexpr (A != 3) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          const R r = P.hover_rpm * (R(1) + R(0.05) * (R)ad[k]);               // BaseRLAviary.py:192
+          if constexpr (A == 4) rpm[k] = r; else rpm[0] = rpm[1] = rpm[2] = rpm[3] = r;
+        }
       }
     } else {
+      if constexpr (A != 3) {
 #pragma unroll
-      for (int k = 0; k < A; ++k) {
-        // numpy evaluates 1 + 0.05*a in float32 for float32 actions (two roundings)
-        const float s = __fadd_rn(1.0f, __fmul_rn(0.05f, af[k]));
-        const R r = P.hover_rpm * (R)s;
-        if constexpr (A == 4) { rpm[k] = r; onep[k] = s; }
-        else { rpm[0] = rpm[1] = rpm[2] = rpm[3] = r; onep[0] = onep[1] = onep[2] = onep[3] = s; }
+        for (int k = 0; k < A; ++k) {
+          // numpy evaluates 1 + 0.05*a in float32 for float32 actions (two roundings)
+          const float s = __fadd_rn(1.0f, __fmul_rn(0.05f, af[k]));
+          const R r = P.hover_rpm * (R)s;
+          if constexpr (A == 4) { rpm[k] = r; onep[k] = s; }
+          else { rpm[0] = rpm[1] = rpm[2] = rpm[3] = r; onep[0] = onep[1] = onep[2] = onep[3] = s; }
+        }
       }
     }
     // newest history entry: ring slot `head` (the stale slot) and the tail of the row
@@ -135,7 +164,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
     float* newest = myrow + 12 + (B - 1) * A;
 #pragma unroll
     for (int k = 0; k < A; ++k) { hp[k] = af[k]; newest[k] = af[k]; }
-    if (GENERIC && (P.aero & AERO_DRAG) && stepc > 0) {
+    if (GENERIC && !pid && (P.aero & AERO_DRAG) && stepc > 0) {
       // last_clipped_action (BaseAviary.py:372,468): previous step's rpm, zero after a reset
       const int prev = head == 0 ? B - 1 : head - 1;
       const float* lp = P.hist + ((size_t)prev * P.n_total + g) * A;
@@ -147,6 +176,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
       }
     }
   } else {
+    rpm[0] = rpm[1] = rpm[2] = rpm[3] = R(0);
     d = Drone<R>{};
     d.qw = R(1);
     rpm[0] = rpm[1] = rpm[2] = rpm[3] = R(0);
@@ -330,6 +360,9 @@ step_kernel(const __grid_constant__ Params<R> P) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) myrow[k] = kin[k];
       avx = avy = avz = R(0);
+      if (GENERIC && P.ctrl != nullptr && P.ctrl_reset) {   // optional: DSLPIDControl.reset() with the env
+        for (int k = 0; k < 9; ++k) P.ctrl[(size_t)k * P.n_total + g] = R(0);
+      }
       if (TASK == TASK_SPIRAL) {   // reset obs is evaluated at step_counter = 0
         R rp[3], rv[3], sphi, cphi;
         spiral_reference(P, 0, drone, rp, rv, sphi, cphi);
@@ -401,6 +434,9 @@ reset_kernel(const __grid_constant__ Params<R> P) {
   P.s3[g] = make4(d.wz, d.tx, d.ty, d.tz);
   if (P.keep_angv) P.s4[g] = make4(R(0), R(0), R(0), R(0));
   if (drone == 0) { P.stepc[env] = 0; if (P.ep_ret != nullptr) P.ep_ret[env] = 0.f; }   // the ring head (total steps) is untouched by a reset
+  if (P.ctrl != nullptr && P.ctrl_reset) {
+    for (int k = 0; k < 9; ++k) P.ctrl[(size_t)k * P.n_total + g] = R(0);
+  }
   if (P.obs != nullptr) {
     float* row = P.obs + (size_t)g * P.D;
     for (int k = 0; k < 12; ++k) row[k] = kin[k];
@@ -443,6 +479,10 @@ __global__ void get_state_kernel(const __grid_constant__ Params<R> P, R* state20
     const int newest = head == 0 ? P.B - 1 : head - 1;
     const float* hp = P.hist + ((size_t)newest * P.n_total + g) * P.A;
     for (int k = 0; k < 4; ++k) {
+      if (P.act_type >= ACT_PID) {
+        o[16 + k] = stepc > 0 ? P.ctrl[(size_t)(9 + k) * P.n_total + g] : R(0);
+        continue;
+      }
       const float a = hp[P.A == 4 ? k : 0];
       const float s = __fadd_rn(1.0f, __fmul_rn(0.05f, a));
       o[16 + k] = stepc > 0 ? P.hover_rpm * (R)s : R(0);
@@ -474,6 +514,18 @@ __global__ void set_state_kernel(const __grid_constant__ Params<R> P, const R* k
   }
   if (step_counter != nullptr && g % P.M == 0) {
     P.stepc[env] = step_counter[env];
+  }
+}
+
+// DSL PID memory (N,M,9): [integral_pos_e, integral_rpy_e, last_rpy]; src == nullptr zeroes it
+// (DSLPIDControl.reset, DSLPIDControl.py:64-79)
+template <typename R>
+__global__ void ctrl_state_kernel(const __grid_constant__ Params<R> P, R* dst, const R* src, int write) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.n_total) return;
+  for (int k = 0; k < 9; ++k) {
+    if (write) P.ctrl[(size_t)k * P.n_total + g] = src != nullptr ? src[g * 9 + k] : R(0);
+    else dst[g * 9 + k] = P.ctrl[(size_t)k * P.n_total + g];
   }
 }
 
@@ -557,6 +609,8 @@ static cudaError_t step_g(const LaunchSpec& ls, const void* p, cudaStream_t st) 
 }
 template <typename R, int TASK>
 static cudaError_t step_a(const LaunchSpec& ls, const void* p, cudaStream_t st) {
+  if (ls.act_a == 3)   // ActionType.PID: waypoint actions, always the generic kernel
+    return launch_step_t<R, TASK, 3, true>(*static_cast<const Params<R>*>(p), ls.device, st);
   return ls.act_a == 4 ? step_g<R, TASK, 4>(ls, p, st) : step_g<R, TASK, 1>(ls, p, st);
 }
 template <typename R>
@@ -574,6 +628,7 @@ cudaError_t launch_step(const LaunchSpec& ls, const void* params, cudaStream_t s
 template <typename R, int TASK>
 static cudaError_t reset_a(const LaunchSpec& ls, const void* p, cudaStream_t st) {
   const Params<R>& P = *static_cast<const Params<R>*>(p);
+  if (ls.act_a == 3) return launch_reset_t<R, TASK, 3>(P, st);
   return ls.act_a == 4 ? launch_reset_t<R, TASK, 4>(P, st) : launch_reset_t<R, TASK, 1>(P, st);
 }
 template <typename R>
@@ -611,6 +666,17 @@ cudaError_t launch_set_state(int precision, const void* p, const void* kin13, co
   } else {
     const auto& P = *static_cast<const Params<float>*>(p);
     set_state_kernel<float><<<flat_grid(P), 256, 0, st>>>(P, (const float*)kin13, (const float*)targets, step_counter);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ctrl_state(int precision, const void* p, void* dst, const void* src, int write, cudaStream_t st) {
+  if (precision) {
+    const auto& P = *static_cast<const Params<double>*>(p);
+    ctrl_state_kernel<double><<<flat_grid(P), 256, 0, st>>>(P, (double*)dst, (const double*)src, write);
+  } else {
+    const auto& P = *static_cast<const Params<float>*>(p);
+    ctrl_state_kernel<float><<<flat_grid(P), 256, 0, st>>>(P, (float*)dst, (const float*)src, write);
   }
   return cudaGetLastError();
 }

@@ -9,6 +9,7 @@ namespace bd {
 constexpr int kBlock = 128;        // threads per CTA; one thread per drone
 constexpr int kMaxDrones = 128;    // M <= kBlock (an env never straddles CTAs)
 constexpr int kMaxJitterTries = 64;
+constexpr int kCtrlPlanesHost = 13;  // 9 DSL PID memory planes + 4 commanded-rpm planes (bd_device.cuh)
 
 template <typename Real> struct V4;
 template <> struct V4<float>  { using type = float4;  };
@@ -32,6 +33,7 @@ struct Params {
   int* gsteps;
   float* ep_ret;                  // running episode return per env (VecRecordEpisodeStatistics, :144-171)
   double* ep_acc;                 // [3] sums over finished episodes: return, length, count
+  Real* ctrl;                     // [13][n_total] DSL PID memory + commanded rpm (PID action types), else nullptr
   const Real* init_xyz;
   const Real* init_rpy;
   int init_env_stride;            // 0 (shared (M,3) table) or M*3
@@ -53,6 +55,9 @@ struct Params {
   double pyb_freq, episode_len;
   int trunc_counter;              // smallest step_counter with step_counter / pyb_freq > episode_len (fp64)
   int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
+  int act_type, ctrl_reset;       // ACT_*; 1: env resets also zero the controller memory (reference: never)
+  Real ctrl_dt, ctrl_gravity, ctrl_4kf, speed_limit;   // DSLPIDControl constants (CF2X), BaseRLAviary.py:95
+  float speed_limit_f;
   int host_total;                 // >= 0: total control steps so far, tracked by the host (ring head with no
                                   // memory latency); -1: read gsteps[0] (CUDA-graph capture / replay)
   int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
@@ -74,6 +79,8 @@ cudaError_t launch_get_state(int precision, const void* params, void* state20, v
 cudaError_t launch_set_state(int precision, const void* params, const void* kin13,
                              const void* targets, const int32_t* step_counter, cudaStream_t st);
 cudaError_t launch_get_targets(int precision, const void* params, void* targets, cudaStream_t st);
+cudaError_t launch_ctrl_state(int precision, const void* params, void* dst, const void* src, int write,
+                              cudaStream_t st);
 cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st);
 size_t step_smem_bytes(int precision, int A, int B, int D);
 

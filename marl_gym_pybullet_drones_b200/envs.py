@@ -11,8 +11,8 @@ against one reference env (`examples/learn.py`, `MAPPO.run` evaluation,
 Differences that are visible on purpose:
 * `physics` defaults to `Physics.DYN` (the reference default `Physics.PYB`
   needs PyBullet's solver and raises `NotImplementedError` here);
-* `act` defaults to `ActionType.RPM` for the spiral env (its reference default,
-  `VEL`, needs the in-loop PID controller — SURVEY.md §8f "next");
+* `ActionType.PID / VEL / ONE_D_PID` run the reference's DSL PID controller inside the step
+  kernel (one controller per drone, never reset by `reset()`, as in `BaseRLAviary.py:73-78`);
 * `obs` is always float32 (the reference returns float64 until the action
   buffer has filled with float32 actions, `BaseRLAviary.py:315-318`).
 """
@@ -199,7 +199,7 @@ class SpiralFormationAviary(_SingleAviary):
 
     def __init__(self, drone_model=DroneModel.CF2X, num_drones=3, neighbourhood_radius=np.inf,
                  initial_xyzs=None, initial_rpys=None, physics=Physics.DYN, pyb_freq=240, ctrl_freq=48,
-                 gui=False, record=False, obs=ObservationType.KIN, act=ActionType.RPM,
+                 gui=False, record=False, obs=ObservationType.KIN, act=ActionType.VEL,
                  spiral_radius=0.4, spiral_period=10.0, height_rate=0.05,
                  target_center=np.array([0.0, 0.0, 0.0]), precision="fp64", device=None):
         super().__init__(drone_model=drone_model, num_drones=num_drones,

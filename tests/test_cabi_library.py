@@ -54,7 +54,7 @@ def test_config_struct_layout_matches_header(lib):
         for part in decl.split(","):
             names.append(re.sub(r"\[.*\]", "", part).strip())
     assert names == [f[0] for f in _native.BdConfig._fields_]
-    assert C.sizeof(_native.BdConfig) == 328
+    assert C.sizeof(_native.BdConfig) == 352
 
 
 def test_create_rejects_bad_configs_with_messages(lib):
@@ -73,7 +73,10 @@ def test_create_rejects_bad_configs_with_messages(lib):
     assert b"pyb_freq is not divisible by env_freq" in lib.bd_last_error()   # BaseAviary.py:79-80 wording
     cfg.ctrl_freq = 30
     cfg.act_type = 7
-    assert lib.bd_create(C.byref(cfg), C.byref(h)) == -1 and b"RPM" in lib.bd_last_error()
+    assert lib.bd_create(C.byref(cfg), C.byref(h)) == -1 and b"act_type" in lib.bd_last_error()
+    cfg.act_type, cfg.drone_model = 3, 2          # VEL on the racer: BaseRLAviary.py:73-78 has no controller
+    assert lib.bd_create(C.byref(cfg), C.byref(h)) == -1 and b"no controller is available" in lib.bd_last_error()
+    cfg.drone_model = 0
     assert not h.value
     # null-handle calls fail cleanly instead of crashing
     assert lib.bd_step(None, None, None, None, None, None, None, None) == -1

@@ -48,7 +48,7 @@ def test_multihover_env_reset_uses_numpy_global_rng_like_reference():
 def test_spiral_env_info_and_shapes():
     from marl_gym_pybullet_drones_b200 import SpiralFormationAviary
     cfg, g = load_golden("spiral5_gauss_f32")
-    env = SpiralFormationAviary(num_drones=5)
+    env = SpiralFormationAviary(num_drones=5, act="rpm")
     assert env.observation_space.shape == (5, 119) and env.CTRL_FREQ == 48 and env.EPISODE_LEN_SEC == 12
     obs, info = env.reset()
     assert rel_err(obs, g["obs0"]) <= 2.5e-7 and info["time"] == 0.0

@@ -29,8 +29,8 @@ def test_unsupported_modes_raise_before_touching_the_device():
     from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
     with pytest.raises(ValueError, match="pyb_freq is not divisible"):
         BatchAviary(pyb_freq=240, ctrl_freq=50)
-    with pytest.raises(NotImplementedError):
-        BatchAviary(act="vel")
+    with pytest.raises(ValueError, match="no controller is available"):      # BaseRLAviary.py:73-78
+        BatchAviary(act="vel", drone_model="racer")
     with pytest.raises(NotImplementedError):
         BatchAviary(obs="rgb")
     with pytest.raises(NotImplementedError):
