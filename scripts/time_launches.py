@@ -19,14 +19,16 @@ ap.add_argument("--task", default="multihover")
 ap.add_argument("--physics", default="dyn")
 ap.add_argument("--ctrl-freq", type=int, default=30)
 ap.add_argument("--precision", default="fp32")
+ap.add_argument("--act", default="rpm")
 args = ap.parse_args()
 N, M = args.envs, args.drones
 side = int(np.ceil(np.sqrt(M)))
 xyz = np.array([[float(i % side), float(i // side), 0.5] for i in range(M)])
 env = BatchAviary(task=args.task, num_envs=N, num_drones=M, initial_xyzs=None if args.task == "spiral" else xyz,
-                  physics=args.physics, ctrl_freq=args.ctrl_freq, precision=args.precision, auto_reset=True, seed=1)
+                  physics=args.physics, ctrl_freq=args.ctrl_freq, precision=args.precision, auto_reset=True, seed=1,
+                  act=args.act)
 S = args.slots
-acts = (torch.rand((S, N, M, 4), device="cuda") * 2 - 1).to(env.action_dtype)
+acts = (torch.rand((S, N, M, env.ACTION_DIM), device="cuda") * 2 - 1).to(env.action_dtype)
 obs = torch.empty((S, N, M, env.OBS_DIM), device="cuda")
 rew = torch.empty((S, N), device="cuda", dtype=env.real_dtype)
 te = torch.empty((S, N), dtype=torch.uint8, device="cuda")
