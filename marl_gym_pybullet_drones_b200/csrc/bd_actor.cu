@@ -31,7 +31,6 @@
 namespace {
 
 constexpr int kRows = 128;   // UMMA M
-constexpr int kThreads = 256; // 8 warps: warp w owns TMEM lanes 32*(w%4).. and the column half w/4 in the epilogues
 constexpr int kNOut = 16;    // layer-3 N (act_dim padded; UMMA needs N % 16 == 0 at M = 128)
 
 thread_local char g_actor_err[256] = "";
@@ -70,28 +69,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -158,31 +139,80 @@ __device__ __forceinline__ void hidden_chunk(const uint32_t v[32], int c0, const
   }
 }
 
-// TMEM accumulator row -> +bias, tanh -> bf16 activation tile (next layer's A operand).  The TMEM
-// read of the next 32 columns is in flight while the current 32 go through the SFU (tanh.approx)
-// and the bf16 pack: the two are the epilogue's bottlenecks (64 B/clk TMEM read, 16 tanh/clk).
+// mbarrier helpers.  A wait that does not complete within ~2 s of SM clocks traps (a protocol bug
+// must fail the launch, not hang the GPU).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    // try_wait suspends the thread in hardware for up to the hinted time: no issue slots are
+    // taken from the other warps of the SM sub-partition while waiting
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (done) break;
+    if ((it & 255u) == 255u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// TMEM accumulator row -> +bias, tanh -> bf16 activation tile (next layer's A operand), 32 columns
+// at a time.  After each chunk the thread publishes it (generic -> async proxy fence, mbarrier
+// arrive): the MMA warp starts the next layer's K-steps over those columns while the remaining
+// chunks are still going through the SFU, so tensor pipe and epilogue overlap inside one tile.
+// The TMEM read of the next 32 columns is in flight while the current 32 are processed.
 template <int HID>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* __restrict__ bias, __nv_bfloat16* sH, int row,
-                                                int cbeg, int cend) {
+                                                int cbeg, int n_chunks, uint32_t chunk_bar0) {
   uint32_t va[32], vb[32];
   tmem_ld32_nowait(tmem_row + (uint32_t)cbeg, va);
   tmem_wait_ld();
 #pragma unroll 1
-  for (int c0 = cbeg; c0 < cend; c0 += 64) {
-    const bool more1 = c0 + 32 < cend;
+  for (int j = 0; j < n_chunks; j += 2) {
+    const int c0 = cbeg + j * 32;
+    const bool more1 = j + 1 < n_chunks;
     if (more1) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 32), vb);
     hidden_chunk<HID>(va, c0, bias, sH, row);
+    proxy_fence();
+    mbar_arrive(chunk_bar0 + 8u * (uint32_t)j);
     tmem_wait_ld();
     if (!more1) break;
-    const bool more2 = c0 + 64 < cend;
+    const bool more2 = j + 2 < n_chunks;
     if (more2) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 64), va);
     hidden_chunk<HID>(vb, c0 + 32, bias, sH, row);
+    proxy_fence();
+    mbar_arrive(chunk_bar0 + 8u * (uint32_t)(j + 1));
     tmem_wait_ld();
   }
 }
 
+constexpr int kEpiThreads = 256;              // warps 0-7: staging + epilogues
+constexpr int kThreads = kEpiThreads + 32;    // warp 8: issues every tcgen05.mma
+constexpr int kMaxChunks = 4;                 // 32-column chunks per column half (HID = 256)
+// barrier indices (one phase per tile each)
+enum { BAR_STAGE = 0, BAR_L1, BAR_L2, BAR_L3, BAR_W1, BAR_W23, BAR_H1, BAR_H2 = BAR_H1 + kMaxChunks,
+       BAR_COUNT = BAR_H2 + kMaxChunks };
+
 template <int HID>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)   // 9 warps: one SM sub-partition hosts 3 of them -> 168 registers
 actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
                      unsigned long long seed, unsigned long long offset, float* __restrict__ act, float* __restrict__ logp,
                      float* __restrict__ mean_out) {
@@ -198,168 +228,203 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
   float* sB2 = sB1 + HID;
   float* sB3 = sB2 + HID;        // [16]
   float* sLs = sB3 + kNOut;      // [16]
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[BAR_COUNT];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool is_mma_warp = warp == kEpiThreads / 32;
   const int row = tid & (kRows - 1);      // my row of the tile = my TMEM lane
-  const int half = tid >> 7;              // which half of the columns I handle in the epilogues
-  constexpr int kHalfCols = (HID / 2 + 31) / 32 * 32 > HID ? HID : (HID / 2 + 31) / 32 * 32;
-  const int cbeg = half == 0 ? 0 : kHalfCols, cend = half == 0 ? kHalfCols : HID;
-  // ---- one-time: resident weights, barrier, tensor memory ------------------------------------
-  for (int i = tid; i < HID * HID / 8; i += kThreads) reinterpret_cast<uint4*>(sW2)[i] = reinterpret_cast<const uint4*>(W.w2)[i];
-  for (int i = tid; i < kNOut * HID / 8; i += kThreads) reinterpret_cast<uint4*>(sW3)[i] = reinterpret_cast<const uint4*>(W.w3)[i];
+  const int half = (tid >> 7) & 1;        // which half of the columns I handle in the epilogues
+  constexpr int kHalfCols = HID / 2;      // 32, 64 or 128
+  constexpr int kChunks = kHalfCols / 32; // 32-column chunks per half
+  constexpr uint32_t kTmemCols = HID == 256 ? 512u : (HID == 128 ? 256u : 128u);   // two accumulators
+  const int cbeg = half * kHalfCols;
+  // ---- one-time: resident weights, barriers, tensor memory ------------------------------------
+  // (W2 / W3 / W1 arrive by TMA bulk copies issued by the MMA thread)
   for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
   if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd[tid]; }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    mbar_init(smem_u32(&mbar[BAR_STAGE]), kEpiThreads);
+    mbar_init(smem_u32(&mbar[BAR_L1]), 1);
+    mbar_init(smem_u32(&mbar[BAR_L2]), 1);
+    mbar_init(smem_u32(&mbar[BAR_L3]), 1);
+    mbar_init(smem_u32(&mbar[BAR_W1]), 1);
+    mbar_init(smem_u32(&mbar[BAR_W23]), 1);
+    for (int j = 0; j < kMaxChunks; ++j) {
+      mbar_init(smem_u32(&mbar[BAR_H1 + j]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[BAR_H2 + j]), kEpiThreads);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // my warp's 32 TMEM lanes
-  const uint32_t bar = smem_u32(&mbar);
-  uint32_t parity = 0;
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)HID;            // L1 / L3 and L2 accumulators
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;                  // my warp's 32 TMEM lanes
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  const long long n_tiles = (rows + kRows - 1) / kRows;
 
-  // W1 never changes: each thread keeps its share of the packed tile in registers (<= 16 x 128 bit) and
-  // re-deposits it after the activation tile has overwritten the staging region.  The next tile's
-  // observation chunks are prefetched into registers while the current tile is in the tensor core
-  // (one CTA per SM leaves 255 registers per thread).
-  constexpr int kMaxW1 = 16, kMaxX = 8;
-  const int w1_chunks = HID * K1 / 8;
-  uint4 w1r[kMaxW1];
+  if (is_mma_warp) {
+    // =============================== MMA issuer (one thread) =====================================
+    if ((tid & 31) == 0) {
+      uint32_t parity = 0;
+      const uint32_t sbo1 = (uint32_t)(K1 / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      const uint32_t w1_bytes = (uint32_t)(HID * K1 * 2);
+      // resident weights: W2, W3 once (they land while the first tile is staged and goes through layer 1)
+      mbar_expect_tx(bar(BAR_W23), (uint32_t)((HID + kNOut) * HID * 2));
+      bulk_g2s(aW2, W.w2, (uint32_t)(HID * HID * 2), bar(BAR_W23));
+      bulk_g2s(aW3, W.w3, (uint32_t)(kNOut * HID * 2), bar(BAR_W23));
+      bool first = true;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // W1 shares region A with the activation tile: re-fetched from L2 (40 KB) once the previous
+        // tile's layer-3 MMAs have finished reading H2
+        if (!first) mbar_wait_guarded(bar(BAR_L3), parity ^ 1);
+        mbar_expect_tx(bar(BAR_W1), w1_bytes);
+        bulk_g2s(aW1, W.w1, w1_bytes, bar(BAR_W1));
+        // layer 1: acc0[128 x HID] = X W1^T, as soon as the tile is staged
+        mbar_wait_guarded(bar(BAR_STAGE), parity);
+        mbar_wait_guarded(bar(BAR_W1), parity);
+        tc_fence_after();
+        for (int s = 0; s < K1 / 16; ++s)
+          umma_bf16(acc0, umma_desc(aA + s * 256, 128, sbo1), umma_desc(aW1 + s * 256, 128, sbo1), umma_idesc(HID), s > 0);
+        umma_commit(bar(BAR_L1));
+        if (first) { mbar_wait_guarded(bar(BAR_W23), 0); first = false; }
+        // layer 2: acc1 = H1 W2^T, K-steps follow the layer-1 epilogue chunk by chunk
+        for (int j = 0; j < kChunks; ++j) {
+          mbar_wait_guarded(bar(BAR_H1 + j), parity);
+          tc_fence_after();
 #pragma unroll
-  for (int i = 0; i < kMaxW1; ++i) {
-    const int idx = i * kThreads + tid;
-    w1r[i] = idx < w1_chunks ? reinterpret_cast<const uint4*>(W.w1)[idx] : make_uint4(0, 0, 0, 0);
-  }
-  const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
-  // raw fp32 chunks stay in registers until the next tile starts: converting right after the load
-  // would stall on the global latency that the prefetch is meant to hide
-  auto load_x = [&](long long tile, float4 (&xa)[kMaxX], float4 (&xb)[kMaxX]) {
-    const long long rg = tile * kRows + row;
-    const bool ok = rg < rows;
-    const float* src = obs + (size_t)rg * W.obs_dim;
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-    for (int c = 0; c < kMaxX; ++c) {
-      const int k0 = half * 8 + c * 16;      // the two threads of a row take alternate 8-column chunks
-      xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      xb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 < K1 && ok) {
-        if (vec4 && k0 + 8 <= W.obs_dim) {
-          xa[c] = __ldg(reinterpret_cast<const float4*>(src + k0));
-          xb[c] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
-        } else {
-          float x[8];
+            for (int q = 0; q < 2; ++q) {
+              const int s = (h * kHalfCols + j * 32) / 16 + q;
+              umma_bf16(acc1, umma_desc(aA + s * 256, 128, sboH), umma_desc(aW2 + s * 256, 128, sboH), umma_idesc(HID),
+                        (j | h | q) != 0);
+            }
+          }
+        }
+        umma_commit(bar(BAR_L2));
+        // layer 3: acc0[128 x 16] = H2 W3^T, same pipelining against the layer-2 epilogue
+        for (int j = 0; j < kChunks; ++j) {
+          mbar_wait_guarded(bar(BAR_H2 + j), parity);
+          tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (k0 + j < W.obs_dim) ? __ldg(src + k0 + j) : 0.0f;
-          xa[c] = make_float4(x[0], x[1], x[2], x[3]);
-          xb[c] = make_float4(x[4], x[5], x[6], x[7]);
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int s = (h * kHalfCols + j * 32) / 16 + q;
+              umma_bf16(acc0, umma_desc(aA + s * 256, 128, sboH), umma_desc(aW3 + s * 256, 128, sboH), umma_idesc(kNOut),
+                        (j | h | q) != 0);
+            }
+          }
+        }
+        umma_commit(bar(BAR_L3));
+        parity ^= 1;
+      }
+    }
+  } else {
+    // =============================== staging + epilogue warps ====================================
+    // The next tile's observation chunks are prefetched into registers while the current tile is in flight.
+    constexpr int kMaxX = 8;
+    const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
+    // raw fp32 chunks stay in registers until the next tile starts: converting right after the load
+    // would stall on the global latency that the prefetch is meant to hide
+    auto load_x = [&](long long tile, float4 (&xa)[kMaxX], float4 (&xb)[kMaxX]) {
+      const long long rg = tile * kRows + row;
+      const bool ok = rg < rows;
+      const float* src = obs + (size_t)rg * W.obs_dim;
+#pragma unroll
+      for (int c = 0; c < kMaxX; ++c) {
+        const int k0 = half * 8 + c * 16;      // the two threads of a row take alternate 8-column chunks
+        xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < K1 && ok) {
+          if (vec4 && k0 + 8 <= W.obs_dim) {
+            xa[c] = __ldg(reinterpret_cast<const float4*>(src + k0));
+            xb[c] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (k0 + j < W.obs_dim) ? __ldg(src + k0 + j) : 0.0f;
+            xa[c] = make_float4(x[0], x[1], x[2], x[3]);
+            xb[c] = make_float4(x[4], x[5], x[6], x[7]);
+          }
         }
       }
-    }
-  };
+    };
 
-  const long long n_tiles = (rows + kRows - 1) / kRows;
-  float4 xa[kMaxX], xb[kMaxX];
-  if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x, xa, xb);
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row_g = tile * kRows + row;
-    const bool valid = row_g < rows;
-    // ---- X tile (prefetched; fp32 -> bf16, canonical K-major layout) and W1 from registers --------
+    float4 xa[kMaxX], xb[kMaxX];
+    uint32_t parity = 0;
+    if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x, xa, xb);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row_g = tile * kRows + row;
+      const bool valid = row_g < rows;
+      // ---- X tile (prefetched; fp32 -> bf16, canonical K-major layout) --------------------------------
+      // (region A is free: every thread waited for the previous tile's layer-3 MMAs below)
 #pragma unroll
-    for (int c = 0; c < kMaxX; ++c) {
-      const int k0 = half * 8 + c * 16;
-      if (k0 < K1)
-        *reinterpret_cast<uint4*>(sA + canon_off(row, k0, K1)) =
-            make_uint4(pack_bf16(xa[c].x, xa[c].y), pack_bf16(xa[c].z, xa[c].w), pack_bf16(xb[c].x, xb[c].y), pack_bf16(xb[c].z, xb[c].w));
-    }
-#pragma unroll
-    for (int i = 0; i < kMaxW1; ++i) {
-      const int idx = i * kThreads + tid;
-      if (idx < w1_chunks) reinterpret_cast<uint4*>(sW1)[idx] = w1r[i];
-    }
-    if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x, xa, xb);   // in flight during the three layers
-    proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();   // my tcgen05.ld of the previous tile are complete (wait::ld) and ordered
-    __syncthreads();
-    // ---- layer 1: acc[128 x HID] = X W1^T ---------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sbo = (uint32_t)(K1 / 8) * 128u;
-      for (int s = 0; s < K1 / 16; ++s)
-        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW1 + s * 256, 128, sbo), umma_idesc(HID), s > 0);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, parity); parity ^= 1;
-    tc_fence_after();
-    epilogue_hidden<HID>(tmem_row, sB1, sA, row, cbeg, cend);   // overwrites X / W1 (layer-1 MMAs are complete)
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2: acc = H1 W2^T ---------------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sbo = (uint32_t)(HID / 8) * 128u;
-      for (int s = 0; s < HID / 16; ++s)
-        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW2 + s * 256, 128, sbo), umma_idesc(HID), s > 0);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, parity); parity ^= 1;
-    tc_fence_after();
-    epilogue_hidden<HID>(tmem_row, sB2, sA, row, cbeg, cend);   // H2 over H1 (layer-2 MMAs are complete)
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 3: acc[128 x 16] = H2 W3^T -------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sbo = (uint32_t)(HID / 8) * 128u;
-      for (int s = 0; s < HID / 16; ++s)
-        umma_bf16(tmem_base, umma_desc(aA + s * 256, 128, sbo), umma_desc(aW3 + s * 256, 128, sbo), umma_idesc(kNOut), s > 0);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, parity); parity ^= 1;
-    tc_fence_after();
-    // ---- epilogue: Gaussian sample + log-prob ----------------------------------------------------------
-    uint32_t v[16];
-    if (half == 0) tmem_ld16(tmem_row, v);   // warp-uniform: warps 0-3 finish the rows
-    if (valid && half == 0) {
-      float eps[4] = {0.f, 0.f, 0.f, 0.f};
-      if (noise != nullptr) {
-        for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
-      } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
-        uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
-        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
-        const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
-        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-        float s0, c0, s1, c1;
-        __sincosf(6.28318530718f * u1, &s0, &c0);
-        __sincosf(6.28318530718f * u3, &s1, &c1);
-        eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+      for (int c = 0; c < kMaxX; ++c) {
+        const int k0 = half * 8 + c * 16;
+        if (k0 < K1)
+          *reinterpret_cast<uint4*>(sA + canon_off(row, k0, K1)) =
+              make_uint4(pack_bf16(xa[c].x, xa[c].y), pack_bf16(xa[c].z, xa[c].w), pack_bf16(xb[c].x, xb[c].y), pack_bf16(xb[c].z, xb[c].w));
       }
-      float lp = 0.f;
-      for (int k = 0; k < W.act_dim; ++k) {
-        const float m = __uint_as_float(v[k]) + sB3[k];
-        const float ls = sLs[k];
-        act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
-        if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
-        lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x, xa, xb);   // in flight during the three layers
+      proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();   // my tcgen05.ld of the previous tile are complete (wait::ld) and ordered
+      mbar_arrive(bar(BAR_STAGE));
+      // ---- layer-1 epilogue: H1 over X / W1 (layer-1 MMAs are complete), chunks feed layer 2 --------
+      mbar_wait_guarded(bar(BAR_L1), parity);
+      tc_fence_after();
+      epilogue_hidden<HID>(acc0 + lane_off, sB1, sA, row, cbeg, kChunks, bar(BAR_H1));
+      tc_fence_before();
+      // ---- layer-2 epilogue: H2 over H1 (layer-2 MMAs are complete), chunks feed layer 3 -------------
+      mbar_wait_guarded(bar(BAR_L2), parity);
+      tc_fence_after();
+      epilogue_hidden<HID>(acc1 + lane_off, sB2, sA, row, cbeg, kChunks, bar(BAR_H2));
+      tc_fence_before();
+      // ---- final epilogue: Gaussian sample + log-prob ---------------------------------------------------
+      mbar_wait_guarded(bar(BAR_L3), parity);
+      tc_fence_after();
+      parity ^= 1;
+      uint32_t v[16];
+      if (half == 0) tmem_ld16(acc0 + lane_off, v);   // warp-uniform: warps 0-3 finish the rows
+      if (valid && half == 0) {
+        float eps[4] = {0.f, 0.f, 0.f, 0.f};
+        if (noise != nullptr) {
+          for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
+        } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
+          uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+          philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+          const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+          const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+          const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+          float s0, c0, s1, c1;
+          __sincosf(6.28318530718f * u1, &s0, &c0);
+          __sincosf(6.28318530718f * u3, &s1, &c1);
+          eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+        }
+        float lp = 0.f;
+        for (int k = 0; k < W.act_dim; ++k) {
+          const float m = __uint_as_float(v[k]) + sB3[k];
+          const float ls = sLs[k];
+          act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
+          if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
+          lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+        }
+        logp[row_g] = lp;
       }
-      logp[row_g] = lp;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
 }
 
 // fp32 [n x k] row-major (torch nn.Linear weight) -> bf16 canonical K-major [n_pad x k_pad], zero padded

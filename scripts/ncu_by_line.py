@@ -19,8 +19,12 @@ LIB = os.path.join(ROOT, "marl_gym_pybullet_drones_b200", "libbatchdrones.so")
 def sass_lines(kernel_sub):
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=td, capture_output=True)
-        cub = os.path.join(td, "bd_kernels.sm_100a.cubin")
-        txt = subprocess.run(["nvdisasm", "--print-line-info", cub], capture_output=True, text=True).stdout
+        txt = ""
+        for cub in sorted(os.listdir(td)):   # one cubin per translation unit; take the one with the kernel
+            t = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(td, cub)], capture_output=True, text=True).stdout
+            if any(l.strip().startswith(".section") and ".text." in l and kernel_sub in l for l in t.split("\n")):
+                txt = t
+                break
     lines = txt.split("\n")
     start = next(i for i, l in enumerate(lines)
                  if l.strip().startswith(".section") and ".text." in l and kernel_sub in l)
@@ -58,7 +62,8 @@ def main(rep, kernel_sub, top=40):
     tot, tots = sum(ex.values()), sum(st.values())
     print(f"total executed warp-instructions {tot}, stall samples {tots}")
     cache = {}
-    for loc, n in sorted(ex.items(), key=lambda kv: -kv[1])[:top]:
+    order = (lambda kv: -st[kv[0]]) if os.environ.get("BY_STALL") else (lambda kv: -kv[1])
+    for loc, n in sorted(ex.items(), key=order)[:top]:
         text = ""
         if loc:
             f = os.path.join(ROOT, "marl_gym_pybullet_drones_b200", "csrc", loc[0])
