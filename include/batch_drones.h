@@ -206,6 +206,10 @@ int bd_actor_set_weights(bd_actor* a, const float* w1, const float* b1, const fl
  * noise_dev (rows,act_dim) standard normals, or NULL: Philox4x32-10(seed; row, offset). */
 int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const float* noise_dev, uint64_t seed,
                      uint64_t offset, float* act_dev, float* logp_dev, float* mean_dev, void* stream);
+/* Diagnostics: when trace_dev != NULL, CTA 0 of the next forward launches writes 16 SM-clock stamps
+ * per tile it processes ([tiles_of_cta0][16] int64) marking the pipeline phases (see bd_actor.cu);
+ * NULL switches tracing off. */
+int bd_actor_set_trace(bd_actor* a, long long* trace_dev);
 int64_t bd_actor_launch_count(const bd_actor* a);
 const char* bd_actor_last_error(void);
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "bd_step_host", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_episode_stats",
     "bd_get_controller_state", "bd_set_controller_state", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
-    "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_launch_count",
+    "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_set_trace", "bd_actor_launch_count",
     "bd_actor_last_error",
 )
 
@@ -118,6 +118,8 @@ def load():
     lib.bd_actor_set_weights.restype = C.c_int
     lib.bd_actor_forward.argtypes = [vp, vp, C.c_int64, vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp]
     lib.bd_actor_forward.restype = C.c_int
+    lib.bd_actor_set_trace.argtypes = [vp, vp]
+    lib.bd_actor_set_trace.restype = C.c_int
     lib.bd_actor_launch_count.argtypes = [vp]
     lib.bd_actor_launch_count.restype = C.c_int64
     lib.bd_actor_last_error.argtypes = []

@@ -23,6 +23,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -112,6 +113,7 @@ struct ActorDev {
   const __nv_bfloat16 *w1, *w2, *w3;   // canonical layouts: [HID x K1], [HID x HID], [16 x HID]
   const float *b1, *b2, *b3, *logstd;  // b3 / logstd padded to 16
   int obs_dim, K1, act_dim;
+  long long* trace;   // optional: [tiles of CTA 0][16] SM-clock stamps of the pipeline phases (bd_actor_set_trace)
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32]) {
@@ -124,12 +126,23 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32])
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* v) {
+  if constexpr (CW == 32) tmem_ld32_nowait(taddr, v); else tmem_ld16_nowait(taddr, v);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int HID>
-__device__ __forceinline__ void hidden_chunk(const uint32_t v[32], int c0, const float* __restrict__ bias, __nv_bfloat16* sH, int row) {
+template <int HID, int CW>
+__device__ __forceinline__ void hidden_chunk(const uint32_t* v, int c0, const float* __restrict__ bias, __nv_bfloat16* sH, int row) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < CW / 8; ++q) {
     float h[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = tanh_fast(__uint_as_float(v[q * 8 + j]) + bias[c0 + q * 8 + j]);
@@ -179,43 +192,51 @@ __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32
 // arrive): the MMA warp starts the next layer's K-steps over those columns while the remaining
 // chunks are still going through the SFU, so tensor pipe and epilogue overlap inside one tile.
 // The TMEM read of the next 32 columns is in flight while the current 32 are processed.
-template <int HID>
+template <int HID, int CW>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* __restrict__ bias, __nv_bfloat16* sH, int row,
                                                 int cbeg, int n_chunks, uint32_t chunk_bar0) {
-  uint32_t va[32], vb[32];
-  tmem_ld32_nowait(tmem_row + (uint32_t)cbeg, va);
+  uint32_t va[CW], vb[CW];
+  tmem_ld_nowait<CW>(tmem_row + (uint32_t)cbeg, va);
   tmem_wait_ld();
 #pragma unroll 1
   for (int j = 0; j < n_chunks; j += 2) {
-    const int c0 = cbeg + j * 32;
+    const int c0 = cbeg + j * CW;
     const bool more1 = j + 1 < n_chunks;
-    if (more1) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 32), vb);
-    hidden_chunk<HID>(va, c0, bias, sH, row);
+    if (more1) tmem_ld_nowait<CW>(tmem_row + (uint32_t)(c0 + CW), vb);
+    hidden_chunk<HID, CW>(va, c0, bias, sH, row);
     proxy_fence();
     mbar_arrive(chunk_bar0 + 8u * (uint32_t)j);
     tmem_wait_ld();
     if (!more1) break;
     const bool more2 = j + 2 < n_chunks;
-    if (more2) tmem_ld32_nowait(tmem_row + (uint32_t)(c0 + 64), va);
-    hidden_chunk<HID>(vb, c0 + 32, bias, sH, row);
+    if (more2) tmem_ld_nowait<CW>(tmem_row + (uint32_t)(c0 + 2 * CW), va);
+    hidden_chunk<HID, CW>(vb, c0 + CW, bias, sH, row);
     proxy_fence();
     mbar_arrive(chunk_bar0 + 8u * (uint32_t)(j + 1));
     tmem_wait_ld();
   }
 }
 
-constexpr int kEpiThreads = 256;              // warps 0-7: staging + epilogues
-constexpr int kThreads = kEpiThreads + 32;    // warp 8: issues every tcgen05.mma
-constexpr int kMaxChunks = 4;                 // 32-column chunks per column half (HID = 256)
+constexpr int kMaxChunks = 4;                 // column chunks per thread and layer
 // barrier indices (one phase per tile each)
 enum { BAR_STAGE = 0, BAR_L1, BAR_L2, BAR_L3, BAR_W1, BAR_W23, BAR_H1, BAR_H2 = BAR_H1 + kMaxChunks,
        BAR_COUNT = BAR_H2 + kMaxChunks };
 
-template <int HID>
-__global__ void __launch_bounds__(kThreads, 1)   // 9 warps: one SM sub-partition hosts 3 of them -> 168 registers
+// G = threads per row (column groups): warps 0..4G-1 stage and run the epilogues (warp w owns TMEM
+// lanes 32*(w%4).. and column group w/4), warp 4G issues every tcgen05.mma and TMA copy.
+// G = 4 (16 epilogue warps, 4 per SM sub-partition) hides the TMEM-load / MUFU latencies of the
+// tanh epilogue twice as well as G = 2; the register file then allows 96 registers per thread.
+template <int G> struct ActorShape {
+  static constexpr int kEpiThreads = kRows * G;
+  static constexpr int kThreads = kEpiThreads + 32;
+};
+
+template <int HID, int G>
+__global__ void __launch_bounds__(ActorShape<G>::kThreads, 1)
 actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
                      unsigned long long seed, unsigned long long offset, float* __restrict__ act, float* __restrict__ logp,
                      float* __restrict__ mean_out) {
+  constexpr int kEpiThreads = ActorShape<G>::kEpiThreads, kThreads = ActorShape<G>::kThreads;
   extern __shared__ __align__(128) unsigned char smem[];
   const int K1 = W.K1;
   const size_t actb = (size_t)kRows * HID * 2, l1b = (size_t)(kRows + HID) * K1 * 2;
@@ -234,11 +255,13 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool is_mma_warp = warp == kEpiThreads / 32;
   const int row = tid & (kRows - 1);      // my row of the tile = my TMEM lane
-  const int half = (tid >> 7) & 1;        // which half of the columns I handle in the epilogues
-  constexpr int kHalfCols = HID / 2;      // 32, 64 or 128
-  constexpr int kChunks = kHalfCols / 32; // 32-column chunks per half
+  const int grp = (tid >> 7) & (G - 1);   // which group of columns I handle in the epilogues
+  constexpr int kGrpCols = HID / G;       // columns per thread and layer
+  constexpr int CW = (G == 2 && kGrpCols >= 32) ? 32 : 16;   // columns per TMEM load / published chunk
+  constexpr int kChunks = kGrpCols / CW;
+  static_assert(kChunks >= 1 && kChunks <= kMaxChunks, "unsupported HID / G");
   constexpr uint32_t kTmemCols = HID == 256 ? 512u : (HID == 128 ? 256u : 128u);   // two accumulators
-  const int cbeg = half * kHalfCols;
+  const int cbeg = grp * kGrpCols;
   // ---- one-time: resident weights, barriers, tensor memory ------------------------------------
   // (W2 / W3 / W1 arrive by TMA bulk copies issued by the MMA thread)
   for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
@@ -292,47 +315,52 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
         mbar_wait_guarded(bar(BAR_STAGE), parity);
         mbar_wait_guarded(bar(BAR_W1), parity);
         tc_fence_after();
+        long long* tr = (W.trace != nullptr && blockIdx.x == 0) ? W.trace + (tile / gridDim.x) * 16 : nullptr;
+        if (tr) tr[8] = clock64();    // MMA thread: tile staged, W1 landed
         for (int s = 0; s < K1 / 16; ++s)
           umma_bf16(acc0, umma_desc(aA + s * 256, 128, sbo1), umma_desc(aW1 + s * 256, 128, sbo1), umma_idesc(HID), s > 0);
         umma_commit(bar(BAR_L1));
+        if (tr) tr[9] = clock64();    // layer-1 MMAs issued
         if (first) { mbar_wait_guarded(bar(BAR_W23), 0); first = false; }
         // layer 2: acc1 = H1 W2^T, K-steps follow the layer-1 epilogue chunk by chunk
         for (int j = 0; j < kChunks; ++j) {
           mbar_wait_guarded(bar(BAR_H1 + j), parity);
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < G; ++h) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int s = (h * kHalfCols + j * 32) / 16 + q;
+            for (int q = 0; q < CW / 16; ++q) {
+              const int s = (h * kGrpCols + j * CW) / 16 + q;
               umma_bf16(acc1, umma_desc(aA + s * 256, 128, sboH), umma_desc(aW2 + s * 256, 128, sboH), umma_idesc(HID),
                         (j | h | q) != 0);
             }
           }
         }
         umma_commit(bar(BAR_L2));
+        if (tr) tr[10] = clock64();   // last layer-2 MMA issued
         // layer 3: acc0[128 x 16] = H2 W3^T, same pipelining against the layer-2 epilogue
         for (int j = 0; j < kChunks; ++j) {
           mbar_wait_guarded(bar(BAR_H2 + j), parity);
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < G; ++h) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int s = (h * kHalfCols + j * 32) / 16 + q;
+            for (int q = 0; q < CW / 16; ++q) {
+              const int s = (h * kGrpCols + j * CW) / 16 + q;
               umma_bf16(acc0, umma_desc(aA + s * 256, 128, sboH), umma_desc(aW3 + s * 256, 128, sboH), umma_idesc(kNOut),
                         (j | h | q) != 0);
             }
           }
         }
         umma_commit(bar(BAR_L3));
+        if (tr) tr[11] = clock64();   // last layer-3 MMA issued
         parity ^= 1;
       }
     }
   } else {
     // =============================== staging + epilogue warps ====================================
     // The next tile's observation chunks are prefetched into registers while the current tile is in flight.
-    constexpr int kMaxX = 8;
+    constexpr int kMaxX = 16 / G;   // K1 <= 128: 16 chunks of 8 columns, dealt round-robin to the row's G threads
     const bool vec4 = (W.obs_dim & 3) == 0;   // rows are 16-byte aligned: two 128-bit loads per 8 columns
     // raw fp32 chunks stay in registers until the next tile starts: converting right after the load
     // would stall on the global latency that the prefetch is meant to hide
@@ -342,7 +370,7 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
       const float* src = obs + (size_t)rg * W.obs_dim;
 #pragma unroll
       for (int c = 0; c < kMaxX; ++c) {
-        const int k0 = half * 8 + c * 16;      // the two threads of a row take alternate 8-column chunks
+        const int k0 = (grp + c * G) * 8;      // the G threads of a row take alternate 8-column chunks
         xa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         xb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k0 < K1 && ok) {
@@ -362,64 +390,87 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
 
     float4 xa[kMaxX], xb[kMaxX];
     uint32_t parity = 0;
-    if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x, xa, xb);
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long row_g = tile * kRows + row;
-      const bool valid = row_g < rows;
-      // ---- X tile (prefetched; fp32 -> bf16, canonical K-major layout) --------------------------------
-      // (region A is free: every thread waited for the previous tile's layer-3 MMAs below)
+    // Gaussian sample + log-prob of one row from the layer-3 accumulator values (already in registers)
+    auto finish_row = [&](long long row_g, const uint32_t (&v)[16]) {
+      float eps[4] = {0.f, 0.f, 0.f, 0.f};
+      if (noise != nullptr) {
+        for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
+      } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
+        uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+        const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.28318530718f * u1, &s0, &c0);
+        __sincosf(6.28318530718f * u3, &s1, &c1);
+        eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+      }
+      float lp = 0.f;
+      for (int k = 0; k < W.act_dim; ++k) {
+        const float m = __uint_as_float(v[k]) + sB3[k];
+        const float ls = sLs[k];
+        act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
+        if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
+        lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+      }
+      logp[row_g] = lp;
+    };
+    auto stage_x = [&]() {   // prefetched fp32 chunks -> bf16, canonical K-major layout
 #pragma unroll
       for (int c = 0; c < kMaxX; ++c) {
-        const int k0 = half * 8 + c * 16;
+        const int k0 = (grp + c * G) * 8;
         if (k0 < K1)
           *reinterpret_cast<uint4*>(sA + canon_off(row, k0, K1)) =
               make_uint4(pack_bf16(xa[c].x, xa[c].y), pack_bf16(xa[c].z, xa[c].w), pack_bf16(xb[c].x, xb[c].y), pack_bf16(xb[c].z, xb[c].w));
       }
-      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x, xa, xb);   // in flight during the three layers
-      proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();   // my tcgen05.ld of the previous tile are complete (wait::ld) and ordered
+    };
+    if ((long long)blockIdx.x < n_tiles) {
+      load_x(blockIdx.x, xa, xb);
+      stage_x();
+      proxy_fence();
       mbar_arrive(bar(BAR_STAGE));
+      if ((long long)blockIdx.x + gridDim.x < n_tiles) load_x(blockIdx.x + gridDim.x, xa, xb);
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row_g = tile * kRows + row;
+      const long long next = tile + gridDim.x;
       // ---- layer-1 epilogue: H1 over X / W1 (layer-1 MMAs are complete), chunks feed layer 2 --------
+      long long* tr = (W.trace != nullptr && blockIdx.x == 0 && tid == 0) ? W.trace + (tile / gridDim.x) * 16 : nullptr;
+      if (tr) tr[0] = clock64();      // waiting for layer 1
       mbar_wait_guarded(bar(BAR_L1), parity);
       tc_fence_after();
-      epilogue_hidden<HID>(acc0 + lane_off, sB1, sA, row, cbeg, kChunks, bar(BAR_H1));
+      if (tr) tr[1] = clock64();      // layer-1 accumulator ready
+      epilogue_hidden<HID, CW>(acc0 + lane_off, sB1, sA, row, cbeg, kChunks, bar(BAR_H1));
       tc_fence_before();
+      if (tr) tr[2] = clock64();      // my layer-1 epilogue done
       // ---- layer-2 epilogue: H2 over H1 (layer-2 MMAs are complete), chunks feed layer 3 -------------
       mbar_wait_guarded(bar(BAR_L2), parity);
       tc_fence_after();
-      epilogue_hidden<HID>(acc1 + lane_off, sB2, sA, row, cbeg, kChunks, bar(BAR_H2));
+      if (tr) tr[3] = clock64();      // layer-2 accumulator ready
+      epilogue_hidden<HID, CW>(acc1 + lane_off, sB2, sA, row, cbeg, kChunks, bar(BAR_H2));
       tc_fence_before();
-      // ---- final epilogue: Gaussian sample + log-prob ---------------------------------------------------
+      if (tr) tr[4] = clock64();      // my layer-2 epilogue done
+      // ---- layer 3 done: pull my row's 16 outputs out of TMEM, hand region A and acc0 to the next
+      //      tile (its layer-1 MMA runs while this tile's rows are sampled and written) --------------
       mbar_wait_guarded(bar(BAR_L3), parity);
       tc_fence_after();
+      if (tr) tr[5] = clock64();      // layer-3 accumulator ready
       parity ^= 1;
       uint32_t v[16];
-      if (half == 0) tmem_ld16(acc0 + lane_off, v);   // warp-uniform: warps 0-3 finish the rows
-      if (valid && half == 0) {
-        float eps[4] = {0.f, 0.f, 0.f, 0.f};
-        if (noise != nullptr) {
-          for (int k = 0; k < W.act_dim; ++k) eps[k] = noise[(size_t)row_g * W.act_dim + k];
-        } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
-          uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
-          philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-          const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
-          const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
-          const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-          float s0, c0, s1, c1;
-          __sincosf(6.28318530718f * u1, &s0, &c0);
-          __sincosf(6.28318530718f * u3, &s1, &c1);
-          eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
-        }
-        float lp = 0.f;
-        for (int k = 0; k < W.act_dim; ++k) {
-          const float m = __uint_as_float(v[k]) + sB3[k];
-          const float ls = sLs[k];
-          act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
-          if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
-          lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
-        }
-        logp[row_g] = lp;
+      if (grp == 0) tmem_ld16(acc0 + lane_off, v);   // warp-uniform: warps 0-3 finish the rows
+      if (next < n_tiles) {
+        stage_x();
+        proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();   // my tcgen05.ld of this tile are complete (wait::ld) and ordered
+        mbar_arrive(bar(BAR_STAGE));
       }
+      if (tr) tr[6] = clock64();      // next tile staged
+      if (grp == 0 && row_g < rows) finish_row(row_g, v);
+      if (tr) tr[7] = clock64();      // rows sampled and written
+      // prefetch the tile after next into registers.  Issued after the fences above and consumed one
+      // tile later: a proxy fence waits for the thread's outstanding global loads
+      if (next + gridDim.x < n_tiles) load_x(next + gridDim.x, xa, xb);
     }
   }
   tc_fence_before();
@@ -442,12 +493,21 @@ __global__ void pad_vector_kernel(const float* __restrict__ v, int n, int n_pad,
 
 }  // namespace
 
+using ActorKernel = void (*)(ActorDev, const float*, long long, const float*, unsigned long long, unsigned long long, float*,
+                             float*, float*);
+static ActorKernel actor_kernel(int hidden, int groups) {
+  if (groups == 2) return hidden == 256 ? actor_forward_kernel<256, 2> : (hidden == 128 ? actor_forward_kernel<128, 2> : actor_forward_kernel<64, 2>);
+  return hidden == 256 ? actor_forward_kernel<256, 4> : (hidden == 128 ? actor_forward_kernel<128, 4> : actor_forward_kernel<64, 4>);
+}
+
 struct bd_actor {
   int device, obs_dim, hidden, act_dim, K1, sm_count;
+  int groups = 4;   // threads per row in the epilogues (BD_ACTOR_GROUPS=2 selects the 8-warp variant)
   __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *logstd = nullptr;
   size_t smem = 0;
   int64_t launches = 0;
+  long long* trace = nullptr;
 };
 
 extern "C" {
@@ -489,9 +549,9 @@ int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor**
                  need, (size_t)prop.sharedMemPerBlockOptin);
   }
   if (e == cudaSuccess) {
-    if (hidden == 256) e = cudaFuncSetAttribute(actor_forward_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
-    else if (hidden == 128) e = cudaFuncSetAttribute(actor_forward_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
-    else e = cudaFuncSetAttribute(actor_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+    const char* g = getenv("BD_ACTOR_GROUPS");
+    if (g && g[0] == '2') a->groups = 2;
+    e = cudaFuncSetAttribute(actor_kernel(hidden, a->groups), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
   }
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -532,16 +592,22 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
                      float* act_dev, float* logp_dev, float* mean_dev, void* stream) {
   if (!a || !obs_dev || !act_dev || !logp_dev) return afail(BD_EINVAL, "bd_actor_forward: obs, act and logp are required");
   if (rows <= 0) return BD_OK;
-  ActorDev W{a->w1, a->w2, a->w3, a->b1, a->b2, a->b3, a->logstd, a->obs_dim, a->K1, a->act_dim};
+  ActorDev W{a->w1, a->w2, a->w3, a->b1, a->b2, a->b3, a->logstd, a->obs_dim, a->K1, a->act_dim, a->trace};
   const long long n_tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(n_tiles < a->sm_count ? n_tiles : a->sm_count);   // persistent: one CTA per SM
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->hidden == 256) actor_forward_kernel<256><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
-  else if (a->hidden == 128) actor_forward_kernel<128><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
-  else actor_forward_kernel<64><<<grid, kThreads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev, mean_dev);
+  const int threads = a->groups == 2 ? ActorShape<2>::kThreads : ActorShape<4>::kThreads;
+  actor_kernel(a->hidden, a->groups)<<<grid, threads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev,
+                                                                    mean_dev);
   a->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_forward: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_actor_set_trace(bd_actor* a, long long* trace_dev) {
+  if (!a) return afail(BD_EINVAL, "bd_actor_set_trace: null handle");
+  a->trace = trace_dev;
   return BD_OK;
 }
 
