@@ -210,8 +210,36 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
  * per tile it processes ([tiles_of_cta0][16] int64) marking the pipeline phases (see bd_actor.cu);
  * NULL switches tracing off. */
 int bd_actor_set_trace(bd_actor* a, long long* trace_dev);
+/* Normalise the input rows on load: x <- clip((x - mean[(row % period) * obs_dim + k]) * rstd[...], +-clip)
+ * with float vectors of period*obs_dim entries (bd_rms_get's mean_f / rstd_f); mean_dev == NULL
+ * switches it off.  `period` = agents per env (the reference's normaliser has the observation
+ * space's shape (M, D), mappo/mappo.py:132). */
+int bd_actor_set_input_norm(bd_actor* a, const float* mean_dev, const float* rstd_dev, int period, float clip);
 int64_t bd_actor_launch_count(const bd_actor* a);
 const char* bd_actor_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Running observation statistics on the device: RunningMeanStd / MeanStdNormalizer of
+ * safe_control_gym/math_and_models/normalization.py:13-96 as MAPPO uses them on every
+ * observation batch (mappo/mappo.py:132,165,804).  cols = prod(observation_space.shape).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bd_rms bd_rms;
+/* mean = 0, var = 1, count = count0 (the reference's epsilon = 1e-4, :24-32); eps = the normaliser's
+ * divide-by-zero offset (1e-8, :71). */
+int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out);
+void bd_rms_destroy(bd_rms* r);
+/* RunningMeanStd.update (:34-58): batch mean / population variance over the `rows` axis of
+ * x_dev (rows, cols) float, merged into the running statistics.  Two launches, stream ordered. */
+int bd_rms_update(bd_rms* r, const float* x_dev, int64_t rows, void* stream);
+/* y = clip((x - mean) / sqrt(var + eps), -clip, clip) (:84-88), y_dev may equal x_dev. */
+int bd_rms_normalize(bd_rms* r, const float* x_dev, float* y_dev, int64_t rows, float clip, void* stream);
+/* state_dict / load_state_dict (:90-96): any pointer may be NULL.  mean_f / rstd_f are the float
+ * vectors (mean, 1/sqrt(var+eps)) fused consumers read (bd_actor_set_input_norm). */
+int bd_rms_get(bd_rms* r, double* mean_dev, double* var_dev, double* count_dev, float* mean_f_dev, float* rstd_f_dev,
+               void* stream);
+int bd_rms_set(bd_rms* r, const double* mean_dev, const double* var_dev, const double* count_dev, void* stream);
+int64_t bd_rms_launch_count(const bd_rms* r);
+const char* bd_rms_last_error(void);
 
 #ifdef __cplusplus
 }

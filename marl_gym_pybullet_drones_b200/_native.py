@@ -25,7 +25,9 @@ EXPORTS = (
     "bd_get_controller_state", "bd_set_controller_state", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
     "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_set_trace", "bd_actor_launch_count",
-    "bd_actor_last_error",
+    "bd_actor_last_error", "bd_actor_set_input_norm",
+    "bd_rms_create", "bd_rms_destroy", "bd_rms_update", "bd_rms_normalize", "bd_rms_get", "bd_rms_set",
+    "bd_rms_launch_count", "bd_rms_last_error",
 )
 
 
@@ -124,6 +126,24 @@ def load():
     lib.bd_actor_launch_count.restype = C.c_int64
     lib.bd_actor_last_error.argtypes = []
     lib.bd_actor_last_error.restype = C.c_char_p
+    lib.bd_actor_set_input_norm.argtypes = [vp, vp, vp, C.c_int, C.c_float]
+    lib.bd_actor_set_input_norm.restype = C.c_int
+    lib.bd_rms_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    lib.bd_rms_create.restype = C.c_int
+    lib.bd_rms_destroy.argtypes = [vp]
+    lib.bd_rms_destroy.restype = None
+    lib.bd_rms_update.argtypes = [vp, vp, C.c_int64, vp]
+    lib.bd_rms_update.restype = C.c_int
+    lib.bd_rms_normalize.argtypes = [vp, vp, vp, C.c_int64, C.c_float, vp]
+    lib.bd_rms_normalize.restype = C.c_int
+    lib.bd_rms_get.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.bd_rms_get.restype = C.c_int
+    lib.bd_rms_set.argtypes = [vp, vp, vp, vp, vp]
+    lib.bd_rms_set.restype = C.c_int
+    lib.bd_rms_launch_count.argtypes = [vp]
+    lib.bd_rms_launch_count.restype = C.c_int64
+    lib.bd_rms_last_error.argtypes = []
+    lib.bd_rms_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

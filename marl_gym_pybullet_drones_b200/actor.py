@@ -71,6 +71,20 @@ class FusedActor:
             C.c_void_p(mean.data_ptr()) if mean is not None else None, self._stream()), "bd_actor_forward")
         return (act, logp, mean) if want_mean else (act, logp)
 
+    def set_input_norm(self, mean: Optional[torch.Tensor], rstd: Optional[torch.Tensor] = None, period: int = 1,
+                       clip: float = 10.0):
+        """Normalise input rows on load with float (mean, 1/std) vectors of `period * obs_dim` entries
+        (`MeanStdNormalizer` of shape (M, D): period = M); `None` switches it off."""
+        if mean is None:
+            self._check(self._lib.bd_actor_set_input_norm(self._h, None, None, 1, 10.0), "bd_actor_set_input_norm")
+            self._norm = None
+            return
+        if mean.dtype != torch.float32 or rstd.dtype != torch.float32 or mean.numel() != period * self.obs_dim:
+            raise ValueError("mean / rstd must be float32 with period * obs_dim entries")
+        self._norm = (mean, rstd)   # keep alive
+        self._check(self._lib.bd_actor_set_input_norm(self._h, C.c_void_p(mean.data_ptr()), C.c_void_p(rstd.data_ptr()),
+                                                      int(period), float(clip)), "bd_actor_set_input_norm")
+
     @property
     def launch_count(self):
         return int(self._lib.bd_actor_launch_count(self._h))

@@ -113,6 +113,9 @@ struct ActorDev {
   const __nv_bfloat16 *w1, *w2, *w3;   // canonical layouts: [HID x K1], [HID x HID], [16 x HID]
   const float *b1, *b2, *b3, *logstd;  // b3 / logstd padded to 16
   int obs_dim, K1, act_dim;
+  const float *nmean, *nrstd;   // optional input normalisation (bd_actor_set_input_norm), period rows
+  int nperiod;
+  float nclip;
   long long* trace;   // optional: [tiles of CTA 0][16] SM-clock stamps of the pipeline phases (bd_actor_set_trace)
 };
 
@@ -387,6 +390,28 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
         }
       }
     };
+    // MeanStdNormalizer on load (normalization.py:84-88): statistics are per (agent, column)
+    auto normalise_x = [&](long long tile, float4 (&xa)[kMaxX], float4 (&xb)[kMaxX]) {
+      const long long rg = tile * kRows + row;
+      const size_t base = (size_t)(rg % W.nperiod) * W.obs_dim;
+      const float cl = W.nclip;
+#pragma unroll
+      for (int c = 0; c < kMaxX; ++c) {
+        const int k0 = (grp + c * G) * 8;
+        if (k0 < W.obs_dim) {
+          float x[8] = {xa[c].x, xa[c].y, xa[c].z, xa[c].w, xb[c].x, xb[c].y, xb[c].z, xb[c].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (k0 + j < W.obs_dim) {
+              const float v = (x[j] - __ldg(W.nmean + base + k0 + j)) * __ldg(W.nrstd + base + k0 + j);
+              x[j] = fminf(fmaxf(v, -cl), cl);
+            }
+          }
+          xa[c] = make_float4(x[0], x[1], x[2], x[3]);
+          xb[c] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+      }
+    };
 
     float4 xa[kMaxX], xb[kMaxX];
     uint32_t parity = 0;
@@ -427,6 +452,7 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
     };
     if ((long long)blockIdx.x < n_tiles) {
       load_x(blockIdx.x, xa, xb);
+      if (W.nmean != nullptr) normalise_x(blockIdx.x, xa, xb);
       stage_x();
       proxy_fence();
       mbar_arrive(bar(BAR_STAGE));
@@ -460,6 +486,7 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
       uint32_t v[16];
       if (grp == 0) tmem_ld16(acc0 + lane_off, v);   // warp-uniform: warps 0-3 finish the rows
       if (next < n_tiles) {
+        if (W.nmean != nullptr) normalise_x(next, xa, xb);
         stage_x();
         proxy_fence();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();   // my tcgen05.ld of this tile are complete (wait::ld) and ordered
@@ -508,6 +535,9 @@ struct bd_actor {
   size_t smem = 0;
   int64_t launches = 0;
   long long* trace = nullptr;
+  const float *nmean = nullptr, *nrstd = nullptr;
+  int nperiod = 1;
+  float nclip = 10.0f;
 };
 
 extern "C" {
@@ -592,7 +622,8 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
                      float* act_dev, float* logp_dev, float* mean_dev, void* stream) {
   if (!a || !obs_dev || !act_dev || !logp_dev) return afail(BD_EINVAL, "bd_actor_forward: obs, act and logp are required");
   if (rows <= 0) return BD_OK;
-  ActorDev W{a->w1, a->w2, a->w3, a->b1, a->b2, a->b3, a->logstd, a->obs_dim, a->K1, a->act_dim, a->trace};
+  ActorDev W{a->w1, a->w2, a->w3, a->b1, a->b2, a->b3, a->logstd, a->obs_dim, a->K1, a->act_dim, a->nmean, a->nrstd, a->nperiod,
+             a->nclip, a->trace};
   const long long n_tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(n_tiles < a->sm_count ? n_tiles : a->sm_count);   // persistent: one CTA per SM
   cudaStream_t st = (cudaStream_t)stream;
@@ -602,6 +633,14 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
   a->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_forward: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_actor_set_input_norm(bd_actor* a, const float* mean_dev, const float* rstd_dev, int period, float clip) {
+  if (!a) return afail(BD_EINVAL, "bd_actor_set_input_norm: null handle");
+  if (mean_dev != nullptr && (rstd_dev == nullptr || period < 1 || !(clip > 0.f)))
+    return afail(BD_EINVAL, "bd_actor_set_input_norm: rstd, period >= 1 and clip > 0 are required");
+  a->nmean = mean_dev; a->nrstd = mean_dev ? rstd_dev : nullptr; a->nperiod = period > 0 ? period : 1; a->nclip = clip;
   return BD_OK;
 }
 

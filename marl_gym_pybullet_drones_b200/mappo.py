@@ -54,6 +54,10 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
+    "norm_obs": False,            # mappo/config.py:7-10; True in the Spiral config (env_select_learn_mappo.py:278)
+    "norm_reward": False,
+    "clip_obs": 10,
+    "clip_reward": 10,
 }
 
 
@@ -83,7 +87,29 @@ class ActorCritic(nn.Module):
         self.critic = MLP(num_agents * obs_dim, 1, [hidden_dim, hidden_dim], activation)
 
     def actor_parameters(self):
-        return list(self.actor.parameters()) + [self.logstd]
+        """Order of `MLPActor.parameters()` in the reference (own parameter first, then `pi_net`), so
+        that Adam states are interchangeable with `model_latest.pt` (`mappo/agent.py:87-110,588-594`)."""
+        return [self.logstd] + list(self.actor.parameters())
+
+    # reference parameter names (`MAPPOActorCritic.state_dict()`, mappo/agent.py:225-320)
+    def reference_state_dict(self):
+        sd = {"actor.logstd": self.logstd.detach().clone()}
+        for k, v in self.actor.state_dict().items():
+            sd["actor.pi_net." + k] = v.detach().clone()
+        for k, v in self.critic.state_dict().items():
+            sd["critic.v_net." + k] = v.detach().clone()
+        return sd
+
+    def load_reference_state_dict(self, sd):
+        if "actor.logstd" not in sd:       # this repo's own key layout
+            return self.load_state_dict(sd)
+        own = {"logstd": sd["actor.logstd"]}
+        for k, v in sd.items():
+            if k.startswith("actor.pi_net."):
+                own["actor." + k[len("actor.pi_net."):]] = v
+            elif k.startswith("critic.v_net."):
+                own["critic." + k[len("critic.v_net."):]] = v
+        return self.load_state_dict(own)
 
     def dist(self, obs):
         return torch.distributions.Normal(self.actor(obs), self.logstd.exp())
@@ -142,12 +168,42 @@ class DeviceMAPPO:
                 self.fused = None   # shape outside the fused kernel's envelope: torch path
         self._fused_seed = seed * 7919 + rank
         self._fused_stale = True
+        # running normalisers (mappo/mappo.py:130-135); statistics live on the device, the rollout buffer
+        # keeps RAW observations plus the (mean, 1/std) that were current when each slot was produced
+        from .normalization import BaseNormalizer, MeanStdNormalizer, RewardStdNormalizer
+        self.obs_normalizer = BaseNormalizer()
+        self.reward_normalizer = BaseNormalizer()
+        self.norm_obs = bool(self.cfg["norm_obs"])
+        if self.norm_obs:
+            self.obs_normalizer = MeanStdNormalizer(shape=(M, D), clip=float(self.cfg["clip_obs"]), epsilon=1e-8, device=dev)
+            self.nmean = torch.zeros((T + 1, M * D), device=dev)
+            self.nrstd = torch.ones((T + 1, M * D), device=dev)
+        if self.cfg["norm_reward"]:
+            self.reward_normalizer = RewardStdNormalizer(gamma=self.cfg["gamma"], clip=float(self.cfg["clip_reward"]),
+                                                         epsilon=1e-8, device=dev)
 
     # ------------------------------------------------------------------ rollout
     def reset(self):
         self.env.reset_device(out=self.obs[0])
         self.env.episode_stats(reset=True)
+        self._observe(0)
         self._reset_done = True
+
+    def _observe(self, t):
+        """`self.obs = self.obs_normalizer(obs)` (mappo.py:165,804) without materialising it: update the
+        running statistics with raw slot t and remember the (mean, 1/std) it is to be read with."""
+        if self.norm_obs:
+            self.obs_normalizer.update(self.obs[t])
+            self.obs_normalizer.rms.stats(self.nmean[t], self.nrstd[t])
+
+    def _normed(self, obs, t):
+        """Normalised view of raw observations (..., M, D) of slot(s) t (torch path: critic, update)."""
+        if not self.norm_obs:
+            return obs
+        shp = obs.shape
+        o = obs.reshape(-1, self.M * self.D)
+        c = float(self.cfg["clip_obs"])
+        return ((o - self.nmean[t]) * self.nrstd[t]).clamp_(-c, c).view(shp)
 
     @torch.no_grad()
     def collect_rollout(self):
@@ -156,6 +212,9 @@ class DeviceMAPPO:
             self.reset()
         elif self.total_env_steps > 0:
             self.obs[0].copy_(self.obs[self.T])   # the rollout continues where the previous one stopped
+            if self.norm_obs:
+                self.nmean[0].copy_(self.nmean[self.T])
+                self.nrstd[0].copy_(self.nrstd[self.T])
         T, N, M = self.T, self.N, self.M
         std = self.ac.logstd.exp()
         use_critic = self.cfg["rollout_values"] == "critic"
@@ -165,21 +224,26 @@ class DeviceMAPPO:
         for t in range(T):
             obs_t = self.obs[t]
             if self.fused is not None:
+                if self.norm_obs:   # normalised on load inside the kernel
+                    self.fused.set_input_norm(self.nmean[t], self.nrstd[t], period=M, clip=float(self.cfg["clip_obs"]))
                 # one kernel: MLP on tcgen05, Gaussian sample (Philox), summed log-prob; writes act[t], logp[t]
                 self.fused.forward(obs_t.view(N * M, self.D), seed=self._fused_seed,
                                    out_act=self.act[t].view(N * M, self.A), out_logp=self.logp[t].view(N * M))
             else:
-                mean = self.ac.actor(obs_t.view(N * M, self.D)).view(N, M, self.A)
+                mean = self.ac.actor(self._normed(obs_t, t).view(N * M, self.D)).view(N, M, self.A)
                 noise = torch.randn(mean.shape, device=self.device, generator=self.gen)
                 self.act[t] = mean + std * noise                      # unclipped Gaussian (agent.py:399-400)
                 self.logp[t] = (-0.5 * noise.pow(2) - self.ac.logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
             if use_critic:
-                self.val[t] = self.ac.value(obs_t.view(N, M * self.D))
+                self.val[t] = self.ac.value(self._normed(obs_t, t).view(N, M * self.D))
             out = StepResult(self.obs[t + 1], self.rew[t], self.term[t].view(torch.bool),
                              self.trunc[t].view(torch.bool), None)
             self.env.step_device(self.act[t], out=out)   # episode statistics are kept by the step kernel
+            self._observe(t + 1)
+            if self.cfg["norm_reward"]:                  # mappo.py:805, raw rewards stay in the episode statistics
+                self.rew[t] = self.reward_normalizer(self.rew[t], self.term[t] | self.trunc[t])
         # bootstrap value of the last observation (`last_val`, mappo.py:1049-1157)
-        self.val[T] = self.ac.value(self.obs[T].view(N, M * self.D))
+        self.val[T] = self.ac.value(self._normed(self.obs[T], T).view(N, M * self.D))
         if not use_critic:
             self.val[:T].zero_()                                       # agent.py:413: v stored as zeros
         self.total_env_steps += T * N
@@ -228,7 +292,8 @@ class DeviceMAPPO:
             perm = torch.randperm(n, device=self.device, generator=self.gen)
             for i in range(num_mb):
                 idx = perm[i * mb:(i + 1) * mb]
-                o, a = obs[idx].reshape(mb * M, D), act[idx].reshape(mb * M, A)
+                ob = self._normed(obs[idx], torch.div(idx, N, rounding_mode="floor")) if self.norm_obs else obs[idx]
+                o, a = ob.reshape(mb * M, D), act[idx].reshape(mb * M, A)
                 lp_old, ad = logp_old[idx].reshape(mb * M, 1), adv[idx].reshape(mb * M, 1)
                 dist = self.ac.dist(o)
                 lp = dist.log_prob(a).sum(-1, keepdim=True)
@@ -244,7 +309,7 @@ class DeviceMAPPO:
                 # when the minibatch violates the constraint; one scalar read-back per minibatch
                 if cfg["target_kl"] <= 0 or approx_kl.item() <= 1.5 * cfg["target_kl"]:
                     self.actor_opt.step()
-                v = self.ac.value(obs[idx].reshape(mb, M * D))
+                v = self.ac.value(ob.reshape(mb, M * D))
                 value_loss = 0.5 * (v - ret[idx]).pow(2).mean()
                 self.critic_opt.zero_grad(set_to_none=True)
                 value_loss.backward()
@@ -285,20 +350,38 @@ class DeviceMAPPO:
     @torch.no_grad()
     def select_action(self, obs: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
         """`MAPPO.select_action` (mappo.py:272-287): mean action for evaluation."""
+        if self.norm_obs:   # evaluation reads the frozen statistics (mappo.py:537,549)
+            m, r = self.obs_normalizer.rms.stats()
+            c = float(self.cfg["clip_obs"])
+            obs = ((obs.reshape(-1, self.M * self.D) - m) * r).clamp(-c, c).view(obs.shape)
         mean = self.ac.actor(obs.reshape(-1, self.D)).view(*obs.shape[:-1], self.A)
         if deterministic:
             return mean
         return mean + self.ac.logstd.exp() * torch.randn(mean.shape, device=mean.device, generator=self.gen)
 
     def state_dict(self):
-        return {"agent": {"ac": self.ac.state_dict(), "actor_opt": self.actor_opt.state_dict(),
-                          "critic_opt": self.critic_opt.state_dict()},
-                "total_steps": self.total_env_steps}
+        """The reference's checkpoint layout (`MAPPO.save`, mappo/mappo.py:203-232): `agent` =
+        {`ac` with the reference's parameter names, `actor_opt`, `critic_opt`}, `obs_normalizer`,
+        `reward_normalizer`, `total_steps`, `obs` (the current, normalised observation)."""
+        sd = {"agent": {"ac": self.ac.reference_state_dict(), "actor_opt": self.actor_opt.state_dict(),
+                        "critic_opt": self.critic_opt.state_dict()},
+              "obs_normalizer": self.obs_normalizer.state_dict(),
+              "reward_normalizer": self.reward_normalizer.state_dict(),
+              "total_steps": self.total_env_steps,
+              "random_state": None, "env_random_state": None}
+        if self._reset_done:
+            t = self.T if self.total_env_steps > 0 else 0
+            sd["obs"] = self._normed(self.obs[t], t).cpu().numpy()
+        return sd
 
     def load_state_dict(self, sd):
-        self.ac.load_state_dict(sd["agent"]["ac"])
+        self.ac.load_reference_state_dict(sd["agent"]["ac"])
         self.actor_opt.load_state_dict(sd["agent"]["actor_opt"])
         self.critic_opt.load_state_dict(sd["agent"]["critic_opt"])
+        if sd.get("obs_normalizer"):
+            self.obs_normalizer.load_state_dict(sd["obs_normalizer"])
+        if sd.get("reward_normalizer"):
+            self.reward_normalizer.load_state_dict(sd["reward_normalizer"])
         self.total_env_steps = int(sd.get("total_steps", 0))
         self._fused_stale = True
 
@@ -306,4 +389,4 @@ class DeviceMAPPO:
         torch.save(self.state_dict(), path)
 
     def load(self, path):
-        self.load_state_dict(torch.load(path, map_location=self.device))
+        self.load_state_dict(torch.load(path, map_location=self.device, weights_only=False))

@@ -9,13 +9,14 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 AERO = {"gnd": 1, "drag": 2, "dw": 4}
 
 
+TRAINER_FIXTURES = ("normalizers", "checkpoint_layout")   # not trajectories (test_trainer_golden.py)
 CONTROLLER_CASES = ("spiral3_vel", "spiral3_vel_f32", "multihover2_vel_cf2p", "multihover2_pid", "hover_one_d_pid")
 
 
 def golden_names(controller=False):
     """Golden trajectories; `controller=True` selects the PID / VEL / ONE_D_PID cases instead."""
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                   if not os.path.basename(p).startswith("aero"))
+                   if not os.path.basename(p).startswith("aero") and os.path.basename(p)[:-4] not in TRAINER_FIXTURES)
     return [n for n in names if (n in CONTROLLER_CASES) == controller]
 
 
