@@ -35,16 +35,16 @@ int rfail(int code, const char* fmt, ...) {
 
 constexpr int kMomThreads = 256;
 
-// acc[c] += sum_r (x[r][c] - shift[c]),  acc[cols + c] += sum_r (x[r][c] - shift[c])^2
-// (shift = current running mean: keeps the one-pass variance well conditioned)
+// acc[c] += sum_r (x[r][c] - x[0][c]),  acc[cols + c] += sum_r (x[r][c] - x[0][c])^2
+// (shifting by a sample of the batch keeps the one-pass variance well conditioned whatever the
+// column's offset: the differences are of the order of the spread and exact for constant columns)
 __global__ void __launch_bounds__(kMomThreads)
-moments_kernel(const float* __restrict__ x, long long rows, int cols, const double* __restrict__ shift,
-               double* __restrict__ acc) {
+moments_kernel(const float* __restrict__ x, long long rows, int cols, double* __restrict__ acc) {
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * per;
   const long long r1 = r0 + per < rows ? r0 + per : rows;
   for (int c = threadIdx.x; c < cols; c += kMomThreads) {
-    const float sh = (float)shift[c];
+    const float sh = __ldg(x + c);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains per thread
     long long r = r0;
     for (; r + 3 < r1; r += 4) {
@@ -64,14 +64,14 @@ moments_kernel(const float* __restrict__ x, long long rows, int cols, const doub
 }
 
 // RunningMeanStd.update_from_moments (normalization.py:44-58) in fp64; clears the accumulators
-__global__ void merge_kernel(double* __restrict__ mean, double* __restrict__ var, double* __restrict__ count,
-                             double* __restrict__ acc, double batch_count, int cols, double eps,
+__global__ void merge_kernel(const float* __restrict__ x, double* __restrict__ mean, double* __restrict__ var,
+                             double* __restrict__ count, double* __restrict__ acc, double batch_count, int cols, double eps,
                              float* __restrict__ mean_f, float* __restrict__ rstd_f) {
   const double cnt = count[0];
   const double tot = cnt + batch_count;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     const double s = acc[c] / batch_count, q = acc[cols + c] / batch_count;
-    const double bm = (double)(float)mean[c] + s;   // shift was the running mean, rounded to float
+    const double bm = (double)x[c] + s;     // the shift was the batch's first row
     double bv = q - s * s;                  // np.var: population variance
     bv = bv > 0.0 ? bv : 0.0;
     const double delta = bm - mean[c];
@@ -173,8 +173,8 @@ int bd_rms_update(bd_rms* r, const float* x_dev, int64_t rows, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   long long grid = (long long)r->sm_count * 8;
   if (grid > rows) grid = rows;
-  moments_kernel<<<(int)grid, kMomThreads, 0, st>>>(x_dev, rows, r->cols, r->mean, r->acc);
-  merge_kernel<<<1, 256, 0, st>>>(r->mean, r->var, r->count, r->acc, (double)rows, r->cols, r->eps, r->mean_f, r->rstd_f);
+  moments_kernel<<<(int)grid, kMomThreads, 0, st>>>(x_dev, rows, r->cols, r->acc);
+  merge_kernel<<<1, 256, 0, st>>>(x_dev, r->mean, r->var, r->count, r->acc, (double)rows, r->cols, r->eps, r->mean_f, r->rstd_f);
   r->launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return rfail(BD_ECUDA, "bd_rms_update: %s", cudaGetErrorString(e));

@@ -2,8 +2,8 @@
 (tests/golden/normalizers.npz, produced by the unmodified `normalization.py` classes) and against the
 numpy oracle on larger seeded batches; the fused actor's normalise-on-load; MAPPO with `norm_obs`.
 
-Tolerances: statistics are merged in fp64 from float32 one-pass batch sums (shifted by the running
-mean) -> mean / var within 2e-6 relative of the reference's float32-numpy moments (numpy's own
+Tolerances: statistics are merged in fp64 from float32 one-pass batch sums (shifted by the batch's
+first row) -> mean / var within 2e-6 relative of the reference's float32-numpy moments (numpy's own
 float32 pairwise sums carry ~1e-7); normalised values are float32 -> 2e-5 absolute on O(1) outputs.
 """
 import os
@@ -64,14 +64,32 @@ def test_running_moments_match_oracle_on_large_batches(rows, shape):
     o = MeanStdNormalizerOracle(shape=shape, clip=5.0, epsilon=1e-8)
     n = MeanStdNormalizer(shape=shape, clip=5.0, epsilon=1e-8, device="cuda:0")
     scale, off = rng.uniform(0.01, 20, shape), rng.uniform(-100, 100, shape)     # |mean| >> std columns included
+    from oracle.normalization import RunningMeanStdOracle
+    tm = RunningMeanStdOracle(shape=shape)
     for t in range(3):
         x = (rng.standard_normal((rows,) + shape) * scale + off).astype(np.float32)
         yo = o(x)
         y = n(torch.as_tensor(x, device="cuda:0"))
-        assert _close(n.rms.mean.cpu().numpy(), o.rms.mean, 3e-6, 1e-6)
+        # The kernel follows the float64 value of the reference's formulas.  numpy reduces axis 0 of a float32
+        # array by sequential float32 accumulation, so the reference's own moments drift from that value with
+        # the batch size (measured at 65 536 rows: mean 2.6e-4 of |offset| + spread, variance 9 % on a column
+        # whose spread is 1e-4 of its offset); up to 4096 rows the drift stays below 8 sqrt(rows) 2^-24 and
+        # the oracle is compared directly.
+        tm.update(x.astype(np.float64))
+        mean, var = n.rms.mean.cpu().numpy(), n.rms.var.cpu().numpy()
+        assert _close(mean, tm.mean, 1e-6, 1e-6)
+        assert _close(var, tm.var, 2e-5, 1e-12)
         if rows > 1:
-            assert _close(n.rms.var.cpu().numpy(), o.rms.var, 2e-4, 1e-7)
-            assert _close(y.cpu().numpy(), yo, 3e-4, 3e-4)
+            yt = np.clip((x - tm.mean) / np.sqrt(tm.var + 1e-8), -5.0, 5.0)
+            assert np.all(np.abs(y.cpu().numpy() - yt) <= 3e-5 + 3e-5 * np.abs(yt) + 2e-6 * np.abs(off / scale))
+        if rows <= 4096:
+            loose = 8 * np.sqrt(rows) * 2.0 ** -24
+            assert np.all(np.abs(mean - o.rms.mean) <= 1e-6 + loose * (np.abs(off) + scale))
+            small = np.abs(off) < 100 * scale          # the reference's variance is only meaningful there
+            assert _close(var[small], o.rms.var[small], 1e-3, 1e-9)
+            if rows > 1:
+                ok = np.abs(y.cpu().numpy() - yo) <= 1e-3 + 1e-3 * np.abs(yo) + loose * (1 + np.abs(off / scale))
+                assert ok.all()
     assert n.rms._lib.bd_rms_launch_count(n.rms._h) == 3 * 3 + 0   # moments + merge + normalise per call
 
 
@@ -137,7 +155,7 @@ def test_mappo_with_obs_and_reward_normalisation(tmp_path):
     sd = torch.load(p, weights_only=False)
     assert set(sd["obs_normalizer"]) == {"mean", "var"} and sd["obs_normalizer"]["mean"].shape == (M, D)
     assert sd["obs"].shape == (N, M, D) and np.abs(sd["obs"]).max() <= 10.0
-    assert "actor.logstd" in sd["agent"]["ac"] and "critic.v_net.0.weight" in sd["agent"]["ac"]
+    assert "actor.logstd" in sd["agent"]["ac"] and "critic.v_net.fcs.0.weight" in sd["agent"]["ac"]
     algo2 = DeviceMAPPO(env, rollout_steps=24, hidden_dim=256, norm_obs=True, norm_reward=True, seed=9)
     algo2.load(p)
     ob = algo.obs[T]
