@@ -229,8 +229,14 @@ typedef struct bd_rms bd_rms;
 int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out);
 void bd_rms_destroy(bd_rms* r);
 /* RunningMeanStd.update (:34-58): batch mean / population variance over the `rows` axis of
- * x_dev (rows, cols) float, merged into the running statistics.  Two launches, stream ordered. */
+ * x_dev (rows, cols) float, merged into the running statistics.  Three launches, stream ordered. */
 int bd_rms_update(bd_rms* r, const float* x_dev, int64_t rows, void* stream);
+/* The two halves of bd_rms_update, for envs sharded over ranks: batch moments of the local rows into
+ * moments_dev = [mean(cols) | var(cols) | count] doubles (:37-39), then — after the caller has
+ * all-gathered every rank's moments into (parts, 2*cols+1) — update_from_moments (:44-58) with the
+ * moments of the union of the parts (combined in order, so every rank gets identical statistics). */
+int bd_rms_batch_moments(bd_rms* r, const float* x_dev, int64_t rows, double* moments_dev, void* stream);
+int bd_rms_merge_moments(bd_rms* r, const double* moments_dev, int parts, void* stream);
 /* y = clip((x - mean) / sqrt(var + eps), -clip, clip) (:84-88), y_dev may equal x_dev. */
 int bd_rms_normalize(bd_rms* r, const float* x_dev, float* y_dev, int64_t rows, float clip, void* stream);
 /* state_dict / load_state_dict (:90-96): any pointer may be NULL.  mean_f / rstd_f are the float

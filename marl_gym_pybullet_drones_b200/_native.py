@@ -26,7 +26,7 @@ EXPORTS = (
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
     "bd_actor_create", "bd_actor_destroy", "bd_actor_set_weights", "bd_actor_forward", "bd_actor_set_trace", "bd_actor_launch_count",
     "bd_actor_last_error", "bd_actor_set_input_norm",
-    "bd_rms_create", "bd_rms_destroy", "bd_rms_update", "bd_rms_normalize", "bd_rms_get", "bd_rms_set",
+    "bd_rms_create", "bd_rms_destroy", "bd_rms_update", "bd_rms_batch_moments", "bd_rms_merge_moments", "bd_rms_normalize", "bd_rms_get", "bd_rms_set",
     "bd_rms_launch_count", "bd_rms_last_error",
 )
 
@@ -134,6 +134,10 @@ def load():
     lib.bd_rms_destroy.restype = None
     lib.bd_rms_update.argtypes = [vp, vp, C.c_int64, vp]
     lib.bd_rms_update.restype = C.c_int
+    lib.bd_rms_batch_moments.argtypes = [vp, vp, C.c_int64, vp, vp]
+    lib.bd_rms_batch_moments.restype = C.c_int
+    lib.bd_rms_merge_moments.argtypes = [vp, vp, C.c_int, vp]
+    lib.bd_rms_merge_moments.restype = C.c_int
     lib.bd_rms_normalize.argtypes = [vp, vp, vp, C.c_int64, C.c_float, vp]
     lib.bd_rms_normalize.restype = C.c_int
     lib.bd_rms_get.argtypes = [vp, vp, vp, vp, vp, vp, vp]

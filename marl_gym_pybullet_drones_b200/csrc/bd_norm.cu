@@ -6,10 +6,11 @@
 // over the env axis, parallel-variance merge into the running statistics, then
 // clip((x - mean) / sqrt(var + eps), +-clip).
 //
-// Two kernels per update: `moments_kernel` reads the (rows x cols) batch once (HBM-bound; per-CTA
-// row slabs, coalesced along the columns, one fp64 atomic per column and CTA) and `merge_kernel`
-// (one CTA) folds the batch moments into mean / var / count in fp64 and emits float mean and
-// 1/sqrt(var + eps) vectors for fused consumers: the actor kernel normalises its input tile while it
+// Three kernels per update: `moments_kernel` reads the (rows x cols) batch once (HBM-bound; per-CTA
+// row slabs, coalesced along the columns, one fp64 atomic per column and CTA), `finalize_kernel`
+// turns the sums into [mean | var | count] (the unit ranks exchange: one small all-gather when the
+// envs are sharded over GPUs), and `merge_kernel` (one CTA) folds one or several such parts into
+// mean / var / count in fp64 and emits float mean and 1/sqrt(var + eps) vectors for fused consumers: the actor kernel normalises its input tile while it
 // converts it to bf16 (bd_actor_set_input_norm), so the normalised observations are never written
 // to HBM during the rollout.  `normalize_kernel` is the standalone form (evaluation, critic input).
 #include <cuda_runtime.h>
@@ -63,27 +64,55 @@ moments_kernel(const float* __restrict__ x, long long rows, int cols, double* __
   }
 }
 
-// RunningMeanStd.update_from_moments (normalization.py:44-58) in fp64; clears the accumulators
-__global__ void merge_kernel(const float* __restrict__ x, double* __restrict__ mean, double* __restrict__ var,
-                             double* __restrict__ count, double* __restrict__ acc, double batch_count, int cols, double eps,
-                             float* __restrict__ mean_f, float* __restrict__ rstd_f) {
-  const double cnt = count[0];
-  const double tot = cnt + batch_count;
+// batch mean / population variance / row count from the shifted sums; clears the accumulators.
+// out: [mean(cols) | var(cols) | count]
+__global__ void finalize_kernel(const float* __restrict__ x, double* __restrict__ acc, double batch_count, int cols,
+                                double* __restrict__ out) {
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     const double s = acc[c] / batch_count, q = acc[cols + c] / batch_count;
-    const double bm = (double)x[c] + s;     // the shift was the batch's first row
-    double bv = q - s * s;                  // np.var: population variance
-    bv = bv > 0.0 ? bv : 0.0;
-    const double delta = bm - mean[c];
-    const double new_mean = mean[c] + delta * batch_count / tot;
-    const double m2 = var[c] * cnt + bv * batch_count + delta * delta * cnt * batch_count / tot;
-    const double new_var = m2 / tot;
-    mean[c] = new_mean;
-    var[c] = new_var;
-    mean_f[c] = (float)new_mean;
-    rstd_f[c] = (float)(1.0 / sqrt(new_var + eps));
+    const double bv = q - s * s;              // np.var: population variance
+    out[c] = (double)x[c] + s;                // the shift was the batch's first row
+    out[cols + c] = bv > 0.0 ? bv : 0.0;
     acc[c] = 0.0;
     acc[cols + c] = 0.0;
+  }
+  if (threadIdx.x == 0) out[2 * cols] = batch_count;
+}
+
+// `parts` batch moments ([mean | var | count] each, e.g. one per rank) are first combined, in order,
+// into the moments of their union (Chan's parallel-variance formula = what np.mean / np.var of the
+// concatenated batch give), then folded into the running statistics exactly like
+// RunningMeanStd.update_from_moments (normalization.py:44-58).  All fp64.
+__global__ void merge_kernel(const double* __restrict__ parts_buf, int parts, double* __restrict__ mean,
+                             double* __restrict__ var, double* __restrict__ count, int cols, double eps,
+                             float* __restrict__ mean_f, float* __restrict__ rstd_f) {
+  const int stride = 2 * cols + 1;
+  const double cnt = count[0];
+  double batch_count = 0.0;
+  for (int p = 0; p < parts; ++p) batch_count += parts_buf[(size_t)p * stride + 2 * cols];
+  const double tot = cnt + batch_count;
+  if (batch_count > 0.0) {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      double bn = 0.0, bm = 0.0, bm2 = 0.0;
+      for (int p = 0; p < parts; ++p) {
+        const double* P = parts_buf + (size_t)p * stride;
+        const double n = P[2 * cols];
+        if (n <= 0.0) continue;
+        const double d = P[c] - bm, t = bn + n;
+        bm2 += P[cols + c] * n + d * d * bn * n / t;
+        bm += d * n / t;
+        bn = t;
+      }
+      const double bv = bm2 / bn;
+      const double delta = bm - mean[c];
+      const double new_mean = mean[c] + delta * batch_count / tot;
+      const double m2 = var[c] * cnt + bv * batch_count + delta * delta * cnt * batch_count / tot;
+      const double new_var = m2 / tot;
+      mean[c] = new_mean;
+      var[c] = new_var;
+      mean_f[c] = (float)new_mean;
+      rstd_f[c] = (float)(1.0 / sqrt(new_var + eps));
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) count[0] = tot;
@@ -115,7 +144,7 @@ __global__ void normalize_kernel(const float* __restrict__ x, float* __restrict_
 struct bd_rms {
   int device = 0, cols = 0, sm_count = 0;
   double eps = 1e-8;
-  double *mean = nullptr, *var = nullptr, *count = nullptr, *acc = nullptr;
+  double *mean = nullptr, *var = nullptr, *count = nullptr, *acc = nullptr, *part = nullptr;
   float *mean_f = nullptr, *rstd_f = nullptr;
   int64_t launches = 0;
 };
@@ -140,7 +169,7 @@ int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out)
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); };
   alloc((void**)&r->mean, cols * 8); alloc((void**)&r->var, cols * 8); alloc((void**)&r->count, 8);
-  alloc((void**)&r->acc, 2 * cols * 8); alloc((void**)&r->mean_f, cols * 4); alloc((void**)&r->rstd_f, cols * 4);
+  alloc((void**)&r->acc, 2 * cols * 8); alloc((void**)&r->part, (2 * cols + 1) * 8); alloc((void**)&r->mean_f, cols * 4); alloc((void**)&r->rstd_f, cols * 4);
   if (e == cudaSuccess) {   // RunningMeanStd.__init__ (:24-32): mean 0, var 1, count = epsilon
     double* ones = new (std::nothrow) double[cols];
     if (ones) {
@@ -153,7 +182,7 @@ int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out)
   }
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
-    cudaFree(r->mean); cudaFree(r->var); cudaFree(r->count); cudaFree(r->acc); cudaFree(r->mean_f); cudaFree(r->rstd_f);
+    cudaFree(r->mean); cudaFree(r->var); cudaFree(r->count); cudaFree(r->acc); cudaFree(r->part); cudaFree(r->mean_f); cudaFree(r->rstd_f);
     delete r;
     return rfail(BD_ECUDA, "bd_rms_create: %s", cudaGetErrorString(e));
   }
@@ -163,22 +192,40 @@ int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out)
 
 void bd_rms_destroy(bd_rms* r) {
   if (!r) return;
-  cudaFree(r->mean); cudaFree(r->var); cudaFree(r->count); cudaFree(r->acc); cudaFree(r->mean_f); cudaFree(r->rstd_f);
+  cudaFree(r->mean); cudaFree(r->var); cudaFree(r->count); cudaFree(r->acc); cudaFree(r->part); cudaFree(r->mean_f); cudaFree(r->rstd_f);
   delete r;
+}
+
+int bd_rms_batch_moments(bd_rms* r, const float* x_dev, int64_t rows, double* moments_dev, void* stream) {
+  if (!r || !x_dev || !moments_dev) return rfail(BD_EINVAL, "bd_rms_batch_moments: null argument");
+  if (rows <= 0) return rfail(BD_EINVAL, "bd_rms_batch_moments: rows must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long grid = (long long)r->sm_count * 8;
+  if (grid > rows) grid = rows;
+  moments_kernel<<<(int)grid, kMomThreads, 0, st>>>(x_dev, rows, r->cols, r->acc);
+  finalize_kernel<<<1, 256, 0, st>>>(x_dev, r->acc, (double)rows, r->cols, moments_dev);
+  r->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return rfail(BD_ECUDA, "bd_rms_batch_moments: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+int bd_rms_merge_moments(bd_rms* r, const double* moments_dev, int parts, void* stream) {
+  if (!r || !moments_dev || parts < 1) return rfail(BD_EINVAL, "bd_rms_merge_moments: moments and parts >= 1 are required");
+  merge_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(moments_dev, parts, r->mean, r->var, r->count, r->cols, r->eps,
+                                                    r->mean_f, r->rstd_f);
+  r->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return rfail(BD_ECUDA, "bd_rms_merge_moments: %s", cudaGetErrorString(e));
+  return BD_OK;
 }
 
 int bd_rms_update(bd_rms* r, const float* x_dev, int64_t rows, void* stream) {
   if (!r || !x_dev) return rfail(BD_EINVAL, "bd_rms_update: null argument");
   if (rows <= 0) return BD_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  long long grid = (long long)r->sm_count * 8;
-  if (grid > rows) grid = rows;
-  moments_kernel<<<(int)grid, kMomThreads, 0, st>>>(x_dev, rows, r->cols, r->acc);
-  merge_kernel<<<1, 256, 0, st>>>(x_dev, r->mean, r->var, r->count, r->acc, (double)rows, r->cols, r->eps, r->mean_f, r->rstd_f);
-  r->launches += 2;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return rfail(BD_ECUDA, "bd_rms_update: %s", cudaGetErrorString(e));
-  return BD_OK;
+  int rc = bd_rms_batch_moments(r, x_dev, rows, r->part, stream);
+  if (rc != BD_OK) return rc;
+  return bd_rms_merge_moments(r, r->part, 1, stream);
 }
 
 int bd_rms_normalize(bd_rms* r, const float* x_dev, float* y_dev, int64_t rows, float clip, void* stream) {

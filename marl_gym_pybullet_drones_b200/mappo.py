@@ -288,6 +288,7 @@ class DeviceMAPPO:
         mb = min(int(cfg["mini_batch_size"]), n)
         num_mb = n // mb
         stats = torch.zeros(5, device=self.device)
+        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         for _ in range(int(cfg["opt_epochs"])):
             perm = torch.randperm(n, device=self.device, generator=self.gen)
             for i in range(num_mb):
@@ -302,6 +303,9 @@ class DeviceMAPPO:
                 policy_loss = -torch.min(ratio * ad, clip_adv).mean()
                 entropy_loss = -dist.entropy().sum(-1).mean()
                 approx_kl = (lp_old - lp).mean().detach()
+                if world > 1:   # every rank must take the same gate decision or the replicas drift apart
+                    torch.distributed.all_reduce(approx_kl)
+                    approx_kl = approx_kl / world
                 self.actor_opt.zero_grad(set_to_none=True)
                 (policy_loss + cfg["entropy_coef"] * entropy_loss).backward()
                 allreduce_gradients(self.ac.actor_parameters())

@@ -14,6 +14,7 @@ import ctypes as C
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _native
 
@@ -68,7 +69,28 @@ class RunningMeanStd:
         if arr.dtype != torch.float32 or not arr.is_contiguous() or arr.device != self.device:
             raise ValueError("arr must be a contiguous float32 CUDA tensor")
         rows = arr.numel() // self.cols
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # envs sharded over ranks: the batch is the union of every rank's rows (one small all-gather)
+            mine = self.batch_moments(arr)
+            parts = torch.empty((dist.get_world_size(), mine.numel()), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(parts, mine)
+            self.merge_moments(parts)
+            return
         self._check(self._lib.bd_rms_update(self._h, C.c_void_p(arr.data_ptr()), rows, self._stream()), "bd_rms_update")
+
+    def batch_moments(self, arr: torch.Tensor) -> torch.Tensor:
+        """[mean(cols) | var(cols) | count] of the local batch (float64, on the device)."""
+        out = torch.empty(2 * self.cols + 1, dtype=torch.float64, device=self.device)
+        self._check(self._lib.bd_rms_batch_moments(self._h, C.c_void_p(arr.data_ptr()), arr.numel() // self.cols,
+                                                   C.c_void_p(out.data_ptr()), self._stream()), "bd_rms_batch_moments")
+        return out
+
+    def merge_moments(self, parts: torch.Tensor):
+        """Fold (parts, 2*cols+1) batch moments — combined as one batch — into the running statistics."""
+        if parts.dtype != torch.float64 or not parts.is_contiguous() or parts.shape[-1] != 2 * self.cols + 1:
+            raise ValueError("parts must be contiguous float64 (parts, 2*cols+1)")
+        self._check(self._lib.bd_rms_merge_moments(self._h, C.c_void_p(parts.data_ptr()), parts.numel() // parts.shape[-1],
+                                                   self._stream()), "bd_rms_merge_moments")
 
     def normalize(self, x: torch.Tensor, clip: float, out: torch.Tensor = None) -> torch.Tensor:
         if x.dtype != torch.float32 or not x.is_contiguous() or x.device != self.device:
@@ -174,6 +196,13 @@ class RewardStdNormalizer(BaseNormalizer):
             self.ret = self.ret * self.gamma + x
             r64 = self.ret.double()
             bm, bv, bc = r64.mean(), r64.var(unbiased=False), float(r64.numel())
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # moments of the union of every rank's returns
+                p = torch.stack([r64.sum(), (r64 * r64).sum(), torch.tensor(bc, dtype=torch.float64, device=r64.device)])
+                dist.all_reduce(p)
+                bc = p[2]                       # stays on the device: no host sync in the rollout
+                bm = p[0] / p[2]
+                bv = (p[1] / p[2] - bm * bm).clamp_min(0.0)
             delta = bm - self.mean
             tot = self.count + bc
             m2 = self.var * self.count + bv * bc + delta * delta * self.count * bc / tot

@@ -90,7 +90,30 @@ def test_running_moments_match_oracle_on_large_batches(rows, shape):
             if rows > 1:
                 ok = np.abs(y.cpu().numpy() - yo) <= 1e-3 + 1e-3 * np.abs(yo) + loose * (1 + np.abs(off / scale))
                 assert ok.all()
-    assert n.rms._lib.bd_rms_launch_count(n.rms._h) == 3 * 3 + 0   # moments + merge + normalise per call
+    assert n.rms._lib.bd_rms_launch_count(n.rms._h) == 3 * 4   # moments + finalize + merge + normalise per call
+
+
+def test_moments_of_sharded_batches_merge_like_one_batch():
+    """What ranks exchange when envs are sharded (bd_rms_batch_moments -> all-gather -> bd_rms_merge_moments):
+    merging the parts of a batch == updating with the whole batch (== np.mean / np.var of the concatenation)."""
+    from marl_gym_pybullet_drones_b200.normalization import RunningMeanStd
+    rng = np.random.default_rng(5)
+    shape = (2, 72)
+    whole, parts = RunningMeanStd(shape=shape, device="cuda:0"), RunningMeanStd(shape=shape, device="cuda:0")
+    for t in range(3):
+        x = torch.as_tensor((rng.standard_normal((600,) + shape) * 3 + rng.uniform(-9, 9, shape)).astype(np.float32),
+                            device="cuda:0")
+        whole.update(x)
+        cut = [0, 100, 101, 350, 600]          # ragged shards, one of a single row
+        m = torch.stack([parts.batch_moments(x[a:b].contiguous()) for a, b in zip(cut[:-1], cut[1:])])
+        assert m[:, -1].tolist() == [100.0, 1.0, 249.0, 250.0]
+        parts.merge_moments(m)
+        assert _close(parts.mean.cpu().numpy(), whole.mean.cpu().numpy(), 1e-9, 1e-9)
+        assert _close(parts.var.cpu().numpy(), whole.var.cpu().numpy(), 1e-7, 1e-12)
+        assert parts.count == whole.count
+    m1, r1 = parts.stats()
+    m2, r2 = whole.stats()
+    assert torch.allclose(m1, m2, atol=1e-6) and torch.allclose(r1, r2, rtol=1e-6)
 
 
 def test_fused_actor_normalises_on_load():
