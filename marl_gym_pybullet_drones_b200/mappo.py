@@ -54,6 +54,7 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
+    "matmul_precision": "tf32",   # PPO-update GEMMs on the tensor cores (fp32 storage / accumulation); "fp32" = CUDA cores
     "norm_obs": False,            # mappo/config.py:7-10; True in the Spiral config (env_select_learn_mappo.py:278)
     "norm_reward": False,
     "clip_obs": 10,
@@ -277,6 +278,14 @@ class DeviceMAPPO:
     # ------------------------------------------------------------------- update
     def update(self) -> Dict[str, float]:
         """`MAPPOAgent.update` (agent.py:702-772) on device tensors."""
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.cfg["matmul_precision"] == "tf32"
+        try:
+            return self._update()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _update(self) -> Dict[str, float]:
         cfg = self.cfg
         T, N, M, D, A = self.T, self.N, self.M, self.D, self.A
         n = T * N

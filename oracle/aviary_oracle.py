@@ -30,9 +30,11 @@ Restated reference locations (all under `gym_pybullet_drones/envs/`):
   BaseAviary.py:815-892    _dynamics, _integrateQ    -> `_dynamics`, `integrate_q`
   BaseRLAviary.py:66-67,132-156,160-239,284-322  action buffer, RPM maps, KIN obs
   HoverAviary.py:51-131, MultiHoverAviary.py:58-285, SpiralAviary.py:20-205  tasks
+  MeetupAviary.py:56-154, FlockAviary.py:56-189, LeaderFollowerAviary.py:55-145  swarm tasks
   safe_control_gym/envs/gym_pybullet_drones/base_aviary.py:462-511  Euler-angle integrator variant
   safe_control_gym/envs/env_wrappers/vectorized_env/subproc_vec_env.py:186-207  auto-reset
 """
+import math
 from collections import deque
 
 import numpy as np
@@ -100,7 +102,8 @@ class OracleAviary:
     """One environment: M drones, explicit dynamics, KIN observation, RPM/ONE_D_RPM action.
 
     task: 'hover' (HoverAviary), 'multihover' (MultiHoverAviary), 'spiral'
-    (SpiralFormationAviary).  `act`: 'rpm' | 'one_d_rpm' | 'pid' | 'vel' | 'one_d_pid'
+    (SpiralFormationAviary), 'meetup' (MeetupAviary), 'flock' (FlockAviary),
+    'leaderfollower' (LeaderFollowerAviary).  `act`: 'rpm' | 'one_d_rpm' | 'pid' | 'vel' | 'one_d_pid'
     (the last three through `oracle/dsl_pid.py`, BaseRLAviary.py:73-78,193-235).
     """
 
@@ -409,6 +412,54 @@ class OracleAviary:
         if self.task == "hover":                                              # HoverAviary.py:77-79
             s = self.state_vector(0)
             return max(0, 2 - np.linalg.norm(self.TARGET_POS - s[0:3]) ** 4)
+        if self.task == "meetup":                                             # MeetupAviary.py:74-95
+            total_reward = 0
+            states = np.array([self.state_vector(i) for i in range(M)])
+            for i in range(int(M / 2)):
+                pair_reward = -1 * np.linalg.norm(states[i, 0:3] - states[M - 1 - i, 0:3]) ** 2
+                total_reward += pair_reward * 2
+            return total_reward
+        if self.task == "leaderfollower":                                     # LeaderFollowerAviary.py:72-99
+            total_reward = 0
+            states = np.array([self.state_vector(i) for i in range(M)])
+            total_reward += -1 * np.linalg.norm(np.array([0, 0, 0.5]) - states[0, 0:3]) ** 2
+            for i in range(1, M):
+                target_pos = np.array([states[i, 0], states[i, 1], states[0, 2]])
+                total_reward += -(1 / M) * np.linalg.norm(target_pos - states[i, 0:3]) ** 2
+            return total_reward
+        if self.task == "flock":                                              # FlockAviary.py:75-150
+            states = np.array([self.state_vector(i) for i in range(M)])
+            pos, vel = states[None, :, 0:3].copy(), states[None, :, 10:13].copy()
+            ali = 0
+            EPSILON = 1e-3
+            linear_vel_norm = np.linalg.norm(vel, axis=2)
+            for i in range(M):
+                for j in range(M):
+                    if j != i:
+                        d = np.einsum('ij,ij->i', vel[:, i, :], vel[:, j, :])
+                        ali += (d / (linear_vel_norm[:, i] + EPSILON) / (linear_vel_norm[:, j] + EPSILON))
+            if M > 1:
+                ali /= (M * (M - 1))
+            else:
+                ali = np.array([0.0])
+            cof_v = np.mean(vel, axis=1)
+            avg_flock_linear_speed = np.linalg.norm(cof_v, axis=-1)
+            avg_flock_spac_rew = 0.0
+            var_flock_spacing = np.array([0.0])
+            if M > 1:
+                whole_flock_spacing = []
+                for i in range(M):
+                    flck_neighbor_pos = np.delete(pos, [i], 1)
+                    diff = flck_neighbor_pos - np.reshape(pos[:, i, :], (pos[:, i, :].shape[0], 1, -1))
+                    whole_flock_spacing.append(np.amin(np.linalg.norm(diff, axis=-1), axis=-1))
+                whole_flock_spacing = np.stack(whole_flock_spacing, axis=-1)
+                avg_flock_spacing = np.mean(whole_flock_spacing, axis=-1)
+                var_flock_spacing = np.var(whole_flock_spacing, axis=-1)
+                if 1.0 < avg_flock_spacing[0] < 3.0:                          # FLOCK_SPACING_MIN / MAX
+                    avg_flock_spac_rew = 0.0
+                else:
+                    avg_flock_spac_rew = min(math.fabs(avg_flock_spacing[0] - 1.0), math.fabs(avg_flock_spacing[0] - 3.0))
+            return ali[0] + avg_flock_linear_speed[0] - avg_flock_spac_rew - var_flock_spacing[0]
         if self.task == "multihover":                                         # MultiHoverAviary.py:128-186
             reward = 0.0
             for i in range(M):
@@ -449,6 +500,14 @@ class OracleAviary:
         if self.task == "hover":                                              # HoverAviary.py:92-96
             s = self.state_vector(0)
             return bool(np.linalg.norm(self.TARGET_POS - s[0:3]) < .0001)
+        if self.task == "meetup":                                             # MeetupAviary.py:99-121
+            states = np.array([self.state_vector(i) for i in range(self.NUM_DRONES)])
+            for i in range(int(self.NUM_DRONES / 2)):
+                if np.linalg.norm(states[i, 0:3] - states[self.NUM_DRONES - 1 - i, 0:3]) > 0.1:
+                    return False
+            return True
+        if self.task in ("flock", "leaderfollower"):                          # FlockAviary.py:154-165, LeaderFollower:103-115
+            return False
         if self.task == "multihover":                                         # MultiHoverAviary.py:216-241
             terminated, reasons = False, []
             for i in range(self.NUM_DRONES):
@@ -476,10 +535,19 @@ class OracleAviary:
             s = self.state_vector(0)
             if (abs(s[0]) > 1.5 or abs(s[1]) > 1.5 or s[2] > 2.0 or abs(s[7]) > .4 or abs(s[8]) > .4):
                 return True
+        if self.task in ("meetup", "flock", "leaderfollower"):
+            # MeetupAviary.py:125-154 (also z < 0.1), FlockAviary.py:169-189, LeaderFollowerAviary.py:119-145
+            xy, zmax = {"meetup": (5.0, 3.0), "flock": (10.0, 10.0), "leaderfollower": (2.0, 2.0)}[self.task]
+            for i in range(self.NUM_DRONES):
+                s = self.state_vector(i)
+                if (abs(s[0]) > xy or abs(s[1]) > xy or s[2] > zmax
+                        or (self.task == "meetup" and s[2] < 0.1)
+                        or abs(s[7]) > .4 or abs(s[8]) > .4):
+                    return True
         return bool(self.step_counter / self.PYB_FREQ > self.EPISODE_LEN_SEC)  # MultiHover:268, Spiral:196
 
     def _compute_info(self):
-        if self.task == "hover":
+        if self.task in ("hover", "meetup", "flock", "leaderfollower"):
             return {"answer": 42}
         if self.task == "multihover":
             return {"answer": 42, "termination_reasons": self.termination_reasons}

@@ -246,4 +246,8 @@ def reference_classes():
             "gym_pybullet_drones.envs.MultiHoverAviary").MultiHoverAviary,
         "SpiralFormationAviary": importlib.import_module(
             "gym_pybullet_drones.envs.SpiralAviary").SpiralFormationAviary,
+        "MeetupAviary": importlib.import_module("gym_pybullet_drones.envs.MeetupAviary").MeetupAviary,
+        "FlockAviary": importlib.import_module("gym_pybullet_drones.envs.FlockAviary").FlockAviary,
+        "LeaderFollowerAviary": importlib.import_module(
+            "gym_pybullet_drones.envs.LeaderFollowerAviary").LeaderFollowerAviary,
     }

@@ -62,7 +62,7 @@ if rank == 0:
     print(f"world={world}  weight spread {dw:.3e}  obs-normaliser mean/var spread {dm:.3e}/{dv:.3e}  reward-var spread {dr:.3e}  "
           f"rollout spread {dobs:.3e} (must be > 0 for world > 1)")
     print(f"{args.iters * 32 * args.envs_per_gpu * world / dt:.3e} env-steps/s over {world} GPUs "
-          f"(count {algo.obs_normalizer.rms.count:.1f} = {args.iters * 33 * args.envs_per_gpu * world} rows + 1e-4)")
+          f"(count {algo.obs_normalizer.rms.count:.1f} = {(args.iters * 32 + 1) * args.envs_per_gpu * world} rows + 1e-4)")
     assert dw == 0.0 and dm == 0.0 and dv == 0.0 and dr == 0.0, "replicas diverged"
     assert world == 1 or dobs > 0.0
 if world > 1:

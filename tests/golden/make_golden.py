@@ -32,7 +32,8 @@ from oracle import ref_harness as rh  # noqa: E402
 def _make_env(c, task, **kw):
     E = c["enums"]
     cls = {"hover": c["HoverAviary"], "multihover": c["MultiHoverAviary"],
-           "spiral": c["SpiralFormationAviary"]}[task]
+           "spiral": c["SpiralFormationAviary"], "meetup": c["MeetupAviary"], "flock": c["FlockAviary"],
+           "leaderfollower": c["LeaderFollowerAviary"]}[task]
     kw = dict(kw)
     kw["drone_model"] = E.DroneModel(kw.pop("drone_model", "cf2x"))
     kw["act"] = E.ActionType(kw.pop("act", "rpm"))

@@ -108,8 +108,10 @@ def test_moments_of_sharded_batches_merge_like_one_batch():
         m = torch.stack([parts.batch_moments(x[a:b].contiguous()) for a, b in zip(cut[:-1], cut[1:])])
         assert m[:, -1].tolist() == [100.0, 1.0, 249.0, 250.0]
         parts.merge_moments(m)
-        assert _close(parts.mean.cpu().numpy(), whole.mean.cpu().numpy(), 1e-9, 1e-9)
-        assert _close(parts.var.cpu().numpy(), whole.var.cpu().numpy(), 1e-7, 1e-12)
+        # float32 partial sums are grouped differently in the two routes: ~2^-24 per accumulated row slab
+        assert _close(parts.mean.cpu().numpy(), whole.mean.cpu().numpy(), 1e-6, 1e-6)
+        assert _close(parts.var.cpu().numpy(), whole.var.cpu().numpy(), 1e-5, 1e-12)
+        xt = x.double().cpu().numpy()
         assert parts.count == whole.count
     m1, r1 = parts.stats()
     m2, r2 = whole.stats()
