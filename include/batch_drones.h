@@ -36,7 +36,9 @@ extern "C" {
 
 #define BD_VERSION 1
 
-enum { BD_TASK_HOVER = 0, BD_TASK_MULTIHOVER = 1, BD_TASK_SPIRAL = 2 };
+enum { BD_TASK_HOVER = 0, BD_TASK_MULTIHOVER = 1, BD_TASK_SPIRAL = 2,
+       /* envs/MeetupAviary.py:74-154, FlockAviary.py:75-189, LeaderFollowerAviary.py:72-145 */
+       BD_TASK_MEETUP = 3, BD_TASK_FLOCK = 4, BD_TASK_LEADERFOLLOWER = 5 };
 /* ActionType (utils/enums.py:35-41).  PID / VEL / ONE_D_PID run the reference's DSLPIDControl
  * (control/DSLPIDControl.py:82-246) inside the step kernel, one controller per drone. */
 enum { BD_ACT_RPM = 0, BD_ACT_ONE_D_RPM = 1, BD_ACT_PID = 2, BD_ACT_VEL = 3, BD_ACT_ONE_D_PID = 4 };
@@ -81,7 +83,7 @@ typedef struct bd_config {
                                memory; 0 = reference behaviour, the controllers are built once in
                                BaseRLAviary.__init__ (:73-78) and never reset by env.reset()   */
   uint64_t seed;            /* Philox key for BD_RESET_JITTER_PHILOX                  */
-  double episode_len_sec;   /* 8 (hover, multihover) / 12 (spiral)                    */
+  double episode_len_sec;   /* 12 (spiral) / 8 (every other task)                     */
   /* airframe */
   double mass, arm, kf, km, ixx, iyy, izz, g;
   double thrust2weight, gnd_eff_coeff, prop_radius, drag_coeff_xy, drag_coeff_z;

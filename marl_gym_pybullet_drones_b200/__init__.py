@@ -6,7 +6,8 @@ Import map (reference name -> here):
 * `gym_pybullet_drones.utils.enums`            -> `.enums`
 * `BaseAviary` constants / URDF parser          -> `.constants`
 * N aviaries inside `SubprocVecEnv`             -> `.batch_aviary.BatchAviary` (device tensors)
-* `HoverAviary`, `MultiHoverAviary`, `SpiralFormationAviary` (Gymnasium API) -> `.envs`
+* `HoverAviary`, `MultiHoverAviary`, `SpiralFormationAviary`, `MeetupAviary`, `FlockAviary`,
+  `LeaderFollowerAviary` (Gymnasium API) -> `.envs`
 * `make_vec_envs`, `VecRecordEpisodeStatistics` -> `.vec_env`
 
 Importing the package does not need a GPU or torch; constructing an aviary does
@@ -19,12 +20,14 @@ __all__ = [
     "ActionType", "DroneModel", "ImageType", "ObservationType", "Physics",
     "DroneConstants", "drone_constants", "parse_urdf",
     "BatchAviary", "StepResult", "HoverAviary", "MultiHoverAviary", "SpiralFormationAviary",
+    "MeetupAviary", "FlockAviary", "LeaderFollowerAviary",
     "BatchVecEnv", "VecRecordEpisodeStatistics", "make_vec_envs", "DeviceMAPPO",
 ]
 
 _LAZY = {
     "BatchAviary": ".batch_aviary", "StepResult": ".batch_aviary",
     "HoverAviary": ".envs", "MultiHoverAviary": ".envs", "SpiralFormationAviary": ".envs",
+    "MeetupAviary": ".envs", "FlockAviary": ".envs", "LeaderFollowerAviary": ".envs",
     "BatchVecEnv": ".vec_env", "VecRecordEpisodeStatistics": ".vec_env", "make_vec_envs": ".vec_env",
     "DeviceMAPPO": ".mappo",
 }

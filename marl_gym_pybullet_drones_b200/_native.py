@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbatchdrones.so")
 
-BD_TASK = {"hover": 0, "multihover": 1, "spiral": 2}
+BD_TASK = {"hover": 0, "multihover": 1, "spiral": 2, "meetup": 3, "flock": 4, "leaderfollower": 5}
 BD_ACT = {"rpm": 0, "one_d_rpm": 1, "pid": 2, "vel": 3, "one_d_pid": 4}
 BD_MODEL = {"cf2x": 0, "cf2p": 1, "racer": 2}
 BD_PRECISION = {"fp32": 0, "fp64": 1}

@@ -26,7 +26,7 @@ from .constants import DroneConstants, drone_constants
 from .enums import ActionType, DroneModel, ObservationType, Physics, physics_aero_flags
 from .spaces import Box
 
-_TASKS = ("hover", "multihover", "spiral")
+_TASKS = ("hover", "multihover", "spiral", "meetup", "flock", "leaderfollower")
 
 
 class StepResult(NamedTuple):

@@ -128,6 +128,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.sp_omega = (R)(c.spiral_period != 0.0 ? 2 * 3.14159265358979323846 / c.spiral_period : 0.0);
   P.sp_vz = (R)c.height_rate; P.sp_cx = (R)c.target_center[0]; P.sp_cy = (R)c.target_center[1];
   P.pyb_freq = (double)c.pyb_freq; P.episode_len = c.episode_len_sec;
+  P.task = c.task;
   {  // integer form of `step_counter / PYB_FREQ > EPISODE_LEN_SEC` (MultiHoverAviary.py:268), same fp64 division
     long long k = (long long)(c.episode_len_sec * c.pyb_freq) - 2;
     if (k < 0) k = 0;
@@ -236,7 +237,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (cfg->n_envs < 1) return fail(BD_EINVAL, "bd_create: n_envs must be >= 1");
   if (cfg->n_drones < 1 || cfg->n_drones > bd::kMaxDrones)
     return fail(BD_EINVAL, "bd_create: n_drones must be in [1,%d]", bd::kMaxDrones);
-  if (cfg->task < 0 || cfg->task > 2) return fail(BD_EINVAL, "bd_create: unknown task %d", cfg->task);
+  if (cfg->task < 0 || cfg->task > BD_TASK_LEADERFOLLOWER) return fail(BD_EINVAL, "bd_create: unknown task %d", cfg->task);
   if (cfg->task == BD_TASK_HOVER && cfg->n_drones != 1)
     return fail(BD_EINVAL, "bd_create: the hover task is single-drone (HoverAviary.py:54)");
   if (cfg->act_type < BD_ACT_RPM || cfg->act_type > BD_ACT_ONE_D_PID)
@@ -279,7 +280,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   h->spec.act_a = h->A;
   h->spec.precision = cfg->precision;
   h->spec.device = cfg->device;
-  h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel || pid_act) ? 1 : 0;
+  const bool swarm = cfg->task >= BD_TASK_MEETUP;   // coupled rewards: generic kernel only
+  h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel || pid_act || swarm) ? 1 : 0;
   {
     // kernel selection: the fast tile kernel covers the throughput configurations
     // (float, plain DYN, M a power of two <= 32); everything else runs the two-role CTA
@@ -290,13 +292,13 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     // the fast kernel also carries downwash alone (shuffle exchange inside the env's lane group)
     const bool fast_aero = cfg->aero_flags == 0 || cfg->aero_flags == BD_AERO_DW;
     const bool plain = fast_aero && cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
-    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act) ? 1 : 0;
+    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act && !swarm) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
   }
 
-  const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D);
+  const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D, cfg->task);
   cudaDeviceProp prop;
   cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }

@@ -10,7 +10,10 @@
 
 namespace bd {
 
-enum { TASK_HOVER = 0, TASK_MULTIHOVER = 1, TASK_SPIRAL = 2 };
+enum { TASK_HOVER = 0, TASK_MULTIHOVER = 1, TASK_SPIRAL = 2,
+       // Meetup / Flock / LeaderFollower: rewards couple the drones of an env; one template instantiation
+       // (TASK_SWARM) that branches on Params::task (warp-uniform)
+       TASK_SWARM = 3, TASK_MEETUP = 3, TASK_FLOCK = 4, TASK_LEADERFOLLOWER = 5 };
 enum { MODEL_CF2X = 0, MODEL_CF2P = 1, MODEL_RACE = 2 };
 enum { AERO_GND = 1, AERO_DRAG = 2, AERO_DW = 4 };
 enum { RESET_FIXED = 0, RESET_PHILOX = 1, RESET_BUFFER = 2 };
@@ -447,6 +450,83 @@ __device__ __forceinline__ void task_terms(const Params<R>& P, const Drone<R>& d
     contrib = (R(1.0) * r_pos + R(2.0) * r_vel) + R(1.0) * r_tan;               // :179
     if (d.pz < R(0.05) || d.pz > R(3.0)) flags |= 1;                             // :188-190
   }
+}
+
+// Swarm tasks: per-drone part of the coupled reward / flags.  `ep`, `ev` = final positions / velocities
+// of this env's M drones in shared memory.  flags bit1: truncation bound hit, bit2: my pair has not met.
+//   MeetupAviary.py:74-154, FlockAviary.py:75-189, LeaderFollowerAviary.py:72-145
+template <typename R>
+__device__ __forceinline__ void swarm_terms(const Params<R>& P, const R* ep, const R* ev, int M, int drone,
+                                            const Drone<R>& d, R roll, R pitch, R& contrib, R& aux, int& flags) {
+  contrib = R(0); aux = R(0); flags = 0;
+  const bool tilt = abs_(roll) > R(.4) || abs_(pitch) > R(.4);
+  if (P.task == TASK_MEETUP) {
+    if (drone < M / 2) {                                                         // :88-93
+      const R* q = ep + (size_t)(M - 1 - drone) * 3;
+      const R dx = d.px - q[0], dy = d.py - q[1], dz = d.pz - q[2];
+      const R dist = sqrt_(dx * dx + dy * dy + dz * dz);
+      contrib = (R(-1) * (dist * dist)) * R(2);
+      if (dist > R(0.1)) flags |= 4;                                             // :115-118
+    }
+    if (abs_(d.px) > R(5.0) || abs_(d.py) > R(5.0) || d.pz > R(3.0) || d.pz < R(0.1) || tilt) flags |= 2;   // :142-147
+  } else if (P.task == TASK_LEADERFOLLOWER) {
+    if (drone == 0) {                                                            // :88
+      const R ex = R(0) - d.px, ey = R(0) - d.py, ez = R(0.5) - d.pz;
+      const R n = sqrt_(ex * ex + ey * ey + ez * ez);
+      contrib = R(-1) * (n * n);
+    } else {                                                                     // :91-97: target (x_i, y_i, z_leader)
+      const R dz = ep[2] - d.pz;
+      const R n = sqrt_(dz * dz);
+      contrib = -(R(1) / R(M)) * (n * n);
+    }
+    if (abs_(d.px) > R(2.0) || abs_(d.py) > R(2.0) || d.pz > R(2.0) || tilt) flags |= 2;   // :135-140
+  } else {                                                                       // Flock
+    const R eps = R(1e-3);
+    const R ni = sqrt_(d.vx * d.vx + d.vy * d.vy + d.vz * d.vz);
+    R ali = R(0), sp = R(0);
+    bool first = true;
+    for (int j = 0; j < M; ++j) {
+      if (j == drone) continue;
+      const R* pj = ep + (size_t)j * 3;
+      const R* vj = ev + (size_t)j * 3;
+      const R nj = sqrt_(vj[0] * vj[0] + vj[1] * vj[1] + vj[2] * vj[2]);
+      const R dot = d.vx * vj[0] + d.vy * vj[1] + d.vz * vj[2];
+      ali += dot / (ni + eps) / (nj + eps);                                      // :98-103
+      const R dx = pj[0] - d.px, dy = pj[1] - d.py, dz = pj[2] - d.pz;
+      const R dist = sqrt_(dx * dx + dy * dy + dz * dz);
+      sp = (first || dist < sp) ? dist : sp;                                     // :121-125 nearest neighbour
+      first = false;
+    }
+    contrib = ali;
+    aux = sp;
+    if (abs_(d.px) > R(10.0) || abs_(d.py) > R(10.0) || d.pz > R(10.0) || tilt) flags |= 2;   // :181-184
+  }
+}
+
+// env-level reward of the swarm tasks from the per-drone parts (run by the env's first drone)
+template <typename R>
+__device__ __forceinline__ R swarm_reward(const Params<R>& P, int M, const R* part, const R* aux, const R* ev) {
+  R sum = R(0);
+  for (int i = 0; i < M; ++i) sum += part[i];
+  if (P.task != TASK_FLOCK) return sum;
+  R cx = R(0), cy = R(0), cz = R(0);
+  for (int i = 0; i < M; ++i) { cx += ev[i * 3]; cy += ev[i * 3 + 1]; cz += ev[i * 3 + 2]; }
+  cx /= R(M); cy /= R(M); cz /= R(M);                                            // :111-112 centre-of-flock velocity
+  const R speed = sqrt_(cx * cx + cy * cy + cz * cz);
+  if (M == 1) return speed;                                                      // ali = spacing terms = 0 (:106-108,115-117)
+  const R ali = sum / R(M * (M - 1));
+  R avg = R(0);
+  for (int i = 0; i < M; ++i) avg += aux[i];
+  avg /= R(M);
+  R var = R(0);
+  for (int i = 0; i < M; ++i) { const R e = aux[i] - avg; var += e * e; }
+  var /= R(M);                                                                   // np.var (:131)
+  R pen = R(0);
+  if (!(R(1.0) < avg && avg < R(3.0))) {                                         // :137-141
+    const R a = abs_(avg - R(1.0)), b = abs_(avg - R(3.0));
+    pen = a < b ? a : b;
+  }
+  return ((ali + speed) - pen) - var;                                            // :145
 }
 
 // ------------------------------------------------ DSL PID controller (ActionType.PID / VEL / ONE_D_PID)

@@ -63,6 +63,8 @@ step_kernel(const __grid_constant__ Params<R> P) {
   R* spos = sred + kBlock;                                                    // [kBlock][3]
   int* sflag = reinterpret_cast<int*>(spos + 3 * kBlock);                     // [kBlock]
   int* sdone = sflag + kBlock;                                                // [kBlock]
+  R* svel = reinterpret_cast<R*>(sdone + kBlock);                             // [kBlock][3]  (swarm tasks only)
+  R* saux = svel + 3 * kBlock;                                                // [kBlock]     (swarm tasks only)
   float* myrow = tile_s + (size_t)tid * D;
   const bool vec = (A == 4) && ((D & 3) == 0);
 
@@ -306,7 +308,19 @@ step_kernel(const __grid_constant__ Params<R> P) {
     myrow[3] = (float)roll; myrow[4] = (float)pitch; myrow[5] = (float)yaw;
     myrow[6] = (float)d.vx; myrow[7] = (float)d.vy; myrow[8] = (float)d.vz;
     myrow[9] = (float)avx; myrow[10] = (float)avy; myrow[11] = (float)avz;
-    task_terms<R, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
+    if constexpr (TASK != TASK_SWARM)
+      task_terms<R, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
+  }
+  if constexpr (TASK == TASK_SWARM) {
+    // rewards couple the env's drones: stage final positions / velocities, then per-drone parts in parallel
+    __syncthreads();   // the last substep's downwash loop may still be reading spos
+    spos[tid * 3 + 0] = d.px; spos[tid * 3 + 1] = d.py; spos[tid * 3 + 2] = d.pz;
+    svel[tid * 3 + 0] = d.vx; svel[tid * 3 + 1] = d.vy; svel[tid * 3 + 2] = d.vz;
+    __syncthreads();
+    R aux = R(0);
+    if (active)
+      swarm_terms(P, spos + (size_t)env_l * M * 3, svel + (size_t)env_l * M * 3, M, drone, d, roll, pitch, contrib, aux, flags);
+    saux[tid] = aux;
   }
   sred[tid] = contrib;
   sflag[tid] = flags;
@@ -318,9 +332,11 @@ step_kernel(const __grid_constant__ Params<R> P) {
     R sum = R(0);
     int fl = 0;
     for (int i = 0; i < M; ++i) { sum += sred[tid + i]; fl |= sflag[tid + i]; }
-    const R reward = (TASK == TASK_HOVER) ? sum : sum / R(M);
+    R reward = (TASK == TASK_HOVER) ? sum : sum / R(M);
+    if constexpr (TASK == TASK_SWARM) reward = swarm_reward(P, M, sred + tid, saux + tid, svel + (size_t)tid * 3);
     const bool time_up = stepc >= P.trunc_counter;   // step_counter/PYB_FREQ > EPISODE_LEN_SEC, pre-increment (:379,:382)
-    const bool terminated = (fl & 1) != 0;
+    // Meetup terminates when every pair has met (MeetupAviary.py:115-121; no pairs at M = 1: always)
+    const bool terminated = (TASK == TASK_SWARM) ? (P.task == TASK_MEETUP && (fl & 4) == 0) : (fl & 1) != 0;
     const bool truncated = ((fl & 2) != 0) || time_up;
     P.reward[env] = reward;
     P.terminated[env] = terminated ? 1 : 0;
@@ -540,16 +556,17 @@ __global__ void get_targets_kernel(const __grid_constant__ Params<R> P, R* targe
 // =========================================================================
 //                              host-side dispatch
 // =========================================================================
-size_t step_smem_bytes(int precision, int A, int B, int D) {
+size_t step_smem_bytes(int precision, int A, int B, int D, int task) {
   (void)A; (void)B;
   const size_t real = precision ? 8 : 4;
   const size_t tile = ((size_t)kBlock * D * 4 + 15) & ~(size_t)15;
-  return tile + (size_t)kBlock * real * 4 + (size_t)kBlock * 8;
+  const size_t swarm = task >= TASK_SWARM ? (size_t)kBlock * real * 4 : 0;   // svel + saux
+  return tile + (size_t)kBlock * real * 4 + (size_t)kBlock * 8 + swarm;
 }
 
 template <typename R, int TASK, int A, bool GENERIC>
 static cudaError_t launch_step_t(const Params<R>& P, int device, cudaStream_t st) {
-  const size_t smem = step_smem_bytes(sizeof(R) == 8, A, P.B, P.D);
+  const size_t smem = step_smem_bytes(sizeof(R) == 8, A, P.B, P.D, P.task);
   auto kern = step_kernel<R, TASK, A, GENERIC>;
   static size_t configured[64] = {0};   // per device: the attribute is per context
   if (smem > configured[device & 63]) {
@@ -618,7 +635,13 @@ static cudaError_t step_t(const LaunchSpec& ls, const void* p, cudaStream_t st) 
   switch (ls.task) {
     case TASK_HOVER: return step_a<R, TASK_HOVER>(ls, p, st);
     case TASK_MULTIHOVER: return step_a<R, TASK_MULTIHOVER>(ls, p, st);
-    default: return step_a<R, TASK_SPIRAL>(ls, p, st);
+    case TASK_SPIRAL: return step_a<R, TASK_SPIRAL>(ls, p, st);
+    default: {   // swarm tasks: always the generic kernel
+      const Params<R>& P = *static_cast<const Params<R>*>(p);
+      if (ls.act_a == 3) return launch_step_t<R, TASK_SWARM, 3, true>(P, ls.device, st);
+      return ls.act_a == 4 ? launch_step_t<R, TASK_SWARM, 4, true>(P, ls.device, st)
+                           : launch_step_t<R, TASK_SWARM, 1, true>(P, ls.device, st);
+    }
   }
 }
 cudaError_t launch_step(const LaunchSpec& ls, const void* params, cudaStream_t st) {
@@ -636,7 +659,8 @@ static cudaError_t reset_t(const LaunchSpec& ls, const void* p, cudaStream_t st)
   switch (ls.task) {
     case TASK_HOVER: return reset_a<R, TASK_HOVER>(ls, p, st);
     case TASK_MULTIHOVER: return reset_a<R, TASK_MULTIHOVER>(ls, p, st);
-    default: return reset_a<R, TASK_SPIRAL>(ls, p, st);
+    case TASK_SPIRAL: return reset_a<R, TASK_SPIRAL>(ls, p, st);
+    default: return reset_a<R, TASK_SWARM>(ls, p, st);
   }
 }
 cudaError_t launch_reset(const LaunchSpec& ls, const void* params, cudaStream_t st) {

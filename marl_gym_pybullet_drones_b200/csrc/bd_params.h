@@ -55,6 +55,7 @@ struct Params {
   double pyb_freq, episode_len;
   int trunc_counter;              // smallest step_counter with step_counter / pyb_freq > episode_len (fp64)
   int model, aero, integrator, auto_reset, reset_mode, action_is_f32, keep_angv;
+  int task;                       // BD_TASK_* (the swarm tasks share one kernel instantiation and branch on this)
   int act_type, ctrl_reset;       // ACT_*; 1: env resets also zero the controller memory (reference: never)
   Real ctrl_dt, ctrl_gravity, ctrl_4kf, speed_limit;   // DSLPIDControl constants (CF2X), BaseRLAviary.py:95
   float speed_limit_f;
@@ -82,6 +83,6 @@ cudaError_t launch_get_targets(int precision, const void* params, void* targets,
 cudaError_t launch_ctrl_state(int precision, const void* params, void* dst, const void* src, int write,
                               cudaStream_t st);
 cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st);
-size_t step_smem_bytes(int precision, int A, int B, int D);
+size_t step_smem_bytes(int precision, int A, int B, int D, int task);
 
 }  // namespace bd

@@ -214,3 +214,38 @@ class SpiralFormationAviary(_SingleAviary):
 
     def _computeInfo(self, terminated=False):
         return {"time": self.step_counter / self.PYB_FREQ, "omega": self.OMEGA, "radius": self.R}
+
+
+class _SwarmAviary(_SingleAviary):
+    """Shared constructor of the three swarm tasks (`num_drones=2`, RPM action, 8 s episodes:
+    reference `envs/MeetupAviary.py:12-69`, `FlockAviary.py:13-69`, `LeaderFollowerAviary.py:11-68`)."""
+
+    def __init__(self, drone_model=DroneModel.CF2X, num_drones=2, neighbourhood_radius=np.inf,
+                 initial_xyzs=None, initial_rpys=None, physics=Physics.DYN, pyb_freq=240, ctrl_freq=30,
+                 gui=False, record=False, obs=ObservationType.KIN, act=ActionType.RPM,
+                 precision="fp64", device=None):
+        super().__init__(drone_model=drone_model, num_drones=num_drones,
+                         neighbourhood_radius=neighbourhood_radius, initial_xyzs=initial_xyzs,
+                         initial_rpys=initial_rpys, physics=physics, pyb_freq=pyb_freq, ctrl_freq=ctrl_freq,
+                         gui=gui, record=record, obs=obs, act=act, precision=precision, device=device)
+
+
+class MeetupAviary(_SwarmAviary):
+    """Pairs (i, M-1-i) meet mid-flight: reward -2 |p_i - p_partner|^2 per pair, terminated when every
+    pair is within 0.1 m (reference `envs/MeetupAviary.py:74-154`)."""
+
+    TASK = "meetup"
+
+
+class FlockAviary(_SwarmAviary):
+    """Flocking: velocity alignment + flock speed - spacing penalty - spacing variance
+    (reference `envs/FlockAviary.py:75-189`)."""
+
+    TASK = "flock"
+
+
+class LeaderFollowerAviary(_SwarmAviary):
+    """Drone 0 hovers at (0, 0, 0.5), the others match its height (reference
+    `envs/LeaderFollowerAviary.py:72-145`)."""
+
+    TASK = "leaderfollower"

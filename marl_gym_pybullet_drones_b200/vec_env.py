@@ -20,7 +20,8 @@ import numpy as np
 
 from .batch_aviary import BatchAviary
 
-_TASK_OF_CLASS = {"HoverAviary": "hover", "MultiHoverAviary": "multihover", "SpiralFormationAviary": "spiral"}
+_TASK_OF_CLASS = {"HoverAviary": "hover", "MultiHoverAviary": "multihover", "SpiralFormationAviary": "spiral",
+                  "MeetupAviary": "meetup", "FlockAviary": "flock", "LeaderFollowerAviary": "leaderfollower"}
 
 
 class BatchVecEnv:
@@ -235,7 +236,7 @@ def _spec_from_env_func(env_func):
     if spec is not None:
         return spec["task"], {k: v for k, v in spec.items() if k != "task"}
     raise TypeError(
-        "make_vec_envs needs env_func to be HoverAviary / MultiHoverAviary / SpiralFormationAviary (optionally "
+        "make_vec_envs needs env_func to be one of the aviary classes of this package (optionally "
         "wrapped in functools.partial), or a callable with a `batch_spec` dict attribute: the batched simulator "
         "constructs all envs at once instead of calling env_func N times")
 

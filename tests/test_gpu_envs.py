@@ -59,6 +59,27 @@ def test_spiral_env_info_and_shapes():
     env.close()
 
 
+@pytest.mark.parametrize("cls,name", [("MeetupAviary", "meetup2_default"), ("FlockAviary", "flock5"),
+                                      ("LeaderFollowerAviary", "leaderfollower2_climb")])
+def test_swarm_envs_follow_reference_golden(cls, name):
+    """Gymnasium views of the swarm tasks: constructor defaults (2 drones, default spawn) and 5-tuples."""
+    import marl_gym_pybullet_drones_b200 as pkg
+    cfg, g = load_golden(name)
+    kw = {}
+    if "initial_xyzs" in cfg:
+        kw = dict(initial_xyzs=np.array(cfg["initial_xyzs"]), initial_rpys=np.array(cfg["initial_rpys"]))
+    env = getattr(pkg, cls)(num_drones=cfg["num_drones"], **kw) if kw else getattr(pkg, cls)()
+    assert env.NUM_DRONES == cfg["num_drones"] and env.EPISODE_LEN_SEC == 8
+    assert np.allclose(env.INIT_XYZS, g["init_xyzs"], atol=0)
+    obs, info = env.reset()
+    assert rel_err(obs, g["obs0"]) <= 2.5e-7 and info == {"answer": 42}
+    for t in range(min(80, g["actions"].shape[0])):
+        o, r, te, tr, info = env.step(g["actions"][t])
+        assert rel_err(o, g["obs"][t]) <= 2.5e-7 and rel_err(r, g["reward"][t]) <= 1e-9, (name, t)
+        assert te == bool(g["terminated"][t]) and tr == bool(g["truncated"][t]), (name, t)
+    env.close()
+
+
 def test_pyb_physics_is_rejected():
     from marl_gym_pybullet_drones_b200 import HoverAviary, Physics
     with pytest.raises(NotImplementedError):
