@@ -68,7 +68,7 @@ def test_fp32_free_running_matches_reference_golden(name):
         # fall (chaotic: fp32 cannot track it); the free-running horizon stops at twice the flight envelope
         tilt = np.abs(g["states"][:, :, 7:9]).max(axis=(1, 2))
         T = int(np.argmax(tilt > 0.8)) if (tilt > 0.8).any() else T
-        assert T >= 17
+        assert T >= min(17, A.shape[0])
     for t in range(T):
         r = env.step_device(_dev(A[t], torch.float32, 2))
         err = rel_err(r.obs.cpu().numpy()[1][:, :12], g["obs"][t][:, :12])
