@@ -304,7 +304,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 or True:
+        if world == 1:
             cpu, _ = run_cpu_baseline(args.cpu_steps, 2, M)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
