@@ -35,7 +35,8 @@ import torch
 import torch.nn as nn
 
 from .batch_aviary import BatchAviary, StepResult
-from .dist import allreduce_gradients, reduce_episode_stats
+from .dist import reduce_episode_stats
+from .optim import GatedAdam
 
 MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-217 overrides
     "hidden_dim": 256,
@@ -54,6 +55,7 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
+    "graph_update": True,         # replay each PPO minibatch as one CUDA graph (single-GPU; multi-GPU runs it eagerly)
     "matmul_precision": "tf32",   # PPO-update GEMMs on the tensor cores (fp32 storage / accumulation); "fp32" = CUDA cores
     "norm_obs": False,            # mappo/config.py:7-10; True in the Spiral config (env_select_learn_mappo.py:278)
     "norm_reward": False,
@@ -138,8 +140,10 @@ class DeviceMAPPO:
         self.T = int(self.cfg["rollout_steps"])
         torch.manual_seed(seed)   # same initial weights on every rank
         self.ac = ActorCritic(self.D, self.A, self.M, self.cfg["hidden_dim"], self.cfg["activation"]).to(self.device)
-        self.actor_opt = torch.optim.Adam(self.ac.actor_parameters(), lr=self.cfg["actor_lr"])
-        self.critic_opt = torch.optim.Adam(self.ac.critic.parameters(), lr=self.cfg["critic_lr"])
+        # torch.optim.Adam's arithmetic and checkpoint format, with a device-side gate (optim.py)
+        self.actor_opt = GatedAdam(self.ac.actor_parameters(), lr=self.cfg["actor_lr"])
+        self.critic_opt = GatedAdam(self.ac.critic.parameters(), lr=self.cfg["critic_lr"])
+        self._graph = None
         self.gen = torch.Generator(device=self.device)
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.gen.manual_seed(seed * 1000003 + rank)
@@ -155,6 +159,7 @@ class DeviceMAPPO:
         self.trunc = torch.zeros((T, N), dtype=torch.uint8, device=dev)
         self.ret = torch.zeros((T, N, 1), device=dev)
         self.adv = torch.zeros((T, N, 1), device=dev)
+        self.adv_n = torch.zeros((T, N, 1), device=dev)
         # episode statistics (VecRecordEpisodeStatistics semantics, record_episode_statistics.py:144-171)
         # (the step kernel accumulates them: BatchAviary.episode_stats)
         self.total_env_steps = 0
@@ -273,7 +278,7 @@ class DeviceMAPPO:
             torch.distributed.all_reduce(stats)
             mean = stats[0] / stats[2]
             std = (stats[1] / stats[2] - mean * mean).clamp_min(0).sqrt()
-        self.adv_n = (self.adv - mean) / (std + 1e-8)                   # buffer.py:666-695
+        self.adv_n.copy_((self.adv - mean) / (std + 1e-8))              # buffer.py:666-695
 
     # ------------------------------------------------------------------- update
     def update(self) -> Dict[str, float]:
@@ -285,53 +290,96 @@ class DeviceMAPPO:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
 
-    def _update(self) -> Dict[str, float]:
+    def _minibatch(self, idx):
+        """One minibatch of `MAPPOAgent.update` (agent.py:702-772): actor step (KL-gated), critic step,
+        statistics.  No host synchronisation; every tensor it touches has a fixed address, so it is
+        capturable in a CUDA graph."""
         cfg = self.cfg
         T, N, M, D, A = self.T, self.N, self.M, self.D, self.A
         n = T * N
-        obs = self.obs[:T].reshape(n, M, D)
-        act = self.act.reshape(n, M, A)
-        logp_old = self.logp.reshape(n, M, 1)
-        adv = self.adv_n.reshape(n, 1, 1).expand(n, M, 1)             # reward/advantage tiled to every agent
-        ret = self.ret.reshape(n, 1)                                  # = mean over agents of identical returns
+        mb = idx.numel()
+        obs = self.obs[:T].view(n, M, D)
+        ob = obs[idx]
+        if self.norm_obs:
+            ob = self._normed(ob, torch.div(idx, N, rounding_mode="floor"))
+        o, a = ob.reshape(mb * M, D), self.act.view(n, M, A)[idx].reshape(mb * M, A)
+        lp_old = self.logp.view(n, M, 1)[idx].reshape(mb * M, 1)
+        ad = self.adv_n.view(n, 1, 1)[idx].expand(mb, M, 1).reshape(mb * M, 1)   # advantage tiled to every agent
+        ret = self.ret.view(n, 1)[idx]                                            # = mean over agents of identical returns
+        dist = self.ac.dist(o)
+        lp = dist.log_prob(a).sum(-1, keepdim=True)
+        ratio = torch.exp(lp - lp_old)
+        clip_adv = torch.clamp(ratio, 1 - cfg["clip_param"], 1 + cfg["clip_param"]) * ad
+        policy_loss = -torch.min(ratio * ad, clip_adv).mean()
+        entropy_loss = -dist.entropy().sum(-1).mean()
+        approx_kl = (lp_old - lp).mean().detach()
+        self.actor_opt.zero_grad()
+        (policy_loss + cfg["entropy_coef"] * entropy_loss).backward()
+        gate = None
+        if self._world > 1:   # every rank must take the same gate decision or the replicas drift apart
+            self.actor_opt.all_reduce_grad()
+            torch.distributed.all_reduce(approx_kl)
+            approx_kl = approx_kl / self._world
+        if cfg["target_kl"] > 0:
+            # KL gate (agent.py:731): the optimiser step (Adam moments and step count included) is skipped
+            # entirely when the minibatch violates the constraint; decided on the device
+            gate = approx_kl <= 1.5 * cfg["target_kl"]
+        self.actor_opt.step(gate)
+        v = self.ac.value(ob.reshape(mb, M * D))
+        value_loss = 0.5 * (v - ret).pow(2).mean()
+        self.critic_opt.zero_grad()
+        value_loss.backward()
+        if self._world > 1:
+            self.critic_opt.all_reduce_grad()
+        self.critic_opt.step()
+        self._stats += torch.stack([policy_loss.detach(), value_loss.detach(), entropy_loss.detach(), approx_kl,
+                                    torch.ones((), device=self.device)])
+
+    def _capture_minibatch(self, mb):
+        """Capture `_minibatch` into a CUDA graph (one replay per minibatch instead of ~300 launches).
+        The warm-up iterations torch requires before capture really train, so the trainable state is
+        snapshotted and restored around them."""
+        self._idx = torch.zeros(mb, dtype=torch.long, device=self.device)
+        opts = (self.actor_opt, self.critic_opt)
+        keep = [(o.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_t.clone()) for o in opts]
+        stats = self._stats.clone()
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._minibatch(self._idx)
+        cur.wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._minibatch(self._idx)
+        for o, (f, m, v, st) in zip(opts, keep):
+            o.flat.copy_(f); o.exp_avg.copy_(m); o.exp_avg_sq.copy_(v); o.step_t.copy_(st)
+        self._stats.copy_(stats)
+        return graph
+
+    def _update(self) -> Dict[str, float]:
+        cfg = self.cfg
+        n = self.T * self.N
         mb = min(int(cfg["mini_batch_size"]), n)
         num_mb = n // mb
-        stats = torch.zeros(5, device=self.device)
-        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self._world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        if not hasattr(self, "_stats"):
+            self._stats = torch.zeros(5, device=self.device)
+        self._stats.zero_()
+        use_graph = bool(cfg["graph_update"]) and self._world == 1
+        if use_graph and (self._graph is None or self._idx.numel() != mb):
+            self._graph = self._capture_minibatch(mb)
         for _ in range(int(cfg["opt_epochs"])):
             perm = torch.randperm(n, device=self.device, generator=self.gen)
             for i in range(num_mb):
-                idx = perm[i * mb:(i + 1) * mb]
-                ob = self._normed(obs[idx], torch.div(idx, N, rounding_mode="floor")) if self.norm_obs else obs[idx]
-                o, a = ob.reshape(mb * M, D), act[idx].reshape(mb * M, A)
-                lp_old, ad = logp_old[idx].reshape(mb * M, 1), adv[idx].reshape(mb * M, 1)
-                dist = self.ac.dist(o)
-                lp = dist.log_prob(a).sum(-1, keepdim=True)
-                ratio = torch.exp(lp - lp_old)
-                clip_adv = torch.clamp(ratio, 1 - cfg["clip_param"], 1 + cfg["clip_param"]) * ad
-                policy_loss = -torch.min(ratio * ad, clip_adv).mean()
-                entropy_loss = -dist.entropy().sum(-1).mean()
-                approx_kl = (lp_old - lp).mean().detach()
-                if world > 1:   # every rank must take the same gate decision or the replicas drift apart
-                    torch.distributed.all_reduce(approx_kl)
-                    approx_kl = approx_kl / world
-                self.actor_opt.zero_grad(set_to_none=True)
-                (policy_loss + cfg["entropy_coef"] * entropy_loss).backward()
-                allreduce_gradients(self.ac.actor_parameters())
-                # KL gate (agent.py:731): the optimiser step (Adam moments included) is skipped entirely
-                # when the minibatch violates the constraint; one scalar read-back per minibatch
-                if cfg["target_kl"] <= 0 or approx_kl.item() <= 1.5 * cfg["target_kl"]:
-                    self.actor_opt.step()
-                v = self.ac.value(ob.reshape(mb, M * D))
-                value_loss = 0.5 * (v - ret[idx]).pow(2).mean()
-                self.critic_opt.zero_grad(set_to_none=True)
-                value_loss.backward()
-                allreduce_gradients(self.ac.critic.parameters())
-                self.critic_opt.step()
-                stats += torch.stack([policy_loss.detach(), value_loss.detach(), entropy_loss.detach(), approx_kl,
-                                      torch.ones((), device=self.device)])
+                if use_graph:
+                    self._idx.copy_(perm[i * mb:(i + 1) * mb])
+                    self._graph.replay()
+                else:
+                    self._minibatch(perm[i * mb:(i + 1) * mb])
         self._fused_stale = True
-        s = (stats[:4] / stats[4]).tolist()
+        s = (self._stats[:4] / self._stats[4]).tolist()
         return {"policy_loss": s[0], "value_loss": s[1], "entropy_loss": s[2], "approx_kl": s[3]}
 
     # --------------------------------------------------------------------- loop

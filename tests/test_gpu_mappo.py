@@ -87,3 +87,35 @@ def test_fused_and_torch_rollouts_agree_statistically():
     eps = (algo.act.reshape(-1, A) - algo.ac.actor(algo.obs[:T].reshape(-1, D)).detach()) / algo.ac.logstd.exp().detach()
     assert abs(eps.mean().item()) < 2e-2 and abs(eps.std().item() - 1.0) < 2e-2
     env.close()
+
+
+def test_graphed_update_equals_eager_update_and_kl_gate_closes():
+    """The PPO minibatch replayed as a CUDA graph == the same ops launched eagerly (same permutations), and
+    the device-side KL gate skips whole optimiser steps (agent.py:731) without a host read."""
+    from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
+    env = BatchAviary(task="multihover", num_envs=512, num_drones=2, seed=3, track_episode_stats=True,
+                      initial_xyzs=np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5]]))
+    algo = DeviceMAPPO(env, rollout_steps=16, hidden_dim=64, mini_batch_size=1024, opt_epochs=3, actor_lr=3e-3,
+                       target_kl=0.004, seed=1, graph_update=True)
+    algo.collect_rollout()
+    algo.compute_returns()
+    opts = (algo.actor_opt, algo.critic_opt)
+    snap = [(o.flat.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_t.clone()) for o in opts]
+    gen = algo.gen.get_state()
+    res_g = algo.update()
+    assert algo._graph is not None
+    out_g = [o.flat.clone() for o in opts]
+    steps_g = [float(o.step_t) for o in opts]
+    for o, (f, m, v, st) in zip(opts, snap):
+        o.flat.copy_(f); o.exp_avg.copy_(m); o.exp_avg_sq.copy_(v); o.step_t.copy_(st)
+    algo.gen.set_state(gen)
+    algo.cfg["graph_update"] = False
+    res_e = algo.update()
+    n_mb = 3 * (16 * 512 // 1024)
+    assert steps_g == [float(o.step_t) for o in opts]
+    assert steps_g[1] == n_mb and 0 < steps_g[0] < n_mb, steps_g      # the gate closed on some minibatches
+    for a, o in zip(out_g, opts):
+        assert torch.allclose(a, o.flat, rtol=1e-5, atol=1e-6)
+    for k in res_g:
+        assert abs(res_g[k] - res_e[k]) <= 1e-5 * max(1.0, abs(res_e[k])), k
+    env.close()
