@@ -306,12 +306,16 @@ class DeviceMAPPO:
         lp_old = self.logp.view(n, M, 1)[idx].reshape(mb * M, 1)
         ad = self.adv_n.view(n, 1, 1)[idx].expand(mb, M, 1).reshape(mb * M, 1)   # advantage tiled to every agent
         ret = self.ret.view(n, 1)[idx]                                            # = mean over agents of identical returns
-        dist = self.ac.dist(o)
-        lp = dist.log_prob(a).sum(-1, keepdim=True)
+        # torch.distributions.Normal's log_prob / entropy formulas written out: constructing the distribution
+        # validates its arguments with a host read, which a CUDA-graph capture forbids
+        mean, logstd = self.ac.actor(o), self.ac.logstd
+        var = torch.exp(logstd) ** 2
+        lp = (-((a - mean) ** 2) / (2 * var) - logstd - math.log(math.sqrt(2 * math.pi))).sum(-1, keepdim=True)
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum(-1)
         ratio = torch.exp(lp - lp_old)
         clip_adv = torch.clamp(ratio, 1 - cfg["clip_param"], 1 + cfg["clip_param"]) * ad
         policy_loss = -torch.min(ratio * ad, clip_adv).mean()
-        entropy_loss = -dist.entropy().sum(-1).mean()
+        entropy_loss = -ent.mean()
         approx_kl = (lp_old - lp).mean().detach()
         self.actor_opt.zero_grad()
         (policy_loss + cfg["entropy_coef"] * entropy_loss).backward()

@@ -38,7 +38,15 @@ dt = (time.perf_counter() - t0) / 3
 S = 8
 print(f"rollout  : {dt / args.rollout * 1e6:8.1f} us per env step  -> {args.envs * M * S * args.rollout / dt:.3e} drone-substeps/s "
       f"({args.envs * args.rollout / dt:.3e} env-steps/s)  fused={bool(algo.fused)}")
+algo.train_step()      # includes the one-off CUDA-graph capture of the PPO minibatch
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 res = algo.train_step()
 dt = time.perf_counter() - t0
 print(f"train_step: {dt:.3f} s for {args.rollout * args.envs} env-steps -> {args.rollout * args.envs / dt:.3e} env-steps/s  {res}")
+for name, fn in (("collect_rollout", algo.collect_rollout), ("compute_returns", algo.compute_returns), ("update", algo.update)):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fn()
+    torch.cuda.synchronize()
+    print(f"  {name:16s} {1e3 * (time.perf_counter() - t0):8.1f} ms")
