@@ -23,7 +23,7 @@ ap.add_argument("--epochs", type=int, default=2)
 args = ap.parse_args()
 M = args.drones
 side = int(np.ceil(np.sqrt(M)))
-xyz = np.array([[float(i % side), float(i // side), 0.5] for i in range(M)])
+xyz = np.array([[float(i % side) - 0.5 * (side - 1), float(i // side) - 0.5 * (side - 1), 0.5] for i in range(M)])   # 1 m grid centred on the origin (MultiHover's |x|,|y| <= 3 m box)
 env = BatchAviary(task="multihover", num_envs=args.envs, num_drones=M, initial_xyzs=xyz, physics=args.physics, seed=1,
                   track_episode_stats=True)
 algo = DeviceMAPPO(env, rollout_steps=args.rollout, mini_batch_size=args.mb, opt_epochs=args.epochs,
