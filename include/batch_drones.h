@@ -142,7 +142,11 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
 
 /* Same as bd_step with HOST buffers: copies the actions up, steps, copies
  * obs/reward/flags (and terminal obs when not NULL) back and synchronises
- * `stream`.  Buffers should be page-locked for full PCIe rate. */
+ * `stream`.  Buffers should be page-locked for full PCIe rate.  Above ~4 MB of
+ * observations the step runs as a pipeline of up to 8 chunks of whole tiles on two
+ * internal streams (actions up + sub-range launch of the step kernel | observations
+ * down), so the device->host copy — the bound of this call — overlaps everything
+ * else; results are identical to bd_step. */
 int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
                  uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                  void* stream);

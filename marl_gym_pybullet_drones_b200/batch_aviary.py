@@ -302,11 +302,21 @@ class BatchAviary:
                                         C.c_void_p(trunc.data_ptr()), tobs_ptr, self._stream()), "bd_step")
         return StepResult(obs, reward, term.view(torch.bool), trunc.view(torch.bool), tobs)
 
-    def step_host(self, actions: np.ndarray, out: Optional[dict] = None, want_terminal_obs: bool = False) -> dict:
+    @staticmethod
+    def pinned_array(shape, dtype=np.float32) -> np.ndarray:
+        """Page-locked host array (for `step_host(..., actions_pinned=True)`)."""
+        t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        return t.numpy()
+
+    def step_host(self, actions: np.ndarray, out: Optional[dict] = None, want_terminal_obs: bool = False,
+                  actions_pinned: bool = False) -> dict:
         """Host-buffer step through `bd_step_host` (H2D + kernel + D2H + sync).
 
         `actions`: (N,M,A) numpy array.  Returns a dict of numpy arrays backed by
         pinned memory that is reused on the next call (copy what you keep).
+        `actions_pinned=True`: `actions` already lives in page-locked memory (`pinned_array`) with the
+        aviary's action dtype and is handed to the copy engine as it is; otherwise it is first copied
+        into a pinned staging buffer (a 4 MB host memcpy at 65 536 x 4 drones, ~0.35 ms).
         """
         self._check_open()
         N, M = self.num_envs, self.NUM_DRONES
@@ -331,10 +341,16 @@ class BatchAviary:
             out = self._host_bufs
         if want_terminal_obs and out.get("terminal_obs") is None:
             out["terminal_obs"] = torch.zeros((N, M, self.OBS_DIM), dtype=torch.float32, pin_memory=True)
-        out["actions"].numpy()[...] = np.asarray(actions, dtype=np_act).reshape(N, M, self.ACTION_DIM)
+        if actions_pinned:
+            if actions.dtype != np_act or not actions.flags["C_CONTIGUOUS"] or actions.size != N * M * self.ACTION_DIM:
+                raise ValueError("actions_pinned=True needs a C-contiguous (N,M,A) array of the aviary's action dtype")
+            act_ptr = actions.ctypes.data
+        else:
+            out["actions"].numpy()[...] = np.asarray(actions, dtype=np_act).reshape(N, M, self.ACTION_DIM)
+            act_ptr = out["actions"].data_ptr()
         tob = out.get("terminal_obs") if want_terminal_obs else None
         _native.check(self._lib.bd_step_host(
-            self._h, C.c_void_p(out["actions"].data_ptr()), C.c_void_p(out["obs"].data_ptr()),
+            self._h, C.c_void_p(act_ptr), C.c_void_p(out["obs"].data_ptr()),
             C.c_void_p(out["reward"].data_ptr()), C.c_void_p(out["terminated"].data_ptr()),
             C.c_void_p(out["truncated"].data_ptr()),
             C.c_void_p(tob.data_ptr()) if tob is not None else None, self._stream()), "bd_step_host")

@@ -75,6 +75,8 @@ struct bd_handle {
   void* h_reward = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float* h_tobs = nullptr;
+  cudaStream_t hs_a = nullptr, hs_b = nullptr;   // bd_step_host pipeline: (H2D, kernel) chunks / D2H chunks
+  cudaEvent_t hs_start = nullptr, hs_done = nullptr, hs_chunk[8] = {};
   int64_t launches = 0;
   long long total_steps = 0;   // host mirror of gsteps[0]
   bool graph_mode = false;     // a step was captured into a CUDA graph: the device counter is authoritative
@@ -140,6 +142,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.keep_angv = c.keep_ang_vel;
   P.seed = c.seed;
   P.reset_epoch = 0;
+  P.block0 = 0; P.grid_blocks = 0; P.advance = 1;
   P.total_wrap = h->B * ((1 << 30) / h->B);
   P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
 }
@@ -220,6 +223,11 @@ void free_all(bd_handle* h) {
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
+  if (h->hs_a) {
+    cudaStreamDestroy(h->hs_a); cudaStreamDestroy(h->hs_b);
+    cudaEventDestroy(h->hs_start); cudaEventDestroy(h->hs_done);
+    for (auto ev : h->hs_chunk) cudaEventDestroy(ev);
+  }
 }
 
 }  // namespace
@@ -450,16 +458,76 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
     BD_CUDA(cudaMalloc((void**)&h->h_tobs, obs_bytes));
     BD_CUDA(cudaMemsetAsync(h->h_tobs, 0, obs_bytes, st));
   }
-  BD_CUDA(cudaMemcpyAsync(h->h_actions, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
-  int rc = bd_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_term, h->h_trunc,
-                   terminal_obs_host ? h->h_tobs : nullptr, stream);
-  if (rc) return rc;
-  BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  // Pipeline over chunks of whole tiles: while the copy engine drains chunk k's observations to the host,
+  // chunk k+1's actions go up and its tiles are stepped.  One control step = `chunks` sub-range launches of the
+  // same kernel with the same step count; only the last one advances the device-resident counter.
+  const int block_rows = h->spec.impl == 1 ? bd::kBlock : h->E * h->cfg.n_drones;   // drones per tile
+  const int n_blocks = (int)((h->n_total + block_rows - 1) / block_rows);
+  int chunks = (int)(obs_bytes >> 21);   // at least 2 MB of observations per chunk, at most 8 chunks
+  if (chunks > 8) chunks = 8;
+  if (chunks > n_blocks) chunks = n_blocks;
+  if (chunks <= 1 || h->graph_mode) {
+    BD_CUDA(cudaMemcpyAsync(h->h_actions, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
+    int rc = bd_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_term, h->h_trunc,
+                     terminal_obs_host ? h->h_tobs : nullptr, stream);
+    if (rc) return rc;
+    BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
+    if (terminal_obs_host)
+      BD_CUDA(cudaMemcpyAsync(terminal_obs_host, h->h_tobs, obs_bytes, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (h->cfg.auto_reset && h->cfg.reset_mode == BD_RESET_JITTER_BUFFER && h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter)
+      return fail(BD_EINVAL, "bd_step: BD_RESET_JITTER_BUFFER needs bd_set_jitter() first");
+    if (!h->hs_a) {
+      BD_CUDA(cudaStreamCreateWithFlags(&h->hs_a, cudaStreamNonBlocking));
+      BD_CUDA(cudaStreamCreateWithFlags(&h->hs_b, cudaStreamNonBlocking));
+      BD_CUDA(cudaEventCreateWithFlags(&h->hs_start, cudaEventDisableTiming));
+      BD_CUDA(cudaEventCreateWithFlags(&h->hs_done, cudaEventDisableTiming));
+      for (auto& ev : h->hs_chunk) BD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    BD_CUDA(cudaEventRecord(h->hs_start, st));
+    BD_CUDA(cudaStreamWaitEvent(h->hs_a, h->hs_start, 0));
+    BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_start, 0));
+    const size_t act_row = (size_t)h->A * act_elem, obs_row = (size_t)h->D * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < chunks && e == cudaSuccess; ++c) {
+      const int b0 = (int)((long long)n_blocks * c / chunks), b1 = (int)((long long)n_blocks * (c + 1) / chunks);
+      const long long g0 = (long long)b0 * block_rows;
+      long long g1 = (long long)b1 * block_rows;
+      if (g1 > h->n_total) g1 = h->n_total;
+      const size_t rows = (size_t)(g1 - g0);
+      BD_CUDA(cudaMemcpyAsync((char*)h->h_actions + g0 * act_row, (const char*)actions_host + g0 * act_row, rows * act_row,
+                              cudaMemcpyHostToDevice, h->hs_a));
+      with_params(h, [&](auto& P) {
+        P.host_total = (int)h->total_steps;
+        P.actions = h->h_actions;
+        P.obs = h->h_obs;
+        P.reward = (decltype(P.reward))h->h_reward;
+        P.terminated = h->h_term;
+        P.truncated = h->h_trunc;
+        P.terminal_obs = terminal_obs_host ? h->h_tobs : nullptr;
+        P.block0 = b0; P.grid_blocks = b1 - b0; P.advance = (c == chunks - 1) ? 1 : 0;
+        e = bd::launch_step(h->spec, &P, h->hs_a);
+        P.block0 = 0; P.grid_blocks = 0; P.advance = 1;
+      });
+      h->launches++;
+      if (e != cudaSuccess) break;
+      BD_CUDA(cudaEventRecord(h->hs_chunk[c], h->hs_a));
+      BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_chunk[c], 0));
+      BD_CUDA(cudaMemcpyAsync((char*)obs_host + g0 * obs_row, (const char*)h->h_obs + g0 * obs_row, rows * obs_row,
+                              cudaMemcpyDeviceToHost, h->hs_b));
+      if (terminal_obs_host)
+        BD_CUDA(cudaMemcpyAsync((char*)terminal_obs_host + g0 * obs_row, (const char*)h->h_tobs + g0 * obs_row,
+                                rows * obs_row, cudaMemcpyDeviceToHost, h->hs_b));
+    }
+    if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    h->total_steps++;
+    if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) h->total_steps = 0;
+    BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a
+    BD_CUDA(cudaStreamWaitEvent(st, h->hs_done, 0));
+  }
   BD_CUDA(cudaMemcpyAsync(reward_host, h->h_reward, n * h->real, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaMemcpyAsync(terminated_host, h->h_term, n, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaMemcpyAsync(truncated_host, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
-  if (terminal_obs_host)
-    BD_CUDA(cudaMemcpyAsync(terminal_obs_host, h->h_tobs, obs_bytes, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaStreamSynchronize(st));
   return BD_OK;
 }

@@ -70,9 +70,10 @@ step_kernel(const __grid_constant__ Params<R> P) {
 
   const int env_l = tid / M;
   const int drone = tid - env_l * M;
-  const int env = blockIdx.x * E + env_l;
+  const int bid = blockIdx.x + P.block0;   // block0 > 0: a launch over a sub-range of tiles (bd_step_host pipelines chunks)
+  const int env = bid * E + env_l;
   const bool active = (env_l < E) && (env < P.N);
-  const long long g0 = (long long)blockIdx.x * E * M;
+  const long long g0 = (long long)bid * E * M;
   const long long g = g0 + tid;
 
   // ---- 1. every load of the tile is issued before anything is consumed ----------------------
@@ -413,7 +414,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
     if (ticket == gridDim.x - 1) {
       P.gsteps[1] = 0;
-      P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
     }
     if (bulk) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
   }
@@ -574,7 +575,7 @@ static cudaError_t launch_step_t(const Params<R>& P, int device, cudaStream_t st
     if (e != cudaSuccess) return e;
     configured[device & 63] = smem;
   }
-  const int grid = (P.N + P.E - 1) / P.E;
+  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (P.N + P.E - 1) / P.E;
   kern<<<grid, kBlock, smem, st>>>(P);
   return cudaGetLastError();
 }
@@ -601,7 +602,7 @@ static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& 
     if (e != cudaSuccess) return e;
     cfgd[dv] = smem;
   }
-  const int grid = (int)((P.n_total + kBlock - 1) / kBlock);
+  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (int)((P.n_total + kBlock - 1) / kBlock);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kBlock);

@@ -61,7 +61,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   float* myrow = tile_s + (size_t)tid * D;
   const int drone = lane & (M - 1);
   const int group_base = lane & ~(M - 1);
-  const long long g0 = (long long)blockIdx.x * kBlock;
+  const long long g0 = (long long)(blockIdx.x + P.block0) * kBlock;   // block0 > 0: sub-range launch (bd_step_host chunks)
   const long long g = g0 + tid;
   const bool active = g < P.n_total;
   const int env = (int)(g >> log2m);
@@ -259,7 +259,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
     if (ticket == gridDim.x - 1) {
       P.gsteps[1] = 0;
-      P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
     }
     if (bulk) bulk_wait_read0();   // shared memory must outlive the bulk store's reads
   }

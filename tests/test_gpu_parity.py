@@ -364,21 +364,39 @@ def test_reset_mask_and_history_survives_reset():
     env.close()
 
 
-def test_host_step_equals_device_step():
-    cfg = dict(task="multihover", drone_model="cf2x", num_drones=3, pyb_freq=240, ctrl_freq=30, act="rpm")
-    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5]])
+@pytest.mark.parametrize("M,N", [(3, 37), (3, 9000), (4, 30001)])
+def test_host_step_equals_device_step(M, N):
+    """`bd_step_host` == `bd_step` on device buffers; the larger sizes run its chunk pipeline (sub-range launches of
+    the generic kernel, M = 3, and of the fast tile kernel, M = 4, with a ragged last tile), auto-reset on so that
+    the ring head / Philox stream shared by the chunks of a step matter."""
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5], [1.0, 1.0, 0.5]])[:M]
     rng = np.random.default_rng(0)
-    envs = [batch_from_cfg(cfg, xyz, None, num_envs=37, precision="fp32") for _ in range(2)]
+    envs = [batch_from_cfg(cfg, xyz, None, num_envs=N, precision="fp32", auto_reset=True, reset_mode="jitter_philox",
+                           seed=5) for _ in range(2)]
     for e in envs:
         e.reset_device()
-    for t in range(6):
-        a = rng.uniform(-1, 1, (37, 3, 4)).astype(np.float32)
+    for t in range(20 if N > 100 else 6):
+        a = (rng.uniform(-1, 1, (N, M, 4)) - 0.6).astype(np.float32)
         d = envs[0].step_device(torch.as_tensor(a, device="cuda"))
-        h = envs[1].step_host(a)
+        if t % 2:      # caller-provided page-locked actions go to the copy engine without the staging memcpy
+            pa = envs[1].pinned_array(a.shape, np.float32)
+            pa[...] = a
+            h = envs[1].step_host(pa, actions_pinned=True)
+        else:
+            h = envs[1].step_host(a)
         assert np.array_equal(d.obs.cpu().numpy(), h["obs"])
         assert np.array_equal(d.reward.cpu().numpy(), h["reward"])
         assert np.array_equal(d.terminated.cpu().numpy(), h["terminated"])
-    assert envs[0].launch_count == envs[1].launch_count
+        assert np.array_equal(d.truncated.cpu().numpy(), h["truncated"])
+    if N > 100:
+        assert envs[1].launch_count > envs[0].launch_count      # chunked sub-range launches
+    st0, st1 = envs[0].get_state().cpu().numpy(), envs[1].get_state().cpu().numpy()
+    assert np.array_equal(st0, st1, equal_nan=True)      # ang_v columns are NaN without keep_ang_vel
+    # the device-resident step count advanced once per step, not once per chunk: CUDA-graph mode continues correctly
+    a = torch.as_tensor((rng.uniform(-1, 1, (N, M, 4))).astype(np.float32), device="cuda")
+    r0, r1 = envs[0].step_device(a), envs[1].step_device(a)
+    assert torch.equal(r0.obs, r1.obs)
     for e in envs:
         e.close()
 
