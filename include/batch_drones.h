@@ -235,7 +235,7 @@ typedef struct bd_rms bd_rms;
 int bd_rms_create(int cols, int device, double count0, double eps, bd_rms** out);
 void bd_rms_destroy(bd_rms* r);
 /* RunningMeanStd.update (:34-58): batch mean / population variance over the `rows` axis of
- * x_dev (rows, cols) float, merged into the running statistics.  Three launches, stream ordered. */
+ * x_dev (rows, cols) float, merged into the running statistics.  One launch, stream ordered. */
 int bd_rms_update(bd_rms* r, const float* x_dev, int64_t rows, void* stream);
 /* The two halves of bd_rms_update, for envs sharded over ranks: batch moments of the local rows into
  * moments_dev = [mean(cols) | var(cols) | count] doubles (:37-39), then — after the caller has

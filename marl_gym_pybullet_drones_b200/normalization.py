@@ -47,7 +47,9 @@ class RunningMeanStd:
     def __init__(self, epsilon=1e-4, shape=(), device=None, eps_div=1e-8):
         if not torch.cuda.is_available():
             raise RuntimeError("RunningMeanStd needs a CUDA device; there is no CPU fallback")
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.shape = tuple(shape)
         self.cols = int(np.prod(self.shape)) if self.shape else 1
         self._lib = _native.load()

@@ -90,7 +90,27 @@ def test_running_moments_match_oracle_on_large_batches(rows, shape):
             if rows > 1:
                 ok = np.abs(y.cpu().numpy() - yo) <= 1e-3 + 1e-3 * np.abs(yo) + loose * (1 + np.abs(off / scale))
                 assert ok.all()
-    assert n.rms._lib.bd_rms_launch_count(n.rms._h) == 3 * 4   # moments + finalize + merge + normalise per call
+    assert n.rms._lib.bd_rms_launch_count(n.rms._h) == 3 * 2   # one fused moments launch + one normalise launch per call
+
+
+def test_unaligned_batch_takes_the_scalar_path():
+    """A batch whose base pointer is not 16-byte aligned (a view into a larger buffer) cannot use 128-bit loads."""
+    from marl_gym_pybullet_drones_b200.normalization import MeanStdNormalizer
+    rng = np.random.default_rng(11)
+    rows, shape = 1001, (5, 119)                      # Spiral's observation shape, odd width
+    x = (rng.standard_normal((rows,) + shape) * 2 + 3).astype(np.float32)
+    buf = torch.zeros(x.size + 8, device="cuda:0")
+    for off in (0, 1, 2):
+        view = buf[off:off + x.size].view((rows,) + shape)
+        view.copy_(torch.as_tensor(x))
+        assert view.is_contiguous() and (view.data_ptr() % 16 == 0) == (off == 0)
+        n = MeanStdNormalizer(shape=shape, clip=10.0, device="cuda:0")
+        y = n(view)
+        o = MeanStdNormalizerOracle(shape=shape, clip=10.0)
+        yo = o(x.astype(np.float64))
+        assert _close(n.rms.mean.cpu().numpy(), o.rms.mean, 1e-6, 1e-6)
+        assert _close(n.rms.var.cpu().numpy(), o.rms.var, 2e-5, 1e-12)
+        assert _close(y.cpu().numpy(), yo, 3e-5, 3e-5)
 
 
 def test_moments_of_sharded_batches_merge_like_one_batch():
