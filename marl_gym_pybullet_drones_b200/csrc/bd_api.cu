@@ -145,6 +145,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.block0 = 0; P.grid_blocks = 0; P.advance = 1;
   P.total_wrap = h->B * ((1 << 30) / h->B);
   P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
+  P.host_head = (int)(h->total_steps % h->B);
 }
 
 void refresh_params(bd_handle* h) {
@@ -156,6 +157,7 @@ void* params_ptr(bd_handle* h) {
   const int ht = h->graph_mode ? -1 : (int)h->total_steps;
   h->pd.host_total = ht;
   h->pf.host_total = ht;
+  h->pd.host_head = h->pf.host_head = (int)(h->total_steps % h->B);
   return h->cfg.precision == BD_F64 ? (void*)&h->pd : (void*)&h->pf;
 }
 
@@ -420,6 +422,7 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
   cudaError_t e = cudaSuccess;
   with_params(h, [&](auto& P) {
     P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
+    P.host_head = (int)(h->total_steps % h->B);
     P.actions = actions_dev;
     P.obs = obs_dev;
     P.reward = (decltype(P.reward))reward_dev;
@@ -499,6 +502,7 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
                               cudaMemcpyHostToDevice, h->hs_a));
       with_params(h, [&](auto& P) {
         P.host_total = (int)h->total_steps;
+        P.host_head = (int)(h->total_steps % h->B);
         P.actions = h->h_actions;
         P.obs = h->h_obs;
         P.reward = (decltype(P.reward))h->h_reward;

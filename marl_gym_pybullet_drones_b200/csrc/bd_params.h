@@ -61,6 +61,7 @@ struct Params {
   float speed_limit_f;
   int host_total;                 // >= 0: total control steps so far, tracked by the host (ring head with no
                                   // memory latency); -1: read gsteps[0] (CUDA-graph capture / replay)
+  int host_head;                  // host_total % B when host_total >= 0
   int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
   int block0, grid_blocks;        // sub-range launch: first tile and tile count (0 = all tiles)
   int advance;                    // 1: this launch advances the device-resident step count (last chunk of a step)

@@ -77,7 +77,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   int total, head;
   if (P.host_total >= 0) {
     total = P.host_total;
-    head = total % B;   // ring slot overwritten by this step's action
+    head = P.host_head;   // = total % B (ring slot overwritten by this step's action), divided on the host
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
     pdl_wait();
   } else {              // CUDA-graph mode: the step count is read from device memory
@@ -112,7 +112,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   float avx = 0.f, avy = 0.f, avz = 0.f;
   fast_substeps<DW>(P, d, onep, avx, avy, avz, lane);
   float roll, pitch, yaw;
-  quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
+  quat_to_euler_fast(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
 
   // ---- 3. complete my observation row ------------------------------------------------------------
   cp_async_wait_all();
