@@ -62,6 +62,8 @@ struct bd_handle {
   float* hist = nullptr;
   int* stepc = nullptr;
   int* gsteps = nullptr;
+  int* tile_epoch = nullptr;
+  int pipeline = 0;
   float* ep_ret = nullptr;
   double* ep_acc = nullptr;
   void* ctrl = nullptr;        // DSL PID memory + commanded rpm, PID action types only
@@ -94,7 +96,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
   P.E = h->E; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
-  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
+  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.tile_epoch = h->tile_epoch; P.pipeline = h->pipeline; P.pipe_wait = 0; P.early_prefetch = 0; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
   P.ctrl = (R*)h->ctrl;
   P.act_type = c.act_type; P.ctrl_reset = c.ctrl_reset_on_reset;
   P.ctrl_dt = (R)(1.0 / c.ctrl_freq);                      // CTRL_TIMESTEP (BaseAviary.py:83)
@@ -220,7 +222,7 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
 
 void free_all(bd_handle* h) {
   cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
-  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
+  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->tile_epoch); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
   cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
@@ -306,6 +308,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
+    const char* pl = getenv("BD_PIPELINE");
+    h->pipeline = (h->spec.impl == 1 && h->spec.pdl && !(pl && strcmp(pl, "0") == 0)) ? 1 : 0;   // BD_PIPELINE=0 switches it off
   }
 
   const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D, cfg->task);
@@ -313,6 +317,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
   if (h->spec.impl == 1 && (size_t)bd::kBlock * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
+  h->spec.sm_count = prop.multiProcessorCount;
+  if (h->spec.impl != 1) h->pipeline = 0;
   if (smem > prop.sharedMemPerBlockOptin) {
     delete h;
     return fail(BD_EINVAL, "bd_create: the history staging tile needs %zu B of shared memory (> %zu)", smem,
@@ -329,7 +335,8 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (cfg->keep_ang_vel) alloc(&h->s4, plane);
   alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
   alloc((void**)&h->stepc, (size_t)cfg->n_envs * sizeof(int));
-  alloc((void**)&h->gsteps, 2 * sizeof(int));
+  alloc((void**)&h->gsteps, 8 * sizeof(int));   // [0] total steps, [1..4] rotating CTA tickets
+  alloc((void**)&h->tile_epoch, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
   if (cfg->track_episodes) alloc((void**)&h->ep_ret, (size_t)cfg->n_envs * sizeof(float));
   alloc((void**)&h->ep_acc, 3 * sizeof(double));
   if (pid_act) alloc(&h->ctrl, (size_t)bd::kCtrlPlanesHost * h->n_total * h->real);   // zeros: DSLPIDControl.reset()
@@ -433,7 +440,13 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
   });
   h->launches++;
   h->total_steps++;
-  if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) h->total_steps = 0;
+  if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) {
+    h->total_steps = 0;
+    if (h->pipeline) {   // tile epochs restart with the step count (once per ~1e9 steps)
+      cudaStreamSynchronize((cudaStream_t)stream);
+      cudaMemset(h->tile_epoch, 0, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
+    }
+  }
   if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
   return BD_OK;
 }
@@ -525,7 +538,13 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
     }
     if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     h->total_steps++;
-    if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) h->total_steps = 0;
+    if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) {
+      h->total_steps = 0;
+      if (h->pipeline) {
+        cudaDeviceSynchronize();
+        cudaMemset(h->tile_epoch, 0, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
+      }
+    }
     BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a
     BD_CUDA(cudaStreamWaitEvent(st, h->hs_done, 0));
   }

@@ -603,6 +603,16 @@ static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& 
     cfgd[dv] = smem;
   }
   const int grid = P.grid_blocks > 0 ? P.grid_blocks : (int)((P.n_total + kBlock - 1) / kBlock);
+  // resident capacity of this kernel: with a grid at least that large, "every CTA of the previous launch has
+  // started" implies "the launch before it has completed", so at most two launches are ever in flight
+  static int per_sm[4][64] = {{0}};
+  int& occ = per_sm[(vecrow ? 1 : 0) + (dw ? 2 : 0)][dv];
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+  }
+  Params<float> Q = P;
+  Q.early_prefetch = (ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
+  Q.pipe_wait = (P.pipeline && ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kBlock);
@@ -613,7 +623,7 @@ static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ls.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, P);
+  return cudaLaunchKernelEx(&cfg, kern, Q);
 }
 
 template <typename R, int TASK, int A>

@@ -63,6 +63,10 @@ struct Params {
                                   // memory latency); -1: read gsteps[0] (CUDA-graph capture / replay)
   int host_head;                  // host_total % B when host_total >= 0
   int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
+  int* tile_epoch;                // [tiles] control steps completed per tile (tile-level step pipelining)
+  int pipeline;                   // 1: the handle pipelines steps tile by tile: every launch publishes tile epochs
+  int pipe_wait;                  // 1: this launch waits for MY tile's previous step only (no grid-wide dependency wait)
+  int early_prefetch;             // 1: ring planes may be prefetched before griddepcontrol.wait (grid >= resident capacity)
   int block0, grid_blocks;        // sub-range launch: first tile and tile count (0 = all tiles)
   int advance;                    // 1: this launch advances the device-resident step count (last chunk of a step)
   int reset_epoch;                // >=1 for explicit bd_reset calls (Philox stream id), 0 in-step
@@ -73,6 +77,7 @@ struct LaunchSpec {
   int task, act_a, precision, generic, device;
   int pdl;         // launch the fast kernel with programmatic stream serialization
   int impl;        // 0: two-role CTA kernel (any config), 1: fast tile kernel (bd_step_tile.cuh)
+  int sm_count;    // SMs of the device (resident-CTA capacity of the fast kernel)
 };
 
 // implemented in bd_kernels.cu

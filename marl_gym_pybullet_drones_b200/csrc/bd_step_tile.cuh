@@ -75,14 +75,29 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   // previous kernel has even finished.
   pdl_launch_dependents();
   int total, head;
-  if (P.host_total >= 0) {
+  const bool pipe = P.pipe_wait && P.host_total >= 0;   // wait on my tile's epoch instead of the whole previous grid
+  const int tile = blockIdx.x + P.block0;
+  if (pipe) {
+    // Tile-level step pipelining: everything this CTA reads that an earlier launch wrote belongs to ITS tile
+    // (whole environments), and was written by the CTA that stepped this tile in the previous control step.
+    // So instead of griddepcontrol.wait (the whole previous grid finished and flushed) the CTA waits for its own
+    // tile's epoch: launches overlap tile by tile, no lock-step start, no idle tail.  (All CTAs of the previous
+    // launch are resident or done before any CTA of this one starts, so the spin cannot deadlock.)
+    total = P.host_total;
+    head = P.host_head;
+    if (tid == 0) {
+      while (ld_acquire_gpu(P.tile_epoch + tile) - total < 0) __nanosleep(64);
+    }
+    __syncthreads();
+    issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
+  } else if (P.host_total >= 0 && P.early_prefetch) {
     total = P.host_total;
     head = P.host_head;   // = total % B (ring slot overwritten by this step's action), divided on the host
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
     pdl_wait();
-  } else {              // CUDA-graph mode: the step count is read from device memory
-    pdl_wait();
-    total = P.gsteps[0];   // only the last CTA to finish modifies it, after every read
+  } else {              // CUDA-graph mode (the step count is read from device memory), or a grid smaller than the
+    pdl_wait();         // resident capacity (several earlier launches could still be in flight: no early reads)
+    total = P.host_total >= 0 ? P.host_total : P.gsteps[0];   // only the last CTA to finish modifies it, after every read
     head = total % B;
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
   }
@@ -255,6 +270,21 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   // gsteps[0] (ring addresses) before the __syncthreads above, so the ticket needs no fence:
   // a __threadfence here would hold the CTA — and its shared memory — until all of its stores
   // have drained (measured: ~half of the CTA's lifetime).  Kernel completion publishes the data.
+  if (P.pipeline) {    // publish this tile's epoch (every launch of a pipelining handle does, however it waited)
+    __syncthreads();   // every thread's state / ring / reward stores are issued (and ordered before thread 0's release)
+    if (tid == 0) {
+      if (bulk) bulk_wait_all0();   // the observation rows are written
+      const int next = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      int* tk = P.gsteps + 1 + (total & 3);   // launches overlap: rotating tickets
+      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(tk), 1u);
+      if (ticket == gridDim.x - 1) {
+        *tk = 0;
+        if (P.advance) P.gsteps[0] = next;
+      }
+      st_release_gpu(P.tile_epoch + tile, total + 1);   // cumulative: the CTA's stores are visible before the epoch
+    }
+    return;
+  }
   if (tid == 0) {
     const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
     if (ticket == gridDim.x - 1) {
