@@ -150,6 +150,12 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.host_head = (int)(h->total_steps % h->B);
 }
 
+// tiles of either step kernel (128 drones for the fast kernel, E whole envs for the generic one)
+long long epoch_tiles(const bd_handle* h) {
+  const long long a = (h->n_total + bd::kBlock - 1) / bd::kBlock, b = (h->cfg.n_envs + h->E - 1) / h->E;
+  return a > b ? a : b;
+}
+
 void refresh_params(bd_handle* h) {
   if (h->cfg.precision == BD_F64) fill_params<double>(h, h->pd);
   else fill_params<float>(h, h->pf);
@@ -309,7 +315,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
     const char* pl = getenv("BD_PIPELINE");
-    h->pipeline = (h->spec.impl == 1 && h->spec.pdl && !(pl && strcmp(pl, "0") == 0)) ? 1 : 0;   // BD_PIPELINE=0 switches it off
+    h->pipeline = (h->spec.pdl && !(pl && strcmp(pl, "0") == 0)) ? 1 : 0;   // BD_PIPELINE=0 switches it off
   }
 
   const size_t smem = bd::step_smem_bytes(cfg->precision, h->A, h->B, h->D, cfg->task);
@@ -318,7 +324,6 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
   if (h->spec.impl == 1 && (size_t)bd::kBlock * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
   h->spec.sm_count = prop.multiProcessorCount;
-  if (h->spec.impl != 1) h->pipeline = 0;
   if (smem > prop.sharedMemPerBlockOptin) {
     delete h;
     return fail(BD_EINVAL, "bd_create: the history staging tile needs %zu B of shared memory (> %zu)", smem,
@@ -336,7 +341,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
   alloc((void**)&h->stepc, (size_t)cfg->n_envs * sizeof(int));
   alloc((void**)&h->gsteps, 8 * sizeof(int));   // [0] total steps, [1..4] rotating CTA tickets
-  alloc((void**)&h->tile_epoch, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
+  alloc((void**)&h->tile_epoch, (size_t)epoch_tiles(h) * sizeof(int));
   if (cfg->track_episodes) alloc((void**)&h->ep_ret, (size_t)cfg->n_envs * sizeof(float));
   alloc((void**)&h->ep_acc, 3 * sizeof(double));
   if (pid_act) alloc(&h->ctrl, (size_t)bd::kCtrlPlanesHost * h->n_total * h->real);   // zeros: DSLPIDControl.reset()
@@ -444,7 +449,7 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
     h->total_steps = 0;
     if (h->pipeline) {   // tile epochs restart with the step count (once per ~1e9 steps)
       cudaStreamSynchronize((cudaStream_t)stream);
-      cudaMemset(h->tile_epoch, 0, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
+      cudaMemset(h->tile_epoch, 0, (size_t)epoch_tiles(h) * sizeof(int));
     }
   }
   if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
@@ -542,7 +547,7 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
       h->total_steps = 0;
       if (h->pipeline) {
         cudaDeviceSynchronize();
-        cudaMemset(h->tile_epoch, 0, (size_t)((h->n_total + bd::kBlock - 1) / bd::kBlock) * sizeof(int));
+        cudaMemset(h->tile_epoch, 0, (size_t)epoch_tiles(h) * sizeof(int));
       }
     }
     BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a

@@ -76,6 +76,20 @@ step_kernel(const __grid_constant__ Params<R> P) {
   const long long g0 = (long long)bid * E * M;
   const long long g = g0 + tid;
 
+  // ---- 0. dependency on the previous control step (see bd_step_tile.cuh): tile-level when this launch fills the
+  // GPU, else grid-wide.  Everything below reads only this tile's data.
+  const bool pipe = P.pipe_wait && P.host_total >= 0;
+  if (P.pipeline) {
+    pdl_launch_dependents();
+    if (pipe) {
+      if (tid == 0) {
+        while (ld_acquire_gpu(P.tile_epoch + bid) - P.host_total < 0) __nanosleep(64);
+      }
+      __syncthreads();
+    } else {
+      pdl_wait();
+    }
+  }
   // ---- 1. every load of the tile is issued before anything is consumed ----------------------
   const int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
   const int head = total % B;   // ring slot overwritten by this step's action
@@ -408,6 +422,20 @@ step_kernel(const __grid_constant__ Params<R> P) {
     P.s3[g] = make4(d.wz, d.tx, d.ty, d.tz);
     if (GENERIC && P.keep_angv) P.s4[g] = make4(avx, avy, avz, R(0));
   }
+  if (P.pipeline) {    // publish this tile's epoch (bd_step_tile.cuh)
+    __syncthreads();
+    if (tid == 0) {
+      if (bulk) bulk_wait_all0();
+      int* tk = P.gsteps + 1 + (total & 3);
+      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(tk), 1u);
+      if (ticket == gridDim.x - 1) {
+        *tk = 0;
+        if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      }
+      st_release_gpu(P.tile_epoch + bid, total + 1);
+    }
+    return;
+  }
   // advance the device-resident step count: last CTA out (every thread consumed `total` before
   // the barrier above; no fence, see bd_step_tile.cuh)
   if (tid == 0) {
@@ -566,18 +594,40 @@ size_t step_smem_bytes(int precision, int A, int B, int D, int task) {
 }
 
 template <typename R, int TASK, int A, bool GENERIC>
-static cudaError_t launch_step_t(const Params<R>& P, int device, cudaStream_t st) {
+static cudaError_t launch_step_t(const Params<R>& P, const LaunchSpec& ls, cudaStream_t st) {
+  const int device = ls.device;
   const size_t smem = step_smem_bytes(sizeof(R) == 8, A, P.B, P.D, P.task);
   auto kern = step_kernel<R, TASK, A, GENERIC>;
   static size_t configured[64] = {0};   // per device: the attribute is per context
+  static int per_sm[64] = {0};
   if (smem > configured[device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[device & 63] = smem;
+    per_sm[device & 63] = 0;
   }
   const int grid = P.grid_blocks > 0 ? P.grid_blocks : (P.N + P.E - 1) / P.E;
-  kern<<<grid, kBlock, smem, st>>>(P);
-  return cudaGetLastError();
+  if (!P.pipeline) {
+    kern<<<grid, kBlock, smem, st>>>(P);
+    return cudaGetLastError();
+  }
+  int& occ = per_sm[device & 63];
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+  }
+  Params<R> Q = P;
+  Q.pipe_wait = (grid >= occ * ls.sm_count) ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, Q);
 }
 
 template <typename R, int TASK, int A>
@@ -632,13 +682,13 @@ static cudaError_t step_g(const LaunchSpec& ls, const void* p, cudaStream_t st) 
   if constexpr (sizeof(R) == 4) {
     if (ls.impl == 1) return launch_step_tile_t<TASK, A>(P, ls, st);
   }
-  return ls.generic ? launch_step_t<R, TASK, A, true>(P, ls.device, st)
-                    : launch_step_t<R, TASK, A, false>(P, ls.device, st);
+  return ls.generic ? launch_step_t<R, TASK, A, true>(P, ls, st)
+                    : launch_step_t<R, TASK, A, false>(P, ls, st);
 }
 template <typename R, int TASK>
 static cudaError_t step_a(const LaunchSpec& ls, const void* p, cudaStream_t st) {
   if (ls.act_a == 3)   // ActionType.PID: waypoint actions, always the generic kernel
-    return launch_step_t<R, TASK, 3, true>(*static_cast<const Params<R>*>(p), ls.device, st);
+    return launch_step_t<R, TASK, 3, true>(*static_cast<const Params<R>*>(p), ls, st);
   return ls.act_a == 4 ? step_g<R, TASK, 4>(ls, p, st) : step_g<R, TASK, 1>(ls, p, st);
 }
 template <typename R>
@@ -649,9 +699,9 @@ static cudaError_t step_t(const LaunchSpec& ls, const void* p, cudaStream_t st) 
     case TASK_SPIRAL: return step_a<R, TASK_SPIRAL>(ls, p, st);
     default: {   // swarm tasks: always the generic kernel
       const Params<R>& P = *static_cast<const Params<R>*>(p);
-      if (ls.act_a == 3) return launch_step_t<R, TASK_SWARM, 3, true>(P, ls.device, st);
-      return ls.act_a == 4 ? launch_step_t<R, TASK_SWARM, 4, true>(P, ls.device, st)
-                           : launch_step_t<R, TASK_SWARM, 1, true>(P, ls.device, st);
+      if (ls.act_a == 3) return launch_step_t<R, TASK_SWARM, 3, true>(P, ls, st);
+      return ls.act_a == 4 ? launch_step_t<R, TASK_SWARM, 4, true>(P, ls, st)
+                           : launch_step_t<R, TASK_SWARM, 1, true>(P, ls, st);
     }
   }
 }
