@@ -56,7 +56,8 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
     "graph_update": True,         # replay each PPO minibatch as one CUDA graph (single-GPU; multi-GPU runs it eagerly)
-    "matmul_precision": "tf32",   # PPO-update GEMMs on the tensor cores (fp32 storage / accumulation); "fp32" = CUDA cores
+    "matmul_precision": "tf32",   # PPO-update GEMMs: "tf32" (tensor cores, fp32 storage / accumulation), "fp32" (CUDA
+                                  # cores), "bf16" (autocast: bf16 operands AND saved activations, fp32 master weights)
     "norm_obs": False,            # mappo/config.py:7-10; True in the Spiral config (env_select_learn_mappo.py:278)
     "norm_reward": False,
     "clip_obs": 10,
@@ -284,7 +285,7 @@ class DeviceMAPPO:
     def update(self) -> Dict[str, float]:
         """`MAPPOAgent.update` (agent.py:702-772) on device tensors."""
         prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.cfg["matmul_precision"] == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = self.cfg["matmul_precision"] in ("tf32", "bf16")
         try:
             return self._update()
         finally:
@@ -308,7 +309,10 @@ class DeviceMAPPO:
         ret = self.ret.view(n, 1)[idx]                                            # = mean over agents of identical returns
         # torch.distributions.Normal's log_prob / entropy formulas written out: constructing the distribution
         # validates its arguments with a host read, which a CUDA-graph capture forbids
-        mean, logstd = self.ac.actor(o), self.ac.logstd
+        bf16 = cfg["matmul_precision"] == "bf16"
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=bf16):
+            mean = self.ac.actor(o)
+        mean, logstd = mean.float(), self.ac.logstd
         var = torch.exp(logstd) ** 2
         lp = (-((a - mean) ** 2) / (2 * var) - logstd - math.log(math.sqrt(2 * math.pi))).sum(-1, keepdim=True)
         ent = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum(-1)
@@ -329,8 +333,9 @@ class DeviceMAPPO:
             # entirely when the minibatch violates the constraint; decided on the device
             gate = approx_kl <= 1.5 * cfg["target_kl"]
         self.actor_opt.step(gate)
-        v = self.ac.value(ob.reshape(mb, M * D))
-        value_loss = 0.5 * (v - ret).pow(2).mean()
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=bf16):
+            v = self.ac.value(ob.reshape(mb, M * D))
+        value_loss = 0.5 * (v.float() - ret).pow(2).mean()
         self.critic_opt.zero_grad()
         value_loss.backward()
         if self._world > 1:

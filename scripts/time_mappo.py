@@ -20,6 +20,7 @@ ap.add_argument("--rollout", type=int, default=32)
 ap.add_argument("--fused", type=int, default=1)
 ap.add_argument("--mb", type=int, default=32768)
 ap.add_argument("--epochs", type=int, default=2)
+ap.add_argument("--precision", default="tf32")
 args = ap.parse_args()
 M = args.drones
 side = int(np.ceil(np.sqrt(M)))
@@ -27,7 +28,7 @@ xyz = np.array([[float(i % side) - 0.5 * (side - 1), float(i // side) - 0.5 * (s
 env = BatchAviary(task="multihover", num_envs=args.envs, num_drones=M, initial_xyzs=xyz, physics=args.physics, seed=1,
                   track_episode_stats=True)
 algo = DeviceMAPPO(env, rollout_steps=args.rollout, mini_batch_size=args.mb, opt_epochs=args.epochs,
-                   fused_actor=bool(args.fused), rollout_values="zeros")
+                   fused_actor=bool(args.fused), rollout_values="zeros", matmul_precision=args.precision)
 algo.collect_rollout()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
