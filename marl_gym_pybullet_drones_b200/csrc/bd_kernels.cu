@@ -426,11 +426,18 @@ step_kernel(const __grid_constant__ Params<R> P) {
     __syncthreads();
     if (tid == 0) {
       if (bulk) bulk_wait_all0();
-      int* tk = P.gsteps + 1 + (total & 3);
-      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(tk), 1u);
-      if (ticket == gridDim.x - 1) {
-        *tk = 0;
-        if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      // device-resident step count (what a later CUDA-graph replay starts from).  Eager launches overlap, so a
+      // "last CTA out" ticket could mix launches; they do not read the counter either, so tile 0's CTA — ordered
+      // after tile 0 of the previous step by the epoch chain — simply writes it.  Graph replays (which read the
+      // counter, and never overlap) keep the ticket.
+      if (P.host_total >= 0) {
+        if (bid == 0) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      } else {
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
+        if (ticket == gridDim.x - 1) {
+          P.gsteps[1] = 0;
+          if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+        }
       }
       st_release_gpu(P.tile_epoch + bid, total + 1);
     }

@@ -274,12 +274,18 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     __syncthreads();   // every thread's state / ring / reward stores are issued (and ordered before thread 0's release)
     if (tid == 0) {
       if (bulk) bulk_wait_all0();   // the observation rows are written
-      const int next = (total + 1 >= P.total_wrap) ? 0 : total + 1;
-      int* tk = P.gsteps + 1 + (total & 3);   // launches overlap: rotating tickets
-      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(tk), 1u);
-      if (ticket == gridDim.x - 1) {
-        *tk = 0;
-        if (P.advance) P.gsteps[0] = next;
+      // device-resident step count (what a later CUDA-graph replay starts from).  Eager launches overlap, so a
+      // "last CTA out" ticket could mix launches; they do not read the counter either, so tile 0's CTA — ordered
+      // after tile 0 of the previous step by the epoch chain — simply writes it.  Graph replays (which read the
+      // counter, and never overlap) keep the ticket.
+      if (P.host_total >= 0) {
+        if (tile == 0) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+      } else {
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
+        if (ticket == gridDim.x - 1) {
+          P.gsteps[1] = 0;
+          if (P.advance) P.gsteps[0] = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+        }
       }
       st_release_gpu(P.tile_epoch + tile, total + 1);   // cumulative: the CTA's stores are visible before the epoch
     }
