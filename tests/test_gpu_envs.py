@@ -119,6 +119,27 @@ def test_vec_env_protocol_and_episode_statistics():
     env.close()
 
 
+def test_vec_env_protocol_for_swarm_tasks():
+    """`make_vec_envs(partial(<swarm aviary>))`: 4-tuples, auto-reset with terminal observation, `info == {"answer": 42}`
+    semantics of the three swarm tasks behind the reference's VecEnv protocol."""
+    from marl_gym_pybullet_drones_b200 import FlockAviary, LeaderFollowerAviary, MeetupAviary, make_vec_envs
+    for cls, M in ((MeetupAviary, 2), (FlockAviary, 3), (LeaderFollowerAviary, 2)):
+        env = make_vec_envs(functools.partial(cls, num_drones=M), batch_size=6, n_processes=2, seed=1)
+        obs, info = env.reset()
+        assert obs.shape == (6, M, 72) and env.action_space.shape == (M, 4)
+        rng = np.random.default_rng(2)
+        dones = 0
+        for t in range(40):
+            obs, rew, done, info = env.step((rng.uniform(-1, 1, (6, M, 4)) - 0.8).astype(np.float32))
+            assert rew.shape == (6,) and np.isfinite(rew).all()
+            for e in np.nonzero(done)[0]:
+                dones += 1
+                assert info["n"][e]["terminal_observation"].shape == (M, 72)
+                assert obs[e, 0, 2] == pytest.approx(0.1125, abs=1e-6)      # default spawn height after the reset
+        assert dones >= 6, cls.__name__
+        env.close()
+
+
 def test_multi_device_handles_are_independent():
     """Two aviaries (two handles) on the same GPU do not share state."""
     from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
