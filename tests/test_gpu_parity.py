@@ -522,15 +522,19 @@ def test_fast_kernel_downwash_matches_oracle(M):
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("N,M,T,precision,physics", [(65536, 4, 400, "fp32", "dyn"), (20000, 3, 150, "fp32", "dyn_dw"),
+@pytest.mark.parametrize("N,M,T,precision,physics", [(65536, 4, 3000, "fp32", "dyn"), (70001, 4, 600, "fp32", "dyn"),
+                                                     (16384, 16, 300, "fp32", "dyn_dw"), (20000, 3, 150, "fp32", "dyn_dw"),
                                                      (20000, 3, 100, "fp64", "dyn")])
 def test_tile_pipelined_launches_equal_grid_serialised_launches(monkeypatch, N, M, T, precision, physics):
     """Tile-level step pipelining (a CTA waits for its own tile's previous step instead of the whole previous grid):
-    400 back-to-back control steps at the headline size, no host synchronisation in between, the SAME output
+    thousands of back-to-back control steps at the headline size (and a ragged last tile, the downwash variant, the
+    generic kernel in float and double), no host synchronisation in between, the SAME output
     buffers every step (write-after-write across overlapping launches), auto-reset on, a chunked host step in the
     middle (sub-range launches must publish tile epochs too) — bit-identical to the grid-serialised mode."""
     from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary, StepResult
-    xyz = np.array([[0.0, 0.0, 0.5], [1.0, 0.0, 0.5], [0.0, 1.0, 0.5], [1.0, 1.0, 0.5]])[:M]   # M = 3: the generic kernel
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[float(i % side) - 0.5 * (side - 1), float(i // side) - 0.5 * (side - 1), 0.5] for i in range(M)])
+    # M = 3: the generic kernel
     gen = torch.Generator(device="cuda").manual_seed(7)
     acts = torch.rand((8, N, M, 4), device="cuda", generator=gen) * 2 - 1.3      # descending: crashes and re-spawns
     host_a = acts[3].cpu().numpy()
