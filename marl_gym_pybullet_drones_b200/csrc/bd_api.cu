@@ -63,6 +63,7 @@ struct bd_handle {
   int* stepc = nullptr;
   int* gsteps = nullptr;
   int* tile_epoch = nullptr;
+  unsigned long long* finished = nullptr;
   int pipeline = 0;
   float* ep_ret = nullptr;
   double* ep_acc = nullptr;
@@ -96,7 +97,9 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
   P.E = h->E; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
-  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.tile_epoch = h->tile_epoch; P.pipeline = h->pipeline; P.pipe_wait = 0; P.early_prefetch = 0; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
+  P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.tile_epoch = h->tile_epoch; P.finished = h->finished;
+  P.step_tiles = h->spec.impl == 1 ? (h->n_total + bd::kBlock - 1) / bd::kBlock : (h->cfg.n_envs + h->E - 1) / h->E;
+  P.pipeline = h->pipeline; P.pipe_wait = 0; P.early_prefetch = 0; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
   P.ctrl = (R*)h->ctrl;
   P.act_type = c.act_type; P.ctrl_reset = c.ctrl_reset_on_reset;
   P.ctrl_dt = (R)(1.0 / c.ctrl_freq);                      // CTRL_TIMESTEP (BaseAviary.py:83)
@@ -228,7 +231,7 @@ int do_reset(bd_handle* h, const uint8_t* mask, float* obs, int force_fixed, cud
 
 void free_all(bd_handle* h) {
   cudaFree(h->s0); cudaFree(h->s1); cudaFree(h->s2); cudaFree(h->s3); cudaFree(h->s4);
-  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->tile_epoch); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
+  cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->tile_epoch); cudaFree(h->finished); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
   cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
@@ -340,8 +343,9 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   if (cfg->keep_ang_vel) alloc(&h->s4, plane);
   alloc((void**)&h->hist, (size_t)h->B * h->n_total * h->A * sizeof(float));   // zeros: BaseRLAviary.py:153-154
   alloc((void**)&h->stepc, (size_t)cfg->n_envs * sizeof(int));
-  alloc((void**)&h->gsteps, 8 * sizeof(int));   // [0] total steps, [1..4] rotating CTA tickets
+  alloc((void**)&h->gsteps, 16 * sizeof(int));   // [0] total steps, [1] CTA ticket, [8..15] per-launch wait decisions
   alloc((void**)&h->tile_epoch, (size_t)epoch_tiles(h) * sizeof(int));
+  alloc((void**)&h->finished, sizeof(unsigned long long));
   if (cfg->track_episodes) alloc((void**)&h->ep_ret, (size_t)cfg->n_envs * sizeof(float));
   alloc((void**)&h->ep_acc, 3 * sizeof(double));
   if (pid_act) alloc(&h->ctrl, (size_t)bd::kCtrlPlanesHost * h->n_total * h->real);   // zeros: DSLPIDControl.reset()
@@ -450,6 +454,8 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
     if (h->pipeline) {   // tile epochs restart with the step count (once per ~1e9 steps)
       cudaStreamSynchronize((cudaStream_t)stream);
       cudaMemset(h->tile_epoch, 0, (size_t)epoch_tiles(h) * sizeof(int));
+      cudaMemset(h->finished, 0, sizeof(unsigned long long));
+      cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
     }
   }
   if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
@@ -548,6 +554,9 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
       if (h->pipeline) {
         cudaDeviceSynchronize();
         cudaMemset(h->tile_epoch, 0, (size_t)epoch_tiles(h) * sizeof(int));
+        cudaMemset(h->finished, 0, sizeof(unsigned long long));
+        cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
+      cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
       }
     }
     BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a

@@ -82,10 +82,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   if (P.pipeline) {
     pdl_launch_dependents();
     if (pipe) {
-      if (tid == 0) {
-        while (ld_acquire_gpu(P.tile_epoch + bid) - P.host_total < 0) __nanosleep(64);
-      }
-      __syncthreads();
+      if (pipe_gate(P, bid, P.host_total, tid)) pdl_wait();
     } else {
       pdl_wait();
     }
@@ -93,6 +90,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   // ---- 1. every load of the tile is issued before anything is consumed ----------------------
   const int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
   const int head = total % B;   // ring slot overwritten by this step's action
+  pipe_recycle_slot(P, bid, total, tid);
   if (active) {
     if (vec) issue_history<R, A, (A == 4)>(P, g, head, myrow, 0, B - 1);
     else issue_history<R, A, false>(P, g, head, myrow, 0, B - 1);
@@ -440,6 +438,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
         }
       }
       st_release_gpu(P.tile_epoch + bid, total + 1);
+      atomicAdd(P.finished, 1ull);
     }
     return;
   }

@@ -64,6 +64,8 @@ struct Params {
   int host_head;                  // host_total % B when host_total >= 0
   int total_wrap;                 // step counters wrap at this multiple of B (ring head stays continuous)
   int* tile_epoch;                // [tiles] control steps completed per tile (tile-level step pipelining)
+  unsigned long long* finished;   // tiles finished since creation, all steps (== total * step_tiles: previous step complete)
+  long long step_tiles;           // tiles of one whole control step with this handle's kernel
   int pipeline;                   // 1: the handle pipelines steps tile by tile: every launch publishes tile epochs
   int pipe_wait;                  // 1: this launch waits for MY tile's previous step only (no grid-wide dependency wait)
   int early_prefetch;             // 1: ring planes may be prefetched before griddepcontrol.wait (grid >= resident capacity)

@@ -33,19 +33,28 @@ struct TileIn {
   float ep_ret;
 };
 
+// the handle's own data (written by the previous step of this tile) ...
 template <int A>
-__device__ __forceinline__ void load_inputs(const Params<float>& P, long long g, int log2m, TileIn<A>& in) {
+__device__ __forceinline__ void load_state(const Params<float>& P, long long g, int log2m, TileIn<A>& in) {
   if (g < P.n_total) {
     in.s0 = P.s0[g]; in.s1 = P.s1[g]; in.s2 = P.s2[g]; in.s3 = P.s3[g];
-    if constexpr (A == 4) in.act = reinterpret_cast<const float4*>(P.actions)[g];
-    else in.act = make_float4(reinterpret_cast<const float*>(P.actions)[g], 0.f, 0.f, 0.f);
     in.stepc = P.stepc[g >> log2m];
     in.ep_ret = P.ep_ret != nullptr ? P.ep_ret[g >> log2m] : 0.f;
   } else {
-    in.s0 = in.s1 = in.s2 = in.s3 = in.act = make_float4(0.f, 0.f, 0.f, 0.f);
+    in.s0 = in.s1 = in.s2 = in.s3 = make_float4(0.f, 0.f, 0.f, 0.f);
     in.s1.z = 1.0f;
     in.stepc = 0;
     in.ep_ret = 0.f;
+  }
+}
+// ... and the caller's (possibly written by the kernel enqueued just before this launch)
+template <int A>
+__device__ __forceinline__ void load_action(const Params<float>& P, long long g, TileIn<A>& in) {
+  if (g < P.n_total) {
+    if constexpr (A == 4) in.act = reinterpret_cast<const float4*>(P.actions)[g];
+    else in.act = make_float4(reinterpret_cast<const float*>(P.actions)[g], 0.f, 0.f, 0.f);
+  } else {
+    in.act = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -82,13 +91,12 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     // (whole environments), and was written by the CTA that stepped this tile in the previous control step.
     // So instead of griddepcontrol.wait (the whole previous grid finished and flushed) the CTA waits for its own
     // tile's epoch: launches overlap tile by tile, no lock-step start, no idle tail.  (All CTAs of the previous
-    // launch are resident or done before any CTA of this one starts, so the spin cannot deadlock.)
+    // launch are resident or done before any CTA of this one starts, so the spin cannot deadlock.)  pipe_gate
+    // also decides, once per launch, whether the grid-wide wait is needed after all (a foreign kernel, e.g. the
+    // one that produced the actions, ran between the two steps).
     total = P.host_total;
     head = P.host_head;
-    if (tid == 0) {
-      while (ld_acquire_gpu(P.tile_epoch + tile) - total < 0) __nanosleep(64);
-    }
-    __syncthreads();
+    if (pipe_gate(P, tile, total, tid)) pdl_wait();
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
   } else if (P.host_total >= 0 && P.early_prefetch) {
     total = P.host_total;
@@ -101,10 +109,12 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     head = total % B;
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
   }
+  pipe_recycle_slot(P, tile, total, tid);
   TileIn<A> cur;
-  load_inputs<A>(P, g, log2m, cur);
+  load_state<A>(P, g, log2m, cur);
   issue_history<float, A, VEC>(P, g, head, myrow, B - 2, B - 1);
   cp_async_commit();
+  load_action<A>(P, g, cur);
   const int stepc = cur.stepc;
 
   Drone<float> d;
@@ -288,6 +298,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
         }
       }
       st_release_gpu(P.tile_epoch + tile, total + 1);   // cumulative: the CTA's stores are visible before the epoch
+      atomicAdd(P.finished, 1ull);
     }
     return;
   }

@@ -553,7 +553,11 @@ def test_tile_pipelined_launches_equal_grid_serialised_launches(monkeypatch, N, 
                 h = env.step_host(host_a)
                 rsum += float(h["reward"].astype(np.float64).sum())
                 continue
-            env.step_device(acts[t % 8], out=out)
+            if 60 <= t % 100 < 80:    # actions written by a foreign kernel enqueued right before the step (a "policy")
+                a = torch.tanh(out.obs[:, :, 6:10] * 0.5) - 0.3
+                env.step_device(a if precision == "fp32" else a.to(env.action_dtype), out=out)
+            else:
+                env.step_device(acts[t % 8], out=out)
             if t % 50 == 49:
                 rsum += out.reward.double().sum()      # a consumer kernel between two steps
         torch.cuda.synchronize()
