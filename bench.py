@@ -382,4 +382,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON result: anything libraries print on file descriptor 1 meanwhile
+    # (e.g. NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
     main()
