@@ -376,20 +376,27 @@ def test_host_step_equals_device_step(M, N):
                            seed=5) for _ in range(2)]
     for e in envs:
         e.reset_device()
+    seen_done = False
     for t in range(20 if N > 100 else 6):
         a = (rng.uniform(-1, 1, (N, M, 4)) - 0.6).astype(np.float32)
-        d = envs[0].step_device(torch.as_tensor(a, device="cuda"))
+        want_t = t >= 12          # by then envs are crashing: terminal observations through the chunk pipeline too
+        d = envs[0].step_device(torch.as_tensor(a, device="cuda"), want_terminal_obs=want_t)
         if t % 2:      # caller-provided page-locked actions go to the copy engine without the staging memcpy
             pa = envs[1].pinned_array(a.shape, np.float32)
             pa[...] = a
-            h = envs[1].step_host(pa, actions_pinned=True)
+            h = envs[1].step_host(pa, actions_pinned=True, want_terminal_obs=want_t)
         else:
-            h = envs[1].step_host(a)
+            h = envs[1].step_host(a, want_terminal_obs=want_t)
+        if want_t:
+            done = (d.terminated | d.truncated).cpu().numpy()
+            seen_done = seen_done or bool(done.any())
+            assert np.array_equal(d.terminal_obs.cpu().numpy()[done], h["terminal_obs"][done])
         assert np.array_equal(d.obs.cpu().numpy(), h["obs"])
         assert np.array_equal(d.reward.cpu().numpy(), h["reward"])
         assert np.array_equal(d.terminated.cpu().numpy(), h["terminated"])
         assert np.array_equal(d.truncated.cpu().numpy(), h["truncated"])
     if N > 100:
+        assert seen_done
         assert envs[1].launch_count > envs[0].launch_count      # chunked sub-range launches
     st0, st1 = envs[0].get_state().cpu().numpy(), envs[1].get_state().cpu().numpy()
     assert np.array_equal(st0, st1, equal_nan=True)      # ang_v columns are NaN without keep_ang_vel
