@@ -301,7 +301,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   h->spec.act_a = h->A;
   h->spec.precision = cfg->precision;
   h->spec.device = cfg->device;
-  const bool swarm = cfg->task >= BD_TASK_MEETUP;   // coupled rewards: generic kernel only
+  const bool swarm = cfg->task >= BD_TASK_MEETUP;   // coupled rewards: fast tile kernel or generic kernel, never the non-generic CTA kernel
   h->spec.generic = (cfg->aero_flags != 0 || cfg->integrator != BD_INTEGRATOR_QUAT || cfg->keep_ang_vel || pid_act || swarm) ? 1 : 0;
   {
     // kernel selection: the fast tile kernel covers the throughput configurations
@@ -313,7 +313,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     // the fast kernel also carries downwash alone (shuffle exchange inside the env's lane group)
     const bool fast_aero = cfg->aero_flags == 0 || cfg->aero_flags == BD_AERO_DW;
     const bool plain = fast_aero && cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
-    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act && !swarm) ? 1 : 0;
+    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;

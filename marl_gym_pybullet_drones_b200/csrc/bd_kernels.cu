@@ -703,8 +703,12 @@ static cudaError_t step_t(const LaunchSpec& ls, const void* p, cudaStream_t st) 
     case TASK_HOVER: return step_a<R, TASK_HOVER>(ls, p, st);
     case TASK_MULTIHOVER: return step_a<R, TASK_MULTIHOVER>(ls, p, st);
     case TASK_SPIRAL: return step_a<R, TASK_SPIRAL>(ls, p, st);
-    default: {   // swarm tasks: always the generic kernel
+    default: {   // swarm tasks: the fast tile kernel where it applies, else the generic kernel (never the non-generic CTA kernel)
       const Params<R>& P = *static_cast<const Params<R>*>(p);
+      if constexpr (sizeof(R) == 4) {
+        if (ls.impl == 1 && ls.act_a != 3)
+          return ls.act_a == 4 ? launch_step_tile_t<TASK_SWARM, 4>(P, ls, st) : launch_step_tile_t<TASK_SWARM, 1>(P, ls, st);
+      }
       if (ls.act_a == 3) return launch_step_t<R, TASK_SWARM, 3, true>(P, ls, st);
       return ls.act_a == 4 ? launch_step_t<R, TASK_SWARM, 4, true>(P, ls, st)
                            : launch_step_t<R, TASK_SWARM, 1, true>(P, ls, st);

@@ -58,6 +58,83 @@ __device__ __forceinline__ void load_action(const Params<float>& P, long long g,
   }
 }
 
+// Swarm tasks (Meetup / Flock / LeaderFollower, bd_device.cuh: swarm_terms / swarm_reward) on the fast kernel: the env's
+// drones are a lane group of M, so partners' final positions / velocities arrive by warp shuffle and the env-level
+// sums by xor butterflies.  Executed by every lane of the warp (inactive lanes carry zeros); returns the env's
+// reward, sets this drone's flag bits (bit1: truncation bound, bit2: my pair has not met).
+__device__ __forceinline__ float swarm_reward_shfl(const Params<float>& P, const Drone<float>& d, float roll, float pitch,
+                                                   int lane, int M, int drone, int& flags) {
+  const unsigned full = 0xffffffffu;
+  const int base = lane & ~(M - 1);
+  const bool tilt = fabsf(roll) > .4f || fabsf(pitch) > .4f;
+  flags = 0;
+  float contrib = 0.f;
+  if (P.task == TASK_MEETUP) {
+    const int src = base | (M - 1 - drone);
+    const float ox = __shfl_sync(full, d.px, src), oy = __shfl_sync(full, d.py, src), oz = __shfl_sync(full, d.pz, src);
+    if (drone < M / 2) {                                                         // MeetupAviary.py:88-93
+      const float dx = d.px - ox, dy = d.py - oy, dz = d.pz - oz;
+      const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      contrib = (-1.f * (dist * dist)) * 2.f;
+      if (dist > 0.1f) flags |= 4;                                               // :115-118
+    }
+    if (fabsf(d.px) > 5.0f || fabsf(d.py) > 5.0f || d.pz > 3.0f || d.pz < 0.1f || tilt) flags |= 2;   // :142-147
+  } else if (P.task == TASK_LEADERFOLLOWER) {
+    const float z0 = __shfl_sync(full, d.pz, base);
+    if (drone == 0) {                                                            // LeaderFollowerAviary.py:88
+      const float ex = 0.f - d.px, ey = 0.f - d.py, ez = 0.5f - d.pz;
+      const float n = sqrtf(ex * ex + ey * ey + ez * ez);
+      contrib = -1.f * (n * n);
+    } else {                                                                     // :91-97
+      const float dz = z0 - d.pz;
+      const float n = sqrtf(dz * dz);
+      contrib = -(1.f / (float)M) * (n * n);
+    }
+    if (fabsf(d.px) > 2.0f || fabsf(d.py) > 2.0f || d.pz > 2.0f || tilt) flags |= 2;   // :135-140
+  } else {                                                                       // FlockAviary.py:75-150
+    const float eps = 1e-3f;
+    const float ni = sqrtf(d.vx * d.vx + d.vy * d.vy + d.vz * d.vz);
+    float ali = 0.f, sp = 0.f;
+#pragma unroll 1
+    for (int o = 1; o < M; ++o) {
+      const int src = base | ((lane + o) & (M - 1));
+      const float ox = __shfl_sync(full, d.px, src), oy = __shfl_sync(full, d.py, src), oz = __shfl_sync(full, d.pz, src);
+      const float ux = __shfl_sync(full, d.vx, src), uy = __shfl_sync(full, d.vy, src), uz = __shfl_sync(full, d.vz, src);
+      const float nj = __shfl_sync(full, ni, src);
+      const float dot = d.vx * ux + d.vy * uy + d.vz * uz;
+      ali += dot / (ni + eps) / (nj + eps);                                      // :98-103
+      const float dx = ox - d.px, dy = oy - d.py, dz = oz - d.pz;
+      const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      sp = (o == 1 || dist < sp) ? dist : sp;                                    // :121-125 nearest neighbour
+    }
+    if (fabsf(d.px) > 10.0f || fabsf(d.py) > 10.0f || d.pz > 10.0f || tilt) flags |= 2;   // :181-184
+    float cx = d.vx, cy = d.vy, cz = d.vz, ssp = sp;
+#pragma unroll 1
+    for (int o = M >> 1; o > 0; o >>= 1) {
+      ali += __shfl_xor_sync(full, ali, o);
+      cx += __shfl_xor_sync(full, cx, o); cy += __shfl_xor_sync(full, cy, o); cz += __shfl_xor_sync(full, cz, o);
+      ssp += __shfl_xor_sync(full, ssp, o);
+    }
+    cx /= (float)M; cy /= (float)M; cz /= (float)M;                              // :111-112
+    const float speed = sqrtf(cx * cx + cy * cy + cz * cz);
+    if (M == 1) return speed;
+    const float avg = ssp / (float)M;
+    float var = (sp - avg) * (sp - avg);
+#pragma unroll 1
+    for (int o = M >> 1; o > 0; o >>= 1) var += __shfl_xor_sync(full, var, o);
+    var /= (float)M;                                                             // np.var (:131)
+    float pen = 0.f;
+    if (!(1.0f < avg && avg < 3.0f)) {                                           // :137-141
+      const float a = fabsf(avg - 1.0f), b = fabsf(avg - 3.0f);
+      pen = a < b ? a : b;
+    }
+    return ((ali / (float)(M * (M - 1)) + speed) - pen) - var;                   // :145
+  }
+#pragma unroll 1
+  for (int o = M >> 1; o > 0; o >>= 1) contrib += __shfl_xor_sync(full, contrib, o);
+  return contrib;
+}
+
 template <int TASK, int A, bool VEC, bool DW>
 __global__ void __launch_bounds__(kBlock, 6)
 step_kernel_tile(const __grid_constant__ Params<float> P) {
@@ -153,7 +230,8 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
       myrow[0] = d.px; myrow[1] = d.py; myrow[2] = d.pz; myrow[3] = roll; myrow[4] = pitch; myrow[5] = yaw;
       myrow[6] = d.vx; myrow[7] = d.vy; myrow[8] = d.vz; myrow[9] = avx; myrow[10] = avy; myrow[11] = avz;
     }
-    task_terms<float, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
+    if constexpr (TASK != TASK_SWARM)
+      task_terms<float, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
     // newest history entry: tail of the row and ring slot `head`
     if constexpr (A == 4) {
       if (vec) *reinterpret_cast<float4*>(myrow + 12 + (B - 1) * 4) = cur.act;
@@ -165,15 +243,22 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     }
   }
 
+  float swarm_reward_env = 0.f;
+  if constexpr (TASK == TASK_SWARM) {
+    int fl = 0;
+    swarm_reward_env = swarm_reward_shfl(P, d, roll, pitch, lane, M, drone, fl);
+    flags = active ? fl : 0;
+  }
   // ---- per-env reduction with shuffles (envs are lane groups of M) --------------------------------
 #pragma unroll 1
   for (int o = M >> 1; o > 0; o >>= 1) {
     contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
     flags |= __shfl_xor_sync(0xffffffffu, flags, o);
   }
-  const float reward = (TASK == TASK_HOVER) ? contrib : contrib / (float)M;
+  const float reward = (TASK == TASK_SWARM) ? swarm_reward_env : ((TASK == TASK_HOVER) ? contrib : contrib / (float)M);
   const bool time_up = stepc >= P.trunc_counter;   // step_counter/PYB_FREQ > EPISODE_LEN_SEC, pre-increment (:379,:382)
-  const bool terminated = (flags & 1) != 0;
+  // Meetup terminates when every pair has met (MeetupAviary.py:115-121; no pairs at M = 1: always)
+  const bool terminated = (TASK == TASK_SWARM) ? (P.task == TASK_MEETUP && (flags & 4) == 0) : (flags & 1) != 0;
   const bool truncated = ((flags & 2) != 0) || time_up;
   const bool done_reset = active && (terminated || truncated) && P.auto_reset;
   if (active && drone == 0) {

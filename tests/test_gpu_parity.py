@@ -265,7 +265,11 @@ def test_autoreset_fixed_mode_hover_and_spiral():
 @pytest.mark.parametrize("task,M,N,precision,tol", [("meetup", 6, 30, "fp64", FP64_TOL), ("flock", 7, 40, "fp64", FP64_TOL),
                                                     ("flock", 16, 9, "fp64", FP64_TOL), ("leaderfollower", 5, 30, "fp64", FP64_TOL),
                                                     ("flock", 7, 40, "fp32", 2e-4), ("meetup", 6, 30, "fp32", 2e-4),
-                                                    ("leaderfollower", 128, 2, "fp64", FP64_TOL)])
+                                                    ("leaderfollower", 128, 2, "fp64", FP64_TOL),
+                                                    # float, M a power of two: the fast tile kernel (shuffle exchange)
+                                                    ("flock", 8, 40, "fp32", 2e-4), ("flock", 32, 9, "fp32", 2e-4),
+                                                    ("meetup", 4, 70, "fp32", 2e-4), ("leaderfollower", 2, 100, "fp32", 2e-4),
+                                                    ("flock", 1, 130, "fp32", 2e-4), ("meetup", 1, 130, "fp32", 2e-4)])
 def test_swarm_tasks_match_oracle(task, M, N, precision, tol):
     """Meetup / Flock / LeaderFollower (coupled rewards): several CTAs, envs that do not fill a
     CTA (M = 6, 7), one env per CTA (M = 128), distinct actions per env; every step vs the oracle."""
