@@ -31,6 +31,7 @@ import math
 import time
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -428,6 +429,42 @@ class DeviceMAPPO:
         if deterministic:
             return mean
         return mean + self.ac.logstd.exp() * torch.randn(mean.shape, device=mean.device, generator=self.gen)
+
+    @torch.no_grad()
+    def run(self, env: Optional[BatchAviary] = None, n_episodes: int = 10, max_steps: Optional[int] = None):
+        """`MAPPO.run` (mappo.py:534-581): evaluation with the current policy — deterministic actions, frozen
+        observation statistics — returning `{'ep_returns', 'ep_lengths'}` of `n_episodes` episodes.  The reference
+        plays them one after the other in a single env; here `env` (default: a fresh aviary configured like the
+        training one with `n_episodes` envs, no auto-reset) plays one episode per env in parallel, each env counted
+        up to its first `done`.  The per-step return is the env reward, = `mean(r)` over agents of the tiled reward
+        (`record_episode_statistics.py:148`)."""
+        own = env is None
+        if own:
+            t = self.env
+            env = BatchAviary(task=t.task, num_envs=int(n_episodes), drone_model=t.DRONE_MODEL, num_drones=t.NUM_DRONES,
+                              initial_xyzs=np.asarray(t.INIT_XYZS, dtype=np.float64).reshape(-1, 3)[:t.NUM_DRONES],
+                              physics=t.PHYSICS, pyb_freq=t.PYB_FREQ, ctrl_freq=t.CTRL_FREQ, act=t.ACT_TYPE,
+                              precision=t.precision, device=self.device, auto_reset=False, seed=12345)
+        if env.auto_reset:
+            raise ValueError("run() needs an aviary with auto_reset=False (episodes are counted up to their first done)")
+        n = env.num_envs
+        obs = env.reset_device()
+        ret = torch.zeros(n, dtype=torch.float64, device=self.device)
+        length = torch.zeros(n, dtype=torch.int64, device=self.device)
+        alive = torch.ones(n, dtype=torch.bool, device=self.device)
+        horizon = int(max_steps) if max_steps is not None else int(env.EPISODE_LEN_SEC * env.CTRL_FREQ) + 2
+        for _ in range(horizon):
+            res = env.step_device(self.select_action(obs, deterministic=True).to(env.action_dtype))
+            ret += torch.where(alive, res.reward.double(), torch.zeros_like(ret))
+            length += alive.long()
+            alive &= ~res.done
+            obs = res.obs
+            if not bool(alive.any()):      # one scalar read-back per control step (evaluation is not the hot path)
+                break
+        out = {"ep_returns": ret.cpu().numpy(), "ep_lengths": length.cpu().numpy()}
+        if own:
+            env.close()
+        return out
 
     def state_dict(self):
         """The reference's checkpoint layout (`MAPPO.save`, mappo/mappo.py:203-232): `agent` =

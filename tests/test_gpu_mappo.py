@@ -119,3 +119,19 @@ def test_graphed_update_equals_eager_update_and_kl_gate_closes():
     for k in res_g:
         assert abs(res_g[k] - res_e[k]) <= 1e-5 * max(1.0, abs(res_e[k])), k
     env.close()
+
+
+def test_run_evaluates_deterministically_like_mappo_run():
+    """`DeviceMAPPO.run` (reference `MAPPO.run`, mappo.py:534-581): n episodes with the mean action, returns and
+    lengths per episode; the untrained hover policy holds altitude-ish and reaches the 242-step truncation or an
+    earlier bound, and two evaluations agree exactly (deterministic actions, fixed spawn)."""
+    from marl_gym_pybullet_drones_b200 import BatchAviary, DeviceMAPPO
+    env = BatchAviary(task="hover", num_envs=64, act="one_d_rpm", seed=1, track_episode_stats=True)
+    algo = DeviceMAPPO(env, rollout_steps=8, hidden_dim=64, seed=0)
+    r1 = algo.run(n_episodes=5)
+    r2 = algo.run(n_episodes=5)
+    assert r1["ep_returns"].shape == (5,) and r1["ep_lengths"].shape == (5,)
+    assert np.array_equal(r1["ep_returns"], r2["ep_returns"]) and np.array_equal(r1["ep_lengths"], r2["ep_lengths"])
+    assert (r1["ep_lengths"] >= 1).all() and (r1["ep_lengths"] <= 242).all() and np.isfinite(r1["ep_returns"]).all()
+    assert len(set(r1["ep_lengths"].tolist())) == 1           # identical envs, identical deterministic episodes
+    env.close()
