@@ -373,6 +373,11 @@ class DeviceMAPPO:
         n = self.T * self.N
         mb = min(int(cfg["mini_batch_size"]), n)
         num_mb = n // mb
+        if num_mb > 8192 and not getattr(self, "_warned_mb", False):
+            import warnings
+            warnings.warn(f"{num_mb} minibatches of {mb} samples per epoch: mini_batch_size is the reference's default "
+                          f"(mappo/config.py:32) sized for a handful of envs; with {self.N} envs use e.g. {max(mb, n // 64)}")
+            self._warned_mb = True
         self._world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         if not hasattr(self, "_stats"):
             self._stats = torch.zeros(5, device=self.device)
