@@ -18,8 +18,14 @@
 // is no reduction scratch; (4) one __syncthreads, then the 128 finished rows (36 864 B for
 // D = 72) leave as ONE TMA bulk store issued by thread 0; state planes and the ring slot
 // are plain 128-bit stores.
-// The global step count (ring head, Philox stream id) lives in device memory and is
-// advanced by the last CTA to finish, so the launch is CUDA-graph replayable.
+// Dependency on the previous control step (0): per tile, not per grid.  A CTA waits (ld.acquire) for the
+// epoch its own tile's previous CTA published (st.release) instead of griddepcontrol.wait, so back-to-back
+// launches overlap tile by tile; a per-launch decision (bd_device.cuh: pipe_gate) falls back to the
+// grid-wide wait when a foreign kernel ran between two steps.  DESIGN.md section 4 has the protocol.
+// The global step count (ring head, Philox stream id) is a host-tracked parameter; a device-resident copy
+// (advanced by tile 0's CTA, or by the last CTA out under CUDA-graph replay) keeps the launch replayable.
+// Tasks: Hover, MultiHover, Spiral, and the swarm tasks (Meetup / Flock / LeaderFollower) through warp-shuffle
+// exchange inside the env's lane group (swarm_reward_shfl).
 #pragma once
 #include "bd_device.cuh"
 
