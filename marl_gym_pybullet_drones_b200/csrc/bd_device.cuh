@@ -147,6 +147,24 @@ __device__ __forceinline__ void quat_to_euler(R x, R y, R z, R w, R& roll, R& pi
   }
 }
 
+// `abs(roll) < pi/2 and abs(pitch) < pi/2` (the ground-effect gate, BaseAviary.py:735) without the three inverse
+// trigonometric calls per substep: pitch = asin(sarg) is below pi/2 exactly when the gimbal branches are not taken,
+// |atan2(ys, xs)| < pi/2 exactly when xs > 0 — except within rounding distance of 90 degrees, where the full
+// extraction decides (so the decision is the reference's in every case).
+template <typename R>
+__device__ __forceinline__ bool tilt_below_half_pi(R x, R y, R z, R w) {
+  const R sarg = R(-2) * (x * z - w * y);
+  if (sarg <= R(-0.99999) || sarg >= R(0.99999)) return false;   // pitch = -+pi/2 exactly
+  const R xs = w * w - x * x - y * y + z * z, ys = R(2) * (y * z + w * x);
+  if (abs_(xs) <= R(1e-5) * abs_(ys)) {
+    R roll, pitch, yaw;
+    quat_to_euler(x, y, z, w, roll, pitch, yaw);
+    const R half_pi = R(0.5 * 3.14159265358979323846);
+    return abs_(roll) < half_pi && abs_(pitch) < half_pi;
+  }
+  return xs > R(0);
+}
+
 // atan2 for the float throughput path: one range reduction to |t| <= tan(pi/8) (through the half-angle identity
 // atan(a) = pi/4 + atan((a - 1) / (a + 1)) when a > tan(pi/8), a = min/max), ONE division, a degree-4 minimax
 // polynomial in t^2 (max error 3.3e-8 in float arithmetic), octant fix-ups.  |error| < 3e-7 rad overall,

@@ -219,10 +219,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
       R fx_extra = R(0), fy_extra = R(0), fz_extra = R(0);
       if (GENERIC && P.aero) {
         if (P.aero & AERO_GND) {             // :739-742, added to the propeller thrusts
-          R roll, pitch, yaw;
-          quat_to_euler(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
-          const R half_pi = R(0.5 * 3.14159265358979323846);
-          if (abs_(roll) < half_pi && abs_(pitch) < half_pi) {
+          if (tilt_below_half_pi(d.qx, d.qy, d.qz, d.qw)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               R h = d.pz + (m[6] * P.prop_x[k] + m[7] * P.prop_y[k]);

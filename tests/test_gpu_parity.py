@@ -149,6 +149,20 @@ def test_aero_terms_match_oracle_cfg3(precision, tol, physics, aero):
               obs_tol=OBS_F32_TOL if precision == "fp64" else tol)
 
 
+@pytest.mark.parametrize("precision,tol", [("fp64", FP64_TOL), ("fp32", 2e-4)])
+def test_ground_effect_gate_at_large_tilt(precision, tol):
+    """The ground-effect term is switched off when |roll| or |pitch| reaches pi/2 (BaseAviary.py:735): the kernel decides
+    it from the sign of the atan2 argument instead of the angles; inverted, beyond-90-degree, near-90-degree and
+    near-gimbal starts close to the ground, where the term matters, must follow the oracle."""
+    cfg = dict(task="multihover", drone_model="cf2x", num_drones=4, pyb_freq=240, ctrl_freq=48, act="rpm")
+    xyz = np.array([[0.0, 0.0, 0.06], [0.6, 0.0, 0.05], [0.0, 0.6, 0.08], [0.6, 0.6, 0.04]])
+    rpy = np.array([[2.0, 0.1, 0.0], [1.5707, 0.05, 0.3], [0.2, 1.56, -0.4], [-1.5709, -0.3, 1.0]])
+    rng = np.random.default_rng(8)
+    actions = (0.3 * rng.standard_normal((10, 3, 4, 4))).astype(np.float32)
+    _run_pair(cfg, xyz, rpy, actions, precision, physics="dyn_gnd", aero=1, tol=tol,
+              obs_tol=OBS_F32_TOL if precision == "fp64" else tol)
+
+
 def test_downwash_stacked_pair_fp64():
     """examples/downwash.py layout moved inside the wake: lower drone is pushed down."""
     cfg = dict(task="multihover", drone_model="cf2x", num_drones=2, pyb_freq=240, ctrl_freq=48, act="rpm")
