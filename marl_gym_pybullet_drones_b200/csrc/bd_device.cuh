@@ -773,18 +773,11 @@ __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
 
 // gsteps layout: [0] total control steps, [1] CTA ticket (graph replays), [8..15] per-launch wait decisions
 constexpr int kModeSlots = 8;
-// Recycle the decision slot of the launch four steps ahead.  Run by tile 0's CTA of EVERY launch of a
-// pipelining handle at its start: all CTAs of launch t have started before any CTA of launch t+1 does, so the
-// slot is clean long before launch t+4 looks at it (and launch t-4, its previous user, is long gone).
-template <typename R>
-__device__ __forceinline__ void pipe_recycle_slot(const Params<R>& P, int tile, int total, int tid) {
-  if (P.pipeline && tid == 0 && tile == 0) st_relaxed_gpu(P.gsteps + 8 + ((total + 4) & (kModeSlots - 1)), 0);
-}
-
 // Tile-level dependency on the previous control step (see bd_step_tile.cuh).  Returns nonzero when the CTA must
 // still execute griddepcontrol.wait.  Two lanes work in parallel: lane 0 of warp 1 spins (ld.acquire) on this
 // tile's epoch; lane 0 of warp 0 reads the launch's decision, made once per launch by the first CTA that finds
-// the slot empty: if the handle's previous step has not finished completely (finished-tile counter), the
+// the slot empty (or left over from an older launch): if the handle's previous step has not finished completely
+// (finished-tile counter), the
 // launch's programmatic primary can only be that step — anything else enqueued between two steps would itself
 // have waited for the first one to finish — and the epochs cover everything: no grid-wide wait for any CTA of
 // this launch (1).  Otherwise every CTA executes griddepcontrol.wait (2): free for our own finished kernel, and
@@ -793,15 +786,18 @@ template <typename R>
 __device__ __forceinline__ int pipe_gate(const Params<R>& P, int tile, int total, int tid) {
   int must_wait = 0;
   if (tid == 0) {
-    int* slot = P.gsteps + 8 + (total & (kModeSlots - 1));
-    int m = ld_relaxed_gpu(slot);
-    if (m == 0) {
+    // decision slots are tagged with the launch they belong to ((total + 1) << 2 | mode), so a slot left over from
+    // the launch that used it eight steps earlier simply reads as empty: no recycling, no ordering to maintain
+    unsigned* slot = reinterpret_cast<unsigned*>(P.gsteps + 8 + (total & (kModeSlots - 1)));
+    const unsigned tag = ((unsigned)(total + 1) & 0x3fffffffu) << 2;
+    unsigned v = (unsigned)ld_relaxed_gpu(reinterpret_cast<const int*>(slot));
+    if ((v & ~3u) != tag || (v & 3u) == 0u) {
       const bool done = ld_relaxed_gpu_u64(P.finished) >= (unsigned long long)total * (unsigned long long)P.step_tiles;
-      const int want = done ? 2 : 1;
-      const int old = atomicCAS(slot, 0, want);
-      m = old == 0 ? want : old;
+      const unsigned want = tag | (done ? 2u : 1u);
+      const unsigned old = atomicCAS(slot, v, want);
+      v = (old == v) ? want : (((old & ~3u) == tag && (old & 3u) != 0u) ? old : want);   // lost the race: take the winner's
     }
-    must_wait = (m == 2);
+    must_wait = ((v & 3u) == 2u);
   } else if (tid == 32) {
     while (ld_acquire_gpu(P.tile_epoch + tile) - total < 0) __nanosleep(64);
   }

@@ -90,7 +90,6 @@ step_kernel(const __grid_constant__ Params<R> P) {
   // ---- 1. every load of the tile is issued before anything is consumed ----------------------
   const int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
   const int head = total % B;   // ring slot overwritten by this step's action
-  pipe_recycle_slot(P, bid, total, tid);
   if (active) {
     if (vec) issue_history<R, A, (A == 4)>(P, g, head, myrow, 0, B - 1);
     else issue_history<R, A, false>(P, g, head, myrow, 0, B - 1);

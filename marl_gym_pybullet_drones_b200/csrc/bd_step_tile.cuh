@@ -192,7 +192,6 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     head = total % B;
     issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
   }
-  pipe_recycle_slot(P, tile, total, tid);
   TileIn<A> cur;
   load_state<A>(P, g, log2m, cur);
   issue_history<float, A, VEC>(P, g, head, myrow, B - 2, B - 1);
