@@ -217,6 +217,8 @@ class BatchAviary:
             lo[:, 12:12 + A * B], hi[:, 12:12 + A * B] = -1.0, 1.0
         self.observation_space = Box(low=lo, high=hi, dtype=np.float32)
         self._terminal_obs = None
+        self._out_cache = None
+        self._bd_step = self._lib.bd_step
         self._closed = False
 
     # ------------------------------------------------------------------ utils
@@ -287,20 +289,32 @@ class BatchAviary:
             reward = torch.empty((N,), dtype=self.real_dtype, device=self.device)
             term = torch.empty((N,), dtype=torch.uint8, device=self.device)
             trunc = torch.empty((N,), dtype=torch.uint8, device=self.device)
+            ptrs = (obs.data_ptr(), reward.data_ptr(), term.data_ptr(), trunc.data_ptr())
+            ret = None
         else:
-            obs, reward = out.obs, out.reward
-            term, trunc = out.terminated.view(torch.uint8), out.truncated.view(torch.uint8)
+            # a caller that steps into the same StepResult again and again (a rollout buffer slot, the bench) pays for
+            # the pointer extraction once: at small batch sizes a step is bound by this call's host time
+            cached = self._out_cache
+            if cached is not None and cached[0] is out:
+                ptrs = cached[1]
+            else:
+                ptrs = (out.obs.data_ptr(), out.reward.data_ptr(), out.terminated.data_ptr(), out.truncated.data_ptr())
+                self._out_cache = (out, ptrs)
+            ret = out
         tobs_ptr = None
         tobs = None
         if want_terminal_obs:
             if self._terminal_obs is None:
                 self._terminal_obs = torch.zeros((N, M, self.OBS_DIM), dtype=torch.float32, device=self.device)
             tobs = self._terminal_obs
-            tobs_ptr = C.c_void_p(tobs.data_ptr())
-        _native.check(self._lib.bd_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()),
-                                        C.c_void_p(reward.data_ptr()), C.c_void_p(term.data_ptr()),
-                                        C.c_void_p(trunc.data_ptr()), tobs_ptr, self._stream()), "bd_step")
-        return StepResult(obs, reward, term.view(torch.bool), trunc.view(torch.bool), tobs)
+            tobs_ptr = tobs.data_ptr()
+        rc = self._bd_step(self._h, actions.data_ptr(), ptrs[0], ptrs[1], ptrs[2], ptrs[3], tobs_ptr,
+                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            _native.check(rc, "bd_step")
+        if ret is None:
+            return StepResult(obs, reward, term.view(torch.bool), trunc.view(torch.bool), tobs)
+        return ret if tobs is None and ret.terminal_obs is None else ret._replace(terminal_obs=tobs)
 
     @staticmethod
     def pinned_array(shape, dtype=np.float32) -> np.ndarray:
