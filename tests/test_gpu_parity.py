@@ -574,6 +574,8 @@ def test_tile_pipelined_launches_equal_grid_serialised_launches(monkeypatch, N, 
         obs = torch.empty((N, M, env.OBS_DIM), device="cuda")
         out = StepResult(obs, torch.empty(N, device="cuda", dtype=env.real_dtype), torch.empty(N, dtype=torch.bool, device="cuda"),
                          torch.empty(N, dtype=torch.bool, device="cuda"), None)
+        # a second output buffer used in an irregular pattern: same-buffer and changed-buffer steps alternate
+        out_b = StepResult(torch.empty_like(obs), out.reward, out.terminated, out.truncated, None)
         env.reset_device()
         rsum = torch.zeros((), dtype=torch.float64, device="cuda")
         for t in range(T):
@@ -584,13 +586,15 @@ def test_tile_pipelined_launches_equal_grid_serialised_launches(monkeypatch, N, 
             if 60 <= t % 100 < 80:    # actions written by a foreign kernel enqueued right before the step (a "policy")
                 a = torch.tanh(out.obs[:, :, 6:10] * 0.5) - 0.3
                 env.step_device(a if precision == "fp32" else a.to(env.action_dtype), out=out)
+            elif (t % 7) in (1, 2, 5) and t != T - 1:
+                env.step_device(acts[t % 8], out=out_b)
             else:
                 env.step_device(acts[t % 8], out=out)
             if t % 50 == 49:
                 rsum += out.reward.double().sum()      # a consumer kernel between two steps
         torch.cuda.synchronize()
-        results.append((env.get_state().cpu(), obs.cpu(), out.reward.cpu(), out.terminated.cpu(), rsum.item(),
-                        env.episode_stats()[2].item()))
+        results.append((env.get_state().cpu(), torch.cat([obs, out_b.obs]).cpu(), out.reward.cpu(), out.terminated.cpu(),
+                        rsum.item(), env.episode_stats()[2].item()))
         env.close()
     a, b = results
     assert a[5] > min(300, N)                                       # many episodes ended and were re-spawned on the way
