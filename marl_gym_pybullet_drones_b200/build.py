@@ -14,7 +14,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = [os.path.join(CSRC, "bd_kernels.cu"), os.path.join(CSRC, "bd_api.cu"), os.path.join(CSRC, "bd_actor.cu"),
+SOURCES = [os.path.join(CSRC, "bd_kernels.cu"), os.path.join(CSRC, "bd_tile_launch.cu"), os.path.join(CSRC, "bd_api.cu"), os.path.join(CSRC, "bd_actor.cu"),
            os.path.join(CSRC, "bd_norm.cu")]
 HEADERS = [os.path.join(CSRC, "bd_params.h"), os.path.join(CSRC, "bd_device.cuh"), os.path.join(CSRC, "bd_step_tile.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "batch_drones.h")]
@@ -42,14 +42,30 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit (in parallel, objects under csrc/_obj/) and link the shared library."""
     if not force and up_to_date():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src + ":\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", OUT] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return OUT
 
 

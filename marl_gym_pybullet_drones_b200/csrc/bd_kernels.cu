@@ -32,7 +32,6 @@
 
 #include "bd_device.cuh"
 #include "bd_params.h"
-#include "bd_step_tile.cuh"
 
 namespace bd {
 
@@ -639,50 +638,11 @@ static cudaError_t launch_reset_t(const Params<R>& P, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int TASK, int A>
-static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
-  const size_t smem = (size_t)kBlock * P.D * 4;   // the [128][D] observation tile and nothing else
-  const bool vecrow = (A == 4) && (P.D % 4 == 0);
-  const bool dw = (P.aero & AERO_DW) != 0;
-  auto kern = vecrow ? (dw ? step_kernel_tile<TASK, A, (A == 4), true> : step_kernel_tile<TASK, A, (A == 4), false>)
-                     : (dw ? step_kernel_tile<TASK, A, false, true> : step_kernel_tile<TASK, A, false, false>);
-  static size_t configured[4][64] = {{0}};
-  size_t* const cfgd = configured[(vecrow ? 1 : 0) + (dw ? 2 : 0)];
-  const int dv = ls.device & 63;
-  if (smem > cfgd[dv]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cfgd[dv] = smem;
-  }
-  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (int)((P.n_total + kBlock - 1) / kBlock);
-  // resident capacity of this kernel: with a grid at least that large, "every CTA of the previous launch has
-  // started" implies "the launch before it has completed", so at most two launches are ever in flight
-  static int per_sm[4][64] = {{0}};
-  int& occ = per_sm[(vecrow ? 1 : 0) + (dw ? 2 : 0)][dv];
-  if (occ == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
-  }
-  Params<float> Q = P;
-  Q.early_prefetch = (ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
-  Q.pipe_wait = (P.pipeline && ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kBlock);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = ls.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, Q);
-}
-
 template <typename R, int TASK, int A>
 static cudaError_t step_g(const LaunchSpec& ls, const void* p, cudaStream_t st) {
   const Params<R>& P = *static_cast<const Params<R>*>(p);
   if constexpr (sizeof(R) == 4) {
-    if (ls.impl == 1) return launch_step_tile_t<TASK, A>(P, ls, st);
+    if (ls.impl == 1) return launch_step_tile(TASK, A, P, ls, st);
   }
   return ls.generic ? launch_step_t<R, TASK, A, true>(P, ls, st)
                     : launch_step_t<R, TASK, A, false>(P, ls, st);
@@ -703,7 +663,7 @@ static cudaError_t step_t(const LaunchSpec& ls, const void* p, cudaStream_t st) 
       const Params<R>& P = *static_cast<const Params<R>*>(p);
       if constexpr (sizeof(R) == 4) {
         if (ls.impl == 1 && ls.act_a != 3)
-          return ls.act_a == 4 ? launch_step_tile_t<TASK_SWARM, 4>(P, ls, st) : launch_step_tile_t<TASK_SWARM, 1>(P, ls, st);
+          return launch_step_tile(TASK_SWARM, ls.act_a, P, ls, st);
       }
       if (ls.act_a == 3) return launch_step_t<R, TASK_SWARM, 3, true>(P, ls, st);
       return ls.act_a == 4 ? launch_step_t<R, TASK_SWARM, 4, true>(P, ls, st)

@@ -82,6 +82,8 @@ struct LaunchSpec {
   int sm_count;    // SMs of the device (resident-CTA capacity of the fast kernel)
 };
 
+// implemented in bd_tile_launch.cu (fast tile kernel; task = template TASK value, act_a in {1, 4})
+cudaError_t launch_step_tile(int task, int act_a, const Params<float>& P, const LaunchSpec& ls, cudaStream_t st);
 // implemented in bd_kernels.cu
 cudaError_t launch_step(const LaunchSpec& ls, const void* params, cudaStream_t st);
 cudaError_t launch_reset(const LaunchSpec& ls, const void* params, cudaStream_t st);

@@ -1,0 +1,66 @@
+// Launch side of the fast tile kernel (bd_step_tile.cuh), in its own translation unit so that its template
+// instantiations compile in parallel with the generic kernel's (bd_kernels.cu).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "bd_device.cuh"
+#include "bd_params.h"
+#include "bd_step_tile.cuh"
+
+namespace bd {
+
+template <int TASK, int A>
+static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
+  const size_t smem = (size_t)kBlock * P.D * 4;   // the [128][D] observation tile and nothing else
+  const bool vecrow = (A == 4) && (P.D % 4 == 0);
+  const bool dw = (P.aero & AERO_DW) != 0;
+  auto kern = vecrow ? (dw ? step_kernel_tile<TASK, A, (A == 4), true> : step_kernel_tile<TASK, A, (A == 4), false>)
+                     : (dw ? step_kernel_tile<TASK, A, false, true> : step_kernel_tile<TASK, A, false, false>);
+  static size_t configured[4][64] = {{0}};
+  size_t* const cfgd = configured[(vecrow ? 1 : 0) + (dw ? 2 : 0)];
+  const int dv = ls.device & 63;
+  if (smem > cfgd[dv]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cfgd[dv] = smem;
+  }
+  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (int)((P.n_total + kBlock - 1) / kBlock);
+  // resident capacity of this kernel: with a grid at least that large, "every CTA of the previous launch has
+  // started" implies "the launch before it has completed", so at most two launches are ever in flight
+  static int per_sm[4][64] = {{0}};
+  int& occ = per_sm[(vecrow ? 1 : 0) + (dw ? 2 : 0)][dv];
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+  }
+  Params<float> Q = P;
+  Q.early_prefetch = (ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
+  Q.pipe_wait = (P.pipeline && ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ls.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, Q);
+}
+
+template <int TASK>
+static cudaError_t tile_a(int act_a, const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
+  return act_a == 4 ? launch_step_tile_t<TASK, 4>(P, ls, st) : launch_step_tile_t<TASK, 1>(P, ls, st);
+}
+
+cudaError_t launch_step_tile(int task, int act_a, const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
+  switch (task) {
+    case TASK_HOVER: return tile_a<TASK_HOVER>(act_a, P, ls, st);
+    case TASK_MULTIHOVER: return tile_a<TASK_MULTIHOVER>(act_a, P, ls, st);
+    case TASK_SPIRAL: return tile_a<TASK_SPIRAL>(act_a, P, ls, st);
+    default: return tile_a<TASK_SWARM>(act_a, P, ls, st);
+  }
+}
+
+}  // namespace bd
