@@ -151,6 +151,38 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
                  uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                  void* stream);
 
+/* bd_step_host with COMPACT terminal observations — what SubprocVecEnv's workers actually send
+ * (subproc_vec_env.py:195-206: only an env that finished carries info['terminal_observation']).
+ * Terminal rows stay on the device; after the step two small kernels gather the finished envs' (M,D)
+ * rows, in ascending env order, into page-locked memory owned by the handle, so the device->host
+ * traffic is obs + flags + n_done rows instead of a second full (N,M,D) buffer.
+ *   *n_done        number of envs that finished in this step
+ *   *done_idx      their env indices (ascending), n_done entries
+ *   *terminal_rows (n_done, M, D) float, row k belongs to env (*done_idx)[k]
+ * The two arrays are owned by the handle and valid until its next step call. */
+int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                         uint8_t* terminated_host, uint8_t* truncated_host, int32_t* n_done,
+                         const int32_t** done_idx, const float** terminal_rows, void* stream);
+
+/* k control steps with ONE host call (the launch-bound regime: small batches, random-action sweeps —
+ * BASELINE configs[3] as literally sharded is 8192 envs per GPU).  actions_dev (k,N,M,A), obs_dev
+ * (k,N,M,D), reward_dev (k,N) Real, terminated_dev / truncated_dev (k,N) uint8; step i reads
+ * action set i and writes output slot i.  Identical to k bd_step calls (no terminal observations). */
+int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, void* reward_dev,
+                 uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
+
+/* RNG state of the on-device re-spawn draws — the counterpart of the workers' np.random states the
+ * reference checkpoints and restores (mappo/mappo.py:203-229; subproc_vec_env.py:101-112
+ * get_env_random_state / set_env_random_state).  state4 = {Philox key (seed), Philox step counter,
+ * explicit-reset epoch, 0}.  After bd_set_rng_state a resumed run continues the random stream
+ * instead of replaying it.  BD_EINVAL once a step has been captured into a CUDA graph. */
+int bd_get_rng_state(const bd_handle* h, uint64_t* state4);
+int bd_set_rng_state(bd_handle* h, const uint64_t* state4);
+
+/* Test hook for the tile-epoch protocol: overwrite one tile's epoch, stream
+ * ordered.  A CTA that waits for an epoch nobody publishes traps after ~1 s instead of hanging. */
+int bd_debug_set_tile_epoch(bd_handle* h, int tile, int value, void* stream);
+
 /* Replaces BaseAviary._getDroneStateVector (BaseAviary.py:541-561) for every
  * drone: state20_dev (N,M,20) Real = [pos3 quat4 rpy3 vel3 ang_v3 last_rpm4];
  * ang_v is NaN unless cfg.keep_ang_vel.  Optional: body rates `self.rpy_rates`

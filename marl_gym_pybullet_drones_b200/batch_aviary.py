@@ -323,14 +323,20 @@ class BatchAviary:
         return t.numpy()
 
     def step_host(self, actions: np.ndarray, out: Optional[dict] = None, want_terminal_obs: bool = False,
-                  actions_pinned: bool = False) -> dict:
+                  actions_pinned: bool = False, compact_terminal_obs: bool = False, buffer_set: int = 0) -> dict:
         """Host-buffer step through `bd_step_host` (H2D + kernel + D2H + sync).
 
         `actions`: (N,M,A) numpy array.  Returns a dict of numpy arrays backed by
-        pinned memory that is reused on the next call (copy what you keep).
+        pinned memory that is reused on a later call (copy what you keep): `buffer_set` (0 / 1) selects one
+        of two sets of output buffers, so a caller that alternates them keeps the previous step's arrays
+        intact for one more step.
         `actions_pinned=True`: `actions` already lives in page-locked memory (`pinned_array`) with the
         aviary's action dtype and is handed to the copy engine as it is; otherwise it is first copied
         into a pinned staging buffer (a 4 MB host memcpy at 65 536 x 4 drones, ~0.35 ms).
+        `want_terminal_obs=True`: a full (N,M,D) `terminal_obs` array (rows valid where done).
+        `compact_terminal_obs=True`: `bd_step_host_compact` instead — `done_idx` (ascending env indices of the
+        envs that finished) and `terminal_rows` (len(done_idx), M, D); views of memory owned by the handle,
+        valid until the next step.
         """
         self._check_open()
         N, M = self.num_envs, self.NUM_DRONES
@@ -339,20 +345,20 @@ class BatchAviary:
             want = torch.float32 if actions.dtype == np.float32 else torch.float64
             if want != self.action_dtype:
                 self._set_action_dtype(want)
-                if hasattr(self, "_host_bufs"):
-                    del self._host_bufs
+                self._host_bufs = {}
         np_act = np.float32 if self.action_dtype == torch.float32 else np.float64
         if out is None:
-            if not hasattr(self, "_host_bufs"):
+            bufs = self.__dict__.setdefault("_host_bufs", {})
+            out = bufs.get(buffer_set)
+            if out is None:
                 pin = dict(pin_memory=True)
-                self._host_bufs = dict(
+                out = bufs[buffer_set] = dict(
                     actions=torch.empty((N, M, self.ACTION_DIM), dtype=self.action_dtype, **pin),
                     obs=torch.empty((N, M, self.OBS_DIM), dtype=torch.float32, **pin),
                     reward=torch.empty((N,), dtype=self.real_dtype, **pin),
                     terminated=torch.empty((N,), dtype=torch.uint8, **pin),
                     truncated=torch.empty((N,), dtype=torch.uint8, **pin),
                     terminal_obs=None)
-            out = self._host_bufs
         if want_terminal_obs and out.get("terminal_obs") is None:
             out["terminal_obs"] = torch.zeros((N, M, self.OBS_DIM), dtype=torch.float32, pin_memory=True)
         if actions_pinned:
@@ -362,16 +368,67 @@ class BatchAviary:
         else:
             out["actions"].numpy()[...] = np.asarray(actions, dtype=np_act).reshape(N, M, self.ACTION_DIM)
             act_ptr = out["actions"].data_ptr()
+        res = dict(obs=out["obs"].numpy(), reward=out["reward"].numpy(),
+                   terminated=out["terminated"].numpy().view(np.bool_),
+                   truncated=out["truncated"].numpy().view(np.bool_), terminal_obs=None)
+        if compact_terminal_obs:
+            n_done, idx_p, rows_p = C.c_int32(0), C.c_void_p(), C.c_void_p()
+            _native.check(self._lib.bd_step_host_compact(
+                self._h, C.c_void_p(act_ptr), C.c_void_p(out["obs"].data_ptr()),
+                C.c_void_p(out["reward"].data_ptr()), C.c_void_p(out["terminated"].data_ptr()),
+                C.c_void_p(out["truncated"].data_ptr()), C.byref(n_done), C.byref(idx_p), C.byref(rows_p),
+                self._stream()), "bd_step_host_compact")
+            k = int(n_done.value)
+            if k > 0:
+                idx = np.ctypeslib.as_array(C.cast(idx_p, C.POINTER(C.c_int32)), shape=(k,))
+                rows = np.ctypeslib.as_array(C.cast(rows_p, C.POINTER(C.c_float)), shape=(k, M, self.OBS_DIM))
+            else:
+                idx, rows = np.zeros((0,), dtype=np.int32), np.zeros((0, M, self.OBS_DIM), dtype=np.float32)
+            res["done_idx"], res["terminal_rows"] = idx, rows
+            return res
         tob = out.get("terminal_obs") if want_terminal_obs else None
         _native.check(self._lib.bd_step_host(
             self._h, C.c_void_p(act_ptr), C.c_void_p(out["obs"].data_ptr()),
             C.c_void_p(out["reward"].data_ptr()), C.c_void_p(out["terminated"].data_ptr()),
             C.c_void_p(out["truncated"].data_ptr()),
             C.c_void_p(tob.data_ptr()) if tob is not None else None, self._stream()), "bd_step_host")
-        return dict(obs=out["obs"].numpy(), reward=out["reward"].numpy(),
-                    terminated=out["terminated"].numpy().view(np.bool_),
-                    truncated=out["truncated"].numpy().view(np.bool_),
-                    terminal_obs=tob.numpy() if tob is not None else None)
+        res["terminal_obs"] = tob.numpy() if tob is not None else None
+        return res
+
+    def step_many(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
+                  truncated: torch.Tensor) -> None:
+        """K control steps with one host call (`bd_step_many`): `actions` (K,N,M,A), outputs (K,N,M,D) / (K,N);
+        step i reads `actions[i]` and writes slot i.  For launch-bound regimes (small batches, action tapes)."""
+        self._check_open()
+        K = int(actions.shape[0])
+        N, M = self.num_envs, self.NUM_DRONES
+        if (actions.dtype != self.action_dtype or not actions.is_contiguous() or actions.device != self.device
+                or actions.numel() != K * N * M * self.ACTION_DIM):
+            raise ValueError(f"actions must be a contiguous ({K},{N},{M},{self.ACTION_DIM}) {self.action_dtype} CUDA tensor")
+        for t, shape, dt in ((obs, (K, N, M, self.OBS_DIM), torch.float32), (reward, (K, N), self.real_dtype)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"output tensor must be contiguous {shape} {dt} on {self.device}")
+        for t in (terminated, truncated):
+            if tuple(t.shape) != (K, N) or t.element_size() != 1 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"flag tensors must be contiguous ({K},{N}) bool / uint8 on {self.device}")
+        rc = self._lib.bd_step_many(self._h, K, actions.data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                    terminated.data_ptr(), truncated.data_ptr(),
+                                    torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            _native.check(rc, "bd_step_many")
+
+    def get_rng_state(self):
+        """Philox key and counters of the on-device re-spawn draws (`bd_get_rng_state`): a 4-tuple of ints."""
+        self._check_open()
+        st = (C.c_uint64 * 4)()
+        _native.check(self._lib.bd_get_rng_state(self._h, st), "bd_get_rng_state")
+        return tuple(int(v) for v in st)
+
+    def set_rng_state(self, state):
+        """Restore what `get_rng_state` returned: a resumed run continues the random stream."""
+        self._check_open()
+        st = (C.c_uint64 * 4)(*[int(v) for v in state])
+        _native.check(self._lib.bd_set_rng_state(self._h, st), "bd_set_rng_state")
 
     def _set_action_dtype(self, dtype):
         """fp64 mode: follow the dtype of the actions handed in, like numpy does in the reference

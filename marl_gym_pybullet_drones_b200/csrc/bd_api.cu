@@ -84,6 +84,13 @@ struct bd_handle {
   long long total_steps = 0;   // host mirror of gsteps[0]
   bool graph_mode = false;     // a step was captured into a CUDA graph: the device counter is authoritative
   int reset_epoch = 0;
+  uint32_t philox_base = 0;    // bd_set_rng_state: offset of the Philox step counter
+  bool poisoned = false;       // a launch failed half-way through a chunked host step: the tile epochs are inconsistent
+  // compact terminal observations (bd_step_host_compact): pinned, device-mapped staging owned by the handle
+  int* c_blockcnt = nullptr;   // [blocks of 1024 envs] done envs per block
+  int* c_host = nullptr;       // pinned+mapped: [0] = count, [1..N] = done env indices (ascending)
+  float* c_rows_host = nullptr;  // pinned+mapped: [cap][M][D] terminal observation rows, same order
+  int c_cap = 0;
   bd::Params<float> pf{};
   bd::Params<double> pd{};
 };
@@ -146,6 +153,8 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   P.auto_reset = c.auto_reset; P.reset_mode = c.reset_mode; P.action_is_f32 = c.action_is_f32;
   P.keep_angv = c.keep_ang_vel;
   P.seed = c.seed;
+  P.philox_base = h->philox_base;
+  P.obs_aligned = 1;
   P.reset_epoch = 0;
   P.block0 = 0; P.grid_blocks = 0; P.advance = 1;
   P.total_wrap = h->B * ((1 << 30) / h->B);
@@ -234,6 +243,9 @@ void free_all(bd_handle* h) {
   cudaFree(h->hist); cudaFree(h->stepc); cudaFree(h->gsteps); cudaFree(h->tile_epoch); cudaFree(h->finished); cudaFree(h->ep_ret); cudaFree(h->ep_acc); cudaFree(h->ctrl);
   cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
+  cudaFree(h->c_blockcnt);
+  if (h->c_host) cudaFreeHost(h->c_host);
+  if (h->c_rows_host) cudaFreeHost(h->c_rows_host);
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
   if (h->hs_a) {
@@ -422,8 +434,17 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
   if (!h) return fail(BD_EINVAL, "bd_step: null handle");
   if (!actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev)
     return fail(BD_EINVAL, "bd_step: actions, obs, reward, terminated and truncated are required");
-  if (((uintptr_t)obs_dev & 15) || ((uintptr_t)actions_dev & 15))
-    return fail(BD_EINVAL, "bd_step: actions and obs must be 16-byte aligned");
+  // 128-bit accesses: action rows when A == 4 (float4 loads), observation rows when D % 4 == 0 on the fast
+  // kernel.  Other shapes (ONE_D_RPM: A = 1, D = 27; PID: A = 3, D = 57) take scalar paths and any 4-byte
+  // aligned pointer — a rollout buffer slot obs[t+1] is 16-byte aligned only when N*M*D % 4 == 0.
+  const size_t act_elem_sz = (h->cfg.precision == BD_F64 && !h->cfg.action_is_f32) ? 8 : 4;
+  if ((h->A == 4 && ((uintptr_t)actions_dev & 15)) || ((uintptr_t)actions_dev & (act_elem_sz - 1)))
+    return fail(BD_EINVAL, "bd_step: actions must be 16-byte aligned (A = 4) / element aligned");
+  const bool obs_vec = h->spec.impl == 1 && h->A == 4 && (h->D & 3) == 0;
+  if ((obs_vec && ((uintptr_t)obs_dev & 15)) || ((uintptr_t)obs_dev & 3))
+    return fail(BD_EINVAL, "bd_step: obs must be 16-byte aligned (A = 4, D %% 4 == 0) / 4-byte aligned");
+  if (h->poisoned)
+    return fail(BD_ECUDA, "bd_step: an earlier launch of this handle failed half-way through a step; destroy the handle");
   if (h->cfg.auto_reset && h->cfg.reset_mode == BD_RESET_JITTER_BUFFER &&
       h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter)
     return fail(BD_EINVAL, "bd_step: BD_RESET_JITTER_BUFFER needs bd_set_jitter() first");
@@ -445,8 +466,12 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
     P.terminated = terminated_dev;
     P.truncated = truncated_dev;
     P.terminal_obs = terminal_obs_dev;
+    P.obs_aligned = (((uintptr_t)obs_dev & 15) == 0) ? 1 : 0;
     e = bd::launch_step(h->spec, &P, (cudaStream_t)stream);
+    P.obs_aligned = 1;
   });
+  // the host step count follows the tile epochs the launch will publish: only a launch that was accepted counts
+  if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
   h->launches++;
   h->total_steps++;
   if (h->total_steps >= (long long)h->B * ((1 << 30) / h->B)) {
@@ -458,16 +483,62 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
       cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
     }
   }
-  if (e != cudaSuccess) return fail(BD_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
   return BD_OK;
 }
+
+}  // extern "C"
+
+namespace {
+int ensure_compact_buffers(bd_handle* h, int cap) {
+  if (!h->c_blockcnt) BD_CUDA(cudaMalloc((void**)&h->c_blockcnt, (size_t)bd::compact_blocks(h->cfg.n_envs) * sizeof(int)));
+  if (!h->c_host) BD_CUDA(cudaHostAlloc((void**)&h->c_host, ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocMapped));
+  if (cap > h->c_cap) {
+    if (h->c_rows_host) { cudaFreeHost(h->c_rows_host); h->c_rows_host = nullptr; h->c_cap = 0; }
+    BD_CUDA(cudaHostAlloc((void**)&h->c_rows_host, (size_t)cap * h->cfg.n_drones * h->D * sizeof(float), cudaHostAllocMapped));
+    h->c_cap = cap;
+  }
+  return BD_OK;
+}
+// compact = true: terminal observations stay in the device-side (N,M,D) buffer; after the step the finished envs'
+// rows are gathered (ascending env order) straight into the handle's mapped pinned buffers.
+int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                   uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host, bool compact,
+                   void* stream);
+}  // namespace
+
+extern "C" {
 
 int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
                  uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host,
                  void* stream) {
+  return step_host_impl(h, actions_host, obs_host, reward_host, terminated_host, truncated_host, terminal_obs_host, false,
+                        stream);
+}
+
+int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                         uint8_t* terminated_host, uint8_t* truncated_host, int32_t* n_done,
+                         const int32_t** done_idx, const float** terminal_rows, void* stream) {
+  if (!n_done || !done_idx || !terminal_rows) return fail(BD_EINVAL, "bd_step_host_compact: null output argument");
+  *n_done = 0; *done_idx = nullptr; *terminal_rows = nullptr;
+  int rc = step_host_impl(h, actions_host, obs_host, reward_host, terminated_host, truncated_host, nullptr, true, stream);
+  if (rc) return rc;
+  *n_done = h->c_host[0];
+  *done_idx = h->c_host + 1;
+  *terminal_rows = h->c_rows_host;
+  return BD_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
+                   uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host, bool compact,
+                   void* stream) {
   if (!h) return fail(BD_EINVAL, "bd_step_host: null handle");
   if (!actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host)
     return fail(BD_EINVAL, "bd_step_host: actions, obs, reward, terminated and truncated are required");
+  if (h->poisoned)
+    return fail(BD_ECUDA, "bd_step_host: an earlier launch of this handle failed half-way through a step; destroy the handle");
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t act_elem = (h->cfg.precision == BD_F64 && !h->cfg.action_is_f32) ? 8 : 4;
@@ -481,9 +552,14 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
     BD_CUDA(cudaMalloc((void**)&h->h_term, n));
     BD_CUDA(cudaMalloc((void**)&h->h_trunc, n));
   }
-  if (terminal_obs_host && !h->h_tobs) {
+  const bool want_tobs = terminal_obs_host != nullptr || compact;
+  if (want_tobs && !h->h_tobs) {
     BD_CUDA(cudaMalloc((void**)&h->h_tobs, obs_bytes));
     BD_CUDA(cudaMemsetAsync(h->h_tobs, 0, obs_bytes, st));
+  }
+  if (compact) {
+    int rc = ensure_compact_buffers(h, h->c_cap > 0 ? h->c_cap : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256));
+    if (rc) return rc;
   }
   // Pipeline over chunks of whole tiles: while the copy engine drains chunk k's observations to the host,
   // chunk k+1's actions go up and its tiles are stepped.  One control step = `chunks` sub-range launches of the
@@ -496,7 +572,7 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
   if (chunks <= 1 || h->graph_mode) {
     BD_CUDA(cudaMemcpyAsync(h->h_actions, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
     int rc = bd_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_term, h->h_trunc,
-                     terminal_obs_host ? h->h_tobs : nullptr, stream);
+                     want_tobs ? h->h_tobs : nullptr, stream);
     if (rc) return rc;
     BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
     if (terminal_obs_host)
@@ -532,13 +608,17 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
         P.reward = (decltype(P.reward))h->h_reward;
         P.terminated = h->h_term;
         P.truncated = h->h_trunc;
-        P.terminal_obs = terminal_obs_host ? h->h_tobs : nullptr;
+        P.terminal_obs = want_tobs ? h->h_tobs : nullptr;
         P.block0 = b0; P.grid_blocks = b1 - b0; P.advance = (c == chunks - 1) ? 1 : 0;
         e = bd::launch_step(h->spec, &P, h->hs_a);
         P.block0 = 0; P.grid_blocks = 0; P.advance = 1;
       });
+      if (e != cudaSuccess) {
+        // chunks 0..c-1 have stepped their tiles and will publish epochs for a step that never completed
+        if (c > 0) h->poisoned = true;
+        break;
+      }
       h->launches++;
-      if (e != cudaSuccess) break;
       BD_CUDA(cudaEventRecord(h->hs_chunk[c], h->hs_a));
       BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_chunk[c], 0));
       BD_CUDA(cudaMemcpyAsync((char*)obs_host + g0 * obs_row, (const char*)h->h_obs + g0 * obs_row, rows * obs_row,
@@ -556,7 +636,6 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
         cudaMemset(h->tile_epoch, 0, (size_t)epoch_tiles(h) * sizeof(int));
         cudaMemset(h->finished, 0, sizeof(unsigned long long));
         cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
-      cudaMemset(h->gsteps + 8, 0, 8 * sizeof(int));
       }
     }
     BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a
@@ -565,7 +644,78 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
   BD_CUDA(cudaMemcpyAsync(reward_host, h->h_reward, n * h->real, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaMemcpyAsync(terminated_host, h->h_term, n, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaMemcpyAsync(truncated_host, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
+  if (compact) {
+    const int row_floats = h->cfg.n_drones * h->D;
+    cudaError_t e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats,
+                                            h->c_cap, h->c_host, h->c_rows_host, st);
+    h->launches += 2;
+    if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
+    BD_CUDA(cudaStreamSynchronize(st));
+    if (h->c_host[0] > h->c_cap) {   // more finished envs than the staging holds: grow it and gather again (rare)
+      int rc = ensure_compact_buffers(h, h->c_host[0] + h->c_host[0] / 4);
+      if (rc) return rc;
+      e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats, h->c_cap,
+                                  h->c_host, h->c_rows_host, st);
+      h->launches += 2;
+      if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
+      BD_CUDA(cudaStreamSynchronize(st));
+    }
+    return BD_OK;
+  }
   BD_CUDA(cudaStreamSynchronize(st));
+  return BD_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// K control steps with one host call (launch-bound regimes: small batches, random-action sweeps).  The K action
+// sets and K output slots are contiguous arrays; identical to K bd_step calls.
+int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+                 uint8_t* truncated_dev, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_step_many: null handle");
+  if (k < 0) return fail(BD_EINVAL, "bd_step_many: k must be >= 0");
+  const size_t act_elem = (h->cfg.precision == BD_F64 && !h->cfg.action_is_f32) ? 8 : 4;
+  const size_t act_step = (size_t)h->n_total * h->A * act_elem, obs_step = (size_t)h->n_total * h->D;
+  const size_t n = (size_t)h->cfg.n_envs;
+  for (int i = 0; i < k; ++i) {
+    int rc = bd_step(h, (const char*)actions_dev + i * act_step, obs_dev + i * obs_step, (char*)reward_dev + i * n * h->real,
+                     terminated_dev + i * n, truncated_dev + i * n, nullptr, stream);
+    if (rc) return rc;
+  }
+  return BD_OK;
+}
+
+// RNG state of the on-device re-spawn draws (the counterpart of the workers' np.random states the reference
+// checkpoints, mappo/mappo.py:203-229, subproc_vec_env.py:101-112): state4 = {seed, Philox step counter
+// (= philox_base + control steps so far), explicit-reset epoch, 0}.  Setting it makes a resumed run continue
+// the stream instead of replaying it; the action ring and the drone states are not part of it.
+int bd_get_rng_state(const bd_handle* h, uint64_t* state4) {
+  if (!h || !state4) return fail(BD_EINVAL, "bd_get_rng_state: null argument");
+  state4[0] = h->cfg.seed;
+  state4[1] = (uint64_t)(uint32_t)(h->philox_base + (uint32_t)h->total_steps);
+  state4[2] = (uint64_t)h->reset_epoch;
+  state4[3] = 0;
+  return BD_OK;
+}
+int bd_set_rng_state(bd_handle* h, const uint64_t* state4) {
+  if (!h || !state4) return fail(BD_EINVAL, "bd_set_rng_state: null argument");
+  if (h->graph_mode) return fail(BD_EINVAL, "bd_set_rng_state: not available after a step was captured into a CUDA graph");
+  h->cfg.seed = state4[0];
+  h->philox_base = (uint32_t)state4[1] - (uint32_t)h->total_steps;
+  h->reset_epoch = (int)state4[2];
+  refresh_params(h);
+  return BD_OK;
+}
+
+// Test hook: overwrite one tile's epoch (stream ordered).  A value below the step count makes the next pipelined
+// launch wait for an epoch nobody will publish; the bounded spin must then trap instead of hanging the GPU.
+int bd_debug_set_tile_epoch(bd_handle* h, int tile, int value, void* stream) {
+  if (!h) return fail(BD_EINVAL, "bd_debug_set_tile_epoch: null handle");
+  if (tile < 0 || tile >= (int)epoch_tiles(h)) return fail(BD_EINVAL, "bd_debug_set_tile_epoch: tile out of range");
+  DeviceGuard guard(h->cfg.device);
+  cudaError_t e = bd::launch_set_epoch(h->tile_epoch, tile, value, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(BD_ECUDA, "bd_debug_set_tile_epoch: %s", cudaGetErrorString(e));
   return BD_OK;
 }
 

@@ -303,7 +303,7 @@ __device__ void sample_jitter(const Params<R>& P, int env, int total_steps, int 
           const long long jb = ((long long)env * M + i) * 3;
           j[0] = P.jitter[jb]; j[1] = P.jitter[jb + 1]; j[2] = P.jitter[jb + 2];
         } else {
-          uint32_t c[4] = {(uint32_t)env, (uint32_t)total_steps, (uint32_t)(attempt * M + i), (uint32_t)epoch << 1};
+          uint32_t c[4] = {(uint32_t)env, (uint32_t)total_steps + P.philox_base, (uint32_t)(attempt * M + i), (uint32_t)epoch << 1};
           uint32_t c2[4] = {c[0], c[1], c[2], c[3] | 1u};
           philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
           philox4x32_10(c2, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
@@ -799,7 +799,18 @@ __device__ __forceinline__ int pipe_gate(const Params<R>& P, int tile, int total
     }
     must_wait = ((v & 3u) == 2u);
   } else if (tid == 32) {
-    while (ld_acquire_gpu(P.tile_epoch + tile) - total < 0) __nanosleep(64);
+    // Bounded: the epoch is published by a CTA that is resident or already done, so the wait is a few
+    // microseconds.  A protocol bug (an epoch that never arrives) must fail the launch, not hang the GPU:
+    // after ~2^31 SM clocks (about one second) the CTA traps, like the actor kernel's mbarrier waits.
+    long long t0 = 0;
+    for (unsigned it = 0; ld_acquire_gpu(P.tile_epoch + tile) - total < 0; ++it) {
+      __nanosleep(64);
+      if ((it & 1023u) == 1023u) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > (1LL << 31)) __trap();
+      }
+    }
   }
   return __syncthreads_or(must_wait);
 }

@@ -400,7 +400,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   const int rows = (int)(left < (long long)E * M ? left : (long long)E * M);
   const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
   float* gobs = P.obs + (size_t)g0 * D;
-  const bool bulk = ((bytes & 15u) == 0) && ((((size_t)g0 * D * 4) & 15) == 0);
+  const bool bulk = P.obs_aligned && ((bytes & 15u) == 0) && ((((size_t)g0 * D * 4) & 15) == 0);
   if (bulk) fence_proxy_async_smem();
   __syncthreads();
   if (bulk) {
@@ -740,6 +740,83 @@ __global__ void episode_stats_kernel(double* acc, double* out3, int reset) {
 }
 cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st) {
   episode_stats_kernel<<<1, 32, 0, st>>>(ep_acc, out3, reset);
+  return cudaGetLastError();
+}
+
+// ---- compact terminal observations (subproc_vec_env.py:195-206: only finished envs carry one) ----------
+// Envs are scanned in blocks of kCompactBlock; pass 1 counts the finished envs per block, pass 2 turns the counts
+// into offsets (every block sums the counts before it), scans its own flags and copies the finished envs'
+// (M,D) rows — in ascending env order, so the result is deterministic — to `rows_out` (at most `cap` envs) and
+// their indices to `idx_out[1..]`; idx_out[0] = total count.  The outputs may live in mapped pinned host memory.
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock)
+count_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int n, int* __restrict__ blockcnt) {
+  const int e = blockIdx.x * kCompactBlock + threadIdx.x;
+  const int done = (e < n) && (term[e] | trunc[e]);
+  const int c = __syncthreads_count(done);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(kCompactBlock)
+gather_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int n, const int* __restrict__ blockcnt,
+                   const float* __restrict__ tobs, int row_floats, int cap, int* __restrict__ idx_out,
+                   float* __restrict__ rows_out) {
+  __shared__ int s_warp[kCompactBlock / 32];
+  __shared__ int s_base, s_total;
+  __shared__ int s_list[kCompactBlock];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // offset of this block = sum of the counts before it; grand total for block 0's header write
+  int before = 0, total = 0;
+  for (int b = tid; b < (int)gridDim.x; b += kCompactBlock) {
+    const int c = blockcnt[b];
+    total += c;
+    if (b < (int)blockIdx.x) before += c;
+  }
+  for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+  if (tid == 0) { s_base = 0; s_total = 0; }
+  __syncthreads();
+  if (lane == 0) { atomicAdd(&s_base, before); atomicAdd(&s_total, total); }
+  __syncthreads();
+  const int e = blockIdx.x * kCompactBlock + tid;
+  const int done = (e < n) && (term[e] | trunc[e]);
+  const unsigned bal = __ballot_sync(0xffffffffu, done);
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_warp[w];
+  int mine = 0;
+  for (int w = 0; w < kCompactBlock / 32; ++w) mine += s_warp[w];
+  const int pos = woff + __popc(bal & ((1u << lane) - 1u));
+  if (done) s_list[pos] = e;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) idx_out[0] = s_total;
+  const int base = s_base;
+  for (int k = tid; k < mine; k += kCompactBlock)
+    if (base + k < cap) idx_out[1 + base + k] = s_list[k];
+  // rows: the block copies its finished envs one after the other, 128-bit where the row allows it
+  for (int k = 0; k < mine; ++k) {
+    if (base + k >= cap) break;
+    const float* src = tobs + (size_t)s_list[k] * row_floats;
+    float* dst = rows_out + (size_t)(base + k) * row_floats;
+    if ((row_floats & 3) == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0) {
+      for (int i = tid; i < row_floats / 4; i += kCompactBlock)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    } else {
+      for (int i = tid; i < row_floats; i += kCompactBlock) dst[i] = src[i];
+    }
+  }
+}
+int compact_blocks(int n) { return (n + kCompactBlock - 1) / kCompactBlock; }
+cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int n, int* blockcnt, const float* tobs,
+                                int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st) {
+  const int blocks = compact_blocks(n);
+  count_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, n, blockcnt);
+  gather_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, n, blockcnt, tobs, row_floats, cap, idx_out, rows_out);
+  return cudaGetLastError();
+}
+
+__global__ void set_epoch_kernel(int* tile_epoch, int tile, int value) { tile_epoch[tile] = value; }
+cudaError_t launch_set_epoch(int* tile_epoch, int tile, int value, cudaStream_t st) {
+  set_epoch_kernel<<<1, 1, 0, st>>>(tile_epoch, tile, value);
   return cudaGetLastError();
 }
 

@@ -73,6 +73,8 @@ struct Params {
   int advance;                    // 1: this launch advances the device-resident step count (last chunk of a step)
   int reset_epoch;                // >=1 for explicit bd_reset calls (Philox stream id), 0 in-step
   unsigned long long seed;
+  int obs_aligned;                // 1: the caller's observation pointer is 16-byte aligned (bulk / 128-bit row stores allowed)
+  uint32_t philox_base;           // added to the step count in the Philox counter (bd_set_rng_state: resumed runs continue the stream)
 };
 
 struct LaunchSpec {
@@ -96,5 +98,9 @@ cudaError_t launch_ctrl_state(int precision, const void* params, void* dst, cons
                               cudaStream_t st);
 cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st);
 size_t step_smem_bytes(int precision, int A, int B, int D, int task);
+int compact_blocks(int n);
+cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int n, int* blockcnt, const float* tobs,
+                                int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st);
+cudaError_t launch_set_epoch(int* tile_epoch, int tile, int value, cudaStream_t st);
 
 }  // namespace bd

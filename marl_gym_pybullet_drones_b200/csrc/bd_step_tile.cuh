@@ -299,7 +299,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
             if (P.reset_mode == RESET_BUFFER && P.jitter != nullptr) {
               j0 = P.jitter[g * 3]; j1 = P.jitter[g * 3 + 1]; j2 = P.jitter[g * 3 + 2];
             } else {
-              uint32_t c[4] = {(uint32_t)env, (uint32_t)total, (uint32_t)(attempt * M + drone), 0u};
+              uint32_t c[4] = {(uint32_t)env, (uint32_t)total + P.philox_base, (uint32_t)(attempt * M + drone), 0u};
               uint32_t c2[4] = {c[0], c[1], c[2], 1u};
               philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
               philox4x32_10(c2, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
@@ -352,7 +352,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   const int rows = (int)(left < (long long)kBlock ? left : (long long)kBlock);
   const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
   float* gobs = P.obs + (size_t)g0 * D;
-  const bool bulk = (bytes & 15u) == 0;
+  const bool bulk = P.obs_aligned && (bytes & 15u) == 0;
   if (bulk) fence_proxy_async_smem();    // my generic-proxy writes -> visible to the async proxy
   __syncthreads();
   if (bulk) {

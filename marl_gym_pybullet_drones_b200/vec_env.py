@@ -7,8 +7,9 @@ reset-on-done (`subproc_vec_env.py:51-73,186-207`), and
 `VecRecordEpisodeStatistics` (`record_episode_statistics.py:100-171`).
 
 `step(actions)` takes/returns numpy arrays and the reference's 4-tuple
-`(obs (N,M,D), rew (N,), done (N,), {'n': infos})`; one `bd_step_host` call does
-the work.  For large N use `BatchAviary.step_device` (device tensors, no infos).
+`(obs (N,M,D), rew (N,), done (N,), {'n': infos})`; one `bd_step_host_compact` call does
+the work (terminal observations only for the envs that finished, info dicts built lazily).
+For rollouts that stay on the GPU use `BatchAviary.step_device` (device tensors, no infos).
 """
 from __future__ import annotations
 
@@ -22,6 +23,38 @@ from .batch_aviary import BatchAviary
 
 _TASK_OF_CLASS = {"HoverAviary": "hover", "MultiHoverAviary": "multihover", "SpiralFormationAviary": "spiral",
                   "MeetupAviary": "meetup", "FlockAviary": "flock", "LeaderFollowerAviary": "leaderfollower"}
+
+
+class LazyInfos:
+    """`info['n']`: a sequence of N per-env info dicts that are built when somebody looks at them.
+
+    `SubprocVecEnv.step` returns a tuple of N dicts (`subproc_vec_env.py:58-64`); at 65 536 envs building them costs
+    more than the simulation step.  Here only the envs that finished get their dict up front (it carries
+    `terminal_observation` / `terminal_info`); the others are created on first access and then cached, so writes
+    such as `info['n'][i]['episode'] = ...` (`record_episode_statistics.py:158`) stick."""
+
+    def __init__(self, n, make, ready=None):
+        self._n, self._make = int(n), make
+        self._cache = dict(ready) if ready else {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        d = self._cache.get(i)
+        if d is None:
+            d = self._cache[i] = self._make(i)
+        return d
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
 
 
 class BatchVecEnv:
@@ -39,14 +72,15 @@ class BatchVecEnv:
         self.waiting = False
         self._pending = None
         self._steps = np.zeros(self.num_envs, dtype=np.int64)   # step_counter mirror for info dicts
+        self._flip = 0
 
     # -- info dicts (HoverAviary.py:119-131, MultiHoverAviary.py:274-285, SpiralAviary.py:200-205)
-    def _info(self, e, kin=None, terminated=False, step_counter=0):
+    def _info(self, kin=None, terminated=False, step_counter=0):
         b = self.batch
-        if b.task == "hover":
-            return {"answer": 42}
         if b.task == "spiral":
             return {"time": step_counter / b.PYB_FREQ, "omega": b.OMEGA, "radius": b.R}
+        if b.task != "multihover":
+            return {"answer": 42}
         reasons = []
         if terminated and kin is not None:
             for i in range(b.NUM_DRONES):
@@ -64,7 +98,7 @@ class BatchVecEnv:
         self._assert_not_closed()
         obs = self.batch.reset_device().cpu().numpy()
         self._steps[:] = 0
-        return obs, {'n': tuple(self._info(e) for e in range(self.num_envs))}
+        return obs, {'n': LazyInfos(self.num_envs, lambda e: self._info())}
 
     def step_async(self, actions):
         self._assert_not_closed()
@@ -72,29 +106,36 @@ class BatchVecEnv:
         self.waiting = True
 
     def step_wait(self):
+        """One `bd_step_host_compact` call: observations, rewards and flags come back in page-locked buffers (two
+        sets, used alternately: what a call returns stays valid until the next-but-one call), terminal observations
+        only for the envs that finished; per-env Python work is done for those envs only."""
         self._assert_not_closed()
         b = self.batch
-        res = b.step_host(self._pending, want_terminal_obs=b.auto_reset)
+        self._flip ^= 1
+        res = b.step_host(self._pending, compact_terminal_obs=b.auto_reset, buffer_set=self._flip)
         self.waiting = False
-        obs = res["obs"].copy()
+        obs, term, trunc = res["obs"], res["terminated"], res["truncated"]
         rews = res["reward"].astype(np.float64)
-        term, trunc = res["terminated"].copy(), res["truncated"].copy()
         dones = np.logical_or(term, trunc)
-        infos = []
         S = b.PYB_STEPS_PER_CTRL
-        for e in range(self.num_envs):
-            if dones[e] and b.auto_reset:
-                end_obs = res["terminal_obs"][e].copy()
-                end_info = self._info(e, end_obs, bool(term[e]), int(self._steps[e]))
-                info = self._info(e)   # info of the fresh episode (reset)
+        steps_before = self._steps
+        ready = {}
+        if b.auto_reset:
+            idx, rows = res["done_idx"], res["terminal_rows"]
+            for k in range(len(idx)):
+                e = int(idx[k])
+                end_obs = rows[k].copy()
+                info = self._info()   # info of the fresh episode (reset)
                 info['terminal_observation'] = end_obs
-                info['terminal_info'] = end_info
-                self._steps[e] = 0
-            else:
-                info = self._info(e, obs[e], bool(term[e]), int(self._steps[e]))
-                self._steps[e] += S
-            infos.append(info)
-        return obs, rews, dones, {'n': tuple(infos)}
+                info['terminal_info'] = self._info(end_obs, bool(term[e]), int(steps_before[e]))
+                ready[e] = info
+            self._steps = np.where(dones, 0, steps_before + S)
+        else:
+            self._steps = steps_before + S
+
+        def make(e, obs=obs, term=term, steps=steps_before):
+            return self._info(obs[e], bool(term[e]), int(steps[e]))
+        return obs, rews, dones, {'n': LazyInfos(self.num_envs, make, ready)}
 
     def step(self, actions):
         self.step_async(actions)
@@ -112,11 +153,19 @@ class BatchVecEnv:
         raise NotImplementedError("per-env methods are not available on a batched aviary; use .batch")
 
     def get_env_random_state(self):
-        """Stand-in for the workers' RNG states (`mappo.py:203-229` checkpoints them)."""
-        return [{"philox_seed": int(self.batch._cfg.seed)}]
+        """The workers' RNG states (`subproc_vec_env.py:101-106`, checkpointed by `mappo.py:203-229`).  There are no
+        workers: ONE state, the batched simulator's Philox key and counters (`bd_get_rng_state`), plus numpy's
+        global state, which the single-env views draw their re-spawn jitter from like the reference does."""
+        return [{"philox": self.batch.get_rng_state(), "numpy": np.random.get_state()}]
 
     def set_env_random_state(self, worker_random_states):
-        return None
+        """`subproc_vec_env.py:108-112`: restore what `get_env_random_state` returned."""
+        states = list(worker_random_states)
+        if len(states) != 1 or "philox" not in states[0]:
+            raise ValueError("set_env_random_state expects the one-element list returned by get_env_random_state")
+        self.batch.set_rng_state(states[0]["philox"])
+        if states[0].get("numpy") is not None:
+            np.random.set_state(states[0]["numpy"])
 
     def _get_indices(self, indices):
         if indices is None:
@@ -146,37 +195,49 @@ class BatchVecEnv:
 
 
 class VecRecordEpisodeStatistics:
-    """Episode returns / lengths per env (record_episode_statistics.py:100-171)."""
+    """Running return / length of every env's current episode, queues of the finished ones, and optional named
+    trackers fed from the info dicts — the protocol of `record_episode_statistics.py:100-171` (attribute names
+    `return_queue`, `length_queue`, `episode_return`, `episode_length`, `add_tracker`, `accumulated_stats`,
+    `queued_stats`; `info['n'][i]['episode'] = {'r', 'l', <tracker>...}` on the step an episode ends).
+
+    Bookkeeping is vectorised: per-env Python work happens only for the envs that finished, and — when trackers are
+    registered — for the envs whose info dict carries a tracked key."""
 
     def __init__(self, venv, deque_size=None, **kwargs):
         self.venv = venv
         self.num_envs = venv.num_envs
-        self.observation_space = venv.observation_space
-        self.action_space = venv.action_space
+        self.observation_space, self.action_space = venv.observation_space, venv.action_space
         self.deque_size = deque_size
-        self.episode_return = np.zeros(self.num_envs)
-        self.episode_length = np.zeros(self.num_envs)
-        self.return_queue = deque(maxlen=deque_size)
-        self.length_queue = deque(maxlen=deque_size)
-        self.episode_stats = {}
-        self.accumulated_stats = {}
-        self.queued_stats = {}
+        self.return_queue, self.length_queue = deque(maxlen=deque_size), deque(maxlen=deque_size)
+        self.episode_return = np.zeros(self.num_envs, dtype=np.float64)
+        self.episode_length = np.zeros(self.num_envs, dtype=np.float64)
+        self._trackers = {}            # name -> (mode, initial value, per-env running values)
+        self.accumulated_stats, self.queued_stats = {}, {}
+
+    # the reference exposes the per-env tracker values as `episode_stats[name][i]`
+    @property
+    def episode_stats(self):
+        return {name: t[2] for name, t in self._trackers.items()}
 
     def add_tracker(self, name, init_value, mode='accumulate'):
-        self.episode_stats[name] = [init_value for _ in range(self.num_envs)]
         if mode == 'accumulate':
             self.accumulated_stats[name] = init_value
         elif mode == 'queue':
             self.queued_stats[name] = deque(maxlen=self.deque_size)
         else:
             raise Exception('Tracker mode not implemented.')
+        self._trackers[name] = (mode, init_value, [deepcopy(init_value) for _ in range(self.num_envs)])
+
+    def _clear_tracker(self, name, i):
+        mode, init, values = self._trackers[name]
+        values[i] = values[i] * 0      # keeps the value's type / shape, like the reference's `*= 0`
 
     def reset(self, **kwargs):
-        self.episode_return = np.zeros(self.num_envs)
-        self.episode_length = np.zeros(self.num_envs)
-        for key in self.episode_stats:
+        self.episode_return[:] = 0.0
+        self.episode_length[:] = 0.0
+        for name in self._trackers:
             for i in range(self.num_envs):
-                self.episode_stats[key][i] *= 0
+                self._clear_tracker(name, i)
         return self.venv.reset(**kwargs)
 
     def step_async(self, actions):
@@ -184,27 +245,34 @@ class VecRecordEpisodeStatistics:
 
     def step_wait(self):
         obs, reward, done, info = self.venv.step_wait()
-        self.episode_return += np.asarray([float(np.mean(r)) for r in reward])   # :148
+        r = np.asarray(reward, dtype=np.float64)
+        self.episode_return += r if r.ndim == 1 else r.reshape(self.num_envs, -1).mean(axis=1)   # mean over agents (:148)
         self.episode_length += 1
-        for i in np.nonzero(np.ones(self.num_envs, dtype=bool) if self.episode_stats else done)[0]:
-            d = bool(done[i])
-            inf = info['n'][i]['terminal_info'] if (d and 'terminal_info' in info['n'][i]) else info['n'][i]
-            for key in self.episode_stats:
-                if key in inf:
-                    self.episode_stats[key][i] += inf[key]
-            if d:
-                info['n'][i]['episode'] = {'r': self.episode_return[i], 'l': self.episode_length[i]}
-                self.return_queue.append(deepcopy(self.episode_return[i]))
-                self.length_queue.append(deepcopy(self.episode_length[i]))
-                self.episode_return[i] = 0
-                self.episode_length[i] = 0
-                for key in self.episode_stats:
-                    info['n'][i]['episode'][key] = deepcopy(self.episode_stats[key][i])
-                    if key in self.accumulated_stats:
-                        self.accumulated_stats[key] += deepcopy(self.episode_stats[key][i])
-                    if key in self.queued_stats:
-                        self.queued_stats[key].append(deepcopy(self.episode_stats[key][i]))
-                    self.episode_stats[key][i] *= 0
+        done = np.asarray(done, dtype=bool)
+        infos = info['n']
+        finished = np.flatnonzero(done)
+        if self._trackers:             # tracked keys may sit in any env's info (or in its terminal_info when it ended)
+            for i in range(self.num_envs):
+                src = infos[i]
+                if done[i] and 'terminal_info' in src:
+                    src = src['terminal_info']
+                for name, (_, _, values) in self._trackers.items():
+                    if name in src:
+                        values[i] = values[i] + src[name]
+        for i in finished:
+            ep = {'r': float(self.episode_return[i]), 'l': float(self.episode_length[i])}
+            self.return_queue.append(ep['r'])
+            self.length_queue.append(ep['l'])
+            for name, (mode, _, values) in self._trackers.items():
+                ep[name] = deepcopy(values[i])
+                if mode == 'accumulate':
+                    self.accumulated_stats[name] = self.accumulated_stats[name] + deepcopy(values[i])
+                else:
+                    self.queued_stats[name].append(deepcopy(values[i]))
+                self._clear_tracker(name, i)
+            infos[i]['episode'] = ep
+        self.episode_return[finished] = 0.0
+        self.episode_length[finished] = 0.0
         return obs, reward, done, info
 
     def step(self, actions):

@@ -1,0 +1,213 @@
+"""BASELINE.json configs[1] and configs[2] run AS STATED, every env against its own oracle.
+
+configs[1]  MultiHoverAviary, M = 2, rollout_batch_size N = 176, T = 256 control steps (`learn_mappo.py:104`),
+            Physics.DYN, 240/30 Hz, driven like `SubprocVecEnv` drives it (reset-on-done, `subproc_vec_env.py:188-207`):
+            default spawn layout + `MultiHoverAviary.reset`'s jitter (`MultiHoverAviary.py:83-102`, the accepted draw of
+            its rejection loop injected into oracle and kernel alike), 176 DISTINCT action sequences, two action
+            distributions: U(-1,1) float64 and 0.3 N(0,1) float32 (policy-like, unclipped).
+configs[2]  SpiralFormationAviary, M = 5, N = 64, 240/48 Hz, RPM, ground effect + drag + downwash all on, the whole
+            578-step episode horizon (580 steps), reset-on-done.  The ring start is staggered in height
+            (z_i = 0.3 + 0.12 i): with all drones at z = 0.3 the reference's downwash term
+            (`BaseAviary.py:798-804`, alpha ~ 1/dz^2) is singular from the second substep on — rounding-level height
+            differences give forces of 1e6 N.  Plus 8 envs WITHOUT reset-on-done that fly the full 12 s so that the
+            578th-step truncation is seen with the aero terms on.
+
+Stated tolerances:
+  fp64 : state (pos, quat, rpy, vel, ang_vel) and reward <= 1e-9 relative at every step of the free-running horizon,
+         observations (float32 storage) <= 2.5e-7, terminated / truncated identical, for ALL envs.
+  fp32 : per control step from the oracle's state (teacher-forced, every env, every step):
+         plain DYN (configs[1], fast tile kernel) <= 1e-5; all aero terms (configs[2], generic kernel) <= 5e-5
+         of max(|x|, 1); flags identical except where the deciding quantity is within 1e-5 of its threshold
+         (none occurs on these seeds, so they are asserted identical).
+"""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from _oracle_pool import accepted_jitter, run_oracles
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9
+OBS_F32_TOL = 2.5e-7
+
+
+def _default_xyz(M, L=0.0397):
+    return np.array([[4 * L * i, 4 * L * i, 0.1125] for i in range(M)])          # BaseAviary.py:194-197
+
+
+# ------------------------------------------------------------------------------------------- configs[1]
+@functools.lru_cache(maxsize=None)
+def _cfg1(dist):
+    N, M, T = 176, 2, 256
+    orig = _default_xyz(M)
+    jrng = np.random.default_rng(1)
+    jit = np.array([[accepted_jitter(jrng, orig) for _ in range(N)] for _ in range(T + 1)])     # (T+1,N,M,3)
+    arng = np.random.default_rng(2)
+    if dist == "uniform":
+        actions = arng.uniform(-1, 1, (T, N, M, 4))                                             # float64
+    else:
+        actions = (0.3 * arng.standard_normal((T, N, M, 4))).astype(np.float32)
+    kw = dict(task="multihover", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30, act="rpm")
+    jobs = [dict(kw=kw, actions=actions[:, e], jitter=jit[:, e], auto_reset=True) for e in range(N)]
+    return actions, jit, run_oracles(jobs)
+
+
+def _make_cfg1_env(precision, adt):
+    from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
+    return BatchAviary(task="multihover", num_envs=176, num_drones=2, pyb_freq=240, ctrl_freq=30, act="rpm",
+                       precision=precision, auto_reset=True, reset_mode="jitter_buffer", action_dtype=adt,
+                       keep_ang_vel=(precision == "fp64"))
+
+
+@pytest.mark.parametrize("dist", ["uniform", "normal03_f32"])
+def test_cfg1_fp64_all_176_envs_256_steps(dist):
+    actions, jit, ref = _cfg1(dist)
+    T, N = actions.shape[0], actions.shape[1]
+    adt = torch.float32 if actions.dtype == np.float32 else torch.float64
+    env = _make_cfg1_env("fp64", adt)
+    env.set_jitter(torch.as_tensor(jit[0]))
+    obs0 = env.reset_device().cpu().numpy()
+    assert rel_err(obs0, ref["obs0"]) <= OBS_F32_TOL
+    n_done = 0
+    for t in range(T):
+        env.set_jitter(torch.as_tensor(jit[t + 1]))
+        r = env.step_device(torch.as_tensor(actions[t]).to("cuda", adt), want_terminal_obs=True)
+        st, rates, sc = env.get_state(with_rates=True, with_step_counter=True)
+        st = st.cpu().numpy()
+        assert rel_err(st[..., :16], ref["states"][t][..., :16]) <= FP64_TOL, (dist, t)
+        assert rel_err(rates.cpu().numpy(), ref["rates"][t]) <= FP64_TOL, (dist, t)
+        assert np.array_equal(sc.cpu().numpy(), ref["stepc"][t]), (dist, t)
+        assert rel_err(r.obs.cpu().numpy(), ref["obs"][t]) <= OBS_F32_TOL, (dist, t)
+        assert rel_err(r.reward.cpu().numpy(), ref["reward"][t]) <= FP64_TOL, (dist, t)
+        assert np.array_equal(r.terminated.cpu().numpy(), ref["terminated"][t]), (dist, t)
+        assert np.array_equal(r.truncated.cpu().numpy(), ref["truncated"][t]), (dist, t)
+        done = ref["terminated"][t] | ref["truncated"][t]
+        if done.any():
+            n_done += int(done.sum())
+            assert rel_err(r.terminal_obs.cpu().numpy()[done], ref["term_obs"][t][done]) <= OBS_F32_TOL, (dist, t)
+            assert rel_err(env.get_targets().cpu().numpy(), ref["targets"][t]) <= FP64_TOL, (dist, t)
+    assert n_done >= 100                         # reset-on-done was exercised many times (crashes, the 242-step limit)
+    env.close()
+
+
+@pytest.mark.parametrize("dist", ["uniform", "normal03_f32"])
+def test_cfg1_fp32_per_step_all_176_envs(dist):
+    """fp32 fast tile kernel, teacher-forced from the oracle's state before every step."""
+    actions, jit, ref = _cfg1(dist)
+    T, N = actions.shape[0], actions.shape[1]
+    env = _make_cfg1_env("fp32", torch.float32)
+    env.set_jitter(torch.as_tensor(jit[0]))
+    env.reset_device()
+    worst = 0.0
+    for t in range(T):
+        if t > 0:
+            s = ref["states"][t - 1]
+            kin = np.concatenate([s[..., 0:7], s[..., 10:13], ref["rates"][t - 1]], axis=-1)
+            env.set_state(torch.as_tensor(kin), targets=torch.as_tensor(ref["targets"][t - 1]),
+                          step_counter=torch.as_tensor(ref["stepc"][t - 1], dtype=torch.int32))
+        env.set_jitter(torch.as_tensor(jit[t + 1]))
+        r = env.step_device(torch.as_tensor(actions[t].astype(np.float32), device="cuda"))
+        st = env.get_state().cpu().numpy()
+        ok = ~(ref["terminated"][t] | ref["truncated"][t])          # finished envs hold the re-spawn state (checked below)
+        err = rel_err(st[ok][..., :13], ref["states"][t][ok][..., :13])
+        worst = max(worst, err)
+        assert err <= 1e-5, (dist, t, err)
+        assert rel_err(st[~ok][..., :13], ref["states"][t][~ok][..., :13]) <= 1e-6, (dist, t)
+        assert rel_err(r.reward.cpu().numpy(), ref["reward"][t]) <= 2e-5, (dist, t)
+        assert np.array_equal(r.terminated.cpu().numpy(), ref["terminated"][t]), (dist, t)
+        assert np.array_equal(r.truncated.cpu().numpy(), ref["truncated"][t]), (dist, t)
+    print(f"cfg1 {dist}: worst fp32 per-step error {worst:.2e}")
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------- configs[2]
+def _spiral_xyz(M=5):
+    return np.array([[0.4 * np.cos(2 * np.pi * i / M), 0.4 * np.sin(2 * np.pi * i / M), 0.3 + 0.12 * i] for i in range(M)])
+
+
+@functools.lru_cache(maxsize=None)
+def _cfg2(auto_reset):
+    M = 5
+    N, T = (64, 580) if auto_reset else (8, 580)
+    rng = np.random.default_rng(3)
+    if auto_reset:
+        actions = rng.uniform(-1, 1, (T, N, M, 4))
+        actions[:, N // 2:] = 0.3 * rng.standard_normal((T, N - N // 2, M, 4))
+        actions = actions.astype(np.float32)
+    else:
+        actions = (0.02 * rng.standard_normal((T, N, M, 4))).astype(np.float32)
+    kw = dict(task="spiral", drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=48, act="rpm", aero=7,
+              initial_xyzs=_spiral_xyz(M))
+    jobs = [dict(kw=kw, actions=actions[:, e], auto_reset=auto_reset) for e in range(N)]
+    return actions, run_oracles(jobs)
+
+
+def _make_cfg2_env(precision, N, auto_reset):
+    from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
+    return BatchAviary(task="spiral", num_envs=N, num_drones=5, pyb_freq=240, ctrl_freq=48, act="rpm",
+                       initial_xyzs=_spiral_xyz(5), physics="dyn_gnd_drag_dw", precision=precision,
+                       auto_reset=auto_reset, reset_mode="fixed", action_dtype=torch.float32,
+                       keep_ang_vel=(precision == "fp64"))
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_cfg2_fp64_spiral_aero_full_horizon(auto_reset):
+    actions, ref = _cfg2(auto_reset)
+    T, N = actions.shape[0], actions.shape[1]
+    env = _make_cfg2_env("fp64", N, auto_reset)
+    obs0 = env.reset_device().cpu().numpy()
+    assert rel_err(obs0, ref["obs0"]) <= OBS_F32_TOL
+    n_done, n_trunc = 0, 0
+    for t in range(T):
+        r = env.step_device(torch.as_tensor(actions[t], device="cuda"), want_terminal_obs=auto_reset)
+        st, rates, sc = env.get_state(with_rates=True, with_step_counter=True)
+        st = st.cpu().numpy()
+        assert rel_err(st[..., :16], ref["states"][t][..., :16]) <= FP64_TOL, (t, rel_err(st[..., :16], ref["states"][t][..., :16]))
+        assert rel_err(rates.cpu().numpy(), ref["rates"][t]) <= FP64_TOL, t
+        assert np.array_equal(sc.cpu().numpy(), ref["stepc"][t]), t
+        assert rel_err(r.obs.cpu().numpy(), ref["obs"][t]) <= OBS_F32_TOL, t
+        assert rel_err(r.reward.cpu().numpy(), ref["reward"][t]) <= FP64_TOL, t
+        assert np.array_equal(r.terminated.cpu().numpy(), ref["terminated"][t]), t
+        assert np.array_equal(r.truncated.cpu().numpy(), ref["truncated"][t]), t
+        done = ref["terminated"][t] | ref["truncated"][t]
+        n_done += int(done.sum())
+        n_trunc += int(ref["truncated"][t].sum())
+        if auto_reset and done.any():
+            assert rel_err(r.terminal_obs.cpu().numpy()[done], ref["term_obs"][t][done]) <= OBS_F32_TOL, t
+    if auto_reset:
+        assert n_done >= 64
+    else:
+        assert ref["truncated"][577].all() and not ref["truncated"][576].any() and n_trunc >= N     # SpiralAviary.py:196
+    env.close()
+
+
+def test_cfg2_fp32_per_step_spiral_aero():
+    """Generic float kernel with ground effect + drag + downwash, teacher-forced from the oracle's state."""
+    actions, ref = _cfg2(True)
+    T, N = actions.shape[0], actions.shape[1]
+    env = _make_cfg2_env("fp32", N, True)
+    env.reset_device()
+    worst = 0.0
+    for t in range(T):
+        if t > 0:
+            s = ref["states"][t - 1]
+            kin = np.concatenate([s[..., 0:7], s[..., 10:13], ref["rates"][t - 1]], axis=-1)
+            env.set_state(torch.as_tensor(kin), step_counter=torch.as_tensor(ref["stepc"][t - 1], dtype=torch.int32))
+        r = env.step_device(torch.as_tensor(actions[t], device="cuda"))
+        st = env.get_state().cpu().numpy()
+        # the downwash term is singular where two drones pass through the same height (alpha ~ 1/dz^2): the
+        # reference's own trajectory jumps by kilometres there and relative float32 agreement is meaningless
+        sane = np.abs(ref["states"][t][..., :3]).max(axis=(1, 2)) < 50.0
+        ok = sane & ~(ref["terminated"][t] | ref["truncated"][t])
+        err = rel_err(st[ok][..., :13], ref["states"][t][ok][..., :13])
+        worst = max(worst, err)
+        assert err <= 5e-5, (t, err)
+        assert np.array_equal(r.terminated.cpu().numpy()[sane], ref["terminated"][t][sane]), t
+        assert np.array_equal(r.truncated.cpu().numpy()[sane], ref["truncated"][t][sane]), t
+        assert rel_err(r.reward.cpu().numpy()[ok], ref["reward"][t][ok]) <= 5e-5, t
+    print(f"cfg2: worst fp32 per-step error {worst:.2e}")
+    env.close()
