@@ -285,6 +285,56 @@ int bd_rms_set(bd_rms* r, const double* mean_dev, const double* var_dev, const d
 int64_t bd_rms_launch_count(const bd_rms* r);
 const char* bd_rms_last_error(void);
 
+/* ------------------------------------------------------------------------------------------
+ * PPO update of the MAPPO trainer as hand-written tensor-core kernels (csrc/bd_ppo.cu).
+ * Replaces MAPPOAgent.update / compute_policy_loss / compute_value_loss (mappo/agent.py:602-772)
+ * and _compute_single_agent_returns + normalize_advantages (mappo/buffer.py:561-614, 666-695).
+ * A bd_ppo_net is one MLP in -> 256 -> 256 -> out with tanh (neural_networks.py:18-53):
+ *   actor : in_dim = obs_dim, chunks = 1, out_dim = act_dim, has_logstd = 1; row = (sample, agent)
+ *   critic: in_dim = obs_dim, chunks = M, out_dim = 1 (centralised: the M agents' observations of an
+ *           env-step, agent.py:164-223); row = sample
+ * Master parameters are fp32 in ONE flat caller-owned buffer in torch's parameter order
+ * ([logstd] W1 b1 W2 b2 W3 b3, nn.Linear layout); the library keeps bf16 copies for the tensor cores.
+ * "sample" = env-step index t * n_envs + n into the rollout arrays; obs_dev is (slots, N, M, D).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bd_ppo_net bd_ppo_net;
+int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64_t max_rows, int device,
+                      bd_ppo_net** out);
+void bd_ppo_net_destroy(bd_ppo_net* n);
+int64_t bd_ppo_net_param_count(const bd_ppo_net* n);
+/* device doubles [16] of the last bd_ppo_grad: [0] sum of per-row losses, [1] sum of (logp_old - logp),
+ * [2..5] d loss / d logstd sums, [6..9] output-bias gradient sums, [10] rows */
+double* bd_ppo_net_stats(bd_ppo_net* n);
+/* flat fp32 parameters -> bf16 K-step slabs (stream ordered; bd_ppo_adam_step does it itself) */
+int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream);
+/* out (rows, out_dim) = MLP(rows); idx_dev (samples) int64 or NULL = identity; nmean / nrstd: optional
+ * per-slot observation statistics ((slots, M*D) floats, MeanStdNormalizer on load) */
+int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
+                   int64_t rows, const float* nmean_dev, const float* nrstd_dev, float nclip, float* out_dev,
+                   void* stream);
+/* one minibatch: forward, PPO clipped-ratio loss (actor: act, logp_old (slots,N,M[,A]), adv (slots,N) with
+ * adv_stats = (mean, scale)) or value loss (critic: ret, optional v_old (slots,N)), backward, weight
+ * gradients -> grad_dev (flat, parameter order) = mean over rows_global rows (0 = this call's rows) */
+int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
+                int64_t samples, const float* act_dev, const float* logp_old_dev, const float* adv_dev,
+                const float* adv_stats_dev, const float* ret_dev, const float* v_old_dev, float clip,
+                int use_clipped_value, float entropy_coef, const float* nmean_dev, const float* nrstd_dev,
+                float nclip, int64_t rows_global, float* grad_dev, void* stream);
+/* torch.optim.Adam step on flat buffers, skipped entirely (moments and step count too) when
+ * kl_sum / kl_rows > 1.5 target_kl (agent.py:731; NULL or target_kl <= 0: unconditional); then repack */
+int bd_ppo_adam_step(bd_ppo_net* n, float* param_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                     const float* grad_dev, double* step_dev, float lr, float beta1, float beta2, float eps,
+                     const double* kl_sum_dev, const double* kl_rows_dev, float target_kl, double* gate_count_dev,
+                     void* stream);
+/* returns / advantages of a rollout in one launch: rew (T,N), term / trunc (T,N) uint8, vals (T+1,N) with the
+ * bootstrap value in row T; acc3_dev += (sum adv, sum adv^2, count) */
+int bd_ppo_gae(const float* rew_dev, const uint8_t* term_dev, const uint8_t* trunc_dev, const float* vals_dev, int T,
+               int N, float gamma, float lam, int use_gae, float* ret_dev, float* adv_dev, double* acc3_dev,
+               void* stream);
+int bd_ppo_adv_stats(const double* acc3_dev, float* stats2_dev, void* stream);
+int64_t bd_ppo_launch_count(const bd_ppo_net* n);
+const char* bd_ppo_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,8 @@ EXPORTS = (
     "bd_actor_last_error", "bd_actor_set_input_norm",
     "bd_rms_create", "bd_rms_destroy", "bd_rms_update", "bd_rms_batch_moments", "bd_rms_merge_moments", "bd_rms_normalize", "bd_rms_get", "bd_rms_set",
     "bd_rms_launch_count", "bd_rms_last_error",
+    "bd_ppo_net_create", "bd_ppo_net_destroy", "bd_ppo_net_param_count", "bd_ppo_net_stats", "bd_ppo_net_pack", "bd_ppo_forward",
+    "bd_ppo_grad", "bd_ppo_adam_step", "bd_ppo_gae", "bd_ppo_adv_stats", "bd_ppo_launch_count", "bd_ppo_last_error",
 )
 
 
@@ -159,6 +161,31 @@ def load():
     lib.bd_rms_launch_count.restype = C.c_int64
     lib.bd_rms_last_error.argtypes = []
     lib.bd_rms_last_error.restype = C.c_char_p
+    lib.bd_ppo_net_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(vp)]
+    lib.bd_ppo_net_create.restype = C.c_int
+    lib.bd_ppo_net_destroy.argtypes = [vp]
+    lib.bd_ppo_net_destroy.restype = None
+    lib.bd_ppo_net_param_count.argtypes = [vp]
+    lib.bd_ppo_net_param_count.restype = C.c_int64
+    lib.bd_ppo_net_stats.argtypes = [vp]
+    lib.bd_ppo_net_stats.restype = vp
+    lib.bd_ppo_net_pack.argtypes = [vp, vp, vp]
+    lib.bd_ppo_net_pack.restype = C.c_int
+    lib.bd_ppo_forward.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp, C.c_float, vp, vp]
+    lib.bd_ppo_forward.restype = C.c_int
+    lib.bd_ppo_grad.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int,
+                                C.c_float, vp, vp, C.c_float, C.c_int64, vp, vp]
+    lib.bd_ppo_grad.restype = C.c_int
+    lib.bd_ppo_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, C.c_float, vp, vp]
+    lib.bd_ppo_adam_step.restype = C.c_int
+    lib.bd_ppo_gae.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, vp, vp, vp]
+    lib.bd_ppo_gae.restype = C.c_int
+    lib.bd_ppo_adv_stats.argtypes = [vp, vp, vp]
+    lib.bd_ppo_adv_stats.restype = C.c_int
+    lib.bd_ppo_launch_count.argtypes = [vp]
+    lib.bd_ppo_launch_count.restype = C.c_int64
+    lib.bd_ppo_last_error.argtypes = []
+    lib.bd_ppo_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -149,13 +149,20 @@ __device__ __forceinline__ void quat_to_euler(R x, R y, R z, R w, R& roll, R& pi
 
 // `abs(roll) < pi/2 and abs(pitch) < pi/2` (the ground-effect gate, BaseAviary.py:735) without the three inverse
 // trigonometric calls per substep: pitch = asin(sarg) is below pi/2 exactly when the gimbal branches are not taken,
-// |atan2(ys, xs)| < pi/2 exactly when xs > 0 — except within rounding distance of 90 degrees, where the full
-// extraction decides (so the decision is the reference's in every case).
+// |atan2(ys, xs)| < pi/2 exactly when xs > 0 — except within rounding distance of 90 degrees.  There the reference
+// compares the ROUNDED angle with the rounded constant: fl(atan2(ys, xs)) < fl(pi/2) holds iff the exact angle
+// pi/2 - xs/|ys| lies below the midpoint of fl(pi/2) and its predecessor, i.e. iff
+// xs/|ys| > (pi/2 - fl(pi/2)) + ulp/2 = 6.1232e-17 + 1.1102e-16.  Deciding it in this form (double) reproduces
+// numpy / libm without depending on the last bit of the device's atan2 (found by the round-2 gimbal test: a roll
+// that reaches pi/2 to 5e-16 after 30 substeps).
 template <typename R>
 __device__ __forceinline__ bool tilt_below_half_pi(R x, R y, R z, R w) {
   const R sarg = R(-2) * (x * z - w * y);
   if (sarg <= R(-0.99999) || sarg >= R(0.99999)) return false;   // pitch = -+pi/2 exactly
   const R xs = w * w - x * x - y * y + z * z, ys = R(2) * (y * z + w * x);
+  if constexpr (sizeof(R) == 8) {
+    return xs > R(1.7225464241988331e-16) * abs_(ys);
+  }
   if (abs_(xs) <= R(1e-5) * abs_(ys)) {
     R roll, pitch, yaw;
     quat_to_euler(x, y, z, w, roll, pitch, yaw);

@@ -1,0 +1,1233 @@
+// Hand-written PPO update for MAPPO on sm_100a: the reference's `MAPPOAgent.update`
+// (gym_pybullet_drones/mappo/agent.py:602-772) and `_compute_single_agent_returns` (mappo/buffer.py:561-614)
+// without any library GEMM, autograd graph or elementwise torch kernel.
+//
+//   gae_kernel        returns / advantages as ONE backwards scan per env + the buffer-wide moments (buffer.py:561-695)
+//   mlp_tile_kernel   per 128-row tile: gather rows by minibatch index -> 3-layer tanh MLP forward on tcgen05 (bf16
+//                     operands, fp32 TMEM accumulators) -> PPO clipped-ratio loss / value loss and their gradient at the
+//                     MLP output -> backward through both hidden layers on tcgen05; activations stay in shared memory,
+//                     weights stream from L2 through a TMA slab ring; the tile's X, H1, H2, dZ2, dZ1, dZ3 leave the SM
+//                     once, as bf16 UMMA tiles, for the weight-gradient pass
+//   dw_kernel         weight gradients dW = dZ^T . input as tall-skinny GEMMs on tcgen05 with MN-major (transposed)
+//                     operand descriptors straight over those tiles (TMA bulk loads, 3-stage ring), 256 x N fp32
+//                     accumulators resident in TMEM over a CTA's whole row range; bias gradients by the idle warps
+//   reduce_kernel     per-CTA partials -> flat gradient in torch parameter order (the unit of the NCCL all-reduce)
+//   adam_kernel       torch.optim.Adam's arithmetic with the reference's KL gate decided on the device (agent.py:731)
+//   pack_kernel       fp32 master weights -> bf16 K-step slabs for the next minibatch
+//
+// Why two tensor-core kernels and not one: the weight-gradient accumulators of the 256 x 256 layer are 256 KB of fp32 —
+// all of an SM's tensor memory — so they cannot live next to the activation accumulators of the forward / backward
+// chain; they get their own kernel, and the activations cross HBM exactly once in bf16 (280 KB per 128 rows).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/batch_drones.h"
+#include "bd_umma.cuh"
+
+namespace {
+using namespace bdu;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kRows = 128;          // rows per tile = UMMA M
+constexpr int HID = 256;            // hidden width (both layers)
+constexpr int kNOut = 16;           // output layer padded to the smallest UMMA N
+constexpr int kSlabBytes = 8192;    // one K = 16 step of a 256-row weight operand
+constexpr int kStages = 4;          // weight slab ring
+constexpr int kEpiThreads = 512;    // 4 threads per row (column groups of 64)
+constexpr int kThreads = kEpiThreads + 64;   // + MMA warp + TMA warp
+constexpr int kMaxPieces = 3;       // 8-column input pieces per thread and chunk (K1p <= 96)
+constexpr int kStatSlots = 16;
+
+thread_local char g_err[384] = "";
+int pfail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+//                                   returns / advantages
+// ---------------------------------------------------------------------------------------------
+// One thread per env: the reward is shared by the env's agents (mappo.py:758-772), so every agent's sequence is the
+// same scan.  vals (T+1, N): rollout values (zeros in the reference's rollout, agent.py:413) with the bootstrap value
+// in row T.  acc[0..1] += sum adv, sum adv^2 (fp64); acc[2] += count.
+__global__ void gae_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
+                           const float* __restrict__ vals, int T, int N, float gamma, float lam, int use_gae,
+                           float* __restrict__ ret, float* __restrict__ adv, double* __restrict__ acc) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (n < N) {
+    float r_run = vals[(size_t)T * N + n], a_run = 0.f;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t i = (size_t)t * N + n;
+      const float mask = (term[i] | trunc[i]) ? 0.f : 1.f;
+      const float r = rew[i];                       // terminal_v is always 0 (mappo.py:827,845)
+      r_run = r + gamma * mask * r_run;             // buffer.py:600
+      if (use_gae) {
+        const float td = r + gamma * mask * vals[i + N] - vals[i];
+        a_run = a_run * lam * gamma * mask + td;    // :606-607
+      } else {
+        a_run = r_run - vals[i];
+      }
+      ret[i] = r_run;
+      adv[i] = a_run;
+      s1 += (double)a_run;
+      s2 += (double)a_run * (double)a_run;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  __shared__ double sh[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][warp] = s1; sh[1][warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    s1 = lane < nw ? sh[0][lane] : 0.0;
+    s2 = lane < nw ? sh[1][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) {
+      atomicAdd(acc + 0, s1);
+      atomicAdd(acc + 1, s2);
+      if (blockIdx.x == 0) atomicAdd(acc + 2, (double)T * (double)N);
+    }
+  }
+}
+
+// (sum, sum of squares, count) -> (mean, scale) with normalize_advantages' rule (buffer.py:666-695, numpy branch):
+// population std; (adv - mean) / (std + eps), or adv - mean when std < eps.
+__global__ void adv_stats_kernel(const double* __restrict__ acc, float* __restrict__ out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double n = acc[2] > 0.0 ? acc[2] : 1.0;
+    const double mean = acc[0] / n;
+    double var = acc[1] / n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double sd = sqrt(var);
+    out2[0] = (float)mean;
+    out2[1] = (float)(sd < 1e-8 ? 1.0 : 1.0 / (sd + 1e-8));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+//                       forward + loss + activation backward, one tile at a time
+// ---------------------------------------------------------------------------------------------
+struct NetDev {
+  const bf16* w1_slabs;    // [C][K1p/16] slabs [256 n x 16 k]
+  const bf16* w2f_slabs;   // [16] slabs [256 n x 16 k] in issue order i -> K-step 4*(i&3) + (i>>2)
+  const bf16* w2b_slabs;   // [16] slabs [256 i x 16 j] = W2[j][i] (backward), same issue order over j
+  const bf16* w3f;         // [16 o x 256 j] canonical, resident
+  const bf16* w3b_slab;    // [256 j x 16 o] = W3[o][j]
+  const float *b1, *b2, *b3, *logstd;   // b3 / logstd padded to 16
+  int C, D, K1p, out_dim;
+};
+
+enum { MODE_ACTOR_TRAIN = 0, MODE_CRITIC_TRAIN = 1, MODE_FORWARD = 2 };
+
+struct TileArgs {
+  NetDev net;
+  int mode;
+  const float* obs;          // (slots, N, M, D) raw observations
+  int N, M;                  // envs per slot, agents per env
+  const long long* idx;      // minibatch: sample s -> env-step index (t * N + n); nullptr = identity
+  long long rows;            // actor: samples * M, critic: samples
+  const float *act, *logp_old, *adv, *adv_stats;   // actor loss inputs (adv per env-step, stats = (mean, scale))
+  const float *ret, *v_old;  // critic loss inputs per env-step
+  float clip, use_clipped_value;
+  const float *nmean, *nrstd;   // optional observation normalisation: per slot (t), per (agent, column)
+  float nclip;
+  bf16 *Xt, *H1t, *H2t, *dZ2t, *dZ1t, *dZ3t;   // tile scratch for dw_kernel
+  float* out;                // MODE_FORWARD: (rows, out_dim)
+  double* stats;             // [0] sum loss, [1] sum (logp_old - logp), [2..5] dlogstd sums, [6..9] db3 sums, [10] rows
+};
+
+enum { B_W3 = 0, B_XFULL, B_XEMPTY = B_XFULL + 2, B_L1 = B_XEMPTY + 2, B_L2, B_L3, B_D2, B_D1, B_Z3, B_TDONE, B_H1C,
+       B_H2C = B_H1C + 4, B_Z2C = B_H2C + 4, B_FULL = B_Z2C + 4, B_EMPTY = B_FULL + kStages, B_COUNT = B_EMPTY + kStages };
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_tile_kernel(const __grid_constant__ TileArgs P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const NetDev& W = P.net;
+  const int K1p = W.K1p, C = W.C, D = W.D;
+  bf16* bufH1 = reinterpret_cast<bf16*>(smem);                        // 64 KB: H1, later dZ1
+  bf16* bufH2 = bufH1 + (size_t)kRows * HID;                          // 64 KB: H2, later dZ2
+  bf16* bufX = bufH2 + (size_t)kRows * HID;                           // 2 x [128 x K1p] (K1p <= 96)
+  bf16* bufZ3 = bufX + 2 * (size_t)kRows * 96;                        // [128 x 16]
+  bf16* sW3 = bufZ3 + (size_t)kRows * kNOut;                          // [16 x 256]
+  unsigned char* ring = reinterpret_cast<unsigned char*>(sW3 + (size_t)kNOut * HID);   // kStages x 8 KB
+  float* sB1 = reinterpret_cast<float*>(ring + (size_t)kStages * kSlabBytes);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;      // [16]
+  float* sLs = sB3 + kNOut;    // [16]
+  __shared__ __align__(8) uint64_t mbar[B_COUNT];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool train = P.mode != MODE_FORWARD;
+  for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd != nullptr ? W.logstd[tid] : 0.f; }
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[B_W3]), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&mbar[B_XFULL + i]), kEpiThreads); mbar_init(smem_u32(&mbar[B_XEMPTY + i]), 1); }
+    for (int i = B_L1; i <= B_D1; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+    mbar_init(smem_u32(&mbar[B_Z3]), kRows);
+    mbar_init(smem_u32(&mbar[B_TDONE]), kEpiThreads);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&mbar[B_H1C + i]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[B_H2C + i]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[B_Z2C + i]), kEpiThreads);
+    }
+    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&mbar[B_FULL + i]), 1); mbar_init(smem_u32(&mbar[B_EMPTY + i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)HID;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t aH1 = smem_u32(bufH1), aH2 = smem_u32(bufH2), aX = smem_u32(bufX), aZ3 = smem_u32(bufZ3), aW3 = smem_u32(sW3),
+                 aRing = smem_u32(ring);
+  const long long n_tiles = (P.rows + kRows - 1) / kRows;
+  const int k1_steps = K1p / 16;
+  const int slabs_per_tile = C * k1_steps + 16 + (train ? 17 : 0);
+  const uint32_t xbuf_bytes = (uint32_t)kRows * 96 * 2;
+
+  if (warp == kEpiThreads / 32 + 1) {
+    // ===================================== TMA producer ===========================================
+    if (lane == 0) {
+      mbar_expect_tx(bar(B_W3), (uint32_t)(kNOut * HID * 2));
+      bulk_g2s(aW3, W.w3f, (uint32_t)(kNOut * HID * 2), bar(B_W3));
+      unsigned long long cnt = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int q = 0; q < slabs_per_tile; ++q, ++cnt) {
+          const int st = (int)(cnt % kStages);
+          const uint32_t par = (uint32_t)((cnt / kStages) & 1);
+          if (cnt >= kStages) mbar_wait(bar(B_EMPTY + st), par ^ 1);
+          const bf16* src;
+          const int n1 = C * k1_steps;
+          if (q < n1) src = W.w1_slabs + (size_t)q * (kSlabBytes / 2);
+          else if (q < n1 + 16) src = W.w2f_slabs + (size_t)(q - n1) * (kSlabBytes / 2);
+          else if (q == n1 + 16) src = W.w3b_slab;
+          else src = W.w2b_slabs + (size_t)(q - n1 - 17) * (kSlabBytes / 2);
+          mbar_expect_tx(bar(B_FULL + st), kSlabBytes);
+          bulk_g2s(aRing + (uint32_t)st * kSlabBytes, src, kSlabBytes, bar(B_FULL + st));
+        }
+      }
+    }
+  } else if (warp == kEpiThreads / 32) {
+    // ===================================== MMA issuer =============================================
+    if (lane == 0) {
+      unsigned long long cnt = 0, xcnt = 0;
+      uint32_t tpar = 0;
+      const uint32_t sboX = (uint32_t)(K1p / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      auto next_slab = [&]() -> uint32_t {
+        const int st = (int)(cnt % kStages);
+        mbar_wait(bar(B_FULL + st), (uint32_t)((cnt / kStages) & 1));
+        ++cnt;
+        return (uint32_t)st;
+      };
+      mbar_wait(bar(B_W3), 0);
+      bool first = true;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (!first) { mbar_wait(bar(B_TDONE), tpar ^ 1); }   // previous tile's last epilogue has drained acc0
+        first = false;
+        tc_fence_after();
+        // ---- layer 1: acc0 = sum_c X_c W1_c^T
+        for (int c = 0; c < C; ++c, ++xcnt) {
+          const int xb = (int)(xcnt & 1);
+          mbar_wait(bar(B_XFULL + xb), (uint32_t)((xcnt >> 1) & 1));
+          tc_fence_after();
+          for (int s = 0; s < k1_steps; ++s) {
+            const uint32_t st = next_slab();
+            umma_bf16(acc0, umma_desc(aX + (uint32_t)xb * xbuf_bytes + s * 256, 128, sboX),
+                      umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID), (c | s) != 0);
+            umma_commit(bar(B_EMPTY + st));
+          }
+          umma_commit(bar(B_XEMPTY + xb));
+        }
+        umma_commit(bar(B_L1));
+        // ---- layer 2: acc1 = H1 W2^T, K-steps follow the layer-1 epilogue chunk by chunk
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(bar(B_H1C + j), tpar);
+          tc_fence_after();
+          for (int h = 0; h < 4; ++h) {
+            const int s = h * 4 + j;
+            const uint32_t st = next_slab();
+            umma_bf16(acc1, umma_desc(aH1 + s * 256, 128, sboH), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID),
+                      (j | h) != 0);
+            umma_commit(bar(B_EMPTY + st));
+          }
+        }
+        umma_commit(bar(B_L2));
+        // ---- layer 3: acc0[:, 0:16] = H2 W3^T
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(bar(B_H2C + j), tpar);
+          tc_fence_after();
+          for (int h = 0; h < 4; ++h) {
+            const int s = h * 4 + j;
+            umma_bf16(acc0, umma_desc(aH2 + s * 256, 128, sboH), umma_desc(aW3 + s * 256, 128, sboH), umma_idesc(kNOut),
+                      (j | h) != 0);
+          }
+        }
+        umma_commit(bar(B_L3));
+        if (train) {
+          // ---- dH2 = dZ3 W3 : acc1 = Z3[128 x 16] . slab[256 j x 16 o]^T
+          mbar_wait(bar(B_Z3), tpar);
+          tc_fence_after();
+          {
+            const uint32_t st = next_slab();
+            umma_bf16(acc1, umma_desc(aZ3, 128, 256), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID), 0);
+            umma_commit(bar(B_EMPTY + st));
+          }
+          umma_commit(bar(B_D2));
+          // ---- dH1 = dZ2 W2 : acc0 = dZ2[128 x 256 j] . slab_s[256 i x 16 j]^T over the 16 j-steps
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(bar(B_Z2C + j), tpar);
+            tc_fence_after();
+            for (int h = 0; h < 4; ++h) {
+              const int s = h * 4 + j;
+              const uint32_t st = next_slab();
+              umma_bf16(acc0, umma_desc(aH2 + s * 256, 128, sboH), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID),
+                        (j | h) != 0);
+              umma_commit(bar(B_EMPTY + st));
+            }
+          }
+          umma_commit(bar(B_D1));
+        }
+        tpar ^= 1;
+      }
+    }
+  } else {
+    // ================================ staging + epilogue threads ==================================
+    const int row = tid & (kRows - 1), grp = tid >> 7;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int rps = (P.mode == MODE_CRITIC_TRAIN || (P.mode == MODE_FORWARD && C > 1)) ? 1 : P.M;   // rows per sample
+    const int n_pieces = K1p / 8;
+    const bool vec4 = (D & 3) == 0;
+    float4 xa[kMaxPieces], xb4[kMaxPieces];
+    long long cur_sample = 0;
+
+    // env-step index of the sample a tile row belongs to (-1: padding row)
+    auto sample_of = [&](long long tile) -> long long {
+      const long long r = tile * kRows + row;
+      if (r >= P.rows) return -1;
+      const long long s = r / rps;
+      return P.idx != nullptr ? P.idx[s] : s;
+    };
+    auto load_x = [&](long long tile, int c, long long samp) {
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      const float* src = P.obs + ((size_t)samp * P.M + agent) * D;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int k0 = (grp + i * 4) * 8;
+        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < D && samp >= 0) {
+          if (vec4 && k0 + 8 <= D) {
+            xa[i] = __ldg(reinterpret_cast<const float4*>(src + k0));
+            xb4[i] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (k0 + j < D) ? __ldg(src + k0 + j) : 0.0f;
+            xa[i] = make_float4(x[0], x[1], x[2], x[3]);
+            xb4[i] = make_float4(x[4], x[5], x[6], x[7]);
+          }
+        }
+      }
+    };
+    // MeanStdNormalizer on load (normalization.py:84-88) with the statistics of the slot the row was observed in
+    auto normalise_x = [&](long long tile, int c, long long samp) {
+      if (P.nmean == nullptr || samp < 0) return;
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      const size_t base = ((size_t)(samp / P.N) * P.M + agent) * D;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int k0 = (grp + i * 4) * 8;
+        if (k0 < D) {
+          float x[8] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w, xb4[i].x, xb4[i].y, xb4[i].z, xb4[i].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (k0 + j < D) {
+              const float v = (x[j] - __ldg(P.nmean + base + k0 + j)) * __ldg(P.nrstd + base + k0 + j);
+              x[j] = fminf(fmaxf(v, -P.nclip), P.nclip);
+            }
+          }
+          xa[i] = make_float4(x[0], x[1], x[2], x[3]);
+          xb4[i] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+      }
+    };
+    auto stage_x = [&](int xbuf, long long tile, int c) {
+      bf16* dst = bufX + (size_t)xbuf * kRows * 96;
+      bf16* gdst = train ? P.Xt + ((size_t)tile * C + c) * (size_t)kRows * K1p : nullptr;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int p = grp + i * 4;
+        if (p < n_pieces) {
+          const uint4 pk = make_uint4(pack_bf16(xa[i].x, xa[i].y), pack_bf16(xa[i].z, xa[i].w), pack_bf16(xb4[i].x, xb4[i].y),
+                                      pack_bf16(xb4[i].z, xb4[i].w));
+          const size_t off = canon_off(row, p * 8, K1p);
+          *reinterpret_cast<uint4*>(dst + off) = pk;
+          if (gdst != nullptr) *reinterpret_cast<uint4*>(gdst + off) = pk;
+        }
+      }
+    };
+    // forward epilogue: acc row -> +bias, tanh -> bf16 -> activation tile (next layer's A operand) + global copy
+    auto epi_forward = [&](uint32_t acc, const float* bias, bf16* sH, bf16* gH, int chunk_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = tanh_fast(__uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e]);
+          const uint4 pk = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+          const size_t off = canon_off(row, c0 + q * 8, HID);
+          *reinterpret_cast<uint4*>(sH + off) = pk;
+          if (gH != nullptr) *reinterpret_cast<uint4*>(gH + off) = pk;
+        }
+        proxy_fence();
+        mbar_arrive(bar(chunk_bar + j));
+        tmem_wait_ld();
+      }
+    };
+    // backward epilogue: dZ = dH * (1 - H^2), in place over H (bf16), + global copy
+    auto epi_backward = [&](uint32_t acc, bf16* sH, bf16* gZ, int chunk_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const size_t off = canon_off(row, c0 + q * 8, HID);
+          const uint4 hv = *reinterpret_cast<const uint4*>(sH + off);
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float h0, h1;
+            unpack_bf16(hw[e], h0, h1);
+            const float d0 = __uint_as_float(cur[q * 8 + 2 * e]) * fmaf(-h0, h0, 1.0f);
+            const float d1 = __uint_as_float(cur[q * 8 + 2 * e + 1]) * fmaf(-h1, h1, 1.0f);
+            o[e] = pack_bf16(d0, d1);
+          }
+          const uint4 pk = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(sH + off) = pk;
+          *reinterpret_cast<uint4*>(gZ + off) = pk;
+        }
+        if (chunk_bar >= 0) {
+          proxy_fence();
+          mbar_arrive(bar(chunk_bar + j));
+        }
+        tmem_wait_ld();
+      }
+    };
+
+    unsigned long long xcnt = 0;
+    uint32_t tpar = 0;
+    if ((long long)blockIdx.x < n_tiles) {
+      cur_sample = sample_of(blockIdx.x);
+      load_x(blockIdx.x, 0, cur_sample);
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long next = tile + gridDim.x;
+      const long long samp = cur_sample;
+      // ---- stage the input chunks (actor: one, critic: one per agent); the next chunk is already on its way
+      for (int c = 0; c < C; ++c, ++xcnt) {
+        const int xbuf = (int)(xcnt & 1);
+        if (xcnt >= 2) mbar_wait(bar(B_XEMPTY + xbuf), (uint32_t)(((xcnt >> 1) & 1) ^ 1));
+        normalise_x(tile, c, samp);
+        stage_x(xbuf, tile, c);
+        proxy_fence();
+        mbar_arrive(bar(B_XFULL + xbuf));
+        if (c + 1 < C) load_x(tile, c + 1, samp);
+        else if (next < n_tiles) { cur_sample = sample_of(next); load_x(next, 0, cur_sample); }
+      }
+      const size_t tbase = (size_t)tile * kRows * HID;
+      // ---- H1
+      mbar_wait(bar(B_L1), tpar);
+      tc_fence_after();
+      epi_forward(acc0, sB1, bufH1, train ? P.H1t + tbase : nullptr, B_H1C);
+      tc_fence_before();
+      // ---- H2
+      mbar_wait(bar(B_L2), tpar);
+      tc_fence_after();
+      epi_forward(acc1, sB2, bufH2, train ? P.H2t + tbase : nullptr, B_H2C);
+      tc_fence_before();
+      // ---- output layer, loss, gradient at the output (column group 0 owns the rows)
+      if (grp == 0) {
+        mbar_wait(bar(B_L3), tpar);
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16_nowait(acc0 + lane_off, v);
+        tmem_wait_ld();
+        const long long r = tile * kRows + row;
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        float loss = 0.f, kl = 0.f, dls[4] = {0.f, 0.f, 0.f, 0.f}, cntv = 0.f;
+        if (samp >= 0) {
+          cntv = 1.f;
+          if (P.mode == MODE_FORWARD) {
+            for (int k = 0; k < W.out_dim; ++k) P.out[(size_t)r * W.out_dim + k] = __uint_as_float(v[k]) + sB3[k];
+          } else if (P.mode == MODE_ACTOR_TRAIN) {
+            // agent.py:617-640 with torch.distributions.Normal.log_prob summed over the action dims
+            const int agent = (int)(r % rps);
+            const size_t arow = (size_t)samp * P.M + agent;
+            float lp = 0.f, diff[4], ivar[4];
+            for (int k = 0; k < W.out_dim; ++k) {
+              const float mu = __uint_as_float(v[k]) + sB3[k];
+              const float ls = sLs[k];
+              ivar[k] = __expf(-2.0f * ls);
+              diff[k] = P.act[arow * W.out_dim + k] - mu;
+              lp += -0.5f * diff[k] * diff[k] * ivar[k] - ls - 0.91893853320467f;
+            }
+            const float lpo = P.logp_old[arow];
+            const float ratio = __expf(lp - lpo);
+            const float a = (P.adv[samp] - P.adv_stats[0]) * P.adv_stats[1];
+            const float s1 = ratio * a;
+            const float s2 = fminf(fmaxf(ratio, 1.0f - P.clip), 1.0f + P.clip) * a;
+            loss = -fminf(s1, s2);
+            kl = lpo - lp;
+            // d(-min(s1, s2))/d lp: inside the clip range both branches are ratio * a; outside it the gradient
+            // flows only when the unclipped branch is the minimum
+            const bool inside = ratio >= 1.0f - P.clip && ratio <= 1.0f + P.clip;
+            const float g = (inside || s1 < s2) ? -a * ratio : 0.f;
+            for (int k = 0; k < W.out_dim; ++k) {
+              dz[k] = g * diff[k] * ivar[k];
+              dls[k] = g * (diff[k] * diff[k] * ivar[k] - 1.0f);
+            }
+          } else {
+            // agent.py:643-700, centralised critic: target = mean over agents of identical returns
+            const float vv = __uint_as_float(v[0]) + sB3[0];
+            const float rt = P.ret[samp];
+            float e = vv - rt;
+            float l = e * e;
+            if (P.use_clipped_value > 0.f) {
+              const float vo = P.v_old != nullptr ? P.v_old[samp] : 0.f;
+              const float dvc = fminf(fmaxf(vv - vo, -P.clip), P.clip);
+              const float ec = vo + dvc - rt;
+              if (ec * ec > l) { l = ec * ec; e = (fabsf(vv - vo) <= P.clip) ? ec : 0.f; }
+            }
+            loss = 0.5f * l;
+            dz[0] = e;
+          }
+        }
+        if (train) {
+          // dZ3 tile [128 x 16] bf16, K-major (K = 16): my row's 16 entries = two core-matrix rows
+          const uint4 lo = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+          const size_t off = canon_off(row, 0, kNOut);
+          *reinterpret_cast<uint4*>(bufZ3 + off) = lo;
+          *reinterpret_cast<uint4*>(bufZ3 + off + 64) = zero;
+          bf16* g3 = P.dZ3t + (size_t)tile * kRows * kNOut;
+          *reinterpret_cast<uint4*>(g3 + off) = lo;
+          *reinterpret_cast<uint4*>(g3 + off + 64) = zero;
+          proxy_fence();
+          tc_fence_before();
+          mbar_arrive(bar(B_Z3));
+          // tile statistics: warp reduce, one atomic per value and warp
+          float red[11] = {loss, kl, dls[0], dls[1], dls[2], dls[3], dz[0], dz[1], dz[2], dz[3], cntv};
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            float x = red[i];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0 && x != 0.f) atomicAdd(P.stats + i, (double)x);
+          }
+        }
+      }
+      if (train) {
+        // ---- dZ2 = dH2 * (1 - H2^2), in place over H2; its chunks feed the dH1 MMAs
+        mbar_wait(bar(B_D2), tpar);
+        tc_fence_after();
+        epi_backward(acc1, bufH2, P.dZ2t + tbase, B_Z2C);
+        tc_fence_before();
+        // ---- dZ1 = dH1 * (1 - H1^2)
+        mbar_wait(bar(B_D1), tpar);
+        tc_fence_after();
+        epi_backward(acc0, bufH1, P.dZ1t + tbase, -1);
+      }
+      tc_fence_before();
+      mbar_arrive(bar(B_TDONE));
+      tpar ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+size_t tile_kernel_smem() {
+  return (size_t)2 * kRows * HID * 2 + (size_t)2 * kRows * 96 * 2 + (size_t)kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
+         (size_t)kStages * kSlabBytes + (size_t)(2 * HID + 2 * kNOut) * 4;
+}
+
+// ---------------------------------------------------------------------------------------------
+//                         weight gradients: out[j][n] += sum_r A[r][j] B[r][n]
+// ---------------------------------------------------------------------------------------------
+constexpr int kDwStages = 3;
+constexpr int kDwStageBytes = 65536;   // 64 rows of A (32 KB) + up to 32 KB of B operands
+constexpr int kDwThreads = 192;        // warp 0: TMA, warp 1: MMA, warps 2-5: bias sums + final epilogue
+constexpr int kDwMaxB = 3;
+// input chunks one role-1 job can hold: 2 * K1p TMEM columns each, 32 columns spare, at most kDwMaxB operands
+inline int chunks_per_job(int K1p) { const int c = (512 - 2 * kNOut) / (2 * K1p); return c < kDwMaxB ? c : kDwMaxB; }
+
+struct DwJob {
+  const bf16* A;                 // tiles [128 r x 256 j] canonical, 64 KB apart
+  const bf16* B[kDwMaxB];        // tiles [128 r x nB] canonical
+  long long b_stride[kDwMaxB];   // bytes between tiles of B[b]
+  int nB[kDwMaxB];
+  int n_b;
+  float* out[kDwMaxB];           // partials [n_cta][256][nB]
+  float* bias_out;               // partials [n_cta][256] (column sums of A) or nullptr
+  int cta0, n_cta;
+};
+struct DwArgs {
+  DwJob jobs[12];
+  int n_jobs;
+  long long tiles;
+  int swap_lbo_sbo;              // bring-up switch for the MN-major descriptor fields
+};
+
+enum { DB_FULL = 0, DB_EMPTY = kDwStages, DB_DONE = 2 * kDwStages, DB_COUNT };
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+dw_kernel(const __grid_constant__ DwArgs P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar[DB_COUNT];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int ji = 0;
+  for (int k = 0; k < P.n_jobs; ++k)
+    if ((int)blockIdx.x >= P.jobs[k].cta0 && (int)blockIdx.x < P.jobs[k].cta0 + P.jobs[k].n_cta) ji = k;
+  const DwJob& J = P.jobs[ji];
+  const int local = (int)blockIdx.x - J.cta0;
+  const long long t0 = P.tiles * local / J.n_cta, t1 = P.tiles * (local + 1) / J.n_cta;
+  const long long n_half = (t1 - t0) * 2;   // stages = half tiles (64 rows)
+  const bool has_bias = J.bias_out != nullptr;
+  if (tid == 0) {
+    for (int i = 0; i < kDwStages; ++i) {
+      mbar_init(smem_u32(&mbar[DB_FULL + i]), 1);
+      mbar_init(smem_u32(&mbar[DB_EMPTY + i]), has_bias ? 5 : 1);
+    }
+    mbar_init(smem_u32(&mbar[DB_DONE]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t aS = smem_u32(smem);
+  uint32_t b_off[kDwMaxB], col0[kDwMaxB];
+  {
+    uint32_t o = 32768, c = 0;
+    for (int b = 0; b < J.n_b; ++b) { b_off[b] = o; o += 64u * J.nB[b] * 2u; col0[b] = c; c += 2u * J.nB[b]; }
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (long long h = 0; h < n_half; ++h) {
+        const int st = (int)(h % kDwStages);
+        if (h >= kDwStages) mbar_wait(bar(DB_EMPTY + st), (uint32_t)(((h / kDwStages) & 1) ^ 1));
+        const long long tile = t0 + (h >> 1);
+        const int half = (int)(h & 1);
+        uint32_t bytes = 32768;
+        for (int b = 0; b < J.n_b; ++b) bytes += 64u * J.nB[b] * 2u;
+        mbar_expect_tx(bar(DB_FULL + st), bytes);
+        const uint32_t sbase = aS + (uint32_t)st * kDwStageBytes;
+        bulk_g2s(sbase, reinterpret_cast<const unsigned char*>(J.A) + (size_t)tile * 65536 + (size_t)half * 32768, 32768,
+                 bar(DB_FULL + st));
+        for (int b = 0; b < J.n_b; ++b) {
+          const uint32_t hb = 64u * J.nB[b] * 2u;
+          bulk_g2s(sbase + b_off[b], reinterpret_cast<const unsigned char*>(J.B[b]) + (size_t)tile * J.b_stride[b] + (size_t)half * hb,
+                   hb, bar(DB_FULL + st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (long long h = 0; h < n_half; ++h) {
+        const int st = (int)(h % kDwStages);
+        mbar_wait(bar(DB_FULL + st), (uint32_t)((h / kDwStages) & 1));
+        tc_fence_after();
+        const uint32_t sbase = aS + (uint32_t)st * kDwStageBytes;
+        for (int b = 0; b < J.n_b; ++b) {
+          const uint32_t rg = (uint32_t)(J.nB[b] / 8) * 128u;   // bytes between 8-row groups of the B operand
+          for (int mh = 0; mh < 2; ++mh) {
+            for (int ks = 0; ks < 4; ++ks) {
+              // A: M = j (contiguous in a core-matrix row), K = r.  8-row groups are 4096 B apart, 8-j groups 128 B.
+              uint32_t a_lbo = 4096, a_sbo = 128, b_lbo = rg, b_sbo = 128;
+              if (P.swap_lbo_sbo) { a_lbo = 128; a_sbo = 4096; b_lbo = 128; b_sbo = rg; }
+              const uint64_t ad = umma_desc(sbase + (uint32_t)mh * 2048u + (uint32_t)ks * 8192u, a_lbo, a_sbo);
+              const uint64_t bd = umma_desc(sbase + b_off[b] + (uint32_t)ks * 2u * rg, b_lbo, b_sbo);
+              umma_bf16(tmem_base + col0[b] + (uint32_t)mh * J.nB[b], ad, bd, umma_idesc(J.nB[b], 1, 1), (h | ks) != 0);
+            }
+          }
+        }
+        umma_commit(bar(DB_EMPTY + st));
+      }
+      umma_commit(bar(DB_DONE));
+    }
+  } else {
+    // ---- bias gradient = column sums of A over my row range, while the tensor core works
+    const int bt = tid - 64;          // 0..127
+    const int w4 = bt >> 5;           // warp 0..3 of this group
+    float acc[2][8];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[p][e] = 0.f;
+    if (has_bias) {
+      const int r8 = lane & 7, cgl = lane >> 3;       // row within an 8-row group, column group within my block of 4
+      for (long long h = 0; h < n_half; ++h) {
+        const int st = (int)(h % kDwStages);
+        mbar_wait(bar(DB_FULL + st), (uint32_t)((h / kDwStages) & 1));
+        const unsigned char* sA = smem + (size_t)st * kDwStageBytes;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int cg = p * 16 + w4 * 4 + cgl;       // 8-column group 0..31
+#pragma unroll
+          for (int rgi = 0; rgi < 8; ++rgi) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sA + (size_t)rgi * 4096 + (size_t)cg * 128 + (size_t)r8 * 16);
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a, b;
+              unpack_bf16(u[e], a, b);
+              acc[p][2 * e] += a;
+              acc[p][2 * e + 1] += b;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(DB_EMPTY + st));
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float x = acc[p][e];
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          acc[p][e] = x;
+        }
+        if (r8 == 0) {
+          const int cg = p * 16 + w4 * 4 + cgl;
+          float* o = J.bias_out + (size_t)local * 256 + cg * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = acc[p][e];
+        }
+      }
+    }
+    // ---- final epilogue: TMEM -> per-CTA partial gradient
+    mbar_wait(bar(DB_DONE), 0);
+    tc_fence_after();
+    const int q = warp & 3;                           // my TMEM lane quarter
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int b = 0; b < J.n_b; ++b) {
+      const int nB = J.nB[b];
+      for (int mh = 0; mh < 2; ++mh) {
+        const int j = mh * 128 + q * 32 + lane;
+        float* o = J.out[b] + ((size_t)local * 256 + j) * nB;
+        for (int c0 = 0; c0 < nB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16_nowait(tmem_base + lane_off + col0[b] + (uint32_t)(mh * nB + c0), v);
+          tmem_wait_ld();
+          if (n_half > 0) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(o + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + c0 + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    }
+    if (has_bias && n_half == 0 && bt < 32) {
+      for (int e = 0; e < 8; ++e) J.bias_out[(size_t)local * 256 + bt * 8 + e] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ---------------------------------------------------------------------------------------------
+//                   partials -> flat gradient, Adam, bf16 slab packing (small kernels)
+// ---------------------------------------------------------------------------------------------
+// Flat parameter layout = GatedAdam's: [logstd (actor only)] W1 (256 x Din) b1 W2 (256 x 256) b2 W3 (out x 256) b3,
+// Din = C * D (torch nn.Linear weights are row-major (out, in)).
+struct NetShape {
+  int C, D, K1p, out_dim, has_logstd;
+  __host__ __device__ int din() const { return C * D; }
+  __host__ __device__ long long off_w1() const { return has_logstd ? out_dim : 0; }
+  __host__ __device__ long long off_b1() const { return off_w1() + (long long)HID * din(); }
+  __host__ __device__ long long off_w2() const { return off_b1() + HID; }
+  __host__ __device__ long long off_b2() const { return off_w2() + (long long)HID * HID; }
+  __host__ __device__ long long off_w3() const { return off_b2() + HID; }
+  __host__ __device__ long long off_b3() const { return off_w3() + (long long)out_dim * HID; }
+  __host__ __device__ long long count() const { return off_b3() + out_dim; }
+};
+
+struct ReduceArgs {
+  NetShape s;
+  const float* pw1[16];   // per input chunk: partials [n1][256][K1p]
+  const float* pw2;       // [n2][256][256]
+  const float* pw3;       // [n1][256][16]   (dW3 transposed)
+  const float* pb1;       // [n1][256]
+  const float* pb2;       // [n2][256]
+  int n1, n2;
+  const double* stats;    // tile-kernel statistics (dlogstd sums at [2..5], db3 sums at [6..9], rows at [10])
+  float entropy_coef;
+  long long rows_global;  // rows of the minibatch over ALL ranks (the mean's denominator); 0 = use stats[10]
+  float* grad;            // flat
+};
+
+__global__ void reduce_kernel(const __grid_constant__ ReduceArgs P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const NetShape& s = P.s;
+  if (i >= s.count()) return;
+  const double rows = P.rows_global > 0 ? (double)P.rows_global : (P.stats[10] > 0.0 ? P.stats[10] : 1.0);
+  const float scale = (float)(1.0 / rows);
+  float g = 0.f;
+  if (i < s.off_w1()) {                                   // logstd: policy part + entropy bonus (agent.py:629-633,736)
+    g = (float)P.stats[2 + i] * scale - P.entropy_coef;
+  } else if (i < s.off_b1()) {
+    const long long k = i - s.off_w1();
+    const int j = (int)(k / s.din()), col = (int)(k % s.din());
+    const int c = col / s.D, kk = col % s.D;
+    const float* p = P.pw1[c] + (size_t)j * s.K1p + kk;
+    for (int n = 0; n < P.n1; ++n) g += p[(size_t)n * HID * s.K1p];
+    g *= scale;
+  } else if (i < s.off_w2()) {
+    const int j = (int)(i - s.off_b1());
+    for (int n = 0; n < P.n1; ++n) g += P.pb1[(size_t)n * HID + j];
+    g *= scale;
+  } else if (i < s.off_b2()) {
+    const long long k = i - s.off_w2();
+    const float* p = P.pw2 + k;
+    for (int n = 0; n < P.n2; ++n) g += p[(size_t)n * HID * HID];
+    g *= scale;
+  } else if (i < s.off_w3()) {
+    const int j = (int)(i - s.off_b2());
+    for (int n = 0; n < P.n2; ++n) g += P.pb2[(size_t)n * HID + j];
+    g *= scale;
+  } else if (i < s.off_b3()) {
+    const long long k = i - s.off_w3();
+    const int o = (int)(k / HID), j = (int)(k % HID);
+    const float* p = P.pw3 + (size_t)j * kNOut + o;
+    for (int n = 0; n < P.n1; ++n) g += p[(size_t)n * HID * kNOut];
+    g *= scale;
+  } else {
+    g = (float)P.stats[6 + (i - s.off_b3())] * scale;
+  }
+  P.grad[i] = g;
+}
+
+// torch.optim.Adam (defaults) on the flat buffers, applied only when the gate holds: the reference skips the whole
+// optimiser step — parameters, both moments, the step count — when approx_kl > 1.5 target_kl (agent.py:731).
+// kl_sum / kl_rows: device scalars (after the cross-rank reduction); target_kl <= 0 or kl_sum == nullptr: no gate.
+struct AdamArgs {
+  float *param, *m, *v;
+  const float* grad;
+  double* step;            // torch keeps it as a float tensor; fp64 here for the bias corrections
+  long long n;
+  float lr, b1, b2, eps;
+  const double* kl_sum;
+  const double* kl_rows;
+  float target_kl;
+  double* gate_out;        // optional: 1.0 / 0.0 (statistics)
+};
+__device__ __forceinline__ bool adam_gate(const AdamArgs& P) {
+  if (P.kl_sum == nullptr || !(P.target_kl > 0.f)) return true;
+  const double rows = *P.kl_rows > 0.0 ? *P.kl_rows : 1.0;
+  return (float)(*P.kl_sum / rows) <= 1.5f * P.target_kl;
+}
+__global__ void adam_kernel(const __grid_constant__ AdamArgs P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  if (!adam_gate(P)) return;
+  const double step = *P.step + 1.0;
+  const float g = P.grad[i];
+  const float m = P.m[i] + (g - P.m[i]) * (1.0f - P.b1);            // torch.lerp(exp_avg, grad, 1 - beta1)
+  const float v = P.v[i] * P.b2 + (g * g) * (1.0f - P.b2);
+  const float step_size = (float)((double)P.lr / (1.0 - pow((double)P.b1, step)));
+  const float bias2_sqrt = (float)sqrt(1.0 - pow((double)P.b2, step));
+  const float denom = sqrtf(v) / bias2_sqrt + P.eps;
+  P.param[i] = P.param[i] - step_size * (m / denom);
+  P.m[i] = m;
+  P.v[i] = v;
+}
+__global__ void adam_step_kernel(const __grid_constant__ AdamArgs P) {   // after adam_kernel: advance the step count
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const bool on = adam_gate(P);
+    if (on) *P.step = *P.step + 1.0;
+    if (P.gate_out != nullptr) *P.gate_out += on ? 1.0 : 0.0;
+  }
+}
+
+// fp32 master weights (flat, torch layout) -> bf16 slabs the tile kernel streams
+struct PackArgs {
+  NetShape s;
+  const float* param;
+  bf16 *w1_slabs, *w2f_slabs, *w2b_slabs, *w3f, *w3b_slab;
+  float *b1, *b2, *b3, *logstd;
+};
+__global__ void pack_kernel(const __grid_constant__ PackArgs P) {
+  const NetShape& s = P.s;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k1_steps = s.K1p / 16;
+  const long long n_w1 = (long long)s.C * k1_steps * 4096, n_w2 = 16LL * 4096, n_w3 = (long long)kNOut * HID;
+  if (i < n_w1) {                        // slab (c, ks): [256 n x 16 kk]
+    const long long slab = i / 4096;
+    const int e = (int)(i % 4096), n = e / 16, kk = e % 16;
+    const int c = (int)(slab / k1_steps), ks = (int)(slab % k1_steps);
+    const int col = ks * 16 + kk;
+    const float v = col < s.D ? P.param[s.off_w1() + (long long)n * s.din() + c * s.D + col] : 0.f;
+    P.w1_slabs[slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(v);
+    return;
+  }
+  long long k = i - n_w1;
+  if (k < n_w2) {                        // forward slab i_issue -> K-step ks = 4 (i & 3) + (i >> 2): W2[n][ks*16 + kk]
+    const int slab = (int)(k / 4096), e = (int)(k % 4096), n = e / 16, kk = e % 16;
+    const int ks = 4 * (slab & 3) + (slab >> 2);
+    P.w2f_slabs[(size_t)slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(P.param[s.off_w2() + (long long)n * HID + ks * 16 + kk]);
+    // backward slab, same issue order over j: element (i = n, jj = kk) = W2[ks*16 + kk][n]
+    P.w2b_slabs[(size_t)slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(P.param[s.off_w2() + (long long)(ks * 16 + kk) * HID + n]);
+    return;
+  }
+  k -= n_w2;
+  if (k < n_w3) {                        // W3 forward [16 o x 256 j] canonical; backward slab [256 j x 16 o]
+    const int o = (int)(k / HID), j = (int)(k % HID);
+    const float v = o < s.out_dim ? P.param[s.off_w3() + (long long)o * HID + j] : 0.f;
+    P.w3f[canon_off(o, j, HID)] = __float2bfloat16(v);
+    P.w3b_slab[canon_off(j, o, 16)] = __float2bfloat16(v);
+    return;
+  }
+  k -= n_w3;
+  if (k < HID) { P.b1[k] = P.param[s.off_b1() + k]; P.b2[k] = P.param[s.off_b2() + k]; return; }
+  k -= HID;
+  if (k < kNOut) {
+    P.b3[k] = k < s.out_dim ? P.param[s.off_b3() + k] : 0.f;
+    if (P.logstd != nullptr) P.logstd[k] = (s.has_logstd && k < s.out_dim) ? P.param[k] : 0.f;
+  }
+}
+long long pack_threads(const NetShape& s) { return (long long)s.C * (s.K1p / 16) * 4096 + 16LL * 4096 + (long long)kNOut * HID + HID + kNOut; }
+
+}  // namespace
+
+// =================================================================================================
+//                                          C-ABI
+// =================================================================================================
+struct bd_ppo_net {
+  int device, sm_count;
+  NetShape s;
+  long long max_rows, max_tiles;
+  // packed weights
+  bf16 *w1_slabs = nullptr, *w2f_slabs = nullptr, *w2b_slabs = nullptr, *w3f = nullptr, *w3b_slab = nullptr;
+  float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *logstd = nullptr;
+  // tile scratch
+  bf16 *Xt = nullptr, *H1t = nullptr, *H2t = nullptr, *dZ2t = nullptr, *dZ1t = nullptr, *dZ3t = nullptr;
+  // gradient partials
+  float *pw1 = nullptr, *pw2 = nullptr, *pw3 = nullptr, *pb1 = nullptr, *pb2 = nullptr;
+  int n1 = 0, n2 = 0;            // CTAs of the two weight-gradient roles
+  int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
+  double* stats = nullptr;       // [kStatSlots]
+  int64_t launches = 0;
+  int swap_desc = 0;
+};
+
+namespace {
+void free_net(bd_ppo_net* n) {
+  cudaFree(n->w1_slabs); cudaFree(n->w2f_slabs); cudaFree(n->w2b_slabs); cudaFree(n->w3f); cudaFree(n->w3b_slab);
+  cudaFree(n->b1); cudaFree(n->b2); cudaFree(n->b3); cudaFree(n->logstd);
+  cudaFree(n->Xt); cudaFree(n->H1t); cudaFree(n->H2t); cudaFree(n->dZ2t); cudaFree(n->dZ1t); cudaFree(n->dZ3t);
+  cudaFree(n->pw1); cudaFree(n->pw2); cudaFree(n->pw3); cudaFree(n->pb1); cudaFree(n->pb2); cudaFree(n->stats);
+}
+NetDev net_dev(const bd_ppo_net* n) {
+  NetDev d;
+  d.w1_slabs = n->w1_slabs; d.w2f_slabs = n->w2f_slabs; d.w2b_slabs = n->w2b_slabs; d.w3f = n->w3f; d.w3b_slab = n->w3b_slab;
+  d.b1 = n->b1; d.b2 = n->b2; d.b3 = n->b3; d.logstd = n->s.has_logstd ? n->logstd : nullptr;
+  d.C = n->s.C; d.D = n->s.D; d.K1p = n->s.K1p; d.out_dim = n->s.out_dim;
+  return d;
+}
+}  // namespace
+
+extern "C" {
+
+const char* bd_ppo_last_error(void) { return g_err; }
+
+int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64_t max_rows, int device, bd_ppo_net** out) {
+  if (!out) return pfail(BD_EINVAL, "bd_ppo_net_create: null out");
+  *out = nullptr;
+  if (in_dim < 1 || in_dim > 96) return pfail(BD_EINVAL, "bd_ppo_net_create: in_dim (per chunk) must be in [1,96]");
+  if (chunks < 1 || chunks > 16) return pfail(BD_EINVAL, "bd_ppo_net_create: chunks must be in [1,16]");
+  if (out_dim < 1 || out_dim > 4) return pfail(BD_EINVAL, "bd_ppo_net_create: out_dim must be in [1,4]");
+  if (max_rows < 1) return pfail(BD_EINVAL, "bd_ppo_net_create: max_rows must be positive");
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess)
+    return pfail(BD_ECUDA, "bd_ppo_net_create: cannot select device %d", device);
+  bd_ppo_net* n = new (std::nothrow) bd_ppo_net();
+  if (!n) return pfail(BD_ENOMEM, "bd_ppo_net_create: out of host memory");
+  n->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  n->sm_count = prop.multiProcessorCount;
+  n->s.C = chunks; n->s.D = in_dim; n->s.K1p = (in_dim + 15) & ~15; n->s.out_dim = out_dim; n->s.has_logstd = has_logstd ? 1 : 0;
+  n->max_rows = max_rows;
+  n->max_tiles = (max_rows + kRows - 1) / kRows;
+  const char* sw = getenv("BD_DW_SWAP");
+  n->swap_desc = (sw && sw[0] == '1') ? 1 : 0;
+  // weight-gradient roles: role 2 = dW2 (512 TMEM columns); role 1 = dW1 chunks + dW3, as many jobs as the 512 columns need
+  const int per_job = chunks_per_job(n->s.K1p);
+  n->n1_jobs = (chunks + per_job - 1) / per_job;
+  const int sms = n->sm_count;
+  int n2 = (int)(sms * 0.45), n1 = (sms - n2) / n->n1_jobs;
+  if (n1 < 1) n1 = 1;
+  n2 = sms - n1 * n->n1_jobs;
+  if (n2 < 1) n2 = 1;
+  n->n1 = n1; n->n2 = n2;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); };
+  const size_t k1s = n->s.K1p / 16;
+  alloc((void**)&n->w1_slabs, (size_t)chunks * k1s * kSlabBytes);
+  alloc((void**)&n->w2f_slabs, 16 * (size_t)kSlabBytes); alloc((void**)&n->w2b_slabs, 16 * (size_t)kSlabBytes);
+  alloc((void**)&n->w3f, (size_t)kNOut * HID * 2); alloc((void**)&n->w3b_slab, kSlabBytes);
+  alloc((void**)&n->b1, HID * 4); alloc((void**)&n->b2, HID * 4); alloc((void**)&n->b3, kNOut * 4); alloc((void**)&n->logstd, kNOut * 4);
+  const size_t T = (size_t)n->max_tiles;
+  alloc((void**)&n->Xt, T * chunks * kRows * n->s.K1p * 2);
+  alloc((void**)&n->H1t, T * kRows * HID * 2); alloc((void**)&n->H2t, T * kRows * HID * 2);
+  alloc((void**)&n->dZ2t, T * kRows * HID * 2); alloc((void**)&n->dZ1t, T * kRows * HID * 2);
+  alloc((void**)&n->dZ3t, T * kRows * kNOut * 2);
+  alloc((void**)&n->pw1, (size_t)chunks * n1 * HID * n->s.K1p * 4);
+  alloc((void**)&n->pw2, (size_t)n2 * HID * HID * 4);
+  alloc((void**)&n->pw3, (size_t)n1 * HID * kNOut * 4);
+  alloc((void**)&n->pb1, (size_t)n1 * HID * 4); alloc((void**)&n->pb2, (size_t)n2 * HID * 4);
+  alloc((void**)&n->stats, kStatSlots * sizeof(double));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_kernel_smem());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwStages * kDwStageBytes);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    free_net(n); delete n;
+    return pfail(e == cudaErrorMemoryAllocation ? BD_ENOMEM : BD_ECUDA, "bd_ppo_net_create: %s", cudaGetErrorString(e));
+  }
+  *out = n;
+  return BD_OK;
+}
+
+void bd_ppo_net_destroy(bd_ppo_net* n) {
+  if (!n) return;
+  free_net(n);
+  delete n;
+}
+
+int64_t bd_ppo_net_param_count(const bd_ppo_net* n) { return n ? n->s.count() : 0; }
+int64_t bd_ppo_launch_count(const bd_ppo_net* n) { return n ? n->launches : 0; }
+double* bd_ppo_net_stats(bd_ppo_net* n) { return n ? n->stats : nullptr; }
+
+/* fp32 master weights (flat, torch parameter order) -> bf16 slabs.  Stream ordered. */
+int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream) {
+  if (!n || !flat_params_dev) return pfail(BD_EINVAL, "bd_ppo_net_pack: null argument");
+  PackArgs a;
+  a.s = n->s; a.param = flat_params_dev;
+  a.w1_slabs = n->w1_slabs; a.w2f_slabs = n->w2f_slabs; a.w2b_slabs = n->w2b_slabs; a.w3f = n->w3f; a.w3b_slab = n->w3b_slab;
+  a.b1 = n->b1; a.b2 = n->b2; a.b3 = n->b3; a.logstd = n->logstd;
+  const long long t = pack_threads(n->s);
+  pack_kernel<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  n->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_net_pack: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+/* Forward only: out (rows, out_dim) = MLP(rows of obs).  rows_per_sample: M for the actor (row = (sample, agent)),
+ * 1 for the critic (row = sample, input = the M agents' observations).  idx may be NULL (identity). */
+int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev, int64_t rows,
+                   const float* nmean_dev, const float* nrstd_dev, float nclip, float* out_dev, void* stream) {
+  if (!n || !obs_dev || !out_dev) return pfail(BD_EINVAL, "bd_ppo_forward: null argument");
+  if (rows <= 0) return BD_OK;
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.net = net_dev(n);
+  a.mode = MODE_FORWARD;
+  a.obs = obs_dev; a.N = n_envs; a.M = n_agents; a.idx = (const long long*)idx_dev; a.rows = rows;
+  a.nmean = nmean_dev; a.nrstd = nrstd_dev; a.nclip = nclip;
+  a.out = out_dev; a.stats = n->stats;
+  const long long tiles = (rows + kRows - 1) / kRows;
+  const int grid = (int)(tiles < n->sm_count ? tiles : n->sm_count);
+  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(), (cudaStream_t)stream>>>(a);
+  n->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_forward: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+/* One minibatch: forward, loss, backward (tile kernel), weight gradients (dw kernel), reduction of the per-CTA partials
+ * into grad_dev (flat, torch parameter order, mean over rows_global rows — pass the minibatch rows of ALL ranks so that
+ * a following all-reduce SUM gives the global mean; 0 = this call's rows).  Statistics accumulate in bd_ppo_net_stats:
+ * [0] sum of per-row losses, [1] sum of (logp_old - logp), [10] rows. */
+int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
+                int64_t samples, const float* act_dev, const float* logp_old_dev, const float* adv_dev,
+                const float* adv_stats_dev, const float* ret_dev, const float* v_old_dev, float clip, int use_clipped_value,
+                float entropy_coef, const float* nmean_dev, const float* nrstd_dev, float nclip, int64_t rows_global,
+                float* grad_dev, void* stream) {
+  if (!n || !obs_dev || !grad_dev) return pfail(BD_EINVAL, "bd_ppo_grad: null argument");
+  if (!critic && (!act_dev || !logp_old_dev || !adv_dev || !adv_stats_dev)) return pfail(BD_EINVAL, "bd_ppo_grad: actor inputs missing");
+  if (critic && !ret_dev) return pfail(BD_EINVAL, "bd_ppo_grad: critic inputs missing");
+  const long long rows = critic ? samples : samples * n_agents;
+  if (rows < 1 || rows > n->max_rows) return pfail(BD_EINVAL, "bd_ppo_grad: rows %lld outside [1,%lld]", rows, n->max_rows);
+  if ((critic ? n_agents : 1) != n->s.C) return pfail(BD_EINVAL, "bd_ppo_grad: net has %d input chunks", n->s.C);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(n->stats, 0, kStatSlots * sizeof(double), st);
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad: %s", cudaGetErrorString(e));
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  a.net = net_dev(n);
+  a.mode = critic ? MODE_CRITIC_TRAIN : MODE_ACTOR_TRAIN;
+  a.obs = obs_dev; a.N = n_envs; a.M = n_agents; a.idx = (const long long*)idx_dev; a.rows = rows;
+  a.act = act_dev; a.logp_old = logp_old_dev; a.adv = adv_dev; a.adv_stats = adv_stats_dev;
+  a.ret = ret_dev; a.v_old = v_old_dev; a.clip = clip; a.use_clipped_value = use_clipped_value ? 1.f : 0.f;
+  a.nmean = nmean_dev; a.nrstd = nrstd_dev; a.nclip = nclip;
+  a.Xt = n->Xt; a.H1t = n->H1t; a.H2t = n->H2t; a.dZ2t = n->dZ2t; a.dZ1t = n->dZ1t; a.dZ3t = n->dZ3t;
+  a.stats = n->stats;
+  const long long tiles = (rows + kRows - 1) / kRows;
+  const int grid = (int)(tiles < n->sm_count ? tiles : n->sm_count);
+  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(), st>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (tile kernel): %s", cudaGetErrorString(e));
+  // ---- weight gradients
+  DwArgs d;
+  memset(&d, 0, sizeof(d));
+  d.tiles = tiles;
+  d.swap_lbo_sbo = n->swap_desc;
+  const int C = n->s.C, K1p = n->s.K1p;
+  const int per_job = chunks_per_job(K1p);
+  int cta = 0, nj = 0;
+  for (int jb = 0; jb < n->n1_jobs; ++jb) {          // role 1: A = dZ1 (or H2 for dW3), B = X chunks
+    DwJob& J = d.jobs[nj++];
+    J.A = n->dZ1t;
+    J.n_b = 0;
+    for (int c = jb * per_job; c < C && c < (jb + 1) * per_job; ++c) {
+      J.B[J.n_b] = n->Xt + (size_t)c * kRows * K1p;
+      J.b_stride[J.n_b] = (long long)C * kRows * K1p * 2;
+      J.nB[J.n_b] = K1p;
+      J.out[J.n_b] = n->pw1 + (size_t)c * n->n1 * HID * K1p;
+      J.n_b++;
+    }
+    J.bias_out = jb == 0 ? n->pb1 : nullptr;
+    J.cta0 = cta; J.n_cta = n->n1; cta += n->n1;
+  }
+  {                                                   // role 2: dW2 = dZ2^T H1 (+ db2), all 512 TMEM columns
+    DwJob& J = d.jobs[nj++];
+    J.A = n->dZ2t; J.n_b = 1; J.B[0] = n->H1t; J.b_stride[0] = (long long)kRows * HID * 2; J.nB[0] = HID; J.out[0] = n->pw2;
+    J.bias_out = n->pb2; J.cta0 = cta; J.n_cta = n->n2; cta += n->n2;
+  }
+  d.n_jobs = nj;
+  dw_kernel<<<cta, kDwThreads, kDwStages * kDwStageBytes, st>>>(d);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (dw kernel): %s", cudaGetErrorString(e));
+  // dW3^T = H2^T dZ3: a second, small launch of the same kernel (A = H2) over the role-1 CTA count
+  DwArgs d3;
+  memset(&d3, 0, sizeof(d3));
+  d3.tiles = tiles; d3.swap_lbo_sbo = n->swap_desc; d3.n_jobs = 1;
+  {
+    DwJob& J = d3.jobs[0];
+    J.A = n->H2t; J.n_b = 1; J.B[0] = n->dZ3t; J.b_stride[0] = (long long)kRows * kNOut * 2; J.nB[0] = kNOut; J.out[0] = n->pw3;
+    J.bias_out = nullptr; J.cta0 = 0; J.n_cta = n->n1;
+  }
+  dw_kernel<<<n->n1, kDwThreads, kDwStages * kDwStageBytes, st>>>(d3);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (dw3 kernel): %s", cudaGetErrorString(e));
+  // ---- flat gradient
+  ReduceArgs r;
+  memset(&r, 0, sizeof(r));
+  r.s = n->s;
+  for (int c = 0; c < C; ++c) r.pw1[c] = n->pw1 + (size_t)c * n->n1 * HID * K1p;
+  r.pw2 = n->pw2; r.pw3 = n->pw3; r.pb1 = n->pb1; r.pb2 = n->pb2; r.n1 = n->n1; r.n2 = n->n2;
+  r.stats = n->stats; r.entropy_coef = critic ? 0.f : entropy_coef; r.rows_global = rows_global; r.grad = grad_dev;
+  const long long np = n->s.count();
+  reduce_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(r);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (reduce kernel): %s", cudaGetErrorString(e));
+  n->launches += 4;
+  return BD_OK;
+}
+
+/* torch.optim.Adam's step on flat fp32 buffers with the reference's KL gate evaluated on the device, then the bf16
+ * repack of the network for the next minibatch.  kl_sum_dev / kl_rows_dev: device doubles (e.g. stats + 1, stats + 10,
+ * or their cross-rank sums); NULL or target_kl <= 0: unconditional step.  step_dev: device double (step count). */
+int bd_ppo_adam_step(bd_ppo_net* n, float* param_dev, float* exp_avg_dev, float* exp_avg_sq_dev, const float* grad_dev,
+                     double* step_dev, float lr, float beta1, float beta2, float eps, const double* kl_sum_dev,
+                     const double* kl_rows_dev, float target_kl, double* gate_count_dev, void* stream) {
+  if (!n || !param_dev || !exp_avg_dev || !exp_avg_sq_dev || !grad_dev || !step_dev) return pfail(BD_EINVAL, "bd_ppo_adam_step: null argument");
+  AdamArgs a;
+  a.param = param_dev; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.grad = grad_dev; a.step = step_dev; a.n = n->s.count();
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.kl_sum = kl_sum_dev; a.kl_rows = kl_rows_dev; a.target_kl = target_kl;
+  a.gate_out = gate_count_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, st>>>(a);
+  adam_step_kernel<<<1, 32, 0, st>>>(a);
+  n->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_adam_step: %s", cudaGetErrorString(e));
+  return bd_ppo_net_pack(n, param_dev, stream);
+}
+
+/* Returns and advantages of a whole rollout in one launch (mappo/buffer.py:561-614), plus the buffer-wide advantage
+ * moments: acc3_dev += (sum adv, sum adv^2, count).  rew (T,N) float, term / trunc (T,N) uint8, vals (T+1,N). */
+int bd_ppo_gae(const float* rew_dev, const uint8_t* term_dev, const uint8_t* trunc_dev, const float* vals_dev, int T, int N,
+               float gamma, float lam, int use_gae, float* ret_dev, float* adv_dev, double* acc3_dev, void* stream) {
+  if (!rew_dev || !term_dev || !trunc_dev || !vals_dev || !ret_dev || !adv_dev || !acc3_dev) return pfail(BD_EINVAL, "bd_ppo_gae: null argument");
+  if (T < 1 || N < 1) return pfail(BD_EINVAL, "bd_ppo_gae: T and N must be positive");
+  gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew_dev, term_dev, trunc_dev, vals_dev, T, N, gamma, lam, use_gae,
+                                                                ret_dev, adv_dev, acc3_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_gae: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+/* (sum, sum of squares, count) -> stats2_dev = (mean, 1 / (std + 1e-8)) per normalize_advantages (buffer.py:666-695). */
+int bd_ppo_adv_stats(const double* acc3_dev, float* stats2_dev, void* stream) {
+  if (!acc3_dev || !stats2_dev) return pfail(BD_EINVAL, "bd_ppo_adv_stats: null argument");
+  adv_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc3_dev, stats2_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_adv_stats: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
+}  // extern "C"
