@@ -17,6 +17,11 @@ drone-substeps/s = N_envs * M * S * K / time, aggregated over all ranks.
   (pinned numpy in, pinned numpy out: H2D + kernel + D2H + sync each step).
 * `roofline`: algorithmic bytes / measured kernel time vs the
   measured HBM copy peak in MEASURED_PEAKS.json.
+* `e2e_vecenv`: the same step through the reference-protocol call `BatchVecEnv.step` (the 4-tuple with info dicts
+  that `MAPPO.train_step` consumes): `bd_step_host_compact`, terminal observations only for finished envs.
+* `small_batch`: BASELINE configs[3] as literally sharded (8192 envs per GPU), K steps per host call (`bd_step_many`).
+* `mappo`: env-steps/s of `DeviceMAPPO.train_step` at configs[4]'s per-GPU shape (16 drones, downwash) with the time
+  shares of rollout / returns / update and the measured cost of the NCCL gradient all-reduce (N > 1).
 * `cpu_baseline` / `--impl reference`: the fp64 numpy oracle of the reference's
   Physics.DYN path (the reference itself needs PyBullet, which is not
   installable), run the way the reference runs it: one Python env object per env,
@@ -232,9 +237,15 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
 
     def gpu_steps(n, start):
-        for k in range(n):
+        """n control steps = n launches of the step kernel, issued with one host call per run of consecutive slots
+        (`bd_step_many`; step k reads action set (start+k) % slots and writes observation slot (start+k) % slots)."""
+        k = 0
+        while k < n:
             i = (start + k) % slots
-            env.step_device(act_pool[i], out=outs[i])
+            run = min(n - k, slots - i)
+            env.step_many(act_pool[i:i + run], obs_buf[i:i + run], rew_buf[i:i + run], term_buf[i:i + run],
+                          trunc_buf[i:i + run])
+            k += run
 
     gpu_steps(args.warmup, 0)
     sync_all()
@@ -272,10 +283,66 @@ def run_ours(args):
     h2d = N * M * A * 4
     d2h = N * M * D * 4 + N * 4 + 2 * N
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- e2e through the reference's VecEnv protocol (what MAPPO.train_step calls): 4-tuple + info dicts
+    vec_ms = None
+    if args.vecenv_steps > 0:
+        from marl_gym_pybullet_drones_b200.vec_env import BatchVecEnv
+        venv = BatchVecEnv(env)
+        abuf = venv.action_buffer()             # this step's actions wait in pinned host memory, like the e2e leg's
+        abuf[...] = host_actions[0]
+        for k in range(3):
+            venv.step(abuf)
+        sync_all()
+        t0 = time.perf_counter()
+        n_done = 0
+        for k in range(args.vecenv_steps):
+            o, r_, d_, info = venv.step(abuf)
+            n_done += int(d_.sum())
+        vec_ms = (time.perf_counter() - t0) * 1e3 / args.vecenv_steps
+        first_done = int(np.flatnonzero(d_)[0]) if d_.any() else None
+        if first_done is not None:
+            assert info["n"][first_done]["terminal_observation"].shape == (M, D)
+
+    # ---- configs[3] as literally sharded: 8192 envs per GPU, launch-bound without bd_step_many
+    small = None
+    if args.small_envs > 0 and args.small_envs != N:
+        Ns = args.small_envs
+        env_s = BatchAviary(task="multihover", num_envs=Ns, num_drones=M, initial_xyzs=grid_xyzs(M), pyb_freq=240,
+                            ctrl_freq=30, act="rpm", precision="fp32", device=dev, auto_reset=True,
+                            reset_mode="jitter_philox", seed=4321 + rank)
+        Ks = 256                                # slots: 256 x 8192 x 4 x 72 x 4 B = 2.4 GB of observations (>> L2)
+        a_s = (torch.rand((Ks, Ns, M, A), generator=gen, device=dev) * 2 - 1).contiguous()
+        o_s = torch.empty((Ks, Ns, M, D), dtype=torch.float32, device=dev)
+        r_s = torch.empty((Ks, Ns), dtype=torch.float32, device=dev)
+        f_s = torch.empty((2, Ks, Ns), dtype=torch.uint8, device=dev)
+        env_s.reset_device(out=o_s[0])
+        env_s.step_many(a_s, o_s, r_s, f_s[0], f_s[1])
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 4
+        for _ in range(reps):
+            env_s.step_many(a_s, o_s, r_s, f_s[0], f_s[1])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_many = e0.elapsed_time(e1) / (reps * Ks)
+        out_s = StepResult(o_s[0], r_s[0], f_s[0, 0].view(torch.bool), f_s[1, 0].view(torch.bool), None)
+        e0.record()
+        for k in range(Ks):
+            env_s.step_device(a_s[k], out=out_s)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_single = e0.elapsed_time(e1) / Ks
+        bpl = algorithmic_bytes_per_drone_step(A, Bf, M) * Ns * M
+        small = {"envs_per_gpu": Ns, "ms_per_step_step_many": ms_many, "ms_per_step_one_call_per_step": ms_single,
+                 "value": Ns * M * S / (ms_many * 1e-3), "unit": UNIT,
+                 "roofline_frac": bpl / (ms_many * 1e-3) / 1e9 / 6553.0, "steps_per_host_call": Ks}
+        env_s.close()
+
+    t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, vec_ms_max = float(t[0]), float(t[1]), float(t[2])
     units = world * N * M * S
     value = units * args.steps / (ms_max * 1e-3)
     e2e_value = units * e2e_steps / (e2e_ms_max * 1e-3)
@@ -320,7 +387,10 @@ def run_ours(args):
                               f"{(N * M * (64 + Bf * A * 4)) / 1e6:.0f} MB"),
                 "parallelism": f"env-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "profiles/traffic.json: one isolated `ncu --set full` launch of this kernel "
+                                           "(not measured in this run)" if traffic is not None else None,
+                         "peak_source": peak_src,
                          "kernel": "bd::step_kernel_tile<MULTIHOVER,4,4,false>",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "algorithmic_bytes_per_drone_substep": bytes_per_drone_step / S,
@@ -331,12 +401,103 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if vec_ms is not None:
+            line["e2e_vecenv"] = {"value": units / (vec_ms_max * 1e-3), "unit": UNIT, "ms_per_step": vec_ms_max,
+                                  "ms_per_step_bd_step_host": e2e_ms_max / e2e_steps,
+                                  "ratio_to_bd_step_host": vec_ms_max / (e2e_ms_max / e2e_steps),
+                                  "steps": args.vecenv_steps,
+                                  "api": "BatchVecEnv.step -> bd_step_host_compact (4-tuple, lazy info dicts, terminal "
+                                         "observations of finished envs only)"}
+        if small is not None:
+            line["small_batch"] = small
     env.close()
+    mappo = None
+    if args.mappo_steps > 0:
+        mappo = run_mappo_block(args, dev, rank, world)
+    if line is not None and mappo is not None:
+        line["mappo"] = mappo
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def run_mappo_block(args, dev, rank, world):
+    """`DeviceMAPPO.train_step` at BASELINE configs[4]'s per-GPU shape: 16-drone MultiHover with downwash, one epoch of
+    large minibatches; every hot operation is one of this repo's kernels (step, fused actor, GAE scan, fused PPO
+    update), the gradient all-reduce is NCCL.  Weak scaling: every rank owns `--mappo-envs` envs."""
+    import torch
+    import torch.distributed as dist
+    from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
+    from marl_gym_pybullet_drones_b200.mappo import DeviceMAPPO
+    N, M, T = args.mappo_envs, args.mappo_drones, args.mappo_rollout
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[0.6 * (i % side), 0.6 * (i // side), 0.5 + 0.05 * (i % 3)] for i in range(M)])
+    env = BatchAviary(task="multihover", num_envs=N, num_drones=M, initial_xyzs=xyz, physics="dyn_dw", precision="fp32",
+                      device=dev, auto_reset=True, reset_mode="jitter_philox", seed=99 + rank, track_episode_stats=True)
+    mb = max(1, (N * T) // args.mappo_minibatches)
+    algo = DeviceMAPPO(env, seed=0, rollout_steps=T, hidden_dim=256, mini_batch_size=mb, opt_epochs=1,
+                       update_impl="native", graph_update=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        ev[0].record()
+        algo.collect_rollout()
+        ev[1].record()
+        algo.compute_returns()
+        ev[2].record()
+        res = algo.update()
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        return res, [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+    step()                                  # warm-up: graph capture, allocator
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    tot = np.zeros(3)
+    t0 = time.perf_counter()
+    for _ in range(args.mappo_steps):
+        res, parts = step()
+        tot += parts
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.mappo_steps
+    parts_ms = tot / args.mappo_steps
+    ar_us = None
+    if world > 1:                           # the collective that defines the multi-GPU design, timed on its own
+        g = algo.actor_opt.grad
+        for _ in range(5):
+            dist.all_reduce(g)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            dist.all_reduce(g)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ar_us = e0.elapsed_time(e1) / 50 * 1e3
+    t = torch.tensor([wall_ms, parts_ms[0], parts_ms[1], parts_ms[2]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_ms, r_ms, g_ms, u_ms = [float(x) for x in t]
+    launches = env.launch_count + (algo.fused.launch_count if algo.fused is not None else 0) + \
+        algo.actor_net.launch_count + algo.critic_net.launch_count
+    n_mb = (N * T) // mb
+    out = {"metric": "mappo_env_steps_per_sec", "value": world * N * T / (wall_ms * 1e-3), "unit": "env-steps/s",
+           "drone_substeps_per_sec": world * N * M * 8 * T / (wall_ms * 1e-3),
+           "train_step_ms": wall_ms, "rollout_ms": r_ms, "returns_ms": g_ms, "update_ms": u_ms,
+           "shares": {"rollout": r_ms / wall_ms, "returns": g_ms / wall_ms, "update": u_ms / wall_ms},
+           "config": {"workload": f"BASELINE configs[4] per-GPU shape: MultiHover M={M} + downwash, {N} envs per GPU x {world}, "
+                                  f"rollout {T} steps, 1 epoch x {n_mb} minibatches of {mb} env-steps ({mb * M} actor rows)",
+                      "update_impl": "native (bd_ppo.cu): tcgen05 fwd+bwd tile kernel, tcgen05 weight-gradient kernel, "
+                                     "GAE scan, gated Adam; one CUDA graph per epoch" + (", NCCL all-reduces in the graph" if world > 1 else "")},
+           "collectives_per_train_step": {"gradient_allreduce": 2 * n_mb if world > 1 else 0,
+                                          "kl_pair_allreduce": n_mb if world > 1 else 0},
+           "gradient_allreduce_us": ar_us,
+           "gradient_allreduce_share": (2 * n_mb * ar_us * 1e-3 / wall_ms) if ar_us is not None else 0.0,
+           "limiting_collective": ("actor+critic flat-gradient all-reduce (342 KB + 1.4 MB fp32), latency-bound" if world > 1 else None),
+           "gpu_launches_total": int(launches), "policy_loss": res["policy_loss"], "approx_kl": res["approx_kl"]}
+    env.close()
+    return out if rank == 0 else None
 
 
 def run_reference(args):
@@ -370,6 +531,13 @@ def main():
     ap.add_argument("--rollout-slots", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=200)
+    ap.add_argument("--vecenv-steps", type=int, default=20, help="steps of the VecEnv-protocol e2e leg (0 = skip)")
+    ap.add_argument("--small-envs", type=int, default=8192, help="envs per GPU of the small-batch leg (0 = skip)")
+    ap.add_argument("--mappo-steps", type=int, default=2, help="timed train steps of the MAPPO block (0 = skip)")
+    ap.add_argument("--mappo-envs", type=int, default=131072)
+    ap.add_argument("--mappo-drones", type=int, default=16)
+    ap.add_argument("--mappo-rollout", type=int, default=32)
+    ap.add_argument("--mappo-minibatches", type=int, default=128)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 24 if args.steps is None else args.steps

@@ -302,8 +302,8 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
                       bd_ppo_net** out);
 void bd_ppo_net_destroy(bd_ppo_net* n);
 int64_t bd_ppo_net_param_count(const bd_ppo_net* n);
-/* device doubles [16] of the last bd_ppo_grad: [0] sum of per-row losses, [1] sum of (logp_old - logp),
- * [2..5] d loss / d logstd sums, [6..9] output-bias gradient sums, [10] rows */
+/* device doubles [16] of the last bd_ppo_grad: [0] sum of per-row losses, [1] sum of (logp_old - logp), [2] rows,
+ * [3..6] d loss / d logstd sums, [7..10] output-bias gradient sums */
 double* bd_ppo_net_stats(bd_ppo_net* n);
 /* flat fp32 parameters -> bf16 K-step slabs (stream ordered; bd_ppo_adam_step does it itself) */
 int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream);
@@ -314,12 +314,13 @@ int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents
                    void* stream);
 /* one minibatch: forward, PPO clipped-ratio loss (actor: act, logp_old (slots,N,M[,A]), adv (slots,N) with
  * adv_stats = (mean, scale)) or value loss (critic: ret, optional v_old (slots,N)), backward, weight
- * gradients -> grad_dev (flat, parameter order) = mean over rows_global rows (0 = this call's rows) */
+ * gradients -> grad_dev (flat, parameter order) = mean over rows_global rows (0 = this call's rows);
+ * run_acc_dev (optional, 4 doubles) += per-minibatch (mean loss, approx_kl, 1, entropy loss) */
 int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
                 int64_t samples, const float* act_dev, const float* logp_old_dev, const float* adv_dev,
                 const float* adv_stats_dev, const float* ret_dev, const float* v_old_dev, float clip,
                 int use_clipped_value, float entropy_coef, const float* nmean_dev, const float* nrstd_dev,
-                float nclip, int64_t rows_global, float* grad_dev, void* stream);
+                float nclip, int64_t rows_global, float* grad_dev, double* run_acc_dev, void* stream);
 /* torch.optim.Adam step on flat buffers, skipped entirely (moments and step count too) when
  * kl_sum / kl_rows > 1.5 target_kl (agent.py:731; NULL or target_kl <= 0: unconditional); then repack */
 int bd_ppo_adam_step(bd_ppo_net* n, float* param_dev, float* exp_avg_dev, float* exp_avg_sq_dev,

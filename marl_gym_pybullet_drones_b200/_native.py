@@ -174,7 +174,7 @@ def load():
     lib.bd_ppo_forward.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp, C.c_float, vp, vp]
     lib.bd_ppo_forward.restype = C.c_int
     lib.bd_ppo_grad.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int,
-                                C.c_float, vp, vp, C.c_float, C.c_int64, vp, vp]
+                                C.c_float, vp, vp, C.c_float, C.c_int64, vp, vp, vp]
     lib.bd_ppo_grad.restype = C.c_int
     lib.bd_ppo_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, C.c_float, vp, vp]
     lib.bd_ppo_adam_step.restype = C.c_int

@@ -146,7 +146,7 @@ struct TileArgs {
   float nclip;
   bf16 *Xt, *H1t, *H2t, *dZ2t, *dZ1t, *dZ3t;   // tile scratch for dw_kernel
   float* out;                // MODE_FORWARD: (rows, out_dim)
-  double* stats;             // [0] sum loss, [1] sum (logp_old - logp), [2..5] dlogstd sums, [6..9] db3 sums, [10] rows
+  double* stats;             // [0] sum loss, [1] sum (logp_old - logp), [2] rows, [3..6] dlogstd sums, [7..10] db3 sums
 };
 
 enum { B_W3 = 0, B_XFULL, B_XEMPTY = B_XFULL + 2, B_L1 = B_XEMPTY + 2, B_L2, B_L3, B_D2, B_D1, B_Z3, B_TDONE, B_H1C,
@@ -554,7 +554,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           tc_fence_before();
           mbar_arrive(bar(B_Z3));
           // tile statistics: warp reduce, one atomic per value and warp
-          float red[11] = {loss, kl, dls[0], dls[1], dls[2], dls[3], dz[0], dz[1], dz[2], dz[3], cntv};
+          float red[11] = {loss, kl, cntv, dls[0], dls[1], dls[2], dls[3], dz[0], dz[1], dz[2], dz[3]};
 #pragma unroll
           for (int i = 0; i < 11; ++i) {
             float x = red[i];
@@ -613,7 +613,6 @@ struct DwArgs {
   DwJob jobs[12];
   int n_jobs;
   long long tiles;
-  int swap_lbo_sbo;              // bring-up switch for the MN-major descriptor fields
 };
 
 enum { DB_FULL = 0, DB_EMPTY = kDwStages, DB_DONE = 2 * kDwStages, DB_COUNT };
@@ -689,10 +688,9 @@ dw_kernel(const __grid_constant__ DwArgs P) {
           for (int mh = 0; mh < 2; ++mh) {
             for (int ks = 0; ks < 4; ++ks) {
               // A: M = j (contiguous in a core-matrix row), K = r.  8-row groups are 4096 B apart, 8-j groups 128 B.
-              uint32_t a_lbo = 4096, a_sbo = 128, b_lbo = rg, b_sbo = 128;
-              if (P.swap_lbo_sbo) { a_lbo = 128; a_sbo = 4096; b_lbo = 128; b_sbo = rg; }
-              const uint64_t ad = umma_desc(sbase + (uint32_t)mh * 2048u + (uint32_t)ks * 8192u, a_lbo, a_sbo);
-              const uint64_t bd = umma_desc(sbase + b_off[b] + (uint32_t)ks * 2u * rg, b_lbo, b_sbo);
+              // (MN-major descriptors: LBO = K direction, SBO = M / N direction; verified on the B200 against autograd)
+              const uint64_t ad = umma_desc(sbase + (uint32_t)mh * 2048u + (uint32_t)ks * 8192u, 4096, 128);
+              const uint64_t bd = umma_desc(sbase + b_off[b] + (uint32_t)ks * 2u * rg, rg, 128);
               umma_bf16(tmem_base + col0[b] + (uint32_t)mh * J.nB[b], ad, bd, umma_idesc(J.nB[b], 1, 1), (h | ks) != 0);
             }
           }
@@ -813,7 +811,9 @@ struct ReduceArgs {
   const float* pb1;       // [n1][256]
   const float* pb2;       // [n2][256]
   int n1, n2;
-  const double* stats;    // tile-kernel statistics (dlogstd sums at [2..5], db3 sums at [6..9], rows at [10])
+  const double* stats;    // tile-kernel statistics (rows at [2], dlogstd sums at [3..6], db3 sums at [7..10])
+  double* run_acc;        // optional running statistics over minibatches: [0] += mean loss, [1] += mean kl, [2] += 1, [3] += entropy loss
+  const float* logstd;    // packed logstd (entropy statistic)
   float entropy_coef;
   long long rows_global;  // rows of the minibatch over ALL ranks (the mean's denominator); 0 = use stats[10]
   float* grad;            // flat
@@ -823,11 +823,23 @@ __global__ void reduce_kernel(const __grid_constant__ ReduceArgs P) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const NetShape& s = P.s;
   if (i >= s.count()) return;
-  const double rows = P.rows_global > 0 ? (double)P.rows_global : (P.stats[10] > 0.0 ? P.stats[10] : 1.0);
+  if (i == 0 && P.run_acc != nullptr) {
+    // per-minibatch statistics the reference averages over an update (agent.py:738-741, 763-771); local rows
+    const double lr_ = P.stats[2] > 0.0 ? P.stats[2] : 1.0;
+    P.run_acc[0] += P.stats[0] / lr_;
+    P.run_acc[1] += P.stats[1] / lr_;
+    P.run_acc[2] += 1.0;
+    if (s.has_logstd && P.logstd != nullptr) {
+      double ent = 0.0;
+      for (int k = 0; k < s.out_dim; ++k) ent += 0.5 + 0.91893853320467 + (double)P.logstd[k];   // Normal.entropy summed
+      P.run_acc[3] += -ent;
+    }
+  }
+  const double rows = P.rows_global > 0 ? (double)P.rows_global : (P.stats[2] > 0.0 ? P.stats[2] : 1.0);
   const float scale = (float)(1.0 / rows);
   float g = 0.f;
   if (i < s.off_w1()) {                                   // logstd: policy part + entropy bonus (agent.py:629-633,736)
-    g = (float)P.stats[2 + i] * scale - P.entropy_coef;
+    g = (float)P.stats[3 + i] * scale - P.entropy_coef;
   } else if (i < s.off_b1()) {
     const long long k = i - s.off_w1();
     const int j = (int)(k / s.din()), col = (int)(k % s.din());
@@ -855,7 +867,7 @@ __global__ void reduce_kernel(const __grid_constant__ ReduceArgs P) {
     for (int n = 0; n < P.n1; ++n) g += p[(size_t)n * HID * kNOut];
     g *= scale;
   } else {
-    g = (float)P.stats[6 + (i - s.off_b3())] * scale;
+    g = (float)P.stats[7 + (i - s.off_b3())] * scale;
   }
   P.grad[i] = g;
 }
@@ -970,7 +982,6 @@ struct bd_ppo_net {
   int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
   double* stats = nullptr;       // [kStatSlots]
   int64_t launches = 0;
-  int swap_desc = 0;
 };
 
 namespace {
@@ -1012,8 +1023,6 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   n->s.C = chunks; n->s.D = in_dim; n->s.K1p = (in_dim + 15) & ~15; n->s.out_dim = out_dim; n->s.has_logstd = has_logstd ? 1 : 0;
   n->max_rows = max_rows;
   n->max_tiles = (max_rows + kRows - 1) / kRows;
-  const char* sw = getenv("BD_DW_SWAP");
-  n->swap_desc = (sw && sw[0] == '1') ? 1 : 0;
   // weight-gradient roles: role 2 = dW2 (512 TMEM columns); role 1 = dW1 chunks + dW3, as many jobs as the 512 columns need
   const int per_job = chunks_per_job(n->s.K1p);
   n->n1_jobs = (chunks + per_job - 1) / per_job;
@@ -1100,13 +1109,14 @@ int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents
 
 /* One minibatch: forward, loss, backward (tile kernel), weight gradients (dw kernel), reduction of the per-CTA partials
  * into grad_dev (flat, torch parameter order, mean over rows_global rows — pass the minibatch rows of ALL ranks so that
- * a following all-reduce SUM gives the global mean; 0 = this call's rows).  Statistics accumulate in bd_ppo_net_stats:
- * [0] sum of per-row losses, [1] sum of (logp_old - logp), [10] rows. */
+ * a following all-reduce SUM gives the global mean; 0 = this call's rows).  Statistics of the call are left in
+ * bd_ppo_net_stats: [0] sum of per-row losses, [1] sum of (logp_old - logp), [2] rows; run_acc_dev (optional, 4 doubles)
+ * accumulates per-minibatch means: [0] += loss, [1] += approx_kl, [2] += 1, [3] += entropy loss. */
 int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
                 int64_t samples, const float* act_dev, const float* logp_old_dev, const float* adv_dev,
                 const float* adv_stats_dev, const float* ret_dev, const float* v_old_dev, float clip, int use_clipped_value,
                 float entropy_coef, const float* nmean_dev, const float* nrstd_dev, float nclip, int64_t rows_global,
-                float* grad_dev, void* stream) {
+                float* grad_dev, double* run_acc_dev, void* stream) {
   if (!n || !obs_dev || !grad_dev) return pfail(BD_EINVAL, "bd_ppo_grad: null argument");
   if (!critic && (!act_dev || !logp_old_dev || !adv_dev || !adv_stats_dev)) return pfail(BD_EINVAL, "bd_ppo_grad: actor inputs missing");
   if (critic && !ret_dev) return pfail(BD_EINVAL, "bd_ppo_grad: critic inputs missing");
@@ -1135,7 +1145,6 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   DwArgs d;
   memset(&d, 0, sizeof(d));
   d.tiles = tiles;
-  d.swap_lbo_sbo = n->swap_desc;
   const int C = n->s.C, K1p = n->s.K1p;
   const int per_job = chunks_per_job(K1p);
   int cta = 0, nj = 0;
@@ -1165,7 +1174,7 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   // dW3^T = H2^T dZ3: a second, small launch of the same kernel (A = H2) over the role-1 CTA count
   DwArgs d3;
   memset(&d3, 0, sizeof(d3));
-  d3.tiles = tiles; d3.swap_lbo_sbo = n->swap_desc; d3.n_jobs = 1;
+  d3.tiles = tiles; d3.n_jobs = 1;
   {
     DwJob& J = d3.jobs[0];
     J.A = n->H2t; J.n_b = 1; J.B[0] = n->dZ3t; J.b_stride[0] = (long long)kRows * kNOut * 2; J.nB[0] = kNOut; J.out[0] = n->pw3;
@@ -1181,6 +1190,7 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   for (int c = 0; c < C; ++c) r.pw1[c] = n->pw1 + (size_t)c * n->n1 * HID * K1p;
   r.pw2 = n->pw2; r.pw3 = n->pw3; r.pb1 = n->pb1; r.pb2 = n->pb2; r.n1 = n->n1; r.n2 = n->n2;
   r.stats = n->stats; r.entropy_coef = critic ? 0.f : entropy_coef; r.rows_global = rows_global; r.grad = grad_dev;
+  r.run_acc = run_acc_dev; r.logstd = n->logstd;
   const long long np = n->s.count();
   reduce_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(r);
   e = cudaGetLastError();

@@ -4,13 +4,14 @@ The reference parallelises by spreading env objects over worker processes with
 `np.array_split` (`subproc_vec_env.py:28,53`).  Here every rank owns a contiguous
 env slice resident in its own GPU's HBM for the whole run; stepping needs no
 communication.  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used
-only for what genuinely crosses ranks: episode-statistics reduction and the
-trainer's gradient all-reduce.
+only for what genuinely crosses ranks: episode-statistics reduction here, and in the
+trainer the flat-gradient all-reduce (`optim.GatedAdam.grad`, one collective per optimiser
+step), the KL pair of the gate, the advantage moments and the normalisers' batch moments.
 """
 from __future__ import annotations
 
 import os
-from typing import Iterable, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist
@@ -53,37 +54,3 @@ def reduce_episode_stats(return_sum: torch.Tensor, length_sum: torch.Tensor, epi
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
     n = packed[2].clamp_min(1.0)
     return (packed[0] / n).item(), (packed[1] / n).item(), int(packed[2].item())
-
-
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 8 << 20) -> int:
-    """Average gradients across ranks with bucketed all-reduces (the MAPPO nets are
-    0.2-0.4 M fp32 parameters, i.e. normally ONE bucket; latency-bound, not bandwidth-bound).
-    Returns the number of collectives issued."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return 0
-    world = dist.get_world_size()
-    grads = [p.grad for p in params if p.grad is not None]
-    calls, bucket, size = 0, [], 0
-
-    def flush():
-        nonlocal calls, bucket, size
-        if not bucket:
-            return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world)
-        off = 0
-        for g in bucket:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
-        calls += 1
-        bucket, size = [], 0
-
-    for g in grads:
-        bucket.append(g)
-        size += g.numel() * g.element_size()
-        if size >= bucket_bytes:
-            flush()
-    flush()
-    return calls

@@ -22,8 +22,16 @@ What is kept from the reference (and where it is switchable):
     (`agent.py:643-700`); two Adam optimisers; no gradient clipping (`config.py:32` is unused);
   * truncation is not bootstrapped (the envs never emit 'TimeLimit.truncated', `mappo.py:827,845`).
 
-Multi-GPU: every rank owns its env shard; gradients are averaged with one bucketed all-reduce
-per optimiser step (`dist.allreduce_gradients`), episode statistics with one small all-reduce.
+The update itself is hand-written (`csrc/bd_ppo.cu`, `ppo_native.py`): per minibatch a fused tcgen05 kernel does
+gather -> MLP forward -> loss -> backward through the hidden layers, a second tcgen05 kernel the weight gradients, and
+small kernels the gradient reduction, the KL-gated Adam step and the bf16 repack; returns / advantages are one scan
+kernel.  A whole epoch of minibatches is captured ONCE as a CUDA graph (also under multi-GPU: the NCCL all-reduces
+are part of the graph).  `update_impl="torch"` keeps the round-1 torch-autograd update (library GEMMs) for shapes the
+kernels do not cover (hidden != 256, obs_dim > 96) and for A/B measurements.
+
+Multi-GPU: every rank owns its env shard; per optimiser step ONE NCCL all-reduce of the flat gradient buffer
+(`GatedAdam.grad`), plus 2 doubles for the KL gate; advantage moments, normaliser moments and episode statistics are
+small all-reduces per rollout.
 """
 from __future__ import annotations
 
@@ -56,7 +64,9 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
-    "graph_update": True,         # replay each PPO minibatch as one CUDA graph (single-GPU; multi-GPU runs it eagerly)
+    "graph_update": True,         # replay the update as a CUDA graph (native: one graph per epoch, NCCL included)
+    "update_impl": "auto",        # "native": hand-written kernels (bd_ppo.cu); "torch": autograd + library GEMMs;
+                                  # "auto": native where the kernels cover the shape, else torch
     "matmul_precision": "tf32",   # PPO-update GEMMs: "tf32" (tensor cores, fp32 storage / accumulation), "fp32" (CUDA
                                   # cores), "bf16" (autocast: bf16 operands AND saved activations, fp32 master weights)
     "norm_obs": False,            # mappo/config.py:7-10; True in the Spiral config (env_select_learn_mappo.py:278)
@@ -146,6 +156,19 @@ class DeviceMAPPO:
         self.actor_opt = GatedAdam(self.ac.actor_parameters(), lr=self.cfg["actor_lr"])
         self.critic_opt = GatedAdam(self.ac.critic.parameters(), lr=self.cfg["critic_lr"])
         self._graph = None
+        self._world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        impl = str(self.cfg["update_impl"])
+        if impl not in ("auto", "native", "torch"):
+            raise ValueError("update_impl must be 'auto', 'native' or 'torch'")
+        covered = (int(self.cfg["hidden_dim"]) == 256 and self.cfg["activation"] == "tanh" and self.D <= 96 and self.A <= 4
+                   and self.M <= 16)
+        if impl == "native" and not covered:
+            raise ValueError("update_impl='native' needs hidden_dim 256, tanh, obs_dim <= 96, act_dim <= 4, <= 16 agents")
+        self.native = impl != "torch" and covered
+        if self.cfg["use_clipped_value"] and self.cfg["rollout_values"] != "critic":
+            raise ValueError("use_clipped_value needs rollout_values='critic' (the reference clips around the stored "
+                             "rollout value, which its own rollout leaves at zero: agent.py:413,683)")
+        self.actor_net = self.critic_net = None
         self.gen = torch.Generator(device=self.device)
         rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
         self.gen.manual_seed(seed * 1000003 + rank)
@@ -162,6 +185,17 @@ class DeviceMAPPO:
         self.ret = torch.zeros((T, N, 1), device=dev)
         self.adv = torch.zeros((T, N, 1), device=dev)
         self.adv_n = torch.zeros((T, N, 1), device=dev)
+        self._adv_acc = torch.zeros(3, dtype=torch.float64, device=dev)     # sum adv, sum adv^2, count (all ranks)
+        self._adv_stats = torch.zeros(2, device=dev)                        # mean, 1 / (std + 1e-8)
+        self._run_actor = torch.zeros(4, dtype=torch.float64, device=dev)   # per-update sums of minibatch statistics
+        self._run_critic = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._gates = torch.zeros((), dtype=torch.float64, device=dev)      # actor steps that passed the KL gate
+        self._perm = torch.zeros(T * N, dtype=torch.int64, device=dev)
+        if self.native:
+            from .ppo_native import PpoNet
+            self.critic_net = PpoNet(D, M, 1, False, max_rows=max(1, min(int(self.cfg["mini_batch_size"]), T * N)), device=dev)
+            self.actor_net = PpoNet(D, 1, A, True, max_rows=max(1, min(int(self.cfg["mini_batch_size"]), T * N)) * M, device=dev)
+            self._pack_native()
         # episode statistics (VecRecordEpisodeStatistics semantics, record_episode_statistics.py:144-171)
         # (the step kernel accumulates them: BatchAviary.episode_stats)
         self.total_env_steps = 0
@@ -243,7 +277,7 @@ class DeviceMAPPO:
                 self.act[t] = mean + std * noise                      # unclipped Gaussian (agent.py:399-400)
                 self.logp[t] = (-0.5 * noise.pow(2) - self.ac.logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
             if use_critic:
-                self.val[t] = self.ac.value(self._normed(obs_t, t).view(N, M * self.D))
+                self._value_into(t)
             out = StepResult(self.obs[t + 1], self.rew[t], self.term[t].view(torch.bool),
                              self.trunc[t].view(torch.bool), None)
             self.env.step_device(self.act[t], out=out)   # episode statistics are kept by the step kernel
@@ -251,36 +285,50 @@ class DeviceMAPPO:
             if self.cfg["norm_reward"]:                  # mappo.py:805, raw rewards stay in the episode statistics
                 self.rew[t] = self.reward_normalizer(self.rew[t], self.term[t] | self.trunc[t])
         # bootstrap value of the last observation (`last_val`, mappo.py:1049-1157)
-        self.val[T] = self.ac.value(self._normed(self.obs[T], T).view(N, M * self.D))
+        self._value_into(T)
         if not use_critic:
             self.val[:T].zero_()                                       # agent.py:413: v stored as zeros
         self.total_env_steps += T * N
 
+    def _pack_native(self):
+        """bf16 tensor-core copies of both networks from the fp32 master parameters (GatedAdam's flat buffers)."""
+        if self.native:
+            self.actor_net.pack(self.actor_opt.flat)
+            self.critic_net.pack(self.critic_opt.flat)
+
+    def _norm_args(self, t=None):
+        """Per-slot observation statistics for the native kernels (slot t only, or all slots)."""
+        if not self.norm_obs:
+            return dict(nmean=None, nrstd=None, nclip=10.0)
+        c = float(self.cfg["clip_obs"])
+        if t is None:
+            return dict(nmean=self.nmean, nrstd=self.nrstd, nclip=c)
+        return dict(nmean=self.nmean[t:t + 1], nrstd=self.nrstd[t:t + 1], nclip=c)
+
+    @torch.no_grad()
+    def _value_into(self, t):
+        """val[t] = V(global observation of slot t) (`MAPPOActorCritic.get_value`, agent.py:295-314)."""
+        N, M = self.N, self.M
+        if self.native:
+            self.critic_net.forward(self.obs[t], N, M, N, out=self.val[t], **self._norm_args(t))
+        else:
+            self.val[t] = self.ac.value(self._normed(self.obs[t], t).view(N, M * self.D))
+
     @torch.no_grad()
     def compute_returns(self):
-        """GAE / returns as a backwards scan (`buffer.py:561-614`), per env (reward is shared by the agents)."""
-        g, lam = self.cfg["gamma"], self.cfg["gae_lambda"]
-        mask = 1.0 - (self.term | self.trunc).float().unsqueeze(-1)   # (T,N,1)
-        ret = self.val[self.T].clone()
-        adv = torch.zeros_like(ret)
-        for t in reversed(range(self.T)):
-            r = self.rew[t].unsqueeze(-1)
-            ret = r + g * mask[t] * ret
-            if self.cfg["use_gae"]:
-                td = r + g * mask[t] * self.val[t + 1] - self.val[t]
-                adv = adv * lam * g * mask[t] + td
-            else:
-                adv = ret - self.val[t]
-            self.ret[t] = ret
-            self.adv[t] = adv
-        mean, std = self.adv.mean(), self.adv.std()
-        if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            stats = torch.stack([self.adv.sum(), self.adv.pow(2).sum(),
-                                 torch.tensor(float(self.adv.numel()), device=self.device)])
-            torch.distributed.all_reduce(stats)
-            mean = stats[0] / stats[2]
-            std = (stats[1] / stats[2] - mean * mean).clamp_min(0).sqrt()
-        self.adv_n.copy_((self.adv - mean) / (std + 1e-8))              # buffer.py:666-695
+        """GAE / returns (`buffer.py:561-614`) as ONE scan kernel, per env (the reward is shared by the agents), and the
+        buffer-wide advantage moments for `normalize_advantages` (`buffer.py:666-695`: population std over all ranks'
+        advantages; the update kernels normalise on the fly, the torch path reads `adv_n`)."""
+        from . import ppo_native
+        T, N = self.T, self.N
+        self._adv_acc.zero_()
+        ppo_native.gae(self.rew, self.term, self.trunc, self.val.view(T + 1, N), self.cfg["gamma"], self.cfg["gae_lambda"],
+                       self.cfg["use_gae"], self.ret.view(T, N), self.adv.view(T, N), self._adv_acc)
+        if self._world > 1:
+            torch.distributed.all_reduce(self._adv_acc)
+        ppo_native.adv_stats(self._adv_acc, self._adv_stats)
+        if not self.native:
+            self.adv_n.copy_((self.adv - self._adv_stats[0]) * self._adv_stats[1])
 
     # ------------------------------------------------------------------- update
     def update(self) -> Dict[str, float]:
@@ -336,7 +384,12 @@ class DeviceMAPPO:
         self.actor_opt.step(gate)
         with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=bf16):
             v = self.ac.value(ob.reshape(mb, M * D))
-        value_loss = 0.5 * (v.float() - ret).pow(2).mean()
+        if cfg["use_clipped_value"]:                                              # agent.py:681-686
+            v_old = self.val[:T].reshape(n, 1)[idx]
+            v_clip = v_old + (v.float() - v_old).clamp(-cfg["clip_param"], cfg["clip_param"])
+            value_loss = 0.5 * torch.max((v.float() - ret).pow(2), (v_clip - ret).pow(2)).mean()
+        else:
+            value_loss = 0.5 * (v.float() - ret).pow(2).mean()
         self.critic_opt.zero_grad()
         value_loss.backward()
         if self._world > 1:
@@ -368,17 +421,82 @@ class DeviceMAPPO:
         self._stats.copy_(stats)
         return graph
 
-    def _update(self) -> Dict[str, float]:
+    def _agree_minibatches(self, n_local):
+        """Minibatch size and count every rank uses: each minibatch carries collectives (gradient all-reduce, KL pair),
+        so ranks whose env shards differ in size (`dist.shard_envs` = np.array_split) must agree on the count —
+        the smallest shard decides."""
+        n = n_local
+        if self._world > 1:
+            t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+            n = int(t.item())
+        mb = max(1, min(int(self.cfg["mini_batch_size"]), n))
+        return mb, n // mb
+
+    def _native_minibatch(self, idx, mb):
+        """One minibatch of `MAPPOAgent.update` (agent.py:702-772) on the hand-written kernels: actor gradient,
+        [all-reduce], KL-gated Adam + repack; critic gradient, [all-reduce], Adam + repack.  No host synchronisation."""
+        cfg, N, M, W = self.cfg, self.N, self.M, self._world
+        a, c, ao, co = self.actor_net, self.critic_net, self.actor_opt, self.critic_opt
+        norm = self._norm_args()
+        a.grad(ao.grad, self.obs, N, M, idx, mb, critic=False, act=self.act, logp_old=self.logp, adv=self.adv,
+               adv_stats=self._adv_stats, clip=cfg["clip_param"], entropy_coef=cfg["entropy_coef"],
+               rows_global=mb * M * W, run_acc=self._run_actor, **norm)
+        if W > 1:   # every rank must see the same gradient and take the same gate decision
+            torch.distributed.all_reduce(ao.grad)
+            torch.distributed.all_reduce(a.stats[1:3])
+        a.adam_step(ao.flat, ao.exp_avg, ao.exp_avg_sq, ao.grad, ao.step_t, ao.lr, ao.betas, ao.eps,
+                    kl_sum=a.stats[1:2], kl_rows=a.stats[2:3], target_kl=float(cfg["target_kl"]), gate_count=self._gates)
+        c.grad(co.grad, self.obs, N, M, idx, mb, critic=True, ret=self.ret, v_old=self.val, clip=cfg["clip_param"],
+               use_clipped_value=bool(cfg["use_clipped_value"]), rows_global=mb * W, run_acc=self._run_critic, **norm)
+        if W > 1:
+            torch.distributed.all_reduce(co.grad)
+        c.adam_step(co.flat, co.exp_avg, co.exp_avg_sq, co.grad, co.step_t, co.lr, co.betas, co.eps)
+
+    def _native_epoch(self, mb, num_mb):
+        for i in range(num_mb):
+            self._native_minibatch(self._perm[i * mb:(i + 1) * mb], mb)
+
+    def _update_native(self) -> Dict[str, float]:
         cfg = self.cfg
         n = self.T * self.N
-        mb = min(int(cfg["mini_batch_size"]), n)
-        num_mb = n // mb
+        mb, num_mb = self._agree_minibatches(n)
+        if mb * self.M > self.actor_net.max_rows:
+            raise RuntimeError("minibatch larger than the PpoNet scratch")
+        self._run_actor.zero_()
+        self._run_critic.zero_()
+        use_graph = bool(cfg["graph_update"])
+        if use_graph and (self._graph is None or self._graph_shape != (mb, num_mb)):
+            if self._world > 1:      # the communicator must exist before a collective is captured
+                torch.distributed.all_reduce(self._gates.clone())
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._native_epoch(mb, num_mb)
+            self._graph, self._graph_shape = graph, (mb, num_mb)
+        for _ in range(int(cfg["opt_epochs"])):
+            torch.randperm(n, device=self.device, generator=self.gen, out=self._perm)
+            if use_graph:
+                self._graph.replay()
+            else:
+                self._native_epoch(mb, num_mb)
+        self._fused_stale = True
+        ra, rc = self._run_actor.tolist(), self._run_critic.tolist()
+        k = max(ra[2], 1.0)
+        return {"policy_loss": ra[0] / k, "value_loss": rc[0] / max(rc[2], 1.0), "entropy_loss": ra[3] / k,
+                "approx_kl": ra[1] / k}
+
+    def _update(self) -> Dict[str, float]:
+        if self.native:
+            return self._update_native()
+        cfg = self.cfg
+        n = self.T * self.N
+        mb, num_mb = self._agree_minibatches(n)
         if num_mb > 8192 and not getattr(self, "_warned_mb", False):
             import warnings
             warnings.warn(f"{num_mb} minibatches of {mb} samples per epoch: mini_batch_size is the reference's default "
                           f"(mappo/config.py:32) sized for a handful of envs; with {self.N} envs use e.g. {max(mb, n // 64)}")
             self._warned_mb = True
-        self._world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         if not hasattr(self, "_stats"):
             self._stats = torch.zeros(5, device=self.device)
         self._stats.zero_()
@@ -430,7 +548,11 @@ class DeviceMAPPO:
             m, r = self.obs_normalizer.rms.stats()
             c = float(self.cfg["clip_obs"])
             obs = ((obs.reshape(-1, self.M * self.D) - m) * r).clamp(-c, c).view(obs.shape)
-        mean = self.ac.actor(obs.reshape(-1, self.D)).view(*obs.shape[:-1], self.A)
+        if self.native and obs.dim() == 3 and obs.is_contiguous():
+            n = obs.shape[0]         # obs is already normalised above: no per-slot statistics here
+            mean = self.actor_net.forward(obs, n, self.M, n * self.M).view(n, self.M, self.A)
+        else:
+            mean = self.ac.actor(obs.reshape(-1, self.D)).view(*obs.shape[:-1], self.A)
         if deterministic:
             return mean
         return mean + self.ac.logstd.exp() * torch.randn(mean.shape, device=mean.device, generator=self.gen)
@@ -480,7 +602,10 @@ class DeviceMAPPO:
               "obs_normalizer": self.obs_normalizer.state_dict(),
               "reward_normalizer": self.reward_normalizer.state_dict(),
               "total_steps": self.total_env_steps,
-              "random_state": None, "env_random_state": None}
+              # mappo.py:203-229: the reference stores its RNG states so that a resumed run continues the stream
+              "random_state": {"torch_generator": self.gen.get_state().cpu(),
+                               "fused_calls": int(self.fused._calls) if self.fused is not None else 0},
+              "env_random_state": [{"philox": self.env.get_rng_state()}]}
         if self._reset_done:
             t = self.T if self.total_env_steps > 0 else 0
             sd["obs"] = self._normed(self.obs[t], t).cpu().numpy()
@@ -495,7 +620,17 @@ class DeviceMAPPO:
         if sd.get("reward_normalizer"):
             self.reward_normalizer.load_state_dict(sd["reward_normalizer"])
         self.total_env_steps = int(sd.get("total_steps", 0))
+        rs = sd.get("random_state")
+        if rs:
+            self.gen.set_state(torch.as_tensor(rs["torch_generator"], dtype=torch.uint8).cpu())
+            if self.fused is not None:
+                self.fused._calls = int(rs.get("fused_calls", 0))
+        ers = sd.get("env_random_state")
+        if ers and isinstance(ers[0], dict) and "philox" in ers[0]:
+            self.env.set_rng_state(ers[0]["philox"])
         self._fused_stale = True
+        self._graph = None          # captured graphs have the old hyper-parameters (lr, betas) baked in
+        self._pack_native()
 
     def save(self, path):
         torch.save(self.state_dict(), path)

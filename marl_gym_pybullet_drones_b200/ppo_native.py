@@ -38,7 +38,7 @@ class PpoNet:
         self._check(rc, "bd_ppo_net_create")
         self.param_count = int(self._lib.bd_ppo_net_param_count(self._h))
         # statistics of the last bd_ppo_grad call, as a device tensor view: [0] sum loss, [1] sum (logp_old - logp),
-        # [2:6] dlogstd sums, [6:10] db3 sums, [10] rows
+        # [2] rows, [3:7] dlogstd sums, [7:11] db3 sums
         self.stats = self._wrap_stats()
 
     def _wrap_stats(self):
@@ -78,12 +78,12 @@ class PpoNet:
     def grad(self, grad_out: torch.Tensor, obs: torch.Tensor, n_envs: int, n_agents: int, idx: Optional[torch.Tensor],
              samples: int, *, critic: bool, act=None, logp_old=None, adv=None, adv_stats=None, ret=None, v_old=None,
              clip: float = 0.2, use_clipped_value: bool = False, entropy_coef: float = 0.0, nmean=None, nrstd=None,
-             nclip: float = 10.0, rows_global: int = 0):
+             nclip: float = 10.0, rows_global: int = 0, run_acc=None):
         """One minibatch: forward, loss, backward, weight gradients -> `grad_out` (flat, torch parameter order)."""
         self._check(self._lib.bd_ppo_grad(
             self._h, int(critic), _p(obs), int(n_envs), int(n_agents), _p(idx), int(samples), _p(act), _p(logp_old), _p(adv),
             _p(adv_stats), _p(ret), _p(v_old), float(clip), int(use_clipped_value), float(entropy_coef), _p(nmean), _p(nrstd),
-            float(nclip), int(rows_global), _p(grad_out), self._stream()), "bd_ppo_grad")
+            float(nclip), int(rows_global), _p(grad_out), _p(run_acc), self._stream()), "bd_ppo_grad")
 
     def adam_step(self, param, exp_avg, exp_avg_sq, grad, step, lr, betas=(0.9, 0.999), eps=1e-8, kl_sum=None, kl_rows=None,
                   target_kl: float = 0.0, gate_count=None):

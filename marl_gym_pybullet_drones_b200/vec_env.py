@@ -73,6 +73,16 @@ class BatchVecEnv:
         self._pending = None
         self._steps = np.zeros(self.num_envs, dtype=np.int64)   # step_counter mirror for info dicts
         self._flip = 0
+        self._pin_act = None
+
+    def action_buffer(self):
+        """A page-locked (N,M,A) array.  `step(buf)` with exactly this array hands it to the copy engine as it is;
+        any other array is first copied into pinned staging (what a caller that cannot change its allocation pays)."""
+        if self._pin_act is None:
+            b = self.batch
+            np_act = np.float32 if str(b.action_dtype).endswith("float32") else np.float64
+            self._pin_act = b.pinned_array((self.num_envs, b.NUM_DRONES, b.ACTION_DIM), np_act)
+        return self._pin_act
 
     # -- info dicts (HoverAviary.py:119-131, MultiHoverAviary.py:274-285, SpiralAviary.py:200-205)
     def _info(self, kin=None, terminated=False, step_counter=0):
@@ -102,7 +112,7 @@ class BatchVecEnv:
 
     def step_async(self, actions):
         self._assert_not_closed()
-        self._pending = np.asarray(actions)
+        self._pending = actions if actions is self._pin_act else np.asarray(actions)
         self.waiting = True
 
     def step_wait(self):
@@ -112,7 +122,8 @@ class BatchVecEnv:
         self._assert_not_closed()
         b = self.batch
         self._flip ^= 1
-        res = b.step_host(self._pending, compact_terminal_obs=b.auto_reset, buffer_set=self._flip)
+        res = b.step_host(self._pending, compact_terminal_obs=b.auto_reset, buffer_set=self._flip,
+                          actions_pinned=self._pending is self._pin_act)
         self.waiting = False
         obs, term, trunc = res["obs"], res["terminated"], res["truncated"]
         rews = res["reward"].astype(np.float64)

@@ -1,5 +1,4 @@
-"""Bring-up of the PPO-update kernels: per-parameter gradient error vs torch autograd, with both readings of the
-MN-major shared-memory descriptor fields (BD_DW_SWAP=0/1), and timings of the pieces at the config-4 minibatch shape."""
+"""Bring-up of the PPO-update kernels: per-parameter gradient error vs torch autograd, and timings of the pieces at the config-4 minibatch shape."""
 import os
 import sys
 import time
@@ -29,8 +28,7 @@ def main():
     pl, el, kl = t._actor_reference(mlp, logstd, obs, act, logp_old, adv_n, idx, T, N, M, D, A, 0.2, 0.005)
     params = [logstd] + list(mlp.parameters())
     want = torch.autograd.grad(pl + 0.005 * el, params)
-    for swap in ("0", "1"):
-        os.environ["BD_DW_SWAP"] = swap
+    for swap in ("0",):
         net = PpoNet(D, 1, A, True, samples * M)
         net.pack(t._flat(params))
         out = net.forward(obs, N, M, samples * M, idx=idx)
@@ -41,14 +39,13 @@ def main():
                  clip=0.2, entropy_coef=0.005)
         torch.cuda.synchronize()
         st = net.stats
-        print(f"swap={swap} loss {float(st[0]) / float(st[10]):.5f} vs {float(pl):.5f}  kl {float(st[1]) / float(st[10]):.5f} vs {float(kl):.5f}")
+        print(f"swap={swap} loss {float(st[0]) / float(st[2]):.5f} vs {float(pl):.5f}  kl {float(st[1]) / float(st[2]):.5f} vs {float(kl):.5f}")
         off = 0
         for name, w in zip(["logstd", "W1", "b1", "W2", "b2", "W3", "b3"], want):
             got = grad[off:off + w.numel()].view_as(w)
             off += w.numel()
             print(f"  {name:6s} rel {t._rel(got, w):.3e} cos {t._cos(got, w):+.5f} |ref| {float(w.norm()):.3e}")
         net.close()
-    os.environ["BD_DW_SWAP"] = os.environ.get("BD_DW_SWAP_FINAL", "0")
     # ---- timings at the config-4 minibatch shape: 32 768 samples x 4 agents
     T, N, samples = 32, 16384, 32768
     obs, act, g = t._rollout(T, N, M, D, A, 7)

@@ -1,4 +1,5 @@
-"""world_size=2 gloo test of the only cross-rank traffic: episode-stat reduction + gradient averaging."""
+"""world_size=2 gloo tests of the only cross-rank traffic: episode-stat reduction, the flat-gradient all-reduce of
+`GatedAdam` (the unit the trainer reduces), minibatch-count agreement for unequal shards."""
 import os
 import socket
 
@@ -19,8 +20,8 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
-    from marl_gym_pybullet_drones_b200.dist import (allreduce_gradients, init_distributed, reduce_episode_stats,
-                                                    shard_envs)
+    from marl_gym_pybullet_drones_b200.dist import init_distributed, reduce_episode_stats, shard_envs
+    from marl_gym_pybullet_drones_b200.optim import GatedAdam
     r, lr, w = init_distributed("gloo")
     start, count = shard_envs(10, r, w)
     # each rank finished `count` episodes of return = env index
@@ -29,14 +30,19 @@ def _worker(rank, world, port, q):
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 2))
     x = torch.full((3, 4), float(r + 1))
+    opt = GatedAdam(net.parameters(), lr=1e-2)      # parameters / gradients become views of ONE flat buffer
     net(x).sum().backward()
     local = [p.grad.clone() for p in net.parameters()]
-    calls = allreduce_gradients(net.parameters(), bucket_bytes=64)
+    opt.all_reduce_grad()                           # one collective for the whole network
     gathered = [None] * w
     dist.all_gather_object(gathered, [g.tolist() for g in local])
     avg_ok = all(torch.allclose(p.grad, sum(torch.tensor(gathered[k][i]) for k in range(w)) / w)
                  for i, p in enumerate(net.parameters()))
-    q.put((r, mean_r, mean_l, n, calls, avg_ok))
+    # unequal shards (10 envs over 2 ranks is equal; 11 is not): every rank must run the same number of minibatches
+    s11, c11 = shard_envs(11, r, w)
+    t = torch.tensor([c11 * 8], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    q.put((r, mean_r, mean_l, n, int(t.item()), avg_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,9 +59,9 @@ def test_two_rank_reduction_and_gradient_average():
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    for r, mean_r, mean_l, n, calls, avg_ok in res:
+    for r, mean_r, mean_l, n, n_min, avg_ok in res:
         assert n == 10 and mean_r == pytest.approx(4.5) and mean_l == pytest.approx(242.0)
-        assert calls >= 2 and avg_ok
+        assert n_min == 5 * 8 and avg_ok
 
 
 def _worker_trainer(rank, world, port, q):

@@ -131,8 +131,8 @@ def test_scalar_shapes_accept_unaligned_slices():
         fl = torch.zeros((2, T, N), dtype=torch.bool, device="cuda")
         for e in envs:
             e.reset_device()
+        assert any(obs[t + 1].data_ptr() % 16 for t in range(T))     # some slots really are unaligned
         for t in range(T):
-            assert (obs[t + 1].data_ptr() % 16 != 0) or (N * M * 27) % 4 == 0
             envs[0].step_device(act[t], out=StepResult(obs[t + 1], rew[t], fl[0, t], fl[1, t], None))
             r = envs[1].step_device(act[t].clone())
             assert torch.equal(r.obs, obs[t + 1]), (M, N, t)
