@@ -159,7 +159,8 @@ int bd_step_host(bd_handle* h, const void* actions_host, float* obs_host, void* 
  *   *n_done        number of envs that finished in this step
  *   *done_idx      their env indices (ascending), n_done entries
  *   *terminal_rows (n_done, M, D) float, row k belongs to env (*done_idx)[k]
- * The two arrays are owned by the handle and valid until its next step call. */
+ * The two arrays are owned by the handle (two sets used alternately) and stay valid until the
+ * next-but-one step call. */
 int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
                          uint8_t* terminated_host, uint8_t* truncated_host, int32_t* n_done,
                          const int32_t** done_idx, const float** terminal_rows, void* stream);

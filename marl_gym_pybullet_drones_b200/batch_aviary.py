@@ -335,8 +335,8 @@ class BatchAviary:
         into a pinned staging buffer (a 4 MB host memcpy at 65 536 x 4 drones, ~0.35 ms).
         `want_terminal_obs=True`: a full (N,M,D) `terminal_obs` array (rows valid where done).
         `compact_terminal_obs=True`: `bd_step_host_compact` instead — `done_idx` (ascending env indices of the
-        envs that finished) and `terminal_rows` (len(done_idx), M, D); views of memory owned by the handle,
-        valid until the next step.
+        envs that finished) and `terminal_rows` (len(done_idx), M, D); views of memory owned by the handle
+        (two sets used alternately), valid until the next-but-one step.
         """
         self._check_open()
         N, M = self.num_envs, self.NUM_DRONES

@@ -54,6 +54,7 @@ struct DeviceGuard {
 struct bd_handle {
   bd_config cfg;
   int S = 0, A = 0, B = 0, D = 0, E = 0;
+  int G = 1;                   // fast tile kernel: lanes per env (M rounded up to a power of two)
   long long n_total = 0;
   size_t real = 4;
   bd::LaunchSpec spec{};
@@ -88,9 +89,11 @@ struct bd_handle {
   bool poisoned = false;       // a launch failed half-way through a chunked host step: the tile epochs are inconsistent
   // compact terminal observations (bd_step_host_compact): pinned, device-mapped staging owned by the handle
   int* c_blockcnt = nullptr;   // [blocks of 1024 envs] done envs per block
-  int* c_host = nullptr;       // pinned+mapped: [0] = count, [1..N] = done env indices (ascending)
-  float* c_rows_host = nullptr;  // pinned+mapped: [cap][M][D] terminal observation rows, same order
-  int c_cap = 0;
+  // two sets, used alternately: what a call returns stays valid until the next-but-one step
+  int* c_host[2] = {nullptr, nullptr};         // pinned+mapped: [0] = count, [1..N] = done env indices (ascending)
+  float* c_rows_host[2] = {nullptr, nullptr};  // pinned+mapped: [cap][M][D] terminal observation rows, same order
+  int c_cap[2] = {0, 0};
+  int c_flip = 0;
   bd::Params<float> pf{};
   bd::Params<double> pd{};
 };
@@ -102,10 +105,10 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   const bd_config& c = h->cfg;
   using R4 = typename bd::V4<R>::type;
   P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
-  P.E = h->E; P.n_total = h->n_total;
+  P.E = h->E; P.G = h->G; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
   P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.tile_epoch = h->tile_epoch; P.finished = h->finished;
-  P.step_tiles = h->spec.impl == 1 ? (h->n_total + bd::kBlock - 1) / bd::kBlock : (h->cfg.n_envs + h->E - 1) / h->E;
+  P.step_tiles = h->spec.impl == 1 ? (h->cfg.n_envs + bd::kBlock / h->G - 1) / (bd::kBlock / h->G) : (h->cfg.n_envs + h->E - 1) / h->E;
   P.pipeline = h->pipeline; P.pipe_wait = 0; P.early_prefetch = 0; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
   P.ctrl = (R*)h->ctrl;
   P.act_type = c.act_type; P.ctrl_reset = c.ctrl_reset_on_reset;
@@ -164,7 +167,8 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
 
 // tiles of either step kernel (128 drones for the fast kernel, E whole envs for the generic one)
 long long epoch_tiles(const bd_handle* h) {
-  const long long a = (h->n_total + bd::kBlock - 1) / bd::kBlock, b = (h->cfg.n_envs + h->E - 1) / h->E;
+  const long long ept = bd::kBlock / h->G;
+  const long long a = (h->cfg.n_envs + ept - 1) / ept, b = (h->cfg.n_envs + h->E - 1) / h->E;
   return a > b ? a : b;
 }
 
@@ -244,8 +248,7 @@ void free_all(bd_handle* h) {
   cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->c_blockcnt);
-  if (h->c_host) cudaFreeHost(h->c_host);
-  if (h->c_rows_host) cudaFreeHost(h->c_rows_host);
+  for (int i = 0; i < 2; ++i) { if (h->c_host[i]) cudaFreeHost(h->c_host[i]); if (h->c_rows_host[i]) cudaFreeHost(h->c_rows_host[i]); }
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
   if (h->hs_a) {
@@ -321,11 +324,14 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     // kernel.  BD_STEP_IMPL=cta forces the latter (A/B measurements, tests).
     const int m = cfg->n_drones;
     const bool pow2 = (m & (m - 1)) == 0 && m <= 32;
+    int g = 1;
+    while (g < m) g <<= 1;
+    h->G = g;                   // lanes per env on the fast kernel: other team sizes are padded (5 -> 8)
     const char* force = getenv("BD_STEP_IMPL");
-    // the fast kernel also carries downwash alone (shuffle exchange inside the env's lane group)
-    const bool fast_aero = cfg->aero_flags == 0 || cfg->aero_flags == BD_AERO_DW;
-    const bool plain = fast_aero && cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
-    h->spec.impl = (cfg->precision == BD_F32 && plain && pow2 && !pid_act) ? 1 : 0;
+    // the fast kernel carries ground effect, drag and downwash (shuffle exchange inside the env's lane group); the
+    // swarm tasks' shuffle rewards need M == G
+    const bool plain = cfg->integrator == BD_INTEGRATOR_QUAT && !cfg->keep_ang_vel;
+    h->spec.impl = (cfg->precision == BD_F32 && plain && m <= 32 && (pow2 || !swarm) && !pid_act) ? 1 : 0;
     if (force && strcmp(force, "cta") == 0) h->spec.impl = 0;
     const char* pdl = getenv("BD_PDL");
     h->spec.pdl = (pdl && strcmp(pdl, "0") == 0) ? 0 : 1;
@@ -337,7 +343,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   cudaDeviceProp prop;
   cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
-  if (h->spec.impl == 1 && (size_t)bd::kBlock * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
+  if (h->spec.impl == 1 && (size_t)(bd::kBlock / h->G) * cfg->n_drones * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
   h->spec.sm_count = prop.multiProcessorCount;
   if (smem > prop.sharedMemPerBlockOptin) {
     delete h;
@@ -489,13 +495,15 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
 }  // extern "C"
 
 namespace {
-int ensure_compact_buffers(bd_handle* h, int cap) {
+int ensure_compact_buffers(bd_handle* h, int set, int cap) {
   if (!h->c_blockcnt) BD_CUDA(cudaMalloc((void**)&h->c_blockcnt, (size_t)bd::compact_blocks(h->cfg.n_envs) * sizeof(int)));
-  if (!h->c_host) BD_CUDA(cudaHostAlloc((void**)&h->c_host, ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocMapped));
-  if (cap > h->c_cap) {
-    if (h->c_rows_host) { cudaFreeHost(h->c_rows_host); h->c_rows_host = nullptr; h->c_cap = 0; }
-    BD_CUDA(cudaHostAlloc((void**)&h->c_rows_host, (size_t)cap * h->cfg.n_drones * h->D * sizeof(float), cudaHostAllocMapped));
-    h->c_cap = cap;
+  if (!h->c_host[set])
+    BD_CUDA(cudaHostAlloc((void**)&h->c_host[set], ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocMapped));
+  if (cap > h->c_cap[set]) {
+    if (h->c_rows_host[set]) { cudaFreeHost(h->c_rows_host[set]); h->c_rows_host[set] = nullptr; h->c_cap[set] = 0; }
+    BD_CUDA(cudaHostAlloc((void**)&h->c_rows_host[set], (size_t)cap * h->cfg.n_drones * h->D * sizeof(float),
+                          cudaHostAllocMapped));
+    h->c_cap[set] = cap;
   }
   return BD_OK;
 }
@@ -522,9 +530,10 @@ int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host
   *n_done = 0; *done_idx = nullptr; *terminal_rows = nullptr;
   int rc = step_host_impl(h, actions_host, obs_host, reward_host, terminated_host, truncated_host, nullptr, true, stream);
   if (rc) return rc;
-  *n_done = h->c_host[0];
-  *done_idx = h->c_host + 1;
-  *terminal_rows = h->c_rows_host;
+  const int set = h->c_flip;       // the set this call filled
+  *n_done = h->c_host[set][0];
+  *done_idx = h->c_host[set] + 1;
+  *terminal_rows = h->c_rows_host[set];
   return BD_OK;
 }
 
@@ -558,13 +567,15 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
     BD_CUDA(cudaMemsetAsync(h->h_tobs, 0, obs_bytes, st));
   }
   if (compact) {
-    int rc = ensure_compact_buffers(h, h->c_cap > 0 ? h->c_cap : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256));
+    h->c_flip ^= 1;
+    const int set = h->c_flip;
+    int rc = ensure_compact_buffers(h, set, h->c_cap[set] > 0 ? h->c_cap[set] : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256));
     if (rc) return rc;
   }
   // Pipeline over chunks of whole tiles: while the copy engine drains chunk k's observations to the host,
   // chunk k+1's actions go up and its tiles are stepped.  One control step = `chunks` sub-range launches of the
   // same kernel with the same step count; only the last one advances the device-resident counter.
-  const int block_rows = h->spec.impl == 1 ? bd::kBlock : h->E * h->cfg.n_drones;   // drones per tile
+  const int block_rows = h->spec.impl == 1 ? (bd::kBlock / h->G) * h->cfg.n_drones : h->E * h->cfg.n_drones;   // drones per tile
   const int n_blocks = (int)((h->n_total + block_rows - 1) / block_rows);
   int chunks = (int)(obs_bytes >> 21);   // at least 2 MB of observations per chunk, at most 8 chunks
   if (chunks > 8) chunks = 8;
@@ -646,16 +657,17 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   BD_CUDA(cudaMemcpyAsync(truncated_host, h->h_trunc, n, cudaMemcpyDeviceToHost, st));
   if (compact) {
     const int row_floats = h->cfg.n_drones * h->D;
+    const int set = h->c_flip;
     cudaError_t e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats,
-                                            h->c_cap, h->c_host, h->c_rows_host, st);
+                                            h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
     h->launches += 2;
     if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
     BD_CUDA(cudaStreamSynchronize(st));
-    if (h->c_host[0] > h->c_cap) {   // more finished envs than the staging holds: grow it and gather again (rare)
-      int rc = ensure_compact_buffers(h, h->c_host[0] + h->c_host[0] / 4);
+    if (h->c_host[set][0] > h->c_cap[set]) {   // more finished envs than the staging holds: grow it and gather again (rare)
+      int rc = ensure_compact_buffers(h, set, h->c_host[set][0] + h->c_host[set][0] / 4);
       if (rc) return rc;
-      e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats, h->c_cap,
-                                  h->c_host, h->c_rows_host, st);
+      e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats, h->c_cap[set],
+                                  h->c_host[set], h->c_rows_host[set], st);
       h->launches += 2;
       if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
       BD_CUDA(cudaStreamSynchronize(st));

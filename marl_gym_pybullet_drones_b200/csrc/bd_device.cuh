@@ -369,9 +369,19 @@ namespace bd {
 // DW: pairwise downwash (BaseAviary.py:798-804) for envs that are lane groups of M (M | 32): the
 // substep-start positions of the group's other drones arrive by warp shuffle (Jacobi snapshot,
 // no shared memory, no barrier); the body-z force enters as F R[:,2] / m.
-template <bool DW>
+// MODE 0: plain DYN.  MODE 1: + downwash only.  MODE 2: any combination of ground effect / drag / downwash, chosen
+// at run time by P.aero (warp-uniform).  `G` = lane-group size of an env (M rounded up to a power of two; lanes with
+// drone index >= M are idle and never contribute to another drone's downwash).  `last_sum` = sum over the motors of
+// fl32(1 + 0.05 a) of the PREVIOUS control step (0 right after a reset): the drag model reads last_clipped_action,
+// which during the first substep is still the previous step's (BaseAviary.py:359,372).
+//   ground effect (:739-742): f_k <- f_k (1 + c_k), c_k = GND (r_prop / 4 h_k)^2, h_k = max(z + R20 x_k + R21 y_k, clip);
+//       (1 + u_k)(1 + c_k) = 1 + u_k + e_k with e_k = (1 + u_k) c_k: thrust/m gains (g/4) sum e_k, the roll / pitch
+//       mixes see u_k + e_k, the yaw torque (KM rpm^2) is unchanged; gated by |roll|, |pitch| < pi/2
+//   drag (:773-774): F_world += k (.) v, k = -DRAG sum_k 2 pi rpm_k / 60, v = velocity at the start of the substep
+template <int MODE>
 __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<float>& d, const float onep[4],
-                                              float& avx, float& avy, float& avz, int lane = 0) {
+                                              float& avx, float& avy, float& avz, int lane = 0, int G = 1,
+                                              float last_sum = 0.f) {
   const float dt = P.dt;
   float u[4];
 #pragma unroll
@@ -379,6 +389,8 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
     const float sk = onep[k] - 1.0f;                  // exact (Sterbenz)
     u[k] = sk * (2.0f + sk);
   }
+  const bool gnd = (MODE == 2) && (P.aero & AERO_GND), drag = (MODE == 2) && (P.aero & AERO_DRAG);
+  const bool dw = (MODE == 1) || ((MODE == 2) && (P.aero & AERO_DW));
   const float qf = 0.25f * P.gravity;                   // KF H^2
   const float qm = P.km * (P.hover_rpm * P.hover_rpm);  // KM H^2
   float tz = qm * ((-u[0] + u[1]) + (-u[2] + u[3]));
@@ -392,41 +404,76 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
   const float cg = dt * P.gravity * P.inv_m;            // dt g
   const float c1 = cg * (1.0f + e4), c2 = cg * e4, c3 = -2.0f * cg;
   const float half_dt = 0.5f * dt;
+  // drag factors dt k / m per axis: previous step's rpm in the first substep, this step's afterwards
+  const float kd = -6.28318530717958647692f / 60.0f * P.hover_rpm * dt * P.inv_m;
+  const float cur_sum = (onep[0] + onep[1]) + (onep[2] + onep[3]);
 #pragma unroll 1
   for (int s = 0; s < P.S; ++s) {
     const float x = d.qx, y = d.qy, z = d.qz, w = d.qw;   // unit up to rounding
     const float xxyy = fmaf(x, x, y * y);
     const float r02 = 2.0f * fmaf(x, z, w * y), r12 = 2.0f * fmaf(y, z, -w * x),
                 r22 = fmaf(-2.0f, xxyy, 1.0f);
-    float c1s = c1, c2s = c2;
-    if constexpr (DW) {
-      const int M = P.M, base = lane & ~(M - 1);
-      float fdw = 0.f;
-#pragma unroll 1
-      for (int o = 1; o < M; ++o) {
-        const int src = base | ((lane + o) & (M - 1));
-        const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
-                    oz = __shfl_sync(0xffffffffu, d.pz, src);
-        const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
-        const float dxy2 = fmaf(dx, dx, dy * dy);
-        const float ratio = __fdividef(P.prop_radius, 4.0f * dz);
-        const float alpha = P.dw1 * ratio * ratio;
-        const float beta = fmaf(P.dw2, dz, P.dw3);
-        const float q2 = __fdividef(dxy2, beta * beta);
-        const float f = -alpha * __expf(-0.5f * q2);
-        if (dz > 0.f && dxy2 < 100.f) fdw += f;                 // :801 (delta_xy < 10)
+    float c1s = c1, c2s = c2, kxs = kx, kys = ky;
+    float dvx = d.vx, dvy = d.vy, dvz = d.vz;
+    if constexpr (MODE == 2) {
+      if (gnd && tilt_below_half_pi(x, y, z, w)) {
+        const float r20 = 2.0f * fmaf(x, z, -w * y), r21 = 2.0f * fmaf(y, z, w * x);
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float h = d.pz + fmaf(r20, P.prop_x[k], r21 * P.prop_y[k]);
+          h = fmaxf(h, P.gnd_h_clip);
+          const float ratio = __fdividef(P.prop_radius, 4.0f * h);
+          e[k] = (1.0f + u[k]) * (P.gnd_coeff * ratio * ratio);
+        }
+        const float es = cg * 0.25f * ((e[0] + e[1]) + (e[2] + e[3]));
+        c1s += es;
+        c2s += es;
+        float ex, ey;
+        if (P.model == 0) { ex = -qf * ((e[0] + e[1]) - (e[2] + e[3])) * P.arm; ey = qf * ((-e[0] + e[1]) + (e[2] - e[3])) * P.arm; }
+        else if (P.model == 1) { ex = qf * (e[1] - e[3]) * P.arm; ey = qf * (-e[0] + e[2]) * P.arm; }
+        else { ex = qf * ((e[0] + e[1]) - (e[2] + e[3])) * P.arm; ey = qf * ((-e[0] + e[1]) + (e[2] - e[3])) * P.arm; }
+        kxs = fmaf(dt * P.ijx, ex, kx);
+        kys = fmaf(dt * P.ijy, ey, ky);
       }
-      const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
-      c1s += k;
-      c2s += k;
+      if (drag) {
+        const float sum = kd * (s == 0 ? last_sum : cur_sum);
+        dvx = fmaf(sum * P.drag_xy, d.vx, d.vx);
+        dvy = fmaf(sum * P.drag_xy, d.vy, d.vy);
+        dvz = fmaf(sum * P.drag_z, d.vz, d.vz);
+      }
+    }
+    if constexpr (MODE != 0) {
+      if (dw) {
+        const int M = P.M, base = lane & ~(G - 1);
+        float fdw = 0.f;
+#pragma unroll 1
+        for (int o = 1; o < G; ++o) {
+          const int od = (lane + o) & (G - 1);
+          const int src = base | od;
+          const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
+                      oz = __shfl_sync(0xffffffffu, d.pz, src);
+          const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
+          const float dxy2 = fmaf(dx, dx, dy * dy);
+          const float ratio = __fdividef(P.prop_radius, 4.0f * dz);
+          const float alpha = P.dw1 * ratio * ratio;
+          const float beta = fmaf(P.dw2, dz, P.dw3);
+          const float q2 = __fdividef(dxy2, beta * beta);
+          const float f = -alpha * __expf(-0.5f * q2);
+          if (od < M && dz > 0.f && dxy2 < 100.f) fdw += f;       // :801 (delta_xy < 10); padding lanes carry no drone
+        }
+        const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
+        c1s += k;
+        c2s += k;
+      }
     }
     // a = g [(1+e) R[:,2] - e_z] (+ F_dw R[:,2] / m);  (1+e) r22 - 1 = e r22 - 2 (x^2 + y^2)
-    d.vx = fmaf(c1s, r02, d.vx);
-    d.vy = fmaf(c1s, r12, d.vy);
-    d.vz = fmaf(c2s, r22, fmaf(c3, xxyy, d.vz));
+    d.vx = fmaf(c1s, r02, dvx);
+    d.vy = fmaf(c1s, r12, dvy);
+    d.vz = fmaf(c2s, r22, fmaf(c3, xxyy, dvz));
     const float owx = d.wx, owy = d.wy, owz = d.wz;
-    d.wx = fmaf(-gx, owy * owz, owx + kx);
-    d.wy = fmaf(-gy, owz * owx, owy + ky);
+    d.wx = fmaf(-gx, owy * owz, owx + kxs);
+    d.wy = fmaf(-gy, owz * owx, owy + kys);
     d.wz = fmaf(-gz, owx * owy, owz + kz);
     d.px = fmaf(dt, d.vx, d.px);
     d.py = fmaf(dt, d.vy, d.py);

@@ -200,7 +200,7 @@ step_kernel(const __grid_constant__ Params<R> P) {
   R avx = R(0), avy = R(0), avz = R(0);   // world angular velocity R_old * w_new (:873)
 
   if constexpr (FAST) {
-    fast_substeps<false>(P, d, onep, avx, avy, avz);
+    fast_substeps<0>(P, d, onep, avx, avy, avz);
   } else {
 #pragma unroll 1
     for (int s = 0; s < P.S; ++s) {

@@ -26,6 +26,7 @@ template <> struct V4<double> { using type = double4; };
 template <typename Real>
 struct Params {
   int N, M, S, A, B, D, E;
+  int G;                          // fast tile kernel: lanes per env (M rounded up to a power of two)
   long long n_total;
   typename V4<Real>::type *s0, *s1, *s2, *s3, *s4;
   float* hist;

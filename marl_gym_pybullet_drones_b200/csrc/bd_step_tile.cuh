@@ -1,4 +1,5 @@
-// Fast step kernel (float, DYN with optional downwash, M in {1,2,4,8,16,32}): one CTA per tile of 128 drones.
+// Fast step kernel (float, DYN with optional ground effect / drag / downwash, M <= 32): one CTA per tile of up to 128 drones
+// (an env is a lane group of G = M rounded up to a power of two lanes).
 //
 // Measured facts that shape it (scripts/microbench/*.cu, profiles/README.md):
 //   * observation rows must leave the SM as complete, contiguous rows: 16-byte or
@@ -41,11 +42,11 @@ struct TileIn {
 
 // the handle's own data (written by the previous step of this tile) ...
 template <int A>
-__device__ __forceinline__ void load_state(const Params<float>& P, long long g, int log2m, TileIn<A>& in) {
-  if (g < P.n_total) {
+__device__ __forceinline__ void load_state(const Params<float>& P, long long g, int env, bool active, TileIn<A>& in) {
+  if (active) {
     in.s0 = P.s0[g]; in.s1 = P.s1[g]; in.s2 = P.s2[g]; in.s3 = P.s3[g];
-    in.stepc = P.stepc[g >> log2m];
-    in.ep_ret = P.ep_ret != nullptr ? P.ep_ret[g >> log2m] : 0.f;
+    in.stepc = P.stepc[env];
+    in.ep_ret = P.ep_ret != nullptr ? P.ep_ret[env] : 0.f;
   } else {
     in.s0 = in.s1 = in.s2 = in.s3 = make_float4(0.f, 0.f, 0.f, 0.f);
     in.s1.z = 1.0f;
@@ -55,8 +56,8 @@ __device__ __forceinline__ void load_state(const Params<float>& P, long long g, 
 }
 // ... and the caller's (possibly written by the kernel enqueued just before this launch)
 template <int A>
-__device__ __forceinline__ void load_action(const Params<float>& P, long long g, TileIn<A>& in) {
-  if (g < P.n_total) {
+__device__ __forceinline__ void load_action(const Params<float>& P, long long g, bool active, TileIn<A>& in) {
+  if (active) {
     if constexpr (A == 4) in.act = reinterpret_cast<const float4*>(P.actions)[g];
     else in.act = make_float4(reinterpret_cast<const float*>(P.actions)[g], 0.f, 0.f, 0.f);
   } else {
@@ -141,23 +142,30 @@ __device__ __forceinline__ float swarm_reward_shfl(const Params<float>& P, const
   return contrib;
 }
 
-template <int TASK, int A, bool VEC, bool DW>
+// AERO: 0 plain DYN, 1 downwash only, 2 any aero combination (run-time P.aero) — see fast_substeps.
+// An env is a lane group of G = P.G lanes (M rounded up to a power of two): M == G for the power-of-two team sizes,
+// else the lanes with drone index >= M idle (M = 5 -> 8 lanes, 62 % of the threads work; the memory traffic, which is
+// what bounds the kernel, is unchanged).  A tile = 128 / G whole envs = (128 / G) * M observation rows.
+template <int TASK, int A, bool VEC, int AERO>
 __global__ void __launch_bounds__(kBlock, 6)
 step_kernel_tile(const __grid_constant__ Params<float> P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int M = P.M, B = P.B, D = P.D;
-  const int log2m = 31 - __clz(M);
+  const int M = P.M, B = P.B, D = P.D, G = P.G;
+  const int log2g = 31 - __clz(G);
   constexpr bool vec = VEC;   // A == 4 and D % 4 == 0: 128-bit row accesses
-  float* tile_s = reinterpret_cast<float*>(smem_raw);   // [kBlock][D] row-major, dense
-  float* myrow = tile_s + (size_t)tid * D;
-  const int drone = lane & (M - 1);
-  const int group_base = lane & ~(M - 1);
-  const long long g0 = (long long)(blockIdx.x + P.block0) * kBlock;   // block0 > 0: sub-range launch (bd_step_host chunks)
-  const long long g = g0 + tid;
-  const bool active = g < P.n_total;
-  const int env = (int)(g >> log2m);
+  float* tile_s = reinterpret_cast<float*>(smem_raw);   // [tile rows][D] row-major, dense
+  const int drone = lane & (G - 1);
+  const int group_base = lane & ~(G - 1);
+  const int tile = blockIdx.x + P.block0;               // block0 > 0: sub-range launch (bd_step_host chunks)
+  const int env_l = tid >> log2g;
+  const int env = tile * (kBlock >> log2g) + env_l;
+  const bool active = drone < M && env < P.N;
+  const long long g0 = (long long)tile * (kBlock >> log2g) * M;
+  const long long g = (long long)env * M + drone;       // meaningful for active lanes only
+  float* myrow = tile_s + (size_t)(env_l * M + (drone < M ? drone : 0)) * D;   // idle lanes alias a live row, never write
   const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
+  const long long gh = active ? g : P.n_total;          // idle lanes issue no history copies
 
   // ---- 1. every load of the tile is issued before anything is consumed ------------------------
   // Programmatic dependent launch: this grid may become resident while the previous kernel of
@@ -168,7 +176,6 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   pdl_launch_dependents();
   int total, head;
   const bool pipe = P.pipe_wait && P.host_total >= 0;   // wait on my tile's epoch instead of the whole previous grid
-  const int tile = blockIdx.x + P.block0;
   if (pipe) {
     // Tile-level step pipelining: everything this CTA reads that an earlier launch wrote belongs to ITS tile
     // (whole environments), and was written by the CTA that stepped this tile in the previous control step.
@@ -180,24 +187,40 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     total = P.host_total;
     head = P.host_head;
     if (pipe_gate(P, tile, total, tid)) pdl_wait();
-    issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
+    issue_history<float, A, VEC>(P, gh, head, myrow, 0, B - 2);
   } else if (P.host_total >= 0 && P.early_prefetch) {
     total = P.host_total;
     head = P.host_head;   // = total % B (ring slot overwritten by this step's action), divided on the host
-    issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
+    issue_history<float, A, VEC>(P, gh, head, myrow, 0, B - 2);
     pdl_wait();
   } else {              // CUDA-graph mode (the step count is read from device memory), or a grid smaller than the
     pdl_wait();         // resident capacity (several earlier launches could still be in flight: no early reads)
     total = P.host_total >= 0 ? P.host_total : P.gsteps[0];   // only the last CTA to finish modifies it, after every read
     head = total % B;
-    issue_history<float, A, VEC>(P, g, head, myrow, 0, B - 2);
+    issue_history<float, A, VEC>(P, gh, head, myrow, 0, B - 2);
   }
   TileIn<A> cur;
-  load_state<A>(P, g, log2m, cur);
-  issue_history<float, A, VEC>(P, g, head, myrow, B - 2, B - 1);
+  load_state<A>(P, g, env, active, cur);
+  issue_history<float, A, VEC>(P, gh, head, myrow, B - 2, B - 1);
   cp_async_commit();
-  load_action<A>(P, g, cur);
+  load_action<A>(P, g, active, cur);
   const int stepc = cur.stepc;
+  // drag reads last_clipped_action during the first substep (BaseAviary.py:359,372): the previous step's action,
+  // i.e. ring slot head-1; zero right after a reset (:468)
+  float last_sum = 0.f;
+  if constexpr (AERO == 2) {
+    if ((P.aero & AERO_DRAG) && active && stepc > 0) {
+      const int prev = head == 0 ? B - 1 : head - 1;
+      const float* lp = P.hist + ((size_t)prev * P.n_total + g) * A;
+      if constexpr (A == 4) {
+        const float4 pa = *reinterpret_cast<const float4*>(lp);
+        last_sum = (__fadd_rn(1.0f, __fmul_rn(0.05f, pa.x)) + __fadd_rn(1.0f, __fmul_rn(0.05f, pa.y))) +
+                   (__fadd_rn(1.0f, __fmul_rn(0.05f, pa.z)) + __fadd_rn(1.0f, __fmul_rn(0.05f, pa.w)));
+      } else {
+        last_sum = 4.0f * __fadd_rn(1.0f, __fmul_rn(0.05f, lp[0]));
+      }
+    }
+  }
 
   Drone<float> d;
   d.px = cur.s0.x; d.py = cur.s0.y; d.pz = cur.s0.z; d.qx = cur.s0.w;
@@ -217,7 +240,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
 
   // ---- 2. S substeps in registers while the history lands --------------------------------------
   float avx = 0.f, avy = 0.f, avz = 0.f;
-  fast_substeps<DW>(P, d, onep, avx, avy, avz, lane);
+  fast_substeps<AERO>(P, d, onep, avx, avy, avz, lane, G, last_sum);
   float roll, pitch, yaw;
   quat_to_euler_fast(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
 
@@ -251,12 +274,12 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   float swarm_reward_env = 0.f;
   if constexpr (TASK == TASK_SWARM) {
     int fl = 0;
-    swarm_reward_env = swarm_reward_shfl(P, d, roll, pitch, lane, M, drone, fl);
+    swarm_reward_env = swarm_reward_shfl(P, d, roll, pitch, lane, M, drone, fl);   // swarm tasks: G == M (host side)
     flags = active ? fl : 0;
   }
   // ---- per-env reduction with shuffles (envs are lane groups of M) --------------------------------
 #pragma unroll 1
-  for (int o = M >> 1; o > 0; o >>= 1) {
+  for (int o = G >> 1; o > 0; o >>= 1) {
     contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
     flags |= __shfl_xor_sync(0xffffffffu, flags, o);
   }
@@ -315,15 +338,16 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
         }
         int bad = 0;
 #pragma unroll 1
-        for (int o = 1; o < M; ++o) {
-          const int src = group_base | ((lane + o) & (M - 1));
+        for (int o = 1; o < G; ++o) {
+          const int od = (lane + o) & (G - 1);
+          const int src = group_base | od;
           const float ox = __shfl_sync(0xffffffffu, cx, src), oy = __shfl_sync(0xffffffffu, cy, src),
                       oz = __shfl_sync(0xffffffffu, cz, src);
           const float dx = cx - ox, dy = cy - oy, dz = cz - oz;
-          bad |= (sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
+          bad |= (od < M && drone < M && sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
         }
 #pragma unroll 1
-        for (int o = M >> 1; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        for (int o = G >> 1; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
         if (last || P.reset_mode == RESET_BUFFER) bad = 0;
         retry = retry && (bad != 0);
         if (!__any_sync(0xffffffffu, retry)) break;
@@ -349,7 +373,8 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
 
   // ---- 4. the finished rows leave as one TMA bulk store; state planes as 128-bit stores ------------
   const long long left = P.n_total - g0;
-  const int rows = (int)(left < (long long)kBlock ? left : (long long)kBlock);
+  const int tile_rows = (kBlock >> log2g) * M;
+  const int rows = (int)(left < (long long)tile_rows ? left : (long long)tile_rows);
   const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
   float* gobs = P.obs + (size_t)g0 * D;
   const bool bulk = P.obs_aligned && (bytes & 15u) == 0;

@@ -12,26 +12,30 @@ namespace bd {
 
 template <int TASK, int A>
 static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
-  const size_t smem = (size_t)kBlock * P.D * 4;   // the [128][D] observation tile and nothing else
+  const int envs_per_tile = kBlock / P.G;
+  const size_t smem = (size_t)envs_per_tile * P.M * P.D * 4;   // the [tile rows][D] observation tile and nothing else
   const bool vecrow = (A == 4) && (P.D % 4 == 0);
-  const bool dw = (P.aero & AERO_DW) != 0;
-  auto kern = vecrow ? (dw ? step_kernel_tile<TASK, A, (A == 4), true> : step_kernel_tile<TASK, A, (A == 4), false>)
-                     : (dw ? step_kernel_tile<TASK, A, false, true> : step_kernel_tile<TASK, A, false, false>);
-  static size_t configured[4][64] = {{0}};
-  size_t* const cfgd = configured[(vecrow ? 1 : 0) + (dw ? 2 : 0)];
+  const int aero = P.aero == 0 ? 0 : (P.aero == AERO_DW ? 1 : 2);
+  void (*kern)(Params<float>);
+  if (vecrow) kern = aero == 0 ? step_kernel_tile<TASK, A, (A == 4), 0> : (aero == 1 ? step_kernel_tile<TASK, A, (A == 4), 1> : step_kernel_tile<TASK, A, (A == 4), 2>);
+  else kern = aero == 0 ? step_kernel_tile<TASK, A, false, 0> : (aero == 1 ? step_kernel_tile<TASK, A, false, 1> : step_kernel_tile<TASK, A, false, 2>);
+  static size_t configured[6][64] = {{0}};
+  size_t* const cfgd = configured[(vecrow ? 1 : 0) + 2 * aero];
   const int dv = ls.device & 63;
   if (smem > cfgd[dv]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfgd[dv] = smem;
   }
-  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (int)((P.n_total + kBlock - 1) / kBlock);
+  const int grid = P.grid_blocks > 0 ? P.grid_blocks : (P.N + envs_per_tile - 1) / envs_per_tile;
   // resident capacity of this kernel: with a grid at least that large, "every CTA of the previous launch has
   // started" implies "the launch before it has completed", so at most two launches are ever in flight
-  static int per_sm[4][64] = {{0}};
-  int& occ = per_sm[(vecrow ? 1 : 0) + (dw ? 2 : 0)][dv];
-  if (occ == 0) {
+  static int per_sm[6][64] = {{0}};
+  static size_t per_sm_smem[6][64] = {{0}};
+  int& occ = per_sm[(vecrow ? 1 : 0) + 2 * aero][dv];
+  if (occ == 0 || per_sm_smem[(vecrow ? 1 : 0) + 2 * aero][dv] != smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+    per_sm_smem[(vecrow ? 1 : 0) + 2 * aero][dv] = smem;
   }
   Params<float> Q = P;
   Q.early_prefetch = (ls.pdl && grid >= occ * ls.sm_count) ? 1 : 0;

@@ -36,6 +36,14 @@ class LazyInfos:
     def __init__(self, n, make, ready=None):
         self._n, self._make = int(n), make
         self._cache = dict(ready) if ready else {}
+        self._patches = []          # (env indices as a set, key, value factory): applied when a dict is built
+
+    def patch(self, indices, key, factory):
+        """`info['n'][i][key] = factory(i)` for every i in `indices`, without building the dicts now."""
+        members = set(int(i) for i in indices)
+        for i in members & self._cache.keys():
+            self._cache[i][key] = factory(i)
+        self._patches.append((members, key, factory))
 
     def __len__(self):
         return self._n
@@ -51,6 +59,9 @@ class LazyInfos:
         d = self._cache.get(i)
         if d is None:
             d = self._cache[i] = self._make(i)
+            for members, key, factory in self._patches:
+                if i in members:
+                    d[key] = factory(i)
         return d
 
     def __iter__(self):
@@ -93,13 +104,17 @@ class BatchVecEnv:
             return {"answer": 42}
         reasons = []
         if terminated and kin is not None:
-            for i in range(b.NUM_DRONES):
-                x, y, z, roll, pitch = kin[i, 0], kin[i, 1], kin[i, 2], kin[i, 3], kin[i, 4]
-                if z < 0.03:
+            k5 = np.asarray(kin[:, :5], dtype=np.float64)
+            crashed = k5[:, 2] < 0.03
+            flipped = (np.abs(k5[:, 3]) > 1.2) | (np.abs(k5[:, 4]) > 1.2)
+            out = (np.abs(k5[:, 0]) > 3.0) | (np.abs(k5[:, 1]) > 3.0)
+            for i in np.flatnonzero(crashed | flipped | out):     # same order as MultiHoverAviary.py:221-239
+                x, y, z, roll, pitch = k5[i].tolist()
+                if crashed[i]:
                     reasons.append(f"Drone {i} crashed (z={z:.2f})")
-                if abs(roll) > 1.2 or abs(pitch) > 1.2:
+                if flipped[i]:
                     reasons.append(f"Drone {i} flipped (roll={roll:.2f}, pitch={pitch:.2f})")
-                if abs(x) > 3.0 or abs(y) > 3.0:
+                if out[i]:
                     reasons.append(f"Drone {i} out of bounds (pos=[{x:.2f}, {y:.2f}, {z:.2f}])")
         return {"answer": 42, "termination_reasons": reasons}
 
@@ -130,23 +145,24 @@ class BatchVecEnv:
         dones = np.logical_or(term, trunc)
         S = b.PYB_STEPS_PER_CTRL
         steps_before = self._steps
-        ready = {}
         if b.auto_reset:
+            # compact terminal rows: handle-owned page-locked memory, two sets used alternately, so — like the
+            # observations — they stay valid until the next-but-one step; a dict built from them copies its row
             idx, rows = res["done_idx"], res["terminal_rows"]
-            for k in range(len(idx)):
-                e = int(idx[k])
-                end_obs = rows[k].copy()
-                info = self._info()   # info of the fresh episode (reset)
-                info['terminal_observation'] = end_obs
-                info['terminal_info'] = self._info(end_obs, bool(term[e]), int(steps_before[e]))
-                ready[e] = info
             self._steps = np.where(dones, 0, steps_before + S)
         else:
+            idx, rows = None, None
             self._steps = steps_before + S
 
-        def make(e, obs=obs, term=term, steps=steps_before):
+        def make(e, obs=obs, term=term, steps=steps_before, idx=idx, rows=rows):
+            if idx is not None and dones[e]:
+                k = int(np.searchsorted(idx, e))
+                info = self._info()   # info of the fresh episode (reset)
+                info['terminal_observation'] = rows[k].copy()
+                info['terminal_info'] = self._info(rows[k], bool(term[e]), int(steps[e]))
+                return info
             return self._info(obs[e], bool(term[e]), int(steps[e]))
-        return obs, rews, dones, {'n': LazyInfos(self.num_envs, make, ready)}
+        return obs, rews, dones, {'n': LazyInfos(self.num_envs, make)}
 
     def step(self, actions):
         self.step_async(actions)
@@ -270,20 +286,27 @@ class VecRecordEpisodeStatistics:
                 for name, (_, _, values) in self._trackers.items():
                     if name in src:
                         values[i] = values[i] + src[name]
-        for i in finished:
-            ep = {'r': float(self.episode_return[i]), 'l': float(self.episode_length[i])}
-            self.return_queue.append(ep['r'])
-            self.length_queue.append(ep['l'])
-            for name, (mode, _, values) in self._trackers.items():
-                ep[name] = deepcopy(values[i])
-                if mode == 'accumulate':
-                    self.accumulated_stats[name] = self.accumulated_stats[name] + deepcopy(values[i])
-                else:
-                    self.queued_stats[name].append(deepcopy(values[i]))
-                self._clear_tracker(name, i)
-            infos[i]['episode'] = ep
-        self.episode_return[finished] = 0.0
-        self.episode_length[finished] = 0.0
+        if finished.size:
+            ep_r, ep_l = self.episode_return[finished].tolist(), self.episode_length[finished].tolist()
+            self.return_queue.extend(ep_r)
+            self.length_queue.extend(ep_l)
+            if not self._trackers and hasattr(infos, "patch"):
+                # lazily built info dicts: the episode record is attached when somebody reads the dict
+                pos = dict(zip(finished.tolist(), range(finished.size)))
+                infos.patch(pos.keys(), 'episode', lambda i: {'r': ep_r[pos[i]], 'l': ep_l[pos[i]]})
+            else:
+                for k, i in enumerate(finished.tolist()):
+                    ep = {'r': ep_r[k], 'l': ep_l[k]}
+                    for name, (mode, _, values) in self._trackers.items():
+                        ep[name] = deepcopy(values[i])
+                        if mode == 'accumulate':
+                            self.accumulated_stats[name] = self.accumulated_stats[name] + deepcopy(values[i])
+                        else:
+                            self.queued_stats[name].append(deepcopy(values[i]))
+                        self._clear_tracker(name, i)
+                    infos[i]['episode'] = ep
+            self.episode_return[finished] = 0.0
+            self.episode_length[finished] = 0.0
         return obs, reward, done, info
 
     def step(self, actions):
