@@ -210,6 +210,10 @@ def run_ours(args):
             raise SystemExit("launch with torchrun for --gpus > 1 (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from marl_gym_pybullet_drones_b200.dist import bind_host_thread_to_gpu
+    # NUMA-local pinned buffers for the host-buffer legs when several ranks share the host (the 1-GPU run keeps every
+    # core for the CPU baseline it also times)
+    cpus = bind_host_thread_to_gpu(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -283,6 +287,25 @@ def run_ours(args):
     h2d = N * M * A * 4
     d2h = N * M * D * 4 + N * 4 + 2 * N
 
+    # ---- what the host side can do at best: the same bytes per step as plain copies (H2D actions, D2H observations),
+    # all ranks at the same time — the ceiling the e2e figure is a fraction of (PCIe link on 1 GPU, the host's memory /
+    # root-complex bandwidth shared by the ranks on 8)
+    pin_obs = torch.empty((N, M, D), dtype=torch.float32, pin_memory=True)
+    pin_act = torch.from_numpy(host_actions[0])
+    dev_act = torch.empty((N, M, A), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        dev_act.copy_(pin_act, non_blocking=True)
+        pin_obs.copy_(obs_buf[0], non_blocking=True)
+    sync_all()
+    t0 = time.perf_counter()
+    n_copy = 10
+    for _ in range(n_copy):
+        dev_act.copy_(pin_act, non_blocking=True)
+        pin_obs.copy_(obs_buf[0], non_blocking=True)
+    torch.cuda.synchronize(dev)
+    copy_ms = (time.perf_counter() - t0) * 1e3 / n_copy
+    del pin_obs
+
     # ---- e2e through the reference's VecEnv protocol (what MAPPO.train_step calls): 4-tuple + info dicts
     vec_ms = None
     if args.vecenv_steps > 0:
@@ -339,10 +362,10 @@ def run_ours(args):
                  "roofline_frac": bpl / (ms_many * 1e-3) / 1e9 / 6553.0, "steps_per_host_call": Ks}
         env_s.close()
 
-    t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0, copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, vec_ms_max = float(t[0]), float(t[1]), float(t[2])
+    ms_max, e2e_ms_max, vec_ms_max, copy_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     units = world * N * M * S
     value = units * args.steps / (ms_max * 1e-3)
     e2e_value = units * e2e_steps / (e2e_ms_max * 1e-3)
@@ -385,7 +408,9 @@ def run_ours(args):
                 "l2_policy": (f"inputs larger than L2: obs written to a {slots}-slot rotating rollout buffer "
                               f"({slots * N * M * D * 4 / 1e6:.0f} MB) + {slots}-slot action pool; state+history "
                               f"{(N * M * (64 + Bf * A * 4)) / 1e6:.0f} MB"),
-                "parallelism": f"env-sharded x{world}, no data-path collective"},
+                "parallelism": f"env-sharded x{world}, no data-path collective",
+                "host_cpus_rank0": (f"{len(cpus)} CPUs near the GPU (NVML affinity)" if cpus else
+                                    f"{host_cores()} (container cpuset; NVML affinity not applicable)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": "profiles/traffic.json: one isolated `ncu --set full` launch of this kernel "
@@ -397,7 +422,14 @@ def run_ours(args):
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchAviary.step_host -> bd_step_host (pinned numpy in/out)"},
+                    "steps": e2e_steps, "api": "BatchAviary.step_host -> bd_step_host (pinned numpy in/out)",
+                    # the e2e path is bound by the host link, not by HBM: its own roofline
+                    "roofline": {"bound": "host link (PCIe / host memory shared by the ranks)",
+                                 "achieved": world * (h2d + d2h) / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
+                                 "peak": world * (h2d + d2h) / (copy_ms_max * 1e-3) / 1e9, "unit": "GB/s",
+                                 "frac": copy_ms_max / (e2e_ms_max / e2e_steps),
+                                 "peak_source": "measured in this run: the same bytes per step as plain cudaMemcpyAsync "
+                                                "copies from / to pinned memory, all ranks concurrently"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

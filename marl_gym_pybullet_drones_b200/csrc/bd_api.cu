@@ -54,7 +54,7 @@ struct DeviceGuard {
 struct bd_handle {
   bd_config cfg;
   int S = 0, A = 0, B = 0, D = 0, E = 0;
-  int G = 1;                   // fast tile kernel: lanes per env (M rounded up to a power of two)
+  int EW = 1;                  // fast tile kernel: whole envs per warp (32 / M); a tile = 4 EW envs
   long long n_total = 0;
   size_t real = 4;
   bd::LaunchSpec spec{};
@@ -89,6 +89,7 @@ struct bd_handle {
   bool poisoned = false;       // a launch failed half-way through a chunked host step: the tile epochs are inconsistent
   // compact terminal observations (bd_step_host_compact): pinned, device-mapped staging owned by the handle
   int* c_blockcnt = nullptr;   // [blocks of 1024 envs] done envs per block
+  int* c_total = nullptr;      // running count of finished envs over the chunks of one step
   // two sets, used alternately: what a call returns stays valid until the next-but-one step
   int* c_host[2] = {nullptr, nullptr};         // pinned+mapped: [0] = count, [1..N] = done env indices (ascending)
   float* c_rows_host[2] = {nullptr, nullptr};  // pinned+mapped: [cap][M][D] terminal observation rows, same order
@@ -105,10 +106,10 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
   const bd_config& c = h->cfg;
   using R4 = typename bd::V4<R>::type;
   P.N = c.n_envs; P.M = c.n_drones; P.S = h->S; P.A = h->A; P.B = h->B; P.D = h->D;
-  P.E = h->E; P.G = h->G; P.n_total = h->n_total;
+  P.E = h->E; P.EW = h->EW; P.n_total = h->n_total;
   P.s0 = (R4*)h->s0; P.s1 = (R4*)h->s1; P.s2 = (R4*)h->s2; P.s3 = (R4*)h->s3; P.s4 = (R4*)h->s4;
   P.hist = h->hist; P.stepc = h->stepc; P.gsteps = h->gsteps; P.tile_epoch = h->tile_epoch; P.finished = h->finished;
-  P.step_tiles = h->spec.impl == 1 ? (h->cfg.n_envs + bd::kBlock / h->G - 1) / (bd::kBlock / h->G) : (h->cfg.n_envs + h->E - 1) / h->E;
+  P.step_tiles = h->spec.impl == 1 ? (h->cfg.n_envs + 4 * h->EW - 1) / (4 * h->EW) : (h->cfg.n_envs + h->E - 1) / h->E;
   P.pipeline = h->pipeline; P.pipe_wait = 0; P.early_prefetch = 0; P.ep_ret = h->ep_ret; P.ep_acc = h->ep_acc;
   P.ctrl = (R*)h->ctrl;
   P.act_type = c.act_type; P.ctrl_reset = c.ctrl_reset_on_reset;
@@ -167,7 +168,7 @@ void fill_params(const bd_handle* h, bd::Params<R>& P) {
 
 // tiles of either step kernel (128 drones for the fast kernel, E whole envs for the generic one)
 long long epoch_tiles(const bd_handle* h) {
-  const long long ept = bd::kBlock / h->G;
+  const long long ept = 4 * h->EW;
   const long long a = (h->cfg.n_envs + ept - 1) / ept, b = (h->cfg.n_envs + h->E - 1) / h->E;
   return a > b ? a : b;
 }
@@ -248,6 +249,7 @@ void free_all(bd_handle* h) {
   cudaFree(h->init_xyz); cudaFree(h->init_rpy);
   cudaFree(h->jitter);
   cudaFree(h->c_blockcnt);
+  cudaFree(h->c_total);
   for (int i = 0; i < 2; ++i) { if (h->c_host[i]) cudaFreeHost(h->c_host[i]); if (h->c_rows_host[i]) cudaFreeHost(h->c_rows_host[i]); }
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
@@ -324,9 +326,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
     // kernel.  BD_STEP_IMPL=cta forces the latter (A/B measurements, tests).
     const int m = cfg->n_drones;
     const bool pow2 = (m & (m - 1)) == 0 && m <= 32;
-    int g = 1;
-    while (g < m) g <<= 1;
-    h->G = g;                   // lanes per env on the fast kernel: other team sizes are padded (5 -> 8)
+    h->EW = m <= 32 ? 32 / m : 1;   // whole envs per warp on the fast kernel
     const char* force = getenv("BD_STEP_IMPL");
     // the fast kernel carries ground effect, drag and downwash (shuffle exchange inside the env's lane group); the
     // swarm tasks' shuffle rewards need M == G
@@ -343,7 +343,7 @@ int bd_create(const bd_config* cfg, bd_handle** out) {
   cudaDeviceProp prop;
   cudaError_t pe = cudaGetDeviceProperties(&prop, cfg->device);
   if (pe != cudaSuccess) { delete h; return fail(BD_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(pe)); }
-  if (h->spec.impl == 1 && (size_t)(bd::kBlock / h->G) * cfg->n_drones * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
+  if (h->spec.impl == 1 && (size_t)(4 * h->EW) * cfg->n_drones * h->D * 4 > prop.sharedMemPerBlockOptin) h->spec.impl = 0;
   h->spec.sm_count = prop.multiProcessorCount;
   if (smem > prop.sharedMemPerBlockOptin) {
     delete h;
@@ -497,6 +497,7 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
 namespace {
 int ensure_compact_buffers(bd_handle* h, int set, int cap) {
   if (!h->c_blockcnt) BD_CUDA(cudaMalloc((void**)&h->c_blockcnt, (size_t)bd::compact_blocks(h->cfg.n_envs) * sizeof(int)));
+  if (!h->c_total) BD_CUDA(cudaMalloc((void**)&h->c_total, sizeof(int)));
   if (!h->c_host[set])
     BD_CUDA(cudaHostAlloc((void**)&h->c_host[set], ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocMapped));
   if (cap > h->c_cap[set]) {
@@ -575,7 +576,7 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   // Pipeline over chunks of whole tiles: while the copy engine drains chunk k's observations to the host,
   // chunk k+1's actions go up and its tiles are stepped.  One control step = `chunks` sub-range launches of the
   // same kernel with the same step count; only the last one advances the device-resident counter.
-  const int block_rows = h->spec.impl == 1 ? (bd::kBlock / h->G) * h->cfg.n_drones : h->E * h->cfg.n_drones;   // drones per tile
+  const int block_rows = h->spec.impl == 1 ? (4 * h->EW) * h->cfg.n_drones : h->E * h->cfg.n_drones;   // drones per tile
   const int n_blocks = (int)((h->n_total + block_rows - 1) / block_rows);
   int chunks = (int)(obs_bytes >> 21);   // at least 2 MB of observations per chunk, at most 8 chunks
   if (chunks > 8) chunks = 8;
@@ -585,6 +586,13 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
     int rc = bd_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_term, h->h_trunc,
                      want_tobs ? h->h_tobs : nullptr, stream);
     if (rc) return rc;
+    if (compact) {
+      const int set = h->c_flip;
+      cudaError_t ce = bd::launch_compact_done(h->h_term, h->h_trunc, 0, h->cfg.n_envs, 1, h->c_blockcnt, h->c_total, h->h_tobs,
+                                               h->cfg.n_drones * h->D, h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
+      h->launches += 3;
+      if (ce != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(ce));
+    }
     BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
     if (terminal_obs_host)
       BD_CUDA(cudaMemcpyAsync(terminal_obs_host, h->h_tobs, obs_bytes, cudaMemcpyDeviceToHost, st));
@@ -630,6 +638,17 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
         break;
       }
       h->launches++;
+      if (compact) {   // this chunk's finished envs are gathered while its observations travel
+        const int env_per_block = block_rows / h->cfg.n_drones;
+        const int e0 = b0 * env_per_block;
+        int e1 = b1 * env_per_block;
+        if (e1 > h->cfg.n_envs) e1 = h->cfg.n_envs;
+        const int set = h->c_flip;
+        cudaError_t ce = bd::launch_compact_done(h->h_term, h->h_trunc, e0, e1, c == 0 ? 1 : 0, h->c_blockcnt, h->c_total, h->h_tobs,
+                                                 h->cfg.n_drones * h->D, h->c_cap[set], h->c_host[set], h->c_rows_host[set], h->hs_a);
+        h->launches += 3;
+        if (ce != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(ce));
+      }
       BD_CUDA(cudaEventRecord(h->hs_chunk[c], h->hs_a));
       BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_chunk[c], 0));
       BD_CUDA(cudaMemcpyAsync((char*)obs_host + g0 * obs_row, (const char*)h->h_obs + g0 * obs_row, rows * obs_row,
@@ -658,17 +677,13 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   if (compact) {
     const int row_floats = h->cfg.n_drones * h->D;
     const int set = h->c_flip;
-    cudaError_t e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats,
-                                            h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
-    h->launches += 2;
-    if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
     BD_CUDA(cudaStreamSynchronize(st));
     if (h->c_host[set][0] > h->c_cap[set]) {   // more finished envs than the staging holds: grow it and gather again (rare)
       int rc = ensure_compact_buffers(h, set, h->c_host[set][0] + h->c_host[set][0] / 4);
       if (rc) return rc;
-      e = bd::launch_compact_done(h->h_term, h->h_trunc, h->cfg.n_envs, h->c_blockcnt, h->h_tobs, row_floats, h->c_cap[set],
-                                  h->c_host[set], h->c_rows_host[set], st);
-      h->launches += 2;
+      cudaError_t e = bd::launch_compact_done(h->h_term, h->h_trunc, 0, h->cfg.n_envs, 1, h->c_blockcnt, h->c_total, h->h_tobs,
+                                              row_floats, h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
+      h->launches += 3;
       if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
       BD_CUDA(cudaStreamSynchronize(st));
     }

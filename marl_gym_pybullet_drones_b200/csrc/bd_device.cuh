@@ -370,8 +370,8 @@ namespace bd {
 // substep-start positions of the group's other drones arrive by warp shuffle (Jacobi snapshot,
 // no shared memory, no barrier); the body-z force enters as F R[:,2] / m.
 // MODE 0: plain DYN.  MODE 1: + downwash only.  MODE 2: any combination of ground effect / drag / downwash, chosen
-// at run time by P.aero (warp-uniform).  `G` = lane-group size of an env (M rounded up to a power of two; lanes with
-// drone index >= M are idle and never contribute to another drone's downwash).  `last_sum` = sum over the motors of
+// at run time by P.aero (warp-uniform).  An env is M consecutive lanes starting at `group_base` (a warp holds 32 / M whole
+// envs; left-over lanes idle); `drone` = lane - group_base.  `last_sum` = sum over the motors of
 // fl32(1 + 0.05 a) of the PREVIOUS control step (0 right after a reset): the drag model reads last_clipped_action,
 // which during the first substep is still the previous step's (BaseAviary.py:359,372).
 //   ground effect (:739-742): f_k <- f_k (1 + c_k), c_k = GND (r_prop / 4 h_k)^2, h_k = max(z + R20 x_k + R21 y_k, clip);
@@ -380,7 +380,7 @@ namespace bd {
 //   drag (:773-774): F_world += k (.) v, k = -DRAG sum_k 2 pi rpm_k / 60, v = velocity at the start of the substep
 template <int MODE>
 __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<float>& d, const float onep[4],
-                                              float& avx, float& avy, float& avz, int lane = 0, int G = 1,
+                                              float& avx, float& avy, float& avz, int group_base = 0, int drone = 0,
                                               float last_sum = 0.f) {
   const float dt = P.dt;
   float u[4];
@@ -445,12 +445,13 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
     }
     if constexpr (MODE != 0) {
       if (dw) {
-        const int M = P.M, base = lane & ~(G - 1);
+        const int M = P.M;
         float fdw = 0.f;
-#pragma unroll 1
-        for (int o = 1; o < G; ++o) {
-          const int od = (lane + o) & (G - 1);
-          const int src = base | od;
+#pragma unroll 4
+        for (int o = 1; o < M; ++o) {
+          int t = drone + o;
+          t -= (t >= M) ? M : 0;
+          const int src = group_base + t;
           const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
                       oz = __shfl_sync(0xffffffffu, d.pz, src);
           const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
@@ -460,7 +461,7 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
           const float beta = fmaf(P.dw2, dz, P.dw3);
           const float q2 = __fdividef(dxy2, beta * beta);
           const float f = -alpha * __expf(-0.5f * q2);
-          if (od < M && dz > 0.f && dxy2 < 100.f) fdw += f;       // :801 (delta_xy < 10); padding lanes carry no drone
+          if (dz > 0.f && dxy2 < 100.f) fdw += f;                 // :801 (delta_xy < 10)
         }
         const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
         c1s += k;

@@ -744,51 +744,44 @@ cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaSt
 }
 
 // ---- compact terminal observations (subproc_vec_env.py:195-206: only finished envs carry one) ----------
-// Envs are scanned in blocks of kCompactBlock; pass 1 counts the finished envs per block, pass 2 turns the counts
-// into offsets (every block sums the counts before it), scans its own flags and copies the finished envs'
-// (M,D) rows — in ascending env order, so the result is deterministic — to `rows_out` (at most `cap` envs) and
-// their indices to `idx_out[1..]`; idx_out[0] = total count.  The outputs may live in mapped pinned host memory.
+// Works on an env range [e0, e1) (one chunk of bd_step_host's pipeline, so the compaction of chunk k hides behind the
+// device->host copy of its observations): pass 1 counts the finished envs per block of kCompactBlock envs, pass 2 turns
+// the counts into offsets (running total of the earlier chunks in *total + the counts of the blocks before it), scans
+// its own flags and copies the finished envs' (M,D) rows — in ascending env order, so the result is deterministic — to
+// `rows_out` (at most `cap` envs) and their indices to `idx_out[1..]`; pass 3 adds the chunk's count to *total and
+// mirrors it to idx_out[0].  The outputs may live in mapped pinned host memory.
 constexpr int kCompactBlock = 1024;
 __global__ void __launch_bounds__(kCompactBlock)
-count_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int n, int* __restrict__ blockcnt) {
-  const int e = blockIdx.x * kCompactBlock + threadIdx.x;
-  const int done = (e < n) && (term[e] | trunc[e]);
+count_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int e0, int e1, int* __restrict__ blockcnt) {
+  const int e = e0 + blockIdx.x * kCompactBlock + threadIdx.x;
+  const int done = (e < e1) && (term[e] | trunc[e]);
   const int c = __syncthreads_count(done);
   if (threadIdx.x == 0) blockcnt[blockIdx.x] = c;
 }
 __global__ void __launch_bounds__(kCompactBlock)
-gather_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int n, const int* __restrict__ blockcnt,
-                   const float* __restrict__ tobs, int row_floats, int cap, int* __restrict__ idx_out,
-                   float* __restrict__ rows_out) {
+gather_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int e0, int e1,
+                   const int* __restrict__ blockcnt, const int* __restrict__ total, const float* __restrict__ tobs,
+                   int row_floats, int cap, int* __restrict__ idx_out, float* __restrict__ rows_out) {
   __shared__ int s_warp[kCompactBlock / 32];
-  __shared__ int s_base, s_total;
+  __shared__ int s_base;
   __shared__ int s_list[kCompactBlock];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // offset of this block = sum of the counts before it; grand total for block 0's header write
-  int before = 0, total = 0;
-  for (int b = tid; b < (int)gridDim.x; b += kCompactBlock) {
-    const int c = blockcnt[b];
-    total += c;
-    if (b < (int)blockIdx.x) before += c;
-  }
-  for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
-  if (tid == 0) { s_base = 0; s_total = 0; }
+  int before = 0;
+  for (int b = tid; b < (int)blockIdx.x; b += kCompactBlock) before += blockcnt[b];
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (tid == 0) s_base = *total;
   __syncthreads();
-  if (lane == 0) { atomicAdd(&s_base, before); atomicAdd(&s_total, total); }
-  __syncthreads();
-  const int e = blockIdx.x * kCompactBlock + tid;
-  const int done = (e < n) && (term[e] | trunc[e]);
+  if (lane == 0 && before != 0) atomicAdd(&s_base, before);
+  const int e = e0 + blockIdx.x * kCompactBlock + tid;
+  const int done = (e < e1) && (term[e] | trunc[e]);
   const unsigned bal = __ballot_sync(0xffffffffu, done);
   if (lane == 0) s_warp[warp] = __popc(bal);
   __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_warp[w];
-  int mine = 0;
-  for (int w = 0; w < kCompactBlock / 32; ++w) mine += s_warp[w];
+  int woff = 0, mine = 0;
+  for (int w = 0; w < kCompactBlock / 32; ++w) { if (w < warp) woff += s_warp[w]; mine += s_warp[w]; }
   const int pos = woff + __popc(bal & ((1u << lane) - 1u));
   if (done) s_list[pos] = e;
   __syncthreads();
-  if (blockIdx.x == 0 && tid == 0) idx_out[0] = s_total;
   const int base = s_base;
   for (int k = tid; k < mine; k += kCompactBlock)
     if (base + k < cap) idx_out[1 + base + k] = s_list[k];
@@ -805,12 +798,31 @@ gather_done_kernel(const uint8_t* __restrict__ term, const uint8_t* __restrict__
     }
   }
 }
+__global__ void compact_total_kernel(const int* __restrict__ blockcnt, int blocks, int* __restrict__ total, int* __restrict__ idx_out,
+                                     int reset_first) {
+  int c = 0;
+  for (int b = threadIdx.x; b < blocks; b += 32) c += blockcnt[b];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (threadIdx.x == 0) {
+    const int t = (reset_first ? 0 : *total) + c;
+    *total = t;
+    idx_out[0] = t;
+  }
+}
 int compact_blocks(int n) { return (n + kCompactBlock - 1) / kCompactBlock; }
-cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int n, int* blockcnt, const float* tobs,
-                                int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st) {
-  const int blocks = compact_blocks(n);
-  count_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, n, blockcnt);
-  gather_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, n, blockcnt, tobs, row_floats, cap, idx_out, rows_out);
+// reset_total: 1 for the first chunk of a step (the running total restarts at 0)
+cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int e0, int e1, int reset_total, int* blockcnt, int* total,
+                                const float* tobs, int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st) {
+  const int blocks = compact_blocks(e1 - e0);
+  if (reset_total) {
+    cudaError_t e = cudaMemsetAsync(total, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (blocks > 0) {
+    count_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, e0, e1, blockcnt);
+    gather_done_kernel<<<blocks, kCompactBlock, 0, st>>>(term, trunc, e0, e1, blockcnt, total, tobs, row_floats, cap, idx_out, rows_out);
+  }
+  compact_total_kernel<<<1, 32, 0, st>>>(blockcnt, blocks, total, idx_out, 0);
   return cudaGetLastError();
 }
 

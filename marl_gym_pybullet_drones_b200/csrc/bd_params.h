@@ -26,7 +26,7 @@ template <> struct V4<double> { using type = double4; };
 template <typename Real>
 struct Params {
   int N, M, S, A, B, D, E;
-  int G;                          // fast tile kernel: lanes per env (M rounded up to a power of two)
+  int EW;                         // fast tile kernel: whole envs per warp (32 / M)
   long long n_total;
   typename V4<Real>::type *s0, *s1, *s2, *s3, *s4;
   float* hist;
@@ -100,8 +100,8 @@ cudaError_t launch_ctrl_state(int precision, const void* params, void* dst, cons
 cudaError_t launch_episode_stats(double* ep_acc, double* out3, int reset, cudaStream_t st);
 size_t step_smem_bytes(int precision, int A, int B, int D, int task);
 int compact_blocks(int n);
-cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int n, int* blockcnt, const float* tobs,
-                                int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st);
+cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int e0, int e1, int reset_total, int* blockcnt, int* total,
+                                const float* tobs, int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st);
 cudaError_t launch_set_epoch(int* tile_epoch, int tile, int value, cudaStream_t st);
 
 }  // namespace bd

@@ -1,5 +1,5 @@
 // Fast step kernel (float, DYN with optional ground effect / drag / downwash, M <= 32): one CTA per tile of up to 128 drones
-// (an env is a lane group of G = M rounded up to a power of two lanes).
+// (a warp holds 32 / M whole envs on consecutive lanes).
 //
 // Measured facts that shape it (scripts/microbench/*.cu, profiles/README.md):
 //   * observation rows must leave the SM as complete, contiguous rows: 16-byte or
@@ -143,27 +143,28 @@ __device__ __forceinline__ float swarm_reward_shfl(const Params<float>& P, const
 }
 
 // AERO: 0 plain DYN, 1 downwash only, 2 any aero combination (run-time P.aero) — see fast_substeps.
-// An env is a lane group of G = P.G lanes (M rounded up to a power of two): M == G for the power-of-two team sizes,
-// else the lanes with drone index >= M idle (M = 5 -> 8 lanes, 62 % of the threads work; the memory traffic, which is
-// what bounds the kernel, is unchanged).  A tile = 128 / G whole envs = (128 / G) * M observation rows.
+// Lane packing: a warp holds EW = 32 / M whole envs on its first EW * M lanes (an env = M consecutive lanes), the
+// left-over lanes idle: nothing for the power-of-two team sizes, 2 of 32 lanes for M = 3 or 5 (a first version padded
+// every env to a power-of-two lane group and left 3 of 8 lanes idle at M = 5).  A tile = 4 EW envs = 4 EW M rows.
 template <int TASK, int A, bool VEC, int AERO>
 __global__ void __launch_bounds__(kBlock, 6)
 step_kernel_tile(const __grid_constant__ Params<float> P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int M = P.M, B = P.B, D = P.D, G = P.G;
-  const int log2g = 31 - __clz(G);
+  const int M = P.M, B = P.B, D = P.D, EW = P.EW;
+  const bool pow2 = (M & (M - 1)) == 0;
   constexpr bool vec = VEC;   // A == 4 and D % 4 == 0: 128-bit row accesses
   float* tile_s = reinterpret_cast<float*>(smem_raw);   // [tile rows][D] row-major, dense
-  const int drone = lane & (G - 1);
-  const int group_base = lane & ~(G - 1);
+  const int env_w = pow2 ? (lane >> (31 - __clz(M))) : lane / M;    // env within the warp
+  const int group_base = env_w * M;
+  const int drone = lane - group_base;
   const int tile = blockIdx.x + P.block0;               // block0 > 0: sub-range launch (bd_step_host chunks)
-  const int env_l = tid >> log2g;
-  const int env = tile * (kBlock >> log2g) + env_l;
-  const bool active = drone < M && env < P.N;
-  const long long g0 = (long long)tile * (kBlock >> log2g) * M;
+  const int env_l = (tid >> 5) * EW + env_w;
+  const int env = tile * (4 * EW) + env_l;
+  const bool active = env_w < EW && env < P.N;
+  const long long g0 = (long long)tile * (4 * EW) * M;
   const long long g = (long long)env * M + drone;       // meaningful for active lanes only
-  float* myrow = tile_s + (size_t)(env_l * M + (drone < M ? drone : 0)) * D;   // idle lanes alias a live row, never write
+  float* myrow = tile_s + (size_t)(env_w < EW ? env_l * M + drone : 0) * D;   // idle lanes alias a live row, never write
   const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
   const long long gh = active ? g : P.n_total;          // idle lanes issue no history copies
 
@@ -240,7 +241,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
 
   // ---- 2. S substeps in registers while the history lands --------------------------------------
   float avx = 0.f, avy = 0.f, avz = 0.f;
-  fast_substeps<AERO>(P, d, onep, avx, avy, avz, lane, G, last_sum);
+  fast_substeps<AERO>(P, d, onep, avx, avy, avz, group_base, drone, last_sum);
   float roll, pitch, yaw;
   quat_to_euler_fast(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
 
@@ -278,10 +279,22 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
     flags = active ? fl : 0;
   }
   // ---- per-env reduction with shuffles (envs are lane groups of M) --------------------------------
+  if (pow2) {
 #pragma unroll 1
-  for (int o = G >> 1; o > 0; o >>= 1) {
-    contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+    for (int o = M >> 1; o > 0; o >>= 1) {
+      contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+    }
+  } else {        // team sizes that are not a power of two: every lane gathers its M - 1 partners
+    const float c0 = contrib;
+    const int f0 = flags;
+#pragma unroll 1
+    for (int o = 1; o < M; ++o) {
+      int t = drone + o;
+      t -= (t >= M) ? M : 0;
+      contrib += __shfl_sync(0xffffffffu, c0, group_base + t);
+      flags |= __shfl_sync(0xffffffffu, f0, group_base + t);
+    }
   }
   const float reward = (TASK == TASK_SWARM) ? swarm_reward_env : ((TASK == TASK_HOVER) ? contrib : contrib / (float)M);
   const bool time_up = stepc >= P.trunc_counter;   // step_counter/PYB_FREQ > EPISODE_LEN_SEC, pre-increment (:379,:382)
@@ -338,16 +351,24 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
         }
         int bad = 0;
 #pragma unroll 1
-        for (int o = 1; o < G; ++o) {
-          const int od = (lane + o) & (G - 1);
-          const int src = group_base | od;
+        for (int o = 1; o < M; ++o) {
+          int t = drone + o;
+          t -= (t >= M) ? M : 0;
+          const int src = group_base + t;
           const float ox = __shfl_sync(0xffffffffu, cx, src), oy = __shfl_sync(0xffffffffu, cy, src),
                       oz = __shfl_sync(0xffffffffu, cz, src);
           const float dx = cx - ox, dy = cy - oy, dz = cz - oz;
-          bad |= (od < M && drone < M && sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
+          bad |= (sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
         }
+        {   // any drone of the env too close -> the whole env redraws
+          const int b0 = bad;
 #pragma unroll 1
-        for (int o = G >> 1; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+          for (int o = 1; o < M; ++o) {
+            int t = drone + o;
+            t -= (t >= M) ? M : 0;
+            bad |= __shfl_sync(0xffffffffu, b0, group_base + t);
+          }
+        }
         if (last || P.reset_mode == RESET_BUFFER) bad = 0;
         retry = retry && (bad != 0);
         if (!__any_sync(0xffffffffu, retry)) break;
@@ -373,7 +394,7 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
 
   // ---- 4. the finished rows leave as one TMA bulk store; state planes as 128-bit stores ------------
   const long long left = P.n_total - g0;
-  const int tile_rows = (kBlock >> log2g) * M;
+  const int tile_rows = 4 * EW * M;
   const int rows = (int)(left < (long long)tile_rows ? left : (long long)tile_rows);
   const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
   float* gobs = P.obs + (size_t)g0 * D;

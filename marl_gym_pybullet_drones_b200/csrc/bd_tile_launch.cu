@@ -12,7 +12,7 @@ namespace bd {
 
 template <int TASK, int A>
 static cudaError_t launch_step_tile_t(const Params<float>& P, const LaunchSpec& ls, cudaStream_t st) {
-  const int envs_per_tile = kBlock / P.G;
+  const int envs_per_tile = 4 * P.EW;
   const size_t smem = (size_t)envs_per_tile * P.M * P.D * 4;   // the [tile rows][D] observation tile and nothing else
   const bool vecrow = (A == 4) && (P.D % 4 == 0);
   const int aero = P.aero == 0 ? 0 : (P.aero == AERO_DW ? 1 : 2);

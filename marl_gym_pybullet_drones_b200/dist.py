@@ -54,3 +54,26 @@ def reduce_episode_stats(return_sum: torch.Tensor, length_sum: torch.Tensor, epi
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
     n = packed[2].clamp_min(1.0)
     return (packed[0] / n).item(), (packed[1] / n).item(), int(packed[2].item())
+
+
+def bind_host_thread_to_gpu(local_rank: int):
+    """Pin the calling thread to the CPUs NVML reports as closest to GPU `local_rank` (its NUMA node), so that the
+    page-locked buffers this rank allocates afterwards are first-touched on that node and its copies do not cross
+    the socket interconnect.  Returns the resulting CPU set, or None when NVML is unavailable or the container's
+    cpuset does not contain those CPUs (then nothing changes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return sorted(after)
+    except Exception:
+        return None
+

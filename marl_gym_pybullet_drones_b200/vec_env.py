@@ -145,7 +145,10 @@ class BatchVecEnv:
         dones = np.logical_or(term, trunc)
         S = b.PYB_STEPS_PER_CTRL
         steps_before = self._steps
-        if b.auto_reset:
+        track = b.task == "spiral"          # only the Spiral info dict reports the step counter ("time")
+        if not track:
+            idx, rows = (res["done_idx"], res["terminal_rows"]) if b.auto_reset else (None, None)
+        elif b.auto_reset:
             # compact terminal rows: handle-owned page-locked memory, two sets used alternately, so — like the
             # observations — they stay valid until the next-but-one step; a dict built from them copies its row
             idx, rows = res["done_idx"], res["terminal_rows"]
