@@ -90,9 +90,13 @@ struct bd_handle {
   // compact terminal observations (bd_step_host_compact): pinned, device-mapped staging owned by the handle
   int* c_blockcnt = nullptr;   // [blocks of 1024 envs] done envs per block
   int* c_total = nullptr;      // running count of finished envs over the chunks of one step
-  // two sets, used alternately: what a call returns stays valid until the next-but-one step
-  int* c_host[2] = {nullptr, nullptr};         // pinned+mapped: [0] = count, [1..N] = done env indices (ascending)
-  float* c_rows_host[2] = {nullptr, nullptr};  // pinned+mapped: [cap][M][D] terminal observation rows, same order
+  int* c_idx_dev = nullptr;    // device: [0] = count, [1..N] = done env indices (ascending)
+  float* c_rows_dev = nullptr; // device: [cap][M][D] terminal observation rows, same order
+  int c_cap_dev = 0;
+  cudaEvent_t hs_compact = nullptr;
+  // host side: two page-locked sets, used alternately: what a call returns stays valid until the next-but-one step
+  int* c_host[2] = {nullptr, nullptr};
+  float* c_rows_host[2] = {nullptr, nullptr};
   int c_cap[2] = {0, 0};
   int c_flip = 0;
   bd::Params<float> pf{};
@@ -250,6 +254,9 @@ void free_all(bd_handle* h) {
   cudaFree(h->jitter);
   cudaFree(h->c_blockcnt);
   cudaFree(h->c_total);
+  cudaFree(h->c_idx_dev);
+  cudaFree(h->c_rows_dev);
+  if (h->hs_compact) cudaEventDestroy(h->hs_compact);
   for (int i = 0; i < 2; ++i) { if (h->c_host[i]) cudaFreeHost(h->c_host[i]); if (h->c_rows_host[i]) cudaFreeHost(h->c_rows_host[i]); }
   cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_term);
   cudaFree(h->h_trunc); cudaFree(h->h_tobs);
@@ -496,20 +503,29 @@ int bd_step(bd_handle* h, const void* actions_dev, float* obs_dev, void* reward_
 
 namespace {
 int ensure_compact_buffers(bd_handle* h, int set, int cap) {
+  const size_t row_bytes = (size_t)h->cfg.n_drones * h->D * sizeof(float);
   if (!h->c_blockcnt) BD_CUDA(cudaMalloc((void**)&h->c_blockcnt, (size_t)bd::compact_blocks(h->cfg.n_envs) * sizeof(int)));
   if (!h->c_total) BD_CUDA(cudaMalloc((void**)&h->c_total, sizeof(int)));
+  if (!h->c_idx_dev) BD_CUDA(cudaMalloc((void**)&h->c_idx_dev, ((size_t)h->cfg.n_envs + 1) * sizeof(int)));
+  if (!h->hs_compact) BD_CUDA(cudaEventCreateWithFlags(&h->hs_compact, cudaEventDisableTiming));
+  if (cap > h->c_cap_dev) {
+    if (h->c_rows_dev) { BD_CUDA(cudaDeviceSynchronize()); cudaFree(h->c_rows_dev); h->c_rows_dev = nullptr; h->c_cap_dev = 0; }
+    BD_CUDA(cudaMalloc((void**)&h->c_rows_dev, (size_t)cap * row_bytes));
+    h->c_cap_dev = cap;
+  }
   if (!h->c_host[set])
-    BD_CUDA(cudaHostAlloc((void**)&h->c_host[set], ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocMapped));
+    BD_CUDA(cudaHostAlloc((void**)&h->c_host[set], ((size_t)h->cfg.n_envs + 1) * sizeof(int), cudaHostAllocDefault));
   if (cap > h->c_cap[set]) {
     if (h->c_rows_host[set]) { cudaFreeHost(h->c_rows_host[set]); h->c_rows_host[set] = nullptr; h->c_cap[set] = 0; }
-    BD_CUDA(cudaHostAlloc((void**)&h->c_rows_host[set], (size_t)cap * h->cfg.n_drones * h->D * sizeof(float),
-                          cudaHostAllocMapped));
+    BD_CUDA(cudaHostAlloc((void**)&h->c_rows_host[set], (size_t)cap * row_bytes, cudaHostAllocDefault));
     h->c_cap[set] = cap;
   }
   return BD_OK;
 }
 // compact = true: terminal observations stay in the device-side (N,M,D) buffer; after the step the finished envs'
-// rows are gathered (ascending env order) straight into the handle's mapped pinned buffers.
+// rows are gathered (ascending env order) into a compact device buffer by small kernels that run inside the chunk
+// pipeline; after the flags have arrived the host copies exactly n_done rows (GPU stores straight into mapped host
+// memory were tried first: 16-byte PCIe writes, 2 ms for 3 MB).
 int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void* reward_host,
                    uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host, bool compact,
                    void* stream);
@@ -570,7 +586,8 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   if (compact) {
     h->c_flip ^= 1;
     const int set = h->c_flip;
-    int rc = ensure_compact_buffers(h, set, h->c_cap[set] > 0 ? h->c_cap[set] : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256));
+    int want = h->c_cap_dev > 0 ? h->c_cap_dev : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256);
+    int rc = ensure_compact_buffers(h, set, want);
     if (rc) return rc;
   }
   // Pipeline over chunks of whole tiles: while the copy engine drains chunk k's observations to the host,
@@ -589,8 +606,9 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
     if (compact) {
       const int set = h->c_flip;
       cudaError_t ce = bd::launch_compact_done(h->h_term, h->h_trunc, 0, h->cfg.n_envs, 1, h->c_blockcnt, h->c_total, h->h_tobs,
-                                               h->cfg.n_drones * h->D, h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
+                                               h->cfg.n_drones * h->D, h->c_cap_dev, h->c_idx_dev, h->c_rows_dev, st);
       h->launches += 3;
+      (void)set;
       if (ce != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(ce));
     }
     BD_CUDA(cudaMemcpyAsync(obs_host, h->h_obs, obs_bytes, cudaMemcpyDeviceToHost, st));
@@ -638,19 +656,18 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
         break;
       }
       h->launches++;
-      if (compact) {   // this chunk's finished envs are gathered while its observations travel
+      BD_CUDA(cudaEventRecord(h->hs_chunk[c], h->hs_a));
+      BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_chunk[c], 0));
+      if (compact) {   // this chunk's finished envs are gathered (device to device) while its observations travel
         const int env_per_block = block_rows / h->cfg.n_drones;
         const int e0 = b0 * env_per_block;
         int e1 = b1 * env_per_block;
         if (e1 > h->cfg.n_envs) e1 = h->cfg.n_envs;
-        const int set = h->c_flip;
         cudaError_t ce = bd::launch_compact_done(h->h_term, h->h_trunc, e0, e1, c == 0 ? 1 : 0, h->c_blockcnt, h->c_total, h->h_tobs,
-                                                 h->cfg.n_drones * h->D, h->c_cap[set], h->c_host[set], h->c_rows_host[set], h->hs_a);
+                                                 h->cfg.n_drones * h->D, h->c_cap_dev, h->c_idx_dev, h->c_rows_dev, h->hs_a);
         h->launches += 3;
         if (ce != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(ce));
       }
-      BD_CUDA(cudaEventRecord(h->hs_chunk[c], h->hs_a));
-      BD_CUDA(cudaStreamWaitEvent(h->hs_b, h->hs_chunk[c], 0));
       BD_CUDA(cudaMemcpyAsync((char*)obs_host + g0 * obs_row, (const char*)h->h_obs + g0 * obs_row, rows * obs_row,
                               cudaMemcpyDeviceToHost, h->hs_b));
       if (terminal_obs_host)
@@ -670,6 +687,10 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
     }
     BD_CUDA(cudaEventRecord(h->hs_done, h->hs_b));   // hs_b has waited for every chunk of hs_a
     BD_CUDA(cudaStreamWaitEvent(st, h->hs_done, 0));
+    if (compact) {                                   // ... but not for the compaction kernels behind the last chunk
+      BD_CUDA(cudaEventRecord(h->hs_compact, h->hs_a));
+      BD_CUDA(cudaStreamWaitEvent(st, h->hs_compact, 0));
+    }
   }
   BD_CUDA(cudaMemcpyAsync(reward_host, h->h_reward, n * h->real, cudaMemcpyDeviceToHost, st));
   BD_CUDA(cudaMemcpyAsync(terminated_host, h->h_term, n, cudaMemcpyDeviceToHost, st));
@@ -677,14 +698,25 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   if (compact) {
     const int row_floats = h->cfg.n_drones * h->D;
     const int set = h->c_flip;
+    // the count travels with the flags; then exactly n_done indices and rows
+    BD_CUDA(cudaMemcpyAsync(h->c_host[set], h->c_idx_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     BD_CUDA(cudaStreamSynchronize(st));
-    if (h->c_host[set][0] > h->c_cap[set]) {   // more finished envs than the staging holds: grow it and gather again (rare)
-      int rc = ensure_compact_buffers(h, set, h->c_host[set][0] + h->c_host[set][0] / 4);
+    int cnt = h->c_host[set][0];
+    if (cnt > h->c_cap_dev) {   // more finished envs than the staging holds: grow it and gather again (rare)
+      int rc = ensure_compact_buffers(h, set, cnt + cnt / 4);
       if (rc) return rc;
       cudaError_t e = bd::launch_compact_done(h->h_term, h->h_trunc, 0, h->cfg.n_envs, 1, h->c_blockcnt, h->c_total, h->h_tobs,
-                                              row_floats, h->c_cap[set], h->c_host[set], h->c_rows_host[set], st);
+                                              row_floats, h->c_cap_dev, h->c_idx_dev, h->c_rows_dev, st);
       h->launches += 3;
       if (e != cudaSuccess) return fail(BD_ECUDA, "compaction kernels failed to launch: %s", cudaGetErrorString(e));
+    }
+    if (cnt > h->c_cap[set]) {
+      int rc = ensure_compact_buffers(h, set, cnt + cnt / 4);
+      if (rc) return rc;
+    }
+    if (cnt > 0) {
+      BD_CUDA(cudaMemcpyAsync(h->c_host[set] + 1, h->c_idx_dev + 1, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+      BD_CUDA(cudaMemcpyAsync(h->c_rows_host[set], h->c_rows_dev, (size_t)cnt * row_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
       BD_CUDA(cudaStreamSynchronize(st));
     }
     return BD_OK;
