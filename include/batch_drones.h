@@ -313,6 +313,13 @@ int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream);
 int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev,
                    int64_t rows, const float* nmean_dev, const float* nrstd_dev, float nclip, float* out_dev,
                    void* stream);
+/* rollout-time policy step of an actor net (MAPPOActorCritic.step, mappo/agent.py:389-415) in ONE launch:
+ * obs_dev (n_envs, n_agents, D) = one slot -> act_dev (rows, out_dim) = mean + exp(logstd) eps, logp_dev (rows) = summed
+ * Gaussian log-density, optional mean_dev; rows = n_envs * n_agents.  eps = noise_dev (rows, out_dim) standard normals, or
+ * NULL: Philox4x32-10(seed; row, offset).  nmean / nrstd: that slot's (n_agents * D) statistics or NULL. */
+int bd_ppo_sample(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const float* nmean_dev,
+                  const float* nrstd_dev, float nclip, const float* noise_dev, uint64_t seed, uint64_t offset,
+                  float* act_dev, float* logp_dev, float* mean_dev, void* stream);
 /* one minibatch: forward, PPO clipped-ratio loss (actor: act, logp_old (slots,N,M[,A]), adv (slots,N) with
  * adv_stats = (mean, scale)) or value loss (critic: ret, optional v_old (slots,N)), backward, weight
  * gradients -> grad_dev (flat, parameter order) = mean over rows_global rows (0 = this call's rows);
@@ -334,6 +341,9 @@ int bd_ppo_gae(const float* rew_dev, const uint8_t* term_dev, const uint8_t* tru
                int N, float gamma, float lam, int use_gae, float* ret_dev, float* adv_dev, double* acc3_dev,
                void* stream);
 int bd_ppo_adv_stats(const double* acc3_dev, float* stats2_dev, void* stream);
+/* diagnostics: CTA 0 of the following forward / sample launches writes SM-clock stamps of its pipeline phases
+ * ([tile pair][64] int64, see csrc/bd_ppo.cu); NULL switches tracing off */
+int bd_ppo_set_trace(bd_ppo_net* n, long long* trace_dev);
 int64_t bd_ppo_launch_count(const bd_ppo_net* n);
 const char* bd_ppo_last_error(void);
 

@@ -130,6 +130,7 @@ struct NetDev {
   int C, D, K1p, out_dim;
 };
 
+
 enum { MODE_ACTOR_TRAIN = 0, MODE_CRITIC_TRAIN = 1, MODE_FORWARD = 2 };
 
 struct TileArgs {
@@ -203,7 +204,6 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
                  aRing = smem_u32(ring);
   const long long n_tiles = (P.rows + kRows - 1) / kRows;
   const int k1_steps = K1p / 16;
-  const int slabs_per_tile = C * k1_steps + 16 + (train ? 17 : 0);
   const uint32_t xbuf_bytes = (uint32_t)kRows * 96 * 2;
 
   if (warp == kEpiThreads / 32 + 1) {
@@ -211,34 +211,48 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
     if (lane == 0) {
       mbar_expect_tx(bar(B_W3), (uint32_t)(kNOut * HID * 2));
       bulk_g2s(aW3, W.w3f, (uint32_t)(kNOut * HID * 2), bar(B_W3));
-      unsigned long long cnt = 0;
+      // (replicating the slabs 8x in global memory, one copy per CTA modulo 8, changed nothing: the slab supply is not
+      // an L2 hot-spot problem but the ring's round trip — measured, round 2, scripts/microbench/umma_rate.cu)
+      uint32_t st = 0, epar = 1, lap0 = 1;   // first lap: the stages are free
+      auto push = [&](const bf16* src) {
+        if (!lap0) mbar_wait(bar(B_EMPTY + (int)st), epar);
+        mbar_expect_tx(bar(B_FULL + (int)st), kSlabBytes);
+        bulk_g2s(aRing + st * kSlabBytes, src, kSlabBytes, bar(B_FULL + (int)st));
+        if (++st == (uint32_t)kStages) { st = 0; epar ^= 1; lap0 = 0; }
+      };
+      const int n1 = C * k1_steps;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int q = 0; q < slabs_per_tile; ++q, ++cnt) {
-          const int st = (int)(cnt % kStages);
-          const uint32_t par = (uint32_t)((cnt / kStages) & 1);
-          if (cnt >= kStages) mbar_wait(bar(B_EMPTY + st), par ^ 1);
-          const bf16* src;
-          const int n1 = C * k1_steps;
-          if (q < n1) src = W.w1_slabs + (size_t)q * (kSlabBytes / 2);
-          else if (q < n1 + 16) src = W.w2f_slabs + (size_t)(q - n1) * (kSlabBytes / 2);
-          else if (q == n1 + 16) src = W.w3b_slab;
-          else src = W.w2b_slabs + (size_t)(q - n1 - 17) * (kSlabBytes / 2);
-          mbar_expect_tx(bar(B_FULL + st), kSlabBytes);
-          bulk_g2s(aRing + (uint32_t)st * kSlabBytes, src, kSlabBytes, bar(B_FULL + st));
+        for (int q = 0; q < n1; ++q) push(W.w1_slabs + (size_t)q * (kSlabBytes / 2));
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) push(W.w2f_slabs + (size_t)q * (kSlabBytes / 2));
+        if (train) {
+          push(W.w3b_slab);
+#pragma unroll 4
+          for (int q = 0; q < 16; ++q) push(W.w2b_slabs + (size_t)q * (kSlabBytes / 2));
         }
       }
     }
   } else if (warp == kEpiThreads / 32) {
     // ===================================== MMA issuer =============================================
+    // The issuing thread runs alone: every instruction between two tcgen05.mma is latency the tensor pipe waits for
+    // (scripts/microbench/umma_rate.cu: rebuilding both descriptors per K-step costs ~155 cycles per MMA against the 128
+    // the pipe needs).  Descriptors are built once; a K-step adds 16 address units (256 B) to the activation
+    // descriptor and the ring stage's 512 units (8 KB) select the slab.
     if (lane == 0) {
-      unsigned long long cnt = 0, xcnt = 0;
+      unsigned long long xcnt = 0;
       uint32_t tpar = 0;
       const uint32_t sboX = (uint32_t)(K1p / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
-      auto next_slab = [&]() -> uint32_t {
-        const int st = (int)(cnt % kStages);
-        mbar_wait(bar(B_FULL + st), (uint32_t)((cnt / kStages) & 1));
-        ++cnt;
-        return (uint32_t)st;
+      const uint64_t dX0 = umma_desc(aX, 128, sboX), dX1 = umma_desc(aX + xbuf_bytes, 128, sboX), dH1 = umma_desc(aH1, 128, sboH),
+                     dH2 = umma_desc(aH2, 128, sboH), dW3 = umma_desc(aW3, 128, sboH), dZ3 = umma_desc(aZ3, 128, 256),
+                     dRing = umma_desc(aRing, 128, 256);
+      constexpr uint32_t kIdH = umma_idesc(HID), kIdO = umma_idesc(kNOut);
+      uint32_t st = 0, fpar = 0;          // ring stage and the parity of its next FULL completion
+      // one streamed K-step: wait for the slab, issue, hand the stage back when the MMA has read it
+      auto ring_mma = [&](uint32_t acc, uint64_t adesc, uint32_t accumulate) {
+        mbar_wait(bar(B_FULL + (int)st), fpar);
+        umma_bf16(acc, adesc, dRing + (uint64_t)(st * (kSlabBytes >> 4)), kIdH, accumulate);
+        umma_commit(bar(B_EMPTY + (int)st));
+        if (++st == (uint32_t)kStages) { st = 0; fpar ^= 1; }
       };
       mbar_wait(bar(B_W3), 0);
       bool first = true;
@@ -251,36 +265,29 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           const int xb = (int)(xcnt & 1);
           mbar_wait(bar(B_XFULL + xb), (uint32_t)((xcnt >> 1) & 1));
           tc_fence_after();
-          for (int s = 0; s < k1_steps; ++s) {
-            const uint32_t st = next_slab();
-            umma_bf16(acc0, umma_desc(aX + (uint32_t)xb * xbuf_bytes + s * 256, 128, sboX),
-                      umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID), (c | s) != 0);
-            umma_commit(bar(B_EMPTY + st));
-          }
+          const uint64_t dX = xb ? dX1 : dX0;
+          for (int s = 0; s < k1_steps; ++s) ring_mma(acc0, dX + (uint64_t)(16 * s), (uint32_t)((c | s) != 0));
           umma_commit(bar(B_XEMPTY + xb));
         }
         umma_commit(bar(B_L1));
         // ---- layer 2: acc1 = H1 W2^T, K-steps follow the layer-1 epilogue chunk by chunk
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
           mbar_wait(bar(B_H1C + j), tpar);
           tc_fence_after();
-          for (int h = 0; h < 4; ++h) {
-            const int s = h * 4 + j;
-            const uint32_t st = next_slab();
-            umma_bf16(acc1, umma_desc(aH1 + s * 256, 128, sboH), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID),
-                      (j | h) != 0);
-            umma_commit(bar(B_EMPTY + st));
-          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) ring_mma(acc1, dH1 + (uint64_t)(16 * (h * 4 + j)), (uint32_t)((j | h) != 0));
         }
         umma_commit(bar(B_L2));
         // ---- layer 3: acc0[:, 0:16] = H2 W3^T
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
           mbar_wait(bar(B_H2C + j), tpar);
           tc_fence_after();
+#pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const int s = h * 4 + j;
-            umma_bf16(acc0, umma_desc(aH2 + s * 256, 128, sboH), umma_desc(aW3 + s * 256, 128, sboH), umma_idesc(kNOut),
-                      (j | h) != 0);
+            const uint64_t o = (uint64_t)(16 * (h * 4 + j));
+            umma_bf16(acc0, dH2 + o, dW3 + o, kIdO, (uint32_t)((j | h) != 0));
           }
         }
         umma_commit(bar(B_L3));
@@ -288,23 +295,15 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           // ---- dH2 = dZ3 W3 : acc1 = Z3[128 x 16] . slab[256 j x 16 o]^T
           mbar_wait(bar(B_Z3), tpar);
           tc_fence_after();
-          {
-            const uint32_t st = next_slab();
-            umma_bf16(acc1, umma_desc(aZ3, 128, 256), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID), 0);
-            umma_commit(bar(B_EMPTY + st));
-          }
+          ring_mma(acc1, dZ3, 0u);
           umma_commit(bar(B_D2));
           // ---- dH1 = dZ2 W2 : acc0 = dZ2[128 x 256 j] . slab_s[256 i x 16 j]^T over the 16 j-steps
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             mbar_wait(bar(B_Z2C + j), tpar);
             tc_fence_after();
-            for (int h = 0; h < 4; ++h) {
-              const int s = h * 4 + j;
-              const uint32_t st = next_slab();
-              umma_bf16(acc0, umma_desc(aH2 + s * 256, 128, sboH), umma_desc(aRing + st * kSlabBytes, 128, 256), umma_idesc(HID),
-                        (j | h) != 0);
-              umma_commit(bar(B_EMPTY + st));
-            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) ring_mma(acc0, dH2 + (uint64_t)(16 * (h * 4 + j)), (uint32_t)((j | h) != 0));
           }
           umma_commit(bar(B_D1));
         }
@@ -402,10 +401,10 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
         if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          float h[8];
+          float z[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = tanh_fast(__uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e]);
-          const uint4 pk = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+          for (int e = 0; e < 8; ++e) z[e] = __uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e];
+          const uint4 pk = make_uint4(tanh2_bf16(z[0], z[1]), tanh2_bf16(z[2], z[3]), tanh2_bf16(z[4], z[5]), tanh2_bf16(z[6], z[7]));
           const size_t off = canon_off(row, c0 + q * 8, HID);
           *reinterpret_cast<uint4*>(sH + off) = pk;
           if (gH != nullptr) *reinterpret_cast<uint4*>(gH + off) = pk;
@@ -584,6 +583,394 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
+// ---------------------------------------------------------------------------------------------
+//                    forward only, TWO tiles in flight per CTA (rollout actor / critic values)
+// ---------------------------------------------------------------------------------------------
+// The forward chain of one tile is latency-bound: MMA -> TMEM read -> tanh -> shared memory -> next MMA.  Here a CTA
+// works on a PAIR of tiles (slots A, B) in strict alternation — the tensor core runs layer l of tile B while the 512
+// epilogue threads turn tile A's accumulator into the next layer's operand, and vice versa — so both units always have
+// work: 2 x 256 TMEM columns, 2 x 64 KB activation buffers, one input buffer [128 x K1p] per slot (the NEXT tile's input is
+// staged between the hidden-layer epilogues of the current pair, so layer 1 of the next pair starts as soon as the
+// output accumulator has been read), weights through a TMA slab ring (as many 8 KB stages as the rest leaves room for).
+// mode FWD: out (rows, out_dim).  mode SAMPLE (`MAPPOActorCritic.step`, agent.py:389-415): act = mean + exp(logstd) eps,
+// logp = sum_k [-eps_k^2/2 - logstd_k - log(2 pi)/2], eps from `noise` or Philox4x32-10(seed; row, offset).
+constexpr int kF2MaxStages = 8;
+struct Fwd2Args {
+  NetDev net;
+  int sample;                // 0: FWD, 1: SAMPLE
+  int stages;                // ring depth (<= kF2MaxStages)
+  const float* obs;
+  int N, M;
+  const long long* idx;
+  long long rows;
+  int rows_per_sample;       // M: row = (sample, agent) (actor); 1: row = sample, C input chunks (critic)
+  const float *nmean, *nrstd;
+  float nclip;
+  float* out;                // FWD: (rows, out_dim); SAMPLE: actions (rows, out_dim)
+  float* logp;               // SAMPLE: (rows)
+  float* mean_out;           // SAMPLE: optional (rows, out_dim)
+  const float* noise;        // SAMPLE: optional (rows, out_dim) standard normals
+  unsigned long long seed, offset;
+  long long* trace;          // diagnostics: CTA 0 writes [pair][64] SM-clock stamps (0..31 epilogue thread 0, 32..63 MMA thread)
+};
+enum { F_W3 = 0, F_XFULL, F_XEMPTY = F_XFULL + 2, F_L1 = F_XEMPTY + 2, F_L2 = F_L1 + 2, F_L3 = F_L2 + 2, F_H1 = F_L3 + 2,
+       F_H2 = F_H1 + 2, F_OUT = F_H2 + 2, F_FULL = F_OUT + 2, F_EMPTY = F_FULL + kF2MaxStages, F_COUNT = F_EMPTY + kF2MaxStages };
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_fwd2_kernel(const __grid_constant__ Fwd2Args P) {
+  extern __shared__ __align__(128) unsigned char smem_f2[];   // no swizzle anywhere: 128 B is all the operands need
+  const NetDev& W = P.net;
+  const int K1p = W.K1p, C = W.C, D = W.D, stages = P.stages;
+  bf16* const bufT0 = reinterpret_cast<bf16*>(smem_f2);                         // 2 x 64 KB activations
+  bf16* const bufX0 = bufT0 + 2 * (size_t)kRows * HID;                       // 2 x [128 x K1p] inputs
+  const uint32_t xbytes = (uint32_t)kRows * (uint32_t)K1p * 2u;
+  bf16* sW3 = bufX0 + 2 * (size_t)kRows * K1p;
+  unsigned char* ring = reinterpret_cast<unsigned char*>(sW3 + (size_t)kNOut * HID);
+  float* sB1 = reinterpret_cast<float*>(ring + (size_t)stages * kSlabBytes);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;
+  float* sLs = sB3 + kNOut;
+  // barriers and the TMEM base live in the dynamic region too: static shared memory is accounted in whole KB, which
+  // would cost a ring stage
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLs + kNOut);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(mbar + F_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd != nullptr ? W.logstd[tid] : 0.f; }
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[F_W3]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&mbar[F_XFULL + i]), kEpiThreads); mbar_init(smem_u32(&mbar[F_XEMPTY + i]), 1);
+      mbar_init(smem_u32(&mbar[F_L1 + i]), 1); mbar_init(smem_u32(&mbar[F_L2 + i]), 1); mbar_init(smem_u32(&mbar[F_L3 + i]), 1);
+      mbar_init(smem_u32(&mbar[F_H1 + i]), kEpiThreads); mbar_init(smem_u32(&mbar[F_H2 + i]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[F_OUT + i]), kRows);
+    }
+    for (int i = 0; i < kF2MaxStages; ++i) { mbar_init(smem_u32(&mbar[F_FULL + i]), 1); mbar_init(smem_u32(&mbar[F_EMPTY + i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t aT0 = smem_u32(bufT0), aX0 = smem_u32(bufX0), aW3 = smem_u32(sW3), aRing = smem_u32(ring);
+  const uint32_t tbytes = (uint32_t)kRows * HID * 2u;
+  const long long n_tiles = (P.rows + kRows - 1) / kRows;
+  // this CTA's tiles: blockIdx.x, + gridDim.x, ...; position 2j goes to slot 0, 2j + 1 to slot 1
+  const long long my_tiles = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int k1_steps = K1p / 16;
+
+  if (warp == kEpiThreads / 32 + 1) {
+    // ===================================== TMA producer ===========================================
+    if (lane == 0) {
+      mbar_expect_tx(bar(F_W3), (uint32_t)(kNOut * HID * 2));
+      bulk_g2s(aW3, W.w3f, (uint32_t)(kNOut * HID * 2), bar(F_W3));
+      unsigned long long cnt = 0;
+      int st = 0;
+      uint32_t epar = 1;       // parity of the EMPTY completion the next use of stage `st` must see (first lap: none)
+      auto push = [&](const bf16* src) {
+        if (cnt >= (unsigned long long)stages) mbar_wait(bar(F_EMPTY + st), epar);
+        mbar_expect_tx(bar(F_FULL + st), kSlabBytes);
+        bulk_g2s(aRing + (uint32_t)st * kSlabBytes, src, kSlabBytes, bar(F_FULL + st));
+        ++cnt;
+        if (++st == stages) { st = 0; epar ^= 1; }
+      };
+      const bf16 *w1s = W.w1_slabs, *w2fs = W.w2f_slabs;
+      for (long long p = 0; p < my_tiles; p += 2) {
+        const int nt = (p + 1 < my_tiles) ? 2 : 1;
+        for (int t = 0; t < nt; ++t)
+          for (int q = 0; q < C * k1_steps; ++q) push(w1s + (size_t)q * (kSlabBytes / 2));
+        for (int t = 0; t < nt; ++t)
+          for (int q = 0; q < 16; ++q) push(w2fs + (size_t)q * (kSlabBytes / 2));
+      }
+    }
+  } else if (warp == kEpiThreads / 32) {
+    // ===================================== MMA issuer =============================================
+    // (descriptors built once, a K-step adds a constant: see mlp_tile_kernel; the slot loop stays a loop, the K-steps
+    // of a layer are unrolled)
+    if (lane == 0) {
+      uint32_t st = 0, fpar = 0;
+      uint32_t xpar = 0;                 // bit t: parity of slot t's next XFULL completion
+      const uint32_t sboX = (uint32_t)(K1p / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      const uint64_t dX = umma_desc(aX0, 128, sboX), dT = umma_desc(aT0, 128, sboH), dW3 = umma_desc(aW3, 128, sboH),
+                     dRing = umma_desc(aRing, 128, 256);
+      const uint64_t xstep = (uint64_t)(xbytes >> 4), tstep = (uint64_t)(tbytes >> 4);
+      constexpr uint32_t kIdH = umma_idesc(HID), kIdO = umma_idesc(kNOut);
+      auto ring_mma = [&](uint32_t acc, uint64_t adesc, uint32_t accumulate) {
+        mbar_wait(bar(F_FULL + (int)st), fpar);
+        umma_bf16(acc, adesc, dRing + (uint64_t)(st * (kSlabBytes >> 4)), kIdH, accumulate);
+        umma_commit(bar(F_EMPTY + (int)st));
+        if (++st == (uint32_t)stages) { st = 0; fpar ^= 1; }
+      };
+      mbar_wait(bar(F_W3), 0);
+      uint32_t ppar = 0;
+      long long* tr = (P.trace != nullptr && blockIdx.x == 0) ? P.trace + 32 : nullptr;
+      auto stamp = [&](long long p, int id) { if (tr != nullptr && p < 64) tr[(p >> 1) * 64 + id] = clock64(); };
+      for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+        const int nt = (p + 1 < my_tiles) ? 2 : 1;
+        stamp(p, 0);
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 1 of A, then of B
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          if (p > 0) { mbar_wait(bar(F_OUT + t), ppar ^ 1); tc_fence_after(); }   // the slot's previous output has been read
+          stamp(p, 1 + t);
+          const uint64_t dXt = dX + xstep * (uint64_t)t;
+#pragma unroll 1
+          for (int c = 0; c < C; ++c) {
+            mbar_wait(bar(F_XFULL + t), (xpar >> t) & 1u);
+            xpar ^= 1u << t;
+            tc_fence_after();
+            for (int s = 0; s < k1_steps; ++s) ring_mma(acc, dXt + (uint64_t)(16 * s), (uint32_t)((c | s) != 0));
+            umma_commit(bar(F_XEMPTY + t));
+          }
+          umma_commit(bar(F_L1 + t));
+          stamp(p, 3 + t);
+        }
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 2
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait(bar(F_H1 + t), ppar);
+          tc_fence_after();
+          stamp(p, 5 + t);
+          const uint64_t dTt = dT + tstep * (uint64_t)t;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)                     // K-step 4 (i & 3) + (i >> 2): the slabs' issue order (pack_kernel)
+            ring_mma(acc, dTt + (uint64_t)(16 * (4 * (i & 3) + (i >> 2))), (uint32_t)(i != 0));
+          umma_commit(bar(F_L2 + t));
+          stamp(p, 7 + t);
+        }
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 3
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait(bar(F_H2 + t), ppar);
+          tc_fence_after();
+          stamp(p, 9 + t);
+          const uint64_t dTt = dT + tstep * (uint64_t)t;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) umma_bf16(acc, dTt + (uint64_t)(16 * s), dW3 + (uint64_t)(16 * s), kIdO, (uint32_t)(s != 0));
+          umma_commit(bar(F_L3 + t));
+          stamp(p, 11 + t);
+        }
+      }
+    }
+  } else {
+    // ================================ staging + epilogue threads ==================================
+    const int row = tid & (kRows - 1), grp = tid >> 7;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int rps = P.rows_per_sample;
+    const int n_pieces = K1p / 8;
+    const bool vec4 = (D & 3) == 0;
+    float4 xa[kMaxPieces], xb4[kMaxPieces];      // one input chunk in flight (global -> registers -> bf16 tile)
+    uint32_t xe = 0;                             // bit t: parity of the XEMPTY completion slot t's next staging must see
+    uint32_t xused = 0;                          // bit t: slot t's input buffer has been staged before
+
+    auto tile_of = [&](long long pos) { return (long long)blockIdx.x + pos * gridDim.x; };
+    auto sample_of = [&](long long tile) -> long long {
+      const long long r = tile * kRows + row;
+      if (r >= P.rows) return -1;
+      const long long s = r / rps;
+      return P.idx != nullptr ? P.idx[s] : s;
+    };
+    auto load_x = [&](long long tile, int c, long long sm) {
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      const float* src = P.obs + ((size_t)(sm < 0 ? 0 : sm) * P.M + agent) * D;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int k0 = (grp + i * 4) * 8;
+        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < D && sm >= 0) {
+          if (vec4 && k0 + 8 <= D) {
+            xa[i] = __ldg(reinterpret_cast<const float4*>(src + k0));
+            xb4[i] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (k0 + j < D) ? __ldg(src + k0 + j) : 0.0f;
+            xa[i] = make_float4(x[0], x[1], x[2], x[3]);
+            xb4[i] = make_float4(x[4], x[5], x[6], x[7]);
+          }
+        }
+      }
+    };
+    // registers -> (normalise) -> bf16 canonical tile of slot t; waits until the tensor core has consumed the slot's
+    // previous chunk
+    auto stage_x = [&](int t, long long tile, int c, long long sm) {
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      if ((xused >> t) & 1u) { mbar_wait(bar(F_XEMPTY + t), (xe >> t) & 1u); xe ^= 1u << t; }
+      xused |= 1u << t;
+      bf16* dst = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(bufX0) + (size_t)t * xbytes);
+      const bool norm = P.nmean != nullptr && sm >= 0;
+      const size_t nb = norm ? ((size_t)(sm / P.N) * P.M + agent) * D : 0;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int pc = grp + i * 4;
+        if (pc < n_pieces) {
+          float x[8] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w, xb4[i].x, xb4[i].y, xb4[i].z, xb4[i].w};
+          if (norm) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = pc * 8 + j;
+              if (k < D) {
+                const float v = (x[j] - __ldg(P.nmean + nb + k)) * __ldg(P.nrstd + nb + k);
+                x[j] = fminf(fmaxf(v, -P.nclip), P.nclip);
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + canon_off(row, pc * 8, K1p)) =
+              make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        }
+      }
+      proxy_fence();
+      mbar_arrive(bar(F_XFULL + t));
+    };
+    auto epi_hidden = [&](uint32_t acc, const float* bias, bf16* sH, int done_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float z[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = __uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e];
+          *reinterpret_cast<uint4*>(sH + canon_off(row, c0 + q * 8, HID)) =
+              make_uint4(tanh2_bf16(z[0], z[1]), tanh2_bf16(z[2], z[3]), tanh2_bf16(z[4], z[5]), tanh2_bf16(z[6], z[7]));
+        }
+        tmem_wait_ld();
+      }
+      proxy_fence();
+      tc_fence_before();
+      mbar_arrive(bar(done_bar));
+    };
+    auto finish_row = [&](long long r, const uint32_t (&v)[16]) {
+      if (!P.sample) {
+        for (int k = 0; k < W.out_dim; ++k) P.out[(size_t)r * W.out_dim + k] = __uint_as_float(v[k]) + sB3[k];
+        return;
+      }
+      float eps[4] = {0.f, 0.f, 0.f, 0.f};
+      if (P.noise != nullptr) {
+        for (int k = 0; k < W.out_dim; ++k) eps[k] = P.noise[(size_t)r * W.out_dim + k];
+      } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
+        uint32_t c[4] = {(uint32_t)r, (uint32_t)((unsigned long long)r >> 32), (uint32_t)P.offset, (uint32_t)(P.offset >> 32)};
+        philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+        const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.28318530718f * u1, &s0, &c0);
+        __sincosf(6.28318530718f * u3, &s1, &c1);
+        eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+      }
+      float lp = 0.f;
+      for (int k = 0; k < W.out_dim; ++k) {
+        const float m = __uint_as_float(v[k]) + sB3[k];
+        const float ls = sLs[k];
+        P.out[(size_t)r * W.out_dim + k] = fmaf(__expf(ls), eps[k], m);
+        if (P.mean_out != nullptr) P.mean_out[(size_t)r * W.out_dim + k] = m;
+        lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+      }
+      P.logp[r] = lp;
+    };
+
+    // prologue: chunk 0 of both slots' first tiles
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t)
+      if (t < my_tiles) {
+        const long long tile = tile_of(t), sm = sample_of(tile);
+        load_x(tile, 0, sm);
+        stage_x(t, tile, 0, sm);
+      }
+    uint32_t ppar = 0;
+    long long* tr = (P.trace != nullptr && blockIdx.x == 0 && tid == 0) ? P.trace : nullptr;
+    auto stamp = [&](long long p, int id) { if (tr != nullptr && p < 64) tr[(p >> 1) * 64 + id] = clock64(); };
+    for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+      const int nt = (p + 1 < my_tiles) ? 2 : 1;
+      stamp(p, 0);
+      if (C > 1) {
+        // centralised critic: the remaining input chunks of the current tiles, one by one (each waits for the tensor core
+        // to release the slot's input buffer)
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+          const long long tile = tile_of(p + t), sm = sample_of(tile);
+#pragma unroll 1
+          for (int c = 1; c < C; ++c) { load_x(tile, c, sm); stage_x(t, tile, c, sm); }
+        }
+      }
+      // hidden layers: H1 of A while the tensor core runs layer 1 of B, H1 of B during layer 2 of A, ...
+#pragma unroll 1
+      for (int lt = 0; lt < 4; ++lt) {
+        const int layer = lt >> 1, t = lt & 1;
+        if (t >= nt) continue;
+        const bool has_next = layer == 0 && p + t + 2 < my_tiles;
+        const long long ntile = tile_of(p + t + 2);
+        long long nsm = -1;
+        if (has_next) { nsm = sample_of(ntile); load_x(ntile, 0, nsm); }   // in flight during the epilogue below
+        mbar_wait(bar(F_L1 + 2 * layer + t), ppar);
+        tc_fence_after();
+        stamp(p, 1 + 3 * lt);
+        epi_hidden(tmem_base + (uint32_t)t * HID, layer ? sB2 : sB1, bufT0 + (size_t)t * kRows * HID, F_H1 + 2 * layer + t);
+        stamp(p, 2 + 3 * lt);
+        if (has_next) stage_x(t, ntile, 0, nsm);           // layer 1 of this tile is complete: its input buffer is free
+        stamp(p, 3 + 3 * lt);
+      }
+      if (grp == 0) {
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(bar(F_L3 + t), ppar);
+          tc_fence_after();
+          stamp(p, 13 + 2 * t);
+          uint32_t v[16];
+          tmem_ld16_nowait(tmem_base + (uint32_t)t * HID + lane_off, v);
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive(bar(F_OUT + t));                     // the slot's accumulator may be overwritten by the next layer 1
+          const long long r = tile_of(p + t) * kRows + row;
+          if (r < P.rows) finish_row(r, v);
+          stamp(p, 14 + 2 * t);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+// dynamic shared memory of mlp_fwd2_kernel with `stages` ring stages
+size_t fwd2_kernel_smem(int K1p, int stages) {
+  return (size_t)2 * kRows * HID * 2 + (size_t)2 * kRows * K1p * 2 + (size_t)kNOut * HID * 2 + (size_t)stages * kSlabBytes +
+         (size_t)(2 * HID + 2 * kNOut) * 4 + (size_t)F_COUNT * 8 + 16;
+}
+constexpr size_t kF2SmemBudget = 227 * 1024;          // the opt-in maximum (the kernel has no static shared memory)
+int fwd2_stages(int K1p) {
+  int st = kF2MaxStages;
+  while (st > 2 && fwd2_kernel_smem(K1p, st) > kF2SmemBudget) --st;
+  return st;
+}
+
 size_t tile_kernel_smem() {
   return (size_t)2 * kRows * HID * 2 + (size_t)2 * kRows * 96 * 2 + (size_t)kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
          (size_t)kStages * kSlabBytes + (size_t)(2 * HID + 2 * kNOut) * 4;
@@ -678,24 +1065,41 @@ dw_kernel(const __grid_constant__ DwArgs P) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // descriptors and instruction descriptors once (the issuing thread's own instructions are the tensor pipe's idle
+      // time: scripts/microbench/umma_rate.cu); a stage adds kDwStageBytes / 16 address units, the upper 128 output rows
+      // 2048 / 16, a K = 16 step 8192 / 16 (A) or 2 row groups (B)
+      // A: M = j (contiguous in a core-matrix row), K = r.  8-row groups are 4096 B apart, 8-j groups 128 B.
+      // (MN-major descriptors: LBO = K direction, SBO = M / N direction; verified on the B200 against autograd)
+      const uint64_t adesc0 = umma_desc(aS, 4096, 128);
+      uint64_t bdesc0[kDwMaxB], bstep[kDwMaxB];
+      uint32_t idesc[kDwMaxB];
+#pragma unroll
+      for (int b = 0; b < kDwMaxB; ++b) {
+        const uint32_t nb = b < J.n_b ? (uint32_t)J.nB[b] : 16u;
+        const uint32_t rg = (nb / 8u) * 128u;               // bytes between 8-row groups of the B operand
+        bdesc0[b] = umma_desc(aS + (b < J.n_b ? b_off[b] : 0u), rg, 128);
+        bstep[b] = (uint64_t)((2u * rg) >> 4);
+        idesc[b] = umma_idesc((int)nb, 1, 1);
+      }
+      uint32_t st = 0, fpar = 0;
       for (long long h = 0; h < n_half; ++h) {
-        const int st = (int)(h % kDwStages);
-        mbar_wait(bar(DB_FULL + st), (uint32_t)((h / kDwStages) & 1));
+        mbar_wait(bar(DB_FULL + (int)st), fpar);
         tc_fence_after();
-        const uint32_t sbase = aS + (uint32_t)st * kDwStageBytes;
-        for (int b = 0; b < J.n_b; ++b) {
-          const uint32_t rg = (uint32_t)(J.nB[b] / 8) * 128u;   // bytes between 8-row groups of the B operand
-          for (int mh = 0; mh < 2; ++mh) {
-            for (int ks = 0; ks < 4; ++ks) {
-              // A: M = j (contiguous in a core-matrix row), K = r.  8-row groups are 4096 B apart, 8-j groups 128 B.
-              // (MN-major descriptors: LBO = K direction, SBO = M / N direction; verified on the B200 against autograd)
-              const uint64_t ad = umma_desc(sbase + (uint32_t)mh * 2048u + (uint32_t)ks * 8192u, 4096, 128);
-              const uint64_t bd = umma_desc(sbase + b_off[b] + (uint32_t)ks * 2u * rg, rg, 128);
-              umma_bf16(tmem_base + col0[b] + (uint32_t)mh * J.nB[b], ad, bd, umma_idesc(J.nB[b], 1, 1), (h | ks) != 0);
+        const uint64_t soff = (uint64_t)(st * (uint32_t)(kDwStageBytes >> 4));
+#pragma unroll
+        for (int b = 0; b < kDwMaxB; ++b) {
+          if (b < J.n_b) {
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(tmem_base + col0[b] + (uint32_t)mh * (uint32_t)J.nB[b], adesc0 + soff + (uint64_t)(mh * 128 + ks * 512),
+                          bdesc0[b] + soff + bstep[b] * (uint64_t)ks, idesc[b], (uint32_t)((h | ks) != 0));
             }
           }
         }
-        umma_commit(bar(DB_EMPTY + st));
+        umma_commit(bar(DB_EMPTY + (int)st));
+        if (++st == (uint32_t)kDwStages) { st = 0; fpar ^= 1; }
       }
       umma_commit(bar(DB_DONE));
     }
@@ -981,6 +1385,7 @@ struct bd_ppo_net {
   int n1 = 0, n2 = 0;            // CTAs of the two weight-gradient roles
   int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
   double* stats = nullptr;       // [kStatSlots]
+  long long* trace = nullptr;    // diagnostics (bd_ppo_set_trace)
   int64_t launches = 0;
 };
 
@@ -1050,6 +1455,7 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   alloc((void**)&n->pb1, (size_t)n1 * HID * 4); alloc((void**)&n->pb2, (size_t)n2 * HID * 4);
   alloc((void**)&n->stats, kStatSlots * sizeof(double));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_kernel_smem());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2SmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwStages * kDwStageBytes);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -1066,6 +1472,13 @@ void bd_ppo_net_destroy(bd_ppo_net* n) {
   delete n;
 }
 
+/* Diagnostics: CTA 0 of the following forward / sample launches writes SM-clock stamps of its pipeline phases,
+ * [tile pair][64] int64 (0..31: epilogue thread 0, 32..63: MMA thread; see mlp_fwd2_kernel); NULL switches it off. */
+int bd_ppo_set_trace(bd_ppo_net* n, long long* trace_dev) {
+  if (!n) return pfail(BD_EINVAL, "bd_ppo_set_trace: null net");
+  n->trace = trace_dev;
+  return BD_OK;
+}
 int64_t bd_ppo_net_param_count(const bd_ppo_net* n) { return n ? n->s.count() : 0; }
 int64_t bd_ppo_launch_count(const bd_ppo_net* n) { return n ? n->launches : 0; }
 double* bd_ppo_net_stats(bd_ppo_net* n) { return n ? n->stats : nullptr; }
@@ -1085,12 +1498,45 @@ int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream) {
   return BD_OK;
 }
 
+namespace {
+// forward-only launches: the two-tiles-in-flight kernel (BD_PPO_FWD=1tile: the training kernel's forward mode, for A/B runs)
+bool fwd_single_tile() {
+  static const int v = [] { const char* e = getenv("BD_PPO_FWD"); return (e && strcmp(e, "1tile") == 0) ? 1 : 0; }();
+  return v != 0;
+}
+int launch_fwd2(bd_ppo_net* n, Fwd2Args& a, void* stream, const char* who) {
+  a.net = net_dev(n);
+  const long long tiles = (a.rows + kRows - 1) / kRows;
+  // one CTA per SM, every CTA an even number of tiles where possible (a CTA works on pairs)
+  long long grid = tiles < n->sm_count ? tiles : n->sm_count;
+  if (tiles < 2LL * n->sm_count) grid = (tiles + 1) / 2;
+  if (grid < 1) grid = 1;
+  a.stages = fwd2_stages(n->s.K1p);
+  a.trace = n->trace;
+  mlp_fwd2_kernel<<<(unsigned)grid, kThreads, fwd2_kernel_smem(n->s.K1p, a.stages), (cudaStream_t)stream>>>(a);
+  n->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(BD_ECUDA, "%s: %s", who, cudaGetErrorString(e));
+  return BD_OK;
+}
+}  // namespace
+
 /* Forward only: out (rows, out_dim) = MLP(rows of obs).  rows_per_sample: M for the actor (row = (sample, agent)),
  * 1 for the critic (row = sample, input = the M agents' observations).  idx may be NULL (identity). */
 int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const int64_t* idx_dev, int64_t rows,
                    const float* nmean_dev, const float* nrstd_dev, float nclip, float* out_dev, void* stream) {
   if (!n || !obs_dev || !out_dev) return pfail(BD_EINVAL, "bd_ppo_forward: null argument");
   if (rows <= 0) return BD_OK;
+  if (!fwd_single_tile()) {
+    Fwd2Args f;
+    memset(&f, 0, sizeof(f));
+    f.sample = 0;
+    f.obs = obs_dev; f.N = n_envs; f.M = n_agents; f.idx = (const long long*)idx_dev; f.rows = rows;
+    f.rows_per_sample = n->s.C > 1 ? 1 : n_agents;
+    f.nmean = nmean_dev; f.nrstd = nrstd_dev; f.nclip = nclip;
+    f.out = out_dev;
+    return launch_fwd2(n, f, stream, "bd_ppo_forward");
+  }
   TileArgs a;
   memset(&a, 0, sizeof(a));
   a.net = net_dev(n);
@@ -1105,6 +1551,26 @@ int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_forward: %s", cudaGetErrorString(e));
   return BD_OK;
+}
+
+/* Rollout-time policy step of an actor net (`MAPPOActorCritic.step`, agent.py:389-415), one launch: mean = MLP(row),
+ * act = mean + exp(logstd) eps, logp = sum_k log N(act_k; mean_k, exp(logstd_k)).  obs_dev (n_envs, n_agents, D) = ONE slot,
+ * rows = n_envs * n_agents; nmean / nrstd: that slot's (n_agents * D) statistics or NULL.  eps = noise_dev (rows, out_dim)
+ * standard normals, or NULL: Philox4x32-10(seed; row, offset) + Box-Muller. */
+int bd_ppo_sample(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents, const float* nmean_dev, const float* nrstd_dev,
+                  float nclip, const float* noise_dev, uint64_t seed, uint64_t offset, float* act_dev, float* logp_dev,
+                  float* mean_dev, void* stream) {
+  if (!n || !obs_dev || !act_dev || !logp_dev) return pfail(BD_EINVAL, "bd_ppo_sample: null argument");
+  if (n->s.C != 1 || !n->s.has_logstd) return pfail(BD_EINVAL, "bd_ppo_sample: needs an actor net (1 input chunk, logstd)");
+  const long long rows = (long long)n_envs * n_agents;
+  if (rows <= 0) return BD_OK;
+  Fwd2Args f;
+  memset(&f, 0, sizeof(f));
+  f.sample = 1;
+  f.obs = obs_dev; f.N = n_envs; f.M = n_agents; f.idx = nullptr; f.rows = rows; f.rows_per_sample = n_agents;
+  f.nmean = nmean_dev; f.nrstd = nrstd_dev; f.nclip = nclip;
+  f.out = act_dev; f.logp = logp_dev; f.mean_out = mean_dev; f.noise = noise_dev; f.seed = seed; f.offset = offset;
+  return launch_fwd2(n, f, stream, "bd_ppo_sample");
 }
 
 /* One minibatch: forward, loss, backward (tile kernel), weight gradients (dw kernel), reduction of the per-CTA partials

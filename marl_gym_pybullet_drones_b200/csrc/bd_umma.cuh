@@ -63,6 +63,20 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// bf16x2 (tanh(a), tanh(b)), a in the low half.  tanh.approx.bf16x2 does NOT halve the MUFU work: ptxas lowers it to two
+// MUFU.TANH.BF16 (one per half), so the default stays tanh.approx.f32 per element (more accurate arguments, same MUFU
+// count); -DBD_TANH_BF16X2 selects the packed form.
+__device__ __forceinline__ uint32_t tanh2_bf16(float a, float b) {
+#ifndef BD_TANH_BF16X2
+  const __nv_bfloat162 h = __floats2bfloat162_rn(tanh_fast(a), tanh_fast(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+#else
+  uint32_t x, y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(b), "f"(a));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+#endif
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);

@@ -75,6 +75,19 @@ class PpoNet:
                                              _p(nrstd), float(nclip), _p(out), self._stream()), "bd_ppo_forward")
         return out
 
+    def sample(self, obs: torch.Tensor, out_act: torch.Tensor, out_logp: torch.Tensor, *, seed: int = 0, offset: int = 0,
+               noise: Optional[torch.Tensor] = None, nmean=None, nrstd=None, nclip: float = 10.0,
+               out_mean: Optional[torch.Tensor] = None):
+        """Rollout-time policy step (`MAPPOActorCritic.step`, `mappo/agent.py:389-415`) in one launch: obs (N, M, D) of one
+        slot -> out_act (N, M, A) = mean + exp(logstd) eps, out_logp (N, M[, 1]) = summed log-density.  eps = `noise`
+        (N, M, A) standard normals, else Philox4x32-10 keyed by (seed; row, offset)."""
+        N, M = int(obs.shape[0]), int(obs.shape[1])
+        if out_act.numel() != N * M * self.out_dim or out_logp.numel() != N * M:
+            raise ValueError("out_act / out_logp do not match obs (N, M, D)")
+        self._check(self._lib.bd_ppo_sample(self._h, _p(obs), N, M, _p(nmean), _p(nrstd), float(nclip), _p(noise),
+                                            int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), _p(out_act), _p(out_logp),
+                                            _p(out_mean), self._stream()), "bd_ppo_sample")
+
     def grad(self, grad_out: torch.Tensor, obs: torch.Tensor, n_envs: int, n_agents: int, idx: Optional[torch.Tensor],
              samples: int, *, critic: bool, act=None, logp_old=None, adv=None, adv_stats=None, ret=None, v_old=None,
              clip: float = 0.2, use_clipped_value: bool = False, entropy_coef: float = 0.0, nmean=None, nrstd=None,

@@ -35,6 +35,23 @@ def timeit(fn, n=50):
 flops = rows * 2.0 * (72 * 256 + 256 * 256 + 256 * 4)
 t = timeit(lambda: fa.forward(obs, out_act=act, out_logp=lp))
 print(f"fused tcgen05 actor : {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s (useful flops)")
+from marl_gym_pybullet_drones_b200.ppo_native import PpoNet  # noqa: E402
+net = PpoNet(72, 1, 4, True, 128)
+net.pack(torch.cat([logstd] + [p.detach().reshape(-1) for p in mlp.parameters()]).contiguous())
+obs3 = obs.view(rows // 4, 4, 72)
+t2 = timeit(lambda: net.sample(obs3, act, lp, seed=1, offset=2))
+print(f"two-tile tcgen05 sample: {t2:8.1f} us  {flops / t2 / 1e6:7.1f} TFLOP/s (useful flops)  [bd_ppo_sample]")
+out = torch.empty(rows, 4, device="cuda")
+t3 = timeit(lambda: net.forward(obs3, rows // 4, 4, rows, out=out))
+print(f"two-tile tcgen05 forward: {t3:8.1f} us  [bd_ppo_forward]")
+cn = PpoNet(72, 4, 1, False, 128)
+cm = MLP(4 * 72, 1, [256, 256], "tanh").cuda()
+cn.pack(torch.cat([p.detach().reshape(-1) for p in cm.parameters()]).contiguous())
+val = torch.empty(rows // 4, 1, device="cuda")
+t4 = timeit(lambda: cn.forward(obs3, rows // 4, 4, rows // 4, out=val))
+print(f"two-tile critic values ({rows // 4} rows x 4 chunks): {t4:8.1f} us")
+if "--short" in sys.argv:
+    sys.exit(0)
 with torch.no_grad():
     def torch_fp32():
         m = mlp(obs)

@@ -112,6 +112,78 @@ def test_forward_matches_torch(M, D, A, samples, critic):
     net.close()
 
 
+def test_forward_many_tiles_per_cta():
+    """More tiles than 2 x SMs, odd count, ragged last tile: every CTA of the two-tiles-in-flight kernel runs several
+    pairs plus a single; actor rows and critic rows (M input chunks)."""
+    from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
+    T, N, M, D, A = 3, 30000, 4, 72, 4
+    obs, act, g = _rollout(T, N, M, D, A, 11)
+    samples = 128 * 148 * 5 // M + 77
+    idx = torch.randint(0, T * N, (samples,), device="cuda", generator=g)
+    mlp = _mlp(D, A, 4)
+    net = PpoNet(D, 1, A, True, samples * M)
+    net.pack(_flat([torch.full((A,), -0.5, device="cuda")] + list(mlp.parameters())))
+    out = net.forward(obs, N, M, samples * M, idx=idx)
+    with torch.no_grad():
+        want = mlp(obs[:T].reshape(T * N, M, D)[idx].reshape(samples * M, D))
+    assert float((out - want).abs().max()) <= 2e-2
+    net.close()
+    cm = _mlp(M * D, 1, 3)
+    cnet = PpoNet(D, M, 1, False, T * N)
+    cnet.pack(_flat(list(cm.parameters())))
+    out = cnet.forward(obs, N, M, T * N)              # identity index: values of whole slots, 703 tiles
+    with torch.no_grad():
+        want = cm(obs[:T].reshape(T * N, M * D))
+    assert float((out - want).abs().max()) <= 2e-2
+    cnet.close()
+
+
+@pytest.mark.parametrize("N,M,D,A", [(700, 4, 72, 4), (50, 2, 27, 1), (40000, 4, 72, 4), (3, 16, 72, 4)])
+def test_sample_matches_torch(N, M, D, A):
+    """`MAPPOActorCritic.step` (agent.py:389-415): act = mean + exp(logstd) eps, logp = summed Normal log-density;
+    mean within the forward tolerance, act / logp exact given the mean and the noise (fp32, <= 1e-5)."""
+    from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
+    g = torch.Generator(device="cuda").manual_seed(N + M)
+    obs = torch.randn((N, M, D), device="cuda", generator=g)
+    mlp = _mlp(D, A, 8)
+    logstd = torch.linspace(-0.7, -0.2, A, device="cuda")
+    net = PpoNet(D, 1, A, True, 128)
+    net.pack(_flat([logstd] + list(mlp.parameters())))
+    noise = torch.randn((N, M, A), device="cuda", generator=g)
+    act, logp, mean = (torch.empty((N, M, A), device="cuda"), torch.empty((N, M, 1), device="cuda"),
+                       torch.empty((N, M, A), device="cuda"))
+    net.sample(obs, act, logp, noise=noise, out_mean=mean)
+    with torch.no_grad():
+        want_mean = mlp(obs.view(N * M, D)).view(N, M, A)
+    assert float((mean - want_mean).abs().max()) <= 2e-2
+    assert float((act - (mean + logstd.exp() * noise)).abs().max()) <= 1e-5
+    want_lp = torch.distributions.Normal(mean, logstd.exp()).log_prob(act).sum(-1, keepdim=True)
+    assert float((logp - want_lp).abs().max()) <= 2e-4
+    # normalisation on load (one slot's statistics, per (agent, column))
+    nmean = torch.randn((M * D,), device="cuda", generator=g) * 0.1
+    nrstd = torch.rand((M * D,), device="cuda", generator=g) + 0.5
+    net.sample(obs, act, logp, noise=noise, out_mean=mean, nmean=nmean, nrstd=nrstd, nclip=2.0)
+    with torch.no_grad():
+        xn = ((obs.view(N, M * D) - nmean) * nrstd).clamp(-2.0, 2.0)
+        want_mean = mlp(xn.view(N * M, D)).view(N, M, A)
+    assert float((mean - want_mean).abs().max()) <= 2e-2
+    # Philox noise: deterministic in (seed, offset), different across offsets, standard normal moments
+    a1, a2, a3 = torch.empty_like(act), torch.empty_like(act), torch.empty_like(act)
+    net.sample(obs, a1, logp, seed=5, offset=9, out_mean=mean)
+    net.sample(obs, a2, logp, seed=5, offset=9)
+    net.sample(obs, a3, logp, seed=5, offset=10)
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)
+    eps = (a1 - mean) / logstd.exp()
+    want_lp = (-0.5 * eps.pow(2) - logstd - 0.5 * math.log(2 * math.pi)).sum(-1, keepdim=True)
+    net.sample(obs, a1, logp, seed=5, offset=9)
+    assert float((logp - want_lp).abs().max()) <= 5e-3      # eps recovered through a division: looser
+    if N * M * A >= 10000:
+        assert abs(float(eps.mean())) <= 0.02 and abs(float(eps.var()) - 1.0) <= 0.03
+        e3 = (a3 - mean) / logstd.exp()
+        assert abs(float((eps * e3).mean())) <= 0.02        # streams of different offsets are uncorrelated
+    net.close()
+
+
 def _actor_reference(mlp, logstd, obs, act, logp_old, adv_n, idx, T, N, M, D, A, clip, ent_coef):
     mb = idx.numel()
     o = obs[:T].reshape(T * N, M, D)[idx].reshape(mb * M, D)
