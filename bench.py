@@ -148,13 +148,32 @@ def run_cpu_baseline(steps: int, warmup: int, m: int, envs_per_worker: int = 4):
 
 # ----------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region — in-process through NVML (nvidia_ml_py), every
+    20 ms from a thread.  A child `nvidia-smi -lms 100` (round 1) costs the 20-step window 5 % (36.2 vs 34.5 us per step,
+    `scripts/time_window.py`, profiles/README.md); the NVML thread costs nothing measurable.  Falls back to the child
+    process when the module is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.rows, self.proc, self.thread, self.nvml = [], None, None, None
+        self._stop = threading.Event()
+        self.smax = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -165,11 +184,28 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)), int(get_reasons(self.handle))))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({n for _, m in self.rows for n, bit in self.REASONS if m & bit})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(sm), "source": f"NVML in-process, every {self.period * 1e3:.0f} ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -193,7 +229,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -230,6 +266,7 @@ def run_ours(args):
     rew_buf = torch.empty((slots, N), dtype=torch.float32, device=dev)
     term_buf = torch.empty((slots, N), dtype=torch.uint8, device=dev)
     trunc_buf = torch.empty((slots, N), dtype=torch.uint8, device=dev)
+    obs_buf.zero_()     # first touch of every slot outside the timed window (the warm-up only reaches W of the slots)
     outs = [StepResult(obs_buf[i], rew_buf[i], term_buf[i].view(torch.bool), trunc_buf[i].view(torch.bool), None)
             for i in range(slots)]
     env.reset_device(out=obs_buf[0])
@@ -241,22 +278,32 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
 
     def gpu_steps(n, start):
-        """n control steps = n launches of the step kernel, issued with one host call per run of consecutive slots
-        (`bd_step_many`; step k reads action set (start+k) % slots and writes observation slot (start+k) % slots)."""
+        """n control steps = n launches of the per-step kernel (the one a closed-loop rollout launches), issued with one
+        host call per run of consecutive slots (`bd_step_many` in its k-launches mode; step k reads action set
+        (start+k) % slots and writes observation slot (start+k) % slots).  The K-steps-in-one-launch kernel, which only
+        open-loop action tapes can use, is reported separately (`small_batch`, `open_loop`)."""
         k = 0
         while k < n:
             i = (start + k) % slots
             run = min(n - k, slots - i)
             env.step_many(act_pool[i:i + run], obs_buf[i:i + run], rew_buf[i:i + run], term_buf[i:i + run],
-                          trunc_buf[i:i + run])
+                          trunc_buf[i:i + run], one_launch=False)
             k += run
 
-    gpu_steps(args.warmup, 0)
-    sync_all()
+    # the sampler starts BEFORE the warm-up: its start-up (NVML init) would otherwise leave the GPU idle for a few ms
+    # right before the timed window, and a window that follows an idle gap runs ~1 us per step slower (clock ramp)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = env.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # pre-warm (untimed, before the W warm-up steps): the process has just initialised CUDA on an idle GPU, and W = 5
+    # steps are 0.2 ms of work — not enough for the SM clock to leave its idle state, and too few for the episodes to
+    # reach their stationary mix of running / re-spawning envs (nothing terminates in the first ~20 steps after a reset)
+    t_end = time.time() + args.prewarm_s
+    while time.time() < t_end:
+        gpu_steps(64, 0)
+        torch.cuda.synchronize(dev)
+    gpu_steps(args.warmup, 0)
+    l0 = env.launch_count
     sync_all()
     ev0.record()
     gpu_steps(args.steps, args.warmup)
@@ -359,8 +406,30 @@ def run_ours(args):
         bpl = algorithmic_bytes_per_drone_step(A, Bf, M) * Ns * M
         small = {"envs_per_gpu": Ns, "ms_per_step_step_many": ms_many, "ms_per_step_one_call_per_step": ms_single,
                  "value": Ns * M * S / (ms_many * 1e-3), "unit": UNIT,
-                 "roofline_frac": bpl / (ms_many * 1e-3) / 1e9 / 6553.0, "steps_per_host_call": Ks}
+                 "roofline_frac": bpl / (ms_many * 1e-3) / 1e9 / 6553.0, "steps_per_host_call": Ks,
+                 "note": "bd_step_many = ONE launch for the K steps (step_kernel_tile_many: states in registers, action "
+                         "history in shared memory across steps); roofline_frac counts the ALGORITHMIC bytes of K single "
+                         "steps (state + history re-read every step), of which the one-launch kernel moves only actions, "
+                         "observations, rewards and flags"}
         env_s.close()
+
+    # ---- open-loop tapes at the headline size: the K-steps-in-one-launch kernel (not usable by a closed-loop rollout)
+    open_loop = None
+    if args.open_loop_reps > 0:
+        env.step_many(act_pool, obs_buf, rew_buf, term_buf, trunc_buf)          # warm-up (slots steps, one launch)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.open_loop_reps):
+            env.step_many(act_pool, obs_buf, rew_buf, term_buf, trunc_buf)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_ol = e0.elapsed_time(e1) / (args.open_loop_reps * slots)
+        open_loop = {"ms_per_step": ms_ol, "value": world * N * M * S / (ms_ol * 1e-3), "unit": UNIT, "steps_per_launch": slots,
+                     "hbm_bytes_per_step": N * M * (A * 4 + D * 4) + N * 6,
+                     "hbm_gbs": (N * M * (A * 4 + D * 4) + N * 6) / (ms_ol * 1e-3) / 1e9,
+                     "note": "bd_step_many, one launch per K steps: state and action history never leave the SM between "
+                             "steps, so a step moves 304 B per drone (action in, observation row out) instead of 647.5"}
 
     t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0, copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -409,6 +478,8 @@ def run_ours(args):
                               f"({slots * N * M * D * 4 / 1e6:.0f} MB) + {slots}-slot action pool; state+history "
                               f"{(N * M * (64 + Bf * A * 4)) / 1e6:.0f} MB"),
                 "parallelism": f"env-sharded x{world}, no data-path collective",
+                "prewarm": f"{args.prewarm_s} s of untimed steps before the {args.warmup} warm-up steps (SM clock out of idle, "
+                           "episodes in their stationary running / re-spawning mix)",
                 "host_cpus_rank0": (f"{len(cpus)} CPUs near the GPU (NVML affinity)" if cpus else
                                     f"{host_cores()} (container cpuset; NVML affinity not applicable)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -442,6 +513,8 @@ def run_ours(args):
                                          "observations of finished envs only)"}
         if small is not None:
             line["small_batch"] = small
+        if open_loop is not None:
+            line["open_loop"] = open_loop
     env.close()
     mappo = None
     if args.mappo_steps > 0:
@@ -561,6 +634,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--drones", type=int, default=4)
     ap.add_argument("--rollout-slots", type=int, default=16)
+    ap.add_argument("--open-loop-reps", type=int, default=8, help="timed bd_step_many launches of the open-loop leg (0 = skip)")
+    ap.add_argument("--prewarm-s", type=float, default=0.3, help="seconds of untimed steps before the W warm-up steps")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-steps", type=int, default=200)
     ap.add_argument("--vecenv-steps", type=int, default=20, help="steps of the VecEnv-protocol e2e leg (0 = skip)")

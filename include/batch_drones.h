@@ -168,9 +168,13 @@ int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host
 /* k control steps with ONE host call (the launch-bound regime: small batches, random-action sweeps —
  * BASELINE configs[3] as literally sharded is 8192 envs per GPU).  actions_dev (k,N,M,A), obs_dev
  * (k,N,M,D), reward_dev (k,N) Real, terminated_dev / truncated_dev (k,N) uint8; step i reads
- * action set i and writes output slot i.  Identical to k bd_step calls (no terminal observations). */
+ * action set i and writes output slot i.  Results identical to k bd_step calls (no terminal observations).
+ * On the fast float kernel the k steps are ONE launch (a tile's states stay in registers and its action
+ * history in shared memory from step to step; only actions come in and observations / rewards / flags go
+ * out); other configurations run k launches.  bd_set_step_many_mode(h, 1) forces k launches. */
 int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, void* reward_dev,
                  uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
+int bd_set_step_many_mode(bd_handle* h, int mode);
 
 /* RNG state of the on-device re-spawn draws — the counterpart of the workers' np.random states the
  * reference checkpoints and restores (mappo/mappo.py:203-229; subproc_vec_env.py:101-112

@@ -396,10 +396,16 @@ class BatchAviary:
         return res
 
     def step_many(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
-                  truncated: torch.Tensor) -> None:
+                  truncated: torch.Tensor, one_launch: bool = True) -> None:
         """K control steps with one host call (`bd_step_many`): `actions` (K,N,M,A), outputs (K,N,M,D) / (K,N);
-        step i reads `actions[i]` and writes slot i.  For launch-bound regimes (small batches, action tapes)."""
+        step i reads `actions[i]` and writes slot i.  For open-loop action tapes and latency-bound small batches: on the
+        fast float kernel the K steps are ONE launch (states in registers, action history in shared memory across
+        steps); `one_launch=False` forces K launches of the per-step kernel (what a closed-loop caller pays)."""
         self._check_open()
+        mode = 0 if one_launch else 1
+        if mode != getattr(self, "_many_mode", 0):
+            _native.check(self._lib.bd_set_step_many_mode(self._h, mode), "bd_set_step_many_mode")
+            self._many_mode = mode
         K = int(actions.shape[0])
         N, M = self.num_envs, self.NUM_DRONES
         if (actions.dtype != self.action_dtype or not actions.is_contiguous() or actions.device != self.device

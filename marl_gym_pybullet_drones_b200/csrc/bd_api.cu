@@ -86,6 +86,7 @@ struct bd_handle {
   bool graph_mode = false;     // a step was captured into a CUDA graph: the device counter is authoritative
   int reset_epoch = 0;
   uint32_t philox_base = 0;    // bd_set_rng_state: offset of the Philox step counter
+  int many_mode = 0;           // bd_step_many: 0 = one launch when possible, 1 = always k launches (bd_set_step_many_mode)
   bool poisoned = false;       // a launch failed half-way through a chunked host step: the tile epochs are inconsistent
   // compact terminal observations (bd_step_host_compact): pinned, device-mapped staging owned by the handle
   int* c_blockcnt = nullptr;   // [blocks of 1024 envs] done envs per block
@@ -586,7 +587,10 @@ int step_host_impl(bd_handle* h, const void* actions_host, float* obs_host, void
   if (compact) {
     h->c_flip ^= 1;
     const int set = h->c_flip;
-    int want = h->c_cap_dev > 0 ? h->c_cap_dev : (h->cfg.n_envs / 16 > 256 ? h->cfg.n_envs / 16 : 256);
+    // worst case up front (every env finished): growing the page-locked staging later costs 0.2 - 0.5 s per
+    // cudaFreeHost + cudaHostAlloc (measured: two such calls inside a 20-step window tripled its mean), and the share of
+    // finished envs climbs for many steps after a reset, so any smaller start would grow several times
+    int want = h->cfg.n_envs;
     int rc = ensure_compact_buffers(h, set, want);
     if (rc) return rc;
   }
@@ -737,11 +741,55 @@ int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, v
   const size_t act_elem = (h->cfg.precision == BD_F64 && !h->cfg.action_is_f32) ? 8 : 4;
   const size_t act_step = (size_t)h->n_total * h->A * act_elem, obs_step = (size_t)h->n_total * h->D;
   const size_t n = (size_t)h->cfg.n_envs;
+  // The fast tile kernel takes a tile through all k steps in ONE launch (states in registers, history in shared memory):
+  // a small batch is bound by the latency of a step's launch -> load -> compute -> store chain, not by bandwidth.
+  // BD_STEP_MANY=loop keeps k launches (A/B runs, tests).  Needs rows that leave as TMA bulk stores.
+  static const bool force_loop = [] { const char* e = getenv("BD_STEP_MANY"); return e && strcmp(e, "loop") == 0; }();
+  const long long wrap = (long long)h->B * ((1 << 30) / h->B);
+  const size_t tile_bytes = (size_t)(4 * h->EW) * h->cfg.n_drones * h->D * 4;
+  const size_t last_rows = (size_t)(h->n_total % ((long long)(4 * h->EW) * h->cfg.n_drones));
+  const bool one_launch = !force_loop && h->many_mode == 0 && k >= 2 && h->spec.impl == 1 && h->cfg.precision == BD_F32 && !h->poisoned &&
+                          actions_dev && obs_dev && reward_dev && terminated_dev && truncated_dev &&
+                          ((uintptr_t)obs_dev & 15) == 0 && ((obs_step * 4) & 15) == 0 && (tile_bytes & 15) == 0 &&
+                          ((last_rows * h->D * 4) & 15) == 0 && (h->A != 4 || (((uintptr_t)actions_dev & 15) == 0 && (act_step & 15) == 0)) &&
+                          2 * tile_bytes <= 200 * 1024 && h->total_steps + k < wrap &&
+                          !(h->cfg.auto_reset && h->cfg.reset_mode == BD_RESET_JITTER_BUFFER && h->cfg.task == BD_TASK_MULTIHOVER && !h->jitter);
+  if (one_launch) {
+    DeviceGuard guard(h->cfg.device);
+    if (!h->graph_mode) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing((cudaStream_t)stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) h->graph_mode = true;
+    }
+    cudaError_t e = cudaSuccess;
+    bd::Params<float>& P = h->pf;
+    P.host_total = h->graph_mode ? -1 : (int)h->total_steps;
+    P.host_head = (int)(h->total_steps % h->B);
+    P.actions = actions_dev;
+    P.obs = obs_dev;
+    P.reward = (float*)reward_dev;
+    P.terminated = terminated_dev;
+    P.truncated = truncated_dev;
+    P.terminal_obs = nullptr;
+    e = bd::launch_step_tile_many(h->spec.task, h->spec.act_a, P, k, (long long)(act_step / act_elem), (long long)obs_step, (long long)n,
+                                  h->spec, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(BD_ECUDA, "bd_step_many: kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+    h->total_steps += k;
+    return BD_OK;
+  }
   for (int i = 0; i < k; ++i) {
     int rc = bd_step(h, (const char*)actions_dev + i * act_step, obs_dev + i * obs_step, (char*)reward_dev + i * n * h->real,
                      terminated_dev + i * n, truncated_dev + i * n, nullptr, stream);
     if (rc) return rc;
   }
+  return BD_OK;
+}
+
+// bd_step_many: mode 0 (default) = one launch for the k steps where the configuration allows it, 1 = always k launches
+// (what a closed-loop caller's steps cost; benchmarks of the per-step kernel).
+int bd_set_step_many_mode(bd_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return fail(BD_EINVAL, "bd_set_step_many_mode: mode must be 0 or 1");
+  h->many_mode = mode;
   return BD_OK;
 }
 

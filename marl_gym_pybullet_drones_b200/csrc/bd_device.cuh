@@ -424,9 +424,12 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
           float h = d.pz + fmaf(r20, P.prop_x[k], r21 * P.prop_y[k]);
           h = fmaxf(h, P.gnd_h_clip);
           const float ratio = __fdividef(P.prop_radius, 4.0f * h);
-          e[k] = (1.0f + u[k]) * (P.gnd_coeff * ratio * ratio);
+          // products that feed sums — and the sum 1 + u, whose u is itself a product — are rounded on their own (the _rn
+          // intrinsics are never contracted): whether a multiply is fused into a following add depends on the surrounding kernel, and the one-launch K-step kernel must
+          // reproduce the per-step kernel bit for bit
+          e[k] = __fmul_rn(__fadd_rn(1.0f, u[k]), __fmul_rn(__fmul_rn(P.gnd_coeff, ratio), ratio));
         }
-        const float es = cg * 0.25f * ((e[0] + e[1]) + (e[2] + e[3]));
+        const float es = __fmul_rn(cg * 0.25f, (e[0] + e[1]) + (e[2] + e[3]));
         c1s += es;
         c2s += es;
         float ex, ey;

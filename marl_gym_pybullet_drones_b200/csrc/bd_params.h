@@ -87,6 +87,9 @@ struct LaunchSpec {
 
 // implemented in bd_tile_launch.cu (fast tile kernel; task = template TASK value, act_a in {1, 4})
 cudaError_t launch_step_tile(int task, int act_a, const Params<float>& P, const LaunchSpec& ls, cudaStream_t st);
+// k control steps in one launch (step_kernel_tile_many); strides in elements between consecutive steps' slots
+cudaError_t launch_step_tile_many(int task, int act_a, const Params<float>& P, int k, long long act_step, long long obs_step,
+                                  long long out_step, const LaunchSpec& ls, cudaStream_t st);
 // implemented in bd_kernels.cu
 cudaError_t launch_step(const LaunchSpec& ls, const void* params, cudaStream_t st);
 cudaError_t launch_reset(const LaunchSpec& ls, const void* params, cudaStream_t st);

@@ -448,4 +448,299 @@ step_kernel_tile(const __grid_constant__ Params<float> P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K control steps in ONE launch (bd_step_many): the action tape of all K steps is known up front and tiles are whole
+// environments, so a CTA can take its tile through all K steps without ever meeting another CTA.  The drone states stay
+// in registers from step to step, the action history stays in shared memory (two tiles, used alternately: the next row
+// is the previous row shifted by one ring slot while the TMA engine still reads the previous tile), and per step only
+// the new action comes in and the finished observation rows, reward and flags go out.  What bounds a small batch
+// (BASELINE configs[3] as literally sharded: 8 192 envs per GPU = 256 tiles on 148 SMs) is the latency of one step's
+// chain launch -> loads -> 8 substeps -> stores -> next launch (16 us, 0.20 of the HBM peak); here the chain is the
+// substeps alone.  Results are bit-identical to K single launches (same device functions, same order).
+// Not supported here (the caller falls back to K launches): terminal observations, rows that cannot leave as a TMA
+// bulk store.
+struct ManySpan {
+  int K;
+  long long act_step;   // elements between consecutive steps' action sets
+  long long obs_step;   // floats between consecutive observation slots
+  long long out_step;   // elements between consecutive reward / flag slots
+};
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+
+template <int TASK, int A, bool VEC, int AERO>
+__global__ void __launch_bounds__(kBlock, 3)
+step_kernel_tile_many(const __grid_constant__ Params<float> P, const ManySpan Q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int M = P.M, B = P.B, D = P.D, EW = P.EW;
+  const bool pow2 = (M & (M - 1)) == 0;
+  constexpr bool vec = VEC;
+  const int env_w = pow2 ? (lane >> (31 - __clz(M))) : lane / M;
+  const int group_base = env_w * M;
+  const int drone = lane - group_base;
+  const int tile = blockIdx.x;
+  const int env_l = (tid >> 5) * EW + env_w;
+  const int env = tile * (4 * EW) + env_l;
+  const bool active = env_w < EW && env < P.N;
+  const long long g0 = (long long)tile * (4 * EW) * M;
+  const long long g = (long long)env * M + drone;
+  const int tile_rows = 4 * EW * M;
+  const size_t tile_floats = (size_t)tile_rows * D;            // a multiple of 4 floats (checked on the host)
+  float* const tiles = reinterpret_cast<float*>(smem_raw);     // [2][tile rows][D]
+  const size_t rowoff = (size_t)(env_w < EW ? env_l * M + drone : 0) * D;
+  const bool jit = (TASK == TASK_MULTIHOVER) && (P.reset_mode != RESET_FIXED);
+  const long long gh = active ? g : P.n_total;
+  const long long left = P.n_total - g0;
+  const int rows = (int)(left < (long long)tile_rows ? left : (long long)tile_rows);
+  const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u;
+
+  pdl_wait();     // everything earlier launches wrote (state, ring, counters) is complete and visible
+  int total = P.host_total >= 0 ? P.host_total : P.gsteps[0];
+  int head = total % B;
+  TileIn<A> cur;
+  load_state<A>(P, g, env, active, cur);
+  issue_history<float, A, VEC>(P, gh, head, tiles + rowoff, 0, B - 1);
+  cp_async_commit();
+  load_action<A>(P, g, active, cur);
+  int stepc = cur.stepc;
+  float ep = cur.ep_ret;
+  float last_sum = 0.f;
+  if constexpr (AERO == 2) {
+    if ((P.aero & AERO_DRAG) && active && stepc > 0) {
+      const int prev = head == 0 ? B - 1 : head - 1;
+      const float* lp = P.hist + ((size_t)prev * P.n_total + g) * A;
+      if constexpr (A == 4) {
+        const float4 pa = *reinterpret_cast<const float4*>(lp);
+        last_sum = (__fadd_rn(1.0f, __fmul_rn(0.05f, pa.x)) + __fadd_rn(1.0f, __fmul_rn(0.05f, pa.y))) +
+                   (__fadd_rn(1.0f, __fmul_rn(0.05f, pa.z)) + __fadd_rn(1.0f, __fmul_rn(0.05f, pa.w)));
+      } else {
+        last_sum = 4.0f * __fadd_rn(1.0f, __fmul_rn(0.05f, lp[0]));
+      }
+    }
+  }
+  Drone<float> d;
+  d.px = cur.s0.x; d.py = cur.s0.y; d.pz = cur.s0.z; d.qx = cur.s0.w;
+  d.qy = cur.s1.x; d.qz = cur.s1.y; d.qw = cur.s1.z; d.vx = cur.s1.w;
+  d.vy = cur.s2.x; d.vz = cur.s2.y; d.wx = cur.s2.z; d.wy = cur.s2.w;
+  d.wz = cur.s3.x; d.tx = cur.s3.y; d.ty = cur.s3.z; d.tz = cur.s3.w;
+  float4 act = cur.act;
+
+#pragma unroll 1
+  for (int k = 0; k < Q.K; ++k) {
+    float* const tile_s = tiles + (size_t)(k & 1) * tile_floats;
+    float* const myrow = tile_s + rowoff;
+    // the next step's action is on its way while this step computes
+    float4 act_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k + 1 < Q.K && active) {
+      if constexpr (A == 4) act_next = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.actions) + (size_t)(k + 1) * Q.act_step)[g];
+      else act_next.x = (reinterpret_cast<const float*>(P.actions) + (size_t)(k + 1) * Q.act_step)[g];
+    }
+    if (k > 0) {
+      // this tile buffer was handed to the TMA engine two steps ago: its reads must be over before it is rewritten
+      if (k > 1) {
+        if (tid == 0) bulk_wait_read1();
+        __syncthreads();
+      }
+      // history = the previous row's, one slot older (oldest entry drops out); thread-private rows, no barrier
+      const float* prow = tiles + (size_t)((k - 1) & 1) * tile_floats + rowoff;
+      if (active) {
+        if constexpr (A == 4) {
+          if (vec) {
+#pragma unroll 4
+            for (int j = 0; j < B - 1; ++j)
+              *reinterpret_cast<float4*>(myrow + 12 + j * 4) = *reinterpret_cast<const float4*>(prow + 12 + (j + 1) * 4);
+          } else {
+            for (int j = 0; j < (B - 1) * 4; ++j) myrow[12 + j] = prow[12 + 4 + j];
+          }
+        } else {
+          for (int j = 0; j < B - 1; ++j) myrow[12 + j] = prow[12 + 1 + j];
+        }
+      }
+    }
+    float onep[4];
+    if constexpr (A == 4) {
+      onep[0] = __fadd_rn(1.0f, __fmul_rn(0.05f, act.x));
+      onep[1] = __fadd_rn(1.0f, __fmul_rn(0.05f, act.y));
+      onep[2] = __fadd_rn(1.0f, __fmul_rn(0.05f, act.z));
+      onep[3] = __fadd_rn(1.0f, __fmul_rn(0.05f, act.w));
+    } else {
+      onep[0] = onep[1] = onep[2] = onep[3] = __fadd_rn(1.0f, __fmul_rn(0.05f, act.x));
+    }
+    float avx = 0.f, avy = 0.f, avz = 0.f;
+    fast_substeps<AERO>(P, d, onep, avx, avy, avz, group_base, drone, last_sum);
+    float roll, pitch, yaw;
+    quat_to_euler_fast(d.qx, d.qy, d.qz, d.qw, roll, pitch, yaw);
+    if (k == 0) cp_async_wait_all();
+    float contrib = 0.f;
+    int flags = 0;
+    if (active) {
+      if (vec) {
+        float4* r4 = reinterpret_cast<float4*>(myrow);
+        r4[0] = make_float4(d.px, d.py, d.pz, roll);
+        r4[1] = make_float4(pitch, yaw, d.vx, d.vy);
+        r4[2] = make_float4(d.vz, avx, avy, avz);
+      } else {
+        myrow[0] = d.px; myrow[1] = d.py; myrow[2] = d.pz; myrow[3] = roll; myrow[4] = pitch; myrow[5] = yaw;
+        myrow[6] = d.vx; myrow[7] = d.vy; myrow[8] = d.vz; myrow[9] = avx; myrow[10] = avy; myrow[11] = avz;
+      }
+      if constexpr (TASK != TASK_SWARM)
+        task_terms<float, TASK>(P, d, roll, pitch, stepc, drone, myrow + 12 + B * A, contrib, flags);
+      if constexpr (A == 4) {
+        if (vec) *reinterpret_cast<float4*>(myrow + 12 + (B - 1) * 4) = act;
+        else { float* o = myrow + 12 + (B - 1) * 4; o[0] = act.x; o[1] = act.y; o[2] = act.z; o[3] = act.w; }
+        *reinterpret_cast<float4*>(P.hist + ((size_t)head * P.n_total + g) * 4) = act;
+      } else {
+        myrow[12 + B - 1] = act.x;
+        P.hist[(size_t)head * P.n_total + g] = act.x;
+      }
+    }
+    float swarm_reward_env = 0.f;
+    if constexpr (TASK == TASK_SWARM) {
+      int fl = 0;
+      swarm_reward_env = swarm_reward_shfl(P, d, roll, pitch, lane, M, drone, fl);
+      flags = active ? fl : 0;
+    }
+    if (pow2) {
+#pragma unroll 1
+      for (int o = M >> 1; o > 0; o >>= 1) {
+        contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+      }
+    } else {
+      const float c0 = contrib;
+      const int f0 = flags;
+#pragma unroll 1
+      for (int o = 1; o < M; ++o) {
+        int t = drone + o;
+        t -= (t >= M) ? M : 0;
+        contrib += __shfl_sync(0xffffffffu, c0, group_base + t);
+        flags |= __shfl_sync(0xffffffffu, f0, group_base + t);
+      }
+    }
+    const float reward = (TASK == TASK_SWARM) ? swarm_reward_env : ((TASK == TASK_HOVER) ? contrib : contrib / (float)M);
+    const bool time_up = stepc >= P.trunc_counter;
+    const bool terminated = (TASK == TASK_SWARM) ? (P.task == TASK_MEETUP && (flags & 4) == 0) : (flags & 1) != 0;
+    const bool truncated = ((flags & 2) != 0) || time_up;
+    const bool done_reset = active && (terminated || truncated) && P.auto_reset;
+    if (active && drone == 0) {
+      const size_t o = (size_t)k * Q.out_step + env;
+      P.reward[o] = reward;
+      P.terminated[o] = terminated ? 1 : 0;
+      P.truncated[o] = truncated ? 1 : 0;
+      if (P.ep_ret != nullptr) {
+        ep += reward;
+        if (terminated || truncated) {
+          atomicAdd(P.ep_acc + 0, (double)ep);
+          atomicAdd(P.ep_acc + 1, (double)(stepc / P.S + 1));
+          atomicAdd(P.ep_acc + 2, 1.0);
+          ep = 0.f;
+        }
+      }
+    }
+    // the drag model's last_clipped_action of the next step: this step's action, zero after a reset
+    if constexpr (AERO == 2) last_sum = done_reset ? 0.f : (onep[0] + onep[1]) + (onep[2] + onep[3]);
+    stepc = done_reset ? 0 : stepc + P.S;
+
+    if (__any_sync(0xffffffffu, done_reset)) {
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      if (jit) {
+        const long long ib = (long long)env * P.init_env_stride + drone * 3;
+        bool retry = done_reset;
+#pragma unroll 1
+        for (int attempt = 0; attempt <= kMaxJitterTries; ++attempt) {
+          const bool last = attempt == kMaxJitterTries;
+          if (retry) {
+            float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+            if (!last) {
+              if (P.reset_mode == RESET_BUFFER && P.jitter != nullptr) {
+                j0 = P.jitter[g * 3]; j1 = P.jitter[g * 3 + 1]; j2 = P.jitter[g * 3 + 2];
+              } else {
+                uint32_t c[4] = {(uint32_t)env, (uint32_t)total + P.philox_base, (uint32_t)(attempt * M + drone), 0u};
+                uint32_t c2[4] = {c[0], c[1], c[2], 1u};
+                philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                philox4x32_10(c2, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                j0 = -0.25f + 0.5f * u01(c[0], c[1], 0.f);
+                j1 = -0.25f + 0.5f * u01(c[2], c[3], 0.f);
+                j2 = -0.25f + 0.5f * u01(c2[0], c2[1], 0.f);
+              }
+            }
+            cx = P.init_xyz[ib] + j0;
+            cy = P.init_xyz[ib + 1] + j1;
+            cz = P.init_xyz[ib + 2] + j2;
+            cz = cz < 0.1f ? 0.1f : (cz > 1.0f ? 1.0f : cz);
+          }
+          int bad = 0;
+#pragma unroll 1
+          for (int o = 1; o < M; ++o) {
+            int t = drone + o;
+            t -= (t >= M) ? M : 0;
+            const int src = group_base + t;
+            const float ox = __shfl_sync(0xffffffffu, cx, src), oy = __shfl_sync(0xffffffffu, cy, src),
+                        oz = __shfl_sync(0xffffffffu, cz, src);
+            const float dx = cx - ox, dy = cy - oy, dz = cz - oz;
+            bad |= (sqrtf(dx * dx + dy * dy + dz * dz) < 0.5f) ? 1 : 0;
+          }
+          {
+            const int b0 = bad;
+#pragma unroll 1
+            for (int o = 1; o < M; ++o) {
+              int t = drone + o;
+              t -= (t >= M) ? M : 0;
+              bad |= __shfl_sync(0xffffffffu, b0, group_base + t);
+            }
+          }
+          if (last || P.reset_mode == RESET_BUFFER) bad = 0;
+          retry = retry && (bad != 0);
+          if (!__any_sync(0xffffffffu, retry)) break;
+        }
+      }
+      if (done_reset) {
+        const float cand[3] = {cx, cy, cz};
+        float kin[12];
+        reset_drone<float, TASK>(P, env, drone, jit ? cand : nullptr, d, kin);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) myrow[q] = kin[q];
+        if (TASK == TASK_SPIRAL) {
+          float rp[3], rv[3], sphi, cphi;
+          spiral_reference(P, 0, drone, rp, rv, sphi, cphi);
+          spiral_extras(myrow + 12 + B * A, d, rp, rv, sphi, cphi);
+        }
+      }
+    }
+    // this step's rows leave as one TMA bulk store while the next step computes
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) bulk_store_s2g(P.obs + (size_t)k * Q.obs_step + (size_t)g0 * D, tile_s, bytes);
+    act = act_next;
+    total = (total + 1 >= P.total_wrap) ? 0 : total + 1;
+    head = head + 1 == B ? 0 : head + 1;
+  }
+
+  if (active) {
+    P.s0[g] = make_float4(d.px, d.py, d.pz, d.qx);
+    P.s1[g] = make_float4(d.qy, d.qz, d.qw, d.vx);
+    P.s2[g] = make_float4(d.vy, d.vz, d.wx, d.wy);
+    P.s3[g] = make_float4(d.wz, d.tx, d.ty, d.tz);
+    if (drone == 0) {
+      P.stepc[env] = stepc;
+      if (P.ep_ret != nullptr) P.ep_ret[env] = ep;
+    }
+  }
+  __syncthreads();   // every thread's stores are issued (and ordered before thread 0's release)
+  if (tid == 0) {
+    bulk_wait_all0();
+    if (P.host_total >= 0) {
+      if (tile == 0) P.gsteps[0] = total;
+    } else {            // CUDA-graph replay: other CTAs read the counter when they start, the last one out advances it
+      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(P.gsteps + 1), 1u);
+      if (ticket == gridDim.x - 1) { P.gsteps[1] = 0; P.gsteps[0] = total; }
+    }
+    if (P.pipeline) {   // later pipelined launches wait on this tile's epoch / count finished (tile, step) pairs
+      st_release_gpu(P.tile_epoch + tile, total);
+      atomicAdd(P.finished, (unsigned long long)Q.K);
+    }
+  }
+}
+
 }  // namespace bd

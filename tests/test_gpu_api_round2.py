@@ -90,6 +90,62 @@ def test_step_many_equals_k_steps(M, N, precision):
         e.close()
 
 
+@pytest.mark.parametrize("cfg,M,N,physics,A", [
+    (dict(task="spiral", drone_model="cf2x", num_drones=5, pyb_freq=240, ctrl_freq=48, act="rpm"), 5, 700, "dyn_gnd_drag_dw", 4),
+    (dict(task="multihover", drone_model="cf2x", num_drones=16, pyb_freq=240, ctrl_freq=30, act="rpm"), 16, 300, "dyn_dw", 4),
+    (dict(task="multihover", drone_model="racer", num_drones=2, pyb_freq=240, ctrl_freq=48, act="one_d_rpm"), 2, 1000, "dyn", 1),
+    (dict(task="flock", drone_model="cf2x", num_drones=4, pyb_freq=240, ctrl_freq=30, act="rpm"), 4, 900, "dyn", 4),
+    (dict(task="hover", drone_model="cf2x", num_drones=1, pyb_freq=240, ctrl_freq=30, act="rpm"), 1, 5000, "dyn", 4),
+])
+def test_step_many_one_launch_equals_k_launches_all_flavours(cfg, M, N, physics, A):
+    """The K-steps-in-one-launch kernel (states in registers, history in shared memory across steps) against K single
+    launches: bit-identical observations, rewards, flags, device state and episode statistics for every kernel flavour
+    (aero terms, ONE_D_RPM rows, swarm rewards, Spiral extras), with re-spawns inside the K steps, ragged last tiles,
+    and single steps before / after so that ring head and step counters are in the middle of their ranges."""
+    from marl_gym_pybullet_drones_b200.batch_aviary import StepResult
+    K = 37
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[0.8 * (i % side), 0.8 * (i // side), 0.3 + 0.05 * i] for i in range(M)])
+    envs = [batch_from_cfg(cfg, xyz, None, num_envs=N, precision="fp32", physics=physics, auto_reset=True,
+                           reset_mode="jitter_philox" if cfg["task"] == "multihover" else "fixed", seed=11,
+                           track_episode_stats=True) for _ in range(2)]
+    for e in envs:
+        e.reset_device()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = (torch.rand((K + 7, N, M, A), device="cuda", generator=gen) * 2 - 1.3).contiguous()
+    for k in range(4):                       # a few single steps first: ring head != 0, counters running
+        ra, rb = envs[0].step_device(acts[K + k]), envs[1].step_device(acts[K + k])
+        assert torch.equal(ra.obs, rb.obs)
+    D = envs[0].OBS_DIM
+    obs = torch.empty((K, N, M, D), device="cuda")
+    rew = torch.empty((K, N), device="cuda")
+    term = torch.empty((K, N), device="cuda", dtype=torch.bool)
+    trunc = torch.empty((K, N), device="cuda", dtype=torch.bool)
+    l0 = envs[0].launch_count
+    envs[0].step_many(acts[:K], obs, rew, term, trunc)
+    assert envs[0].launch_count - l0 == 1            # ONE launch, not K
+    for k in range(K):
+        r = envs[1].step_device(acts[k])
+        assert torch.equal(r.obs, obs[k]), (k, float((r.obs - obs[k]).abs().max()))
+        assert torch.equal(r.reward, rew[k]), k
+        assert torch.equal(r.terminated, term[k]) and torch.equal(r.truncated, trunc[k]), k
+    assert bool((term | trunc).any())
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    assert torch.equal(torch.nan_to_num(sa), torch.nan_to_num(sb))   # (the fast kernel does not keep world angular velocities: NaN)
+    ea, eb = envs[0].episode_stats(), envs[1].episode_stats()
+    assert abs(float(ea[2]) - float(eb[2])) == 0 and abs(float(ea[0]) - float(eb[0])) <= 1e-6 * max(1.0, abs(float(eb[0])))
+    for k in range(3):                       # and the handles stay interchangeable (epochs, counters, ring)
+        ra, rb = envs[0].step_device(acts[K + 4 + k]), envs[1].step_device(acts[K + 4 + k])
+        assert torch.equal(ra.obs, rb.obs) and torch.equal(ra.reward, rb.reward)
+    # a second K-step launch right after single steps
+    envs[0].step_many(acts[:K], obs, rew, term, trunc)
+    for k in range(K):
+        r = envs[1].step_device(acts[k])
+        assert torch.equal(r.obs, obs[k]) and torch.equal(r.reward, rew[k]), k
+    for e in envs:
+        e.close()
+
+
 def test_rng_state_roundtrip_continues_the_respawn_stream():
     """A fresh handle that is given the state of a running one draws the SAME re-spawn positions from then on;
     without it, it would replay the stream from the start."""
