@@ -448,23 +448,37 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
     }
     if constexpr (MODE != 0) {
       if (dw) {
+        // Every unordered pair is evaluated ONCE: of two drones only the lower one feels the other's downwash (:801,
+        // dz > 0), and the force depends on |dz| and the horizontal distance alone — so the lane that meets partner
+        // drone + o computes f(|dz|, dxy^2) and keeps it (partner above me) or hands it to the partner (partner below
+        // me) through one more shuffle; offsets 1 .. M/2 cover all pairs (for even M the offset M/2 is visited from both
+        // ends: the lower-indexed drone owns it).  Half the exp / divide work of a loop over all M - 1 partners
+        // (config-5 shape, M = 16: 493 -> see profiles/README.md), identical values, different summation order.
         const int M = P.M;
         float fdw = 0.f;
-#pragma unroll 4
-        for (int o = 1; o < M; ++o) {
+        const int half = M >> 1;
+#pragma unroll 2
+        for (int o = 1; o <= half; ++o) {
           int t = drone + o;
           t -= (t >= M) ? M : 0;
+          int b = drone - o;
+          b += (b < 0) ? M : 0;
           const int src = group_base + t;
           const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
                       oz = __shfl_sync(0xffffffffu, d.pz, src);
           const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
+          const float adz = fabsf(dz);
           const float dxy2 = fmaf(dx, dx, dy * dy);
-          const float ratio = __fdividef(P.prop_radius, 4.0f * dz);
+          const float ratio = __fdividef(P.prop_radius, 4.0f * adz);
           const float alpha = P.dw1 * ratio * ratio;
-          const float beta = fmaf(P.dw2, dz, P.dw3);
+          const float beta = fmaf(P.dw2, adz, P.dw3);
           const float q2 = __fdividef(dxy2, beta * beta);
-          const float f = -alpha * __expf(-0.5f * q2);
-          if (dz > 0.f && dxy2 < 100.f) fdw += f;                 // :801 (delta_xy < 10)
+          float f = -alpha * __expf(-0.5f * q2);
+          const bool mine_to_count = (2 * o != M) || (drone < half);     // the doubly visited offset: one owner
+          if (!(adz > 0.f && dxy2 < 100.f && mine_to_count)) f = 0.f;       // :801 (delta_xy < 10)
+          const float theirs = dz < 0.f ? f : 0.f;                          // the partner is below me
+          const float recv = __shfl_sync(0xffffffffu, theirs, group_base + b);
+          fdw += (dz > 0.f ? f : 0.f) + recv;
         }
         const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
         c1s += k;

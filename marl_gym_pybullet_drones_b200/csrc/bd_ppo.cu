@@ -40,7 +40,7 @@ constexpr int kRows = 128;          // rows per tile = UMMA M
 constexpr int HID = 256;            // hidden width (both layers)
 constexpr int kNOut = 16;           // output layer padded to the smallest UMMA N
 constexpr int kSlabBytes = 8192;    // one K = 16 step of a 256-row weight operand
-constexpr int kStages = 4;          // weight slab ring
+constexpr int kMaxStages = 8;       // weight slab ring: as many 8 KB stages as the tile kernel's other buffers leave room for
 constexpr int kEpiThreads = 512;    // 4 threads per row (column groups of 64)
 constexpr int kThreads = kEpiThreads + 64;   // + MMA warp + TMA warp
 constexpr int kMaxPieces = 3;       // 8-column input pieces per thread and chunk (K1p <= 96)
@@ -148,10 +148,12 @@ struct TileArgs {
   bf16 *Xt, *H1t, *H2t, *dZ2t, *dZ1t, *dZ3t;   // tile scratch for dw_kernel
   float* out;                // MODE_FORWARD: (rows, out_dim)
   double* stats;             // [0] sum loss, [1] sum (logp_old - logp), [2] rows, [3..6] dlogstd sums, [7..10] db3 sums
+  int stages;                // ring depth (<= kMaxStages)
+  long long* trace;          // diagnostics: CTA 0's epilogue thread 0 writes [tile][16] SM-clock stamps of its phases
 };
 
 enum { B_W3 = 0, B_XFULL, B_XEMPTY = B_XFULL + 2, B_L1 = B_XEMPTY + 2, B_L2, B_L3, B_D2, B_D1, B_Z3, B_TDONE, B_H1C,
-       B_H2C = B_H1C + 4, B_Z2C = B_H2C + 4, B_FULL = B_Z2C + 4, B_EMPTY = B_FULL + kStages, B_COUNT = B_EMPTY + kStages };
+       B_H2C = B_H1C + 4, B_Z2C = B_H2C + 4, B_FULL = B_Z2C + 4, B_EMPTY = B_FULL + kMaxStages, B_COUNT = B_EMPTY + kMaxStages };
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tile_kernel(const __grid_constant__ TileArgs P) {
@@ -160,10 +162,14 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
   const int K1p = W.K1p, C = W.C, D = W.D;
   bf16* bufH1 = reinterpret_cast<bf16*>(smem);                        // 64 KB: H1, later dZ1
   bf16* bufH2 = bufH1 + (size_t)kRows * HID;                          // 64 KB: H2, later dZ2
-  bf16* bufX = bufH2 + (size_t)kRows * HID;                           // 2 x [128 x K1p] (K1p <= 96)
-  bf16* bufZ3 = bufX + 2 * (size_t)kRows * 96;                        // [128 x 16]
+  // input chunks [128 x K1p]: one buffer for the actor (one chunk per tile, long consumed when the next tile is staged),
+  // two for the centralised critic (chunk c + 1 is staged while the tensor core reads chunk c)
+  const int nxb = C > 1 ? 2 : 1;
+  const int kStages = P.stages;
+  bf16* bufX = bufH2 + (size_t)kRows * HID;
+  bf16* bufZ3 = bufX + (size_t)nxb * kRows * K1p;                     // [128 x 16]
   bf16* sW3 = bufZ3 + (size_t)kRows * kNOut;                          // [16 x 256]
-  unsigned char* ring = reinterpret_cast<unsigned char*>(sW3 + (size_t)kNOut * HID);   // kStages x 8 KB
+  unsigned char* ring = reinterpret_cast<unsigned char*>(sW3 + (size_t)kNOut * HID);   // stages x 8 KB
   float* sB1 = reinterpret_cast<float*>(ring + (size_t)kStages * kSlabBytes);
   float* sB2 = sB1 + HID;
   float* sB3 = sB2 + HID;      // [16]
@@ -186,7 +192,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       mbar_init(smem_u32(&mbar[B_H2C + i]), kEpiThreads);
       mbar_init(smem_u32(&mbar[B_Z2C + i]), kEpiThreads);
     }
-    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&mbar[B_FULL + i]), 1); mbar_init(smem_u32(&mbar[B_EMPTY + i]), 1); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(smem_u32(&mbar[B_FULL + i]), 1); mbar_init(smem_u32(&mbar[B_EMPTY + i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -204,7 +210,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
                  aRing = smem_u32(ring);
   const long long n_tiles = (P.rows + kRows - 1) / kRows;
   const int k1_steps = K1p / 16;
-  const uint32_t xbuf_bytes = (uint32_t)kRows * 96 * 2;
+  const uint32_t xbuf_bytes = (uint32_t)kRows * (uint32_t)K1p * 2u;
 
   if (warp == kEpiThreads / 32 + 1) {
     // ===================================== TMA producer ===========================================
@@ -262,8 +268,8 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
         tc_fence_after();
         // ---- layer 1: acc0 = sum_c X_c W1_c^T
         for (int c = 0; c < C; ++c, ++xcnt) {
-          const int xb = (int)(xcnt & 1);
-          mbar_wait(bar(B_XFULL + xb), (uint32_t)((xcnt >> 1) & 1));
+          const int xb = nxb == 2 ? (int)(xcnt & 1) : 0;
+          mbar_wait(bar(B_XFULL + xb), (uint32_t)((nxb == 2 ? (xcnt >> 1) : xcnt) & 1));
           tc_fence_after();
           const uint64_t dX = xb ? dX1 : dX0;
           for (int s = 0; s < k1_steps; ++s) ring_mma(acc0, dX + (uint64_t)(16 * s), (uint32_t)((c | s) != 0));
@@ -374,7 +380,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       }
     };
     auto stage_x = [&](int xbuf, long long tile, int c) {
-      bf16* dst = bufX + (size_t)xbuf * kRows * 96;
+      bf16* dst = bufX + (size_t)xbuf * kRows * K1p;
       bf16* gdst = train ? P.Xt + ((size_t)tile * C + c) * (size_t)kRows * K1p : nullptr;
 #pragma unroll
       for (int i = 0; i < kMaxPieces; ++i) {
@@ -457,13 +463,17 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       cur_sample = sample_of(blockIdx.x);
       load_x(blockIdx.x, 0, cur_sample);
     }
+    long long* const tr0 = (P.trace != nullptr && blockIdx.x == 0 && tid == 0) ? P.trace : nullptr;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long next = tile + gridDim.x;
       const long long samp = cur_sample;
+      long long* const tr = (tr0 != nullptr && tile / gridDim.x < 16) ? tr0 + (tile / gridDim.x) * 16 : nullptr;
+      if (tr) tr[0] = clock64();     // tile start
       // ---- stage the input chunks (actor: one, critic: one per agent); the next chunk is already on its way
       for (int c = 0; c < C; ++c, ++xcnt) {
-        const int xbuf = (int)(xcnt & 1);
-        if (xcnt >= 2) mbar_wait(bar(B_XEMPTY + xbuf), (uint32_t)(((xcnt >> 1) & 1) ^ 1));
+        const int xbuf = nxb == 2 ? (int)(xcnt & 1) : 0;
+        const unsigned long long use = nxb == 2 ? (xcnt >> 1) : xcnt;       // how often this buffer has been filled before
+        if (use >= 1) mbar_wait(bar(B_XEMPTY + xbuf), (uint32_t)((use & 1) ^ 1));
         normalise_x(tile, c, samp);
         stage_x(xbuf, tile, c);
         proxy_fence();
@@ -473,19 +483,25 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       }
       const size_t tbase = (size_t)tile * kRows * HID;
       // ---- H1
+      if (tr) tr[1] = clock64();     // inputs staged
       mbar_wait(bar(B_L1), tpar);
       tc_fence_after();
+      if (tr) tr[2] = clock64();     // layer 1 complete
       epi_forward(acc0, sB1, bufH1, train ? P.H1t + tbase : nullptr, B_H1C);
       tc_fence_before();
+      if (tr) tr[3] = clock64();     // H1 written
       // ---- H2
       mbar_wait(bar(B_L2), tpar);
       tc_fence_after();
+      if (tr) tr[4] = clock64();     // layer 2 complete
       epi_forward(acc1, sB2, bufH2, train ? P.H2t + tbase : nullptr, B_H2C);
       tc_fence_before();
+      if (tr) tr[5] = clock64();     // H2 written
       // ---- output layer, loss, gradient at the output (column group 0 owns the rows)
       if (grp == 0) {
         mbar_wait(bar(B_L3), tpar);
         tc_fence_after();
+        if (tr) tr[6] = clock64();   // layer 3 complete
         uint32_t v[16];
         tmem_ld16_nowait(acc0 + lane_off, v);
         tmem_wait_ld();
@@ -562,16 +578,21 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           }
         }
       }
+      if (tr) tr[7] = clock64();     // loss / output rows done
       if (train) {
         // ---- dZ2 = dH2 * (1 - H2^2), in place over H2; its chunks feed the dH1 MMAs
         mbar_wait(bar(B_D2), tpar);
         tc_fence_after();
+        if (tr) tr[8] = clock64();   // dH2 complete
         epi_backward(acc1, bufH2, P.dZ2t + tbase, B_Z2C);
         tc_fence_before();
+        if (tr) tr[9] = clock64();   // dZ2 written
         // ---- dZ1 = dH1 * (1 - H1^2)
         mbar_wait(bar(B_D1), tpar);
         tc_fence_after();
+        if (tr) tr[10] = clock64();  // dH1 complete
         epi_backward(acc0, bufH1, P.dZ1t + tbase, -1);
+        if (tr) tr[11] = clock64();  // dZ1 written
       }
       tc_fence_before();
       mbar_arrive(bar(B_TDONE));
@@ -971,9 +992,16 @@ int fwd2_stages(int K1p) {
   return st;
 }
 
-size_t tile_kernel_smem() {
-  return (size_t)2 * kRows * HID * 2 + (size_t)2 * kRows * 96 * 2 + (size_t)kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
-         (size_t)kStages * kSlabBytes + (size_t)(2 * HID + 2 * kNOut) * 4;
+// dynamic shared memory of mlp_tile_kernel for a net with C input chunks of K1p columns and `stages` ring stages
+size_t tile_kernel_smem(int C, int K1p, int stages) {
+  return (size_t)2 * kRows * HID * 2 + (size_t)(C > 1 ? 2 : 1) * kRows * K1p * 2 + (size_t)kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
+         (size_t)stages * kSlabBytes + (size_t)(2 * HID + 2 * kNOut) * 4;
+}
+constexpr size_t kTileSmemBudget = 227 * 1024 - 1024;   // opt-in maximum minus the kernel's static shared memory (barriers)
+int tile_stages(int C, int K1p) {
+  int st = kMaxStages;
+  while (st > 2 && tile_kernel_smem(C, K1p, st) > kTileSmemBudget) --st;
+  return st;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1454,7 +1482,7 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   alloc((void**)&n->pw3, (size_t)n1 * HID * kNOut * 4);
   alloc((void**)&n->pb1, (size_t)n1 * HID * 4); alloc((void**)&n->pb2, (size_t)n2 * HID * 4);
   alloc((void**)&n->stats, kStatSlots * sizeof(double));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_kernel_smem());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2SmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwStages * kDwStageBytes);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
@@ -1546,7 +1574,8 @@ int bd_ppo_forward(bd_ppo_net* n, const float* obs_dev, int n_envs, int n_agents
   a.out = out_dev; a.stats = n->stats;
   const long long tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(tiles < n->sm_count ? tiles : n->sm_count);
-  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(), (cudaStream_t)stream>>>(a);
+  a.stages = tile_stages(n->s.C, n->s.K1p);
+  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(n->s.C, n->s.K1p, a.stages), (cudaStream_t)stream>>>(a);
   n->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_forward: %s", cudaGetErrorString(e));
@@ -1604,7 +1633,9 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   a.stats = n->stats;
   const long long tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(tiles < n->sm_count ? tiles : n->sm_count);
-  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(), st>>>(a);
+  a.stages = tile_stages(n->s.C, n->s.K1p);
+  a.trace = n->trace;
+  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(n->s.C, n->s.K1p, a.stages), st>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (tile kernel): %s", cudaGetErrorString(e));
   // ---- weight gradients

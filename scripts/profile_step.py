@@ -17,6 +17,7 @@ ap.add_argument("--steps", type=int, default=12)
 ap.add_argument("--physics", default="dyn")
 ap.add_argument("--task", default="multihover")
 ap.add_argument("--ctrl-freq", type=int, default=30)
+ap.add_argument("--many", type=int, default=0, help="also run bd_step_many over this many steps (one launch), twice")
 args = ap.parse_args()
 M = args.drones
 side = int(np.ceil(np.sqrt(M)))
@@ -30,5 +31,13 @@ obs = torch.empty((slots, args.envs, M, env.OBS_DIM), device="cuda")
 env.reset_device(out=obs[0])
 for k in range(args.steps):
     r = env.step_device(acts[k % slots])
+if args.many > 0:
+    K = args.many
+    a = torch.rand((K, args.envs, M, 4), device="cuda") * 2 - 1
+    o = torch.empty((K, args.envs, M, env.OBS_DIM), device="cuda")
+    rw = torch.empty((K, args.envs), device="cuda")
+    f = torch.empty((2, K, args.envs), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        env.step_many(a, o, rw, f[0], f[1])
 torch.cuda.synchronize()
 print("ok", float(r.reward.mean()))
