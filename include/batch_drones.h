@@ -175,6 +175,9 @@ int bd_step_host_compact(bd_handle* h, const void* actions_host, float* obs_host
 int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, void* reward_dev,
                  uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
 int bd_set_step_many_mode(bd_handle* h, int mode);
+/* Benchmark helper: holds `stream` until the host stores a non-zero value into *flag_mapped (page-locked host memory,
+ * mapped device address); gives up after ~2 s.  A timed window enqueued behind it has no host-side gaps. */
+int bd_stream_gate(const uint32_t* flag_mapped, void* stream);
 
 /* RNG state of the on-device re-spawn draws — the counterpart of the workers' np.random states the
  * reference checkpoints and restores (mappo/mappo.py:203-229; subproc_vec_env.py:101-112

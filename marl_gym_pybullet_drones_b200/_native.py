@@ -21,7 +21,7 @@ BD_RESET = {"fixed": 0, "jitter_philox": 1, "jitter_buffer": 2}
 
 EXPORTS = (
     "bd_create", "bd_destroy", "bd_set_init_poses", "bd_set_jitter", "bd_reset", "bd_step",
-    "bd_step_host", "bd_step_host_compact", "bd_step_many", "bd_set_step_many_mode", "bd_get_rng_state", "bd_set_rng_state",
+    "bd_step_host", "bd_step_host_compact", "bd_step_many", "bd_set_step_many_mode", "bd_stream_gate", "bd_get_rng_state", "bd_set_rng_state",
     "bd_debug_set_tile_epoch", "bd_get_state", "bd_set_state", "bd_get_targets", "bd_episode_stats",
     "bd_get_controller_state", "bd_set_controller_state", "bd_set_action_f32", "bd_obs_dim", "bd_act_dim",
     "bd_action_buffer_size", "bd_substeps", "bd_launch_count", "bd_last_error", "bd_version",
@@ -98,6 +98,8 @@ def load():
     lib.bd_step_many.restype = C.c_int
     lib.bd_set_step_many_mode.argtypes = [vp, C.c_int]
     lib.bd_set_step_many_mode.restype = C.c_int
+    lib.bd_stream_gate.argtypes = [vp, vp]
+    lib.bd_stream_gate.restype = C.c_int
     lib.bd_get_rng_state.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.bd_get_rng_state.restype = C.c_int
     lib.bd_set_rng_state.argtypes = [vp, C.POINTER(C.c_uint64)]

@@ -785,6 +785,16 @@ int bd_step_many(bd_handle* h, int k, const void* actions_dev, float* obs_dev, v
   return BD_OK;
 }
 
+// Benchmark helper: a one-thread kernel that holds `stream` until the host stores a non-zero value into *flag (page-locked
+// host memory, read by the GPU through its mapped address) — so that a caller can enqueue a whole timed window behind it
+// and the device timeline of the window has no host-side gaps.  Bounded: gives up after ~2^32 SM clocks (2 s).
+int bd_stream_gate(const uint32_t* flag_mapped, void* stream) {
+  if (!flag_mapped) return fail(BD_EINVAL, "bd_stream_gate: null flag");
+  cudaError_t e = bd::launch_gate(flag_mapped, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(BD_ECUDA, "bd_stream_gate: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+
 // bd_step_many: mode 0 (default) = one launch for the k steps where the configuration allows it, 1 = always k launches
 // (what a closed-loop caller's steps cost; benchmarks of the per-step kernel).
 int bd_set_step_many_mode(bd_handle* h, int mode) {

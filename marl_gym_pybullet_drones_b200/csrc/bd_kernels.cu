@@ -827,6 +827,18 @@ cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int e
 }
 
 __global__ void set_epoch_kernel(int* tile_epoch, int tile, int value) { tile_epoch[tile] = value; }
+__global__ void gate_kernel(const uint32_t* flag) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile uint32_t*>(flag) == 0u) {
+    __nanosleep(500);
+    if (clock64() - t0 > (1LL << 32)) break;
+  }
+}
+cudaError_t launch_gate(const uint32_t* flag_mapped, cudaStream_t st) {
+  gate_kernel<<<1, 1, 0, st>>>(flag_mapped);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_set_epoch(int* tile_epoch, int tile, int value, cudaStream_t st) {
   set_epoch_kernel<<<1, 1, 0, st>>>(tile_epoch, tile, value);
   return cudaGetLastError();

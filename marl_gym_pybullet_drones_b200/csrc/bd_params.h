@@ -106,5 +106,6 @@ int compact_blocks(int n);
 cudaError_t launch_compact_done(const uint8_t* term, const uint8_t* trunc, int e0, int e1, int reset_total, int* blockcnt, int* total,
                                 const float* tobs, int row_floats, int cap, int* idx_out, float* rows_out, cudaStream_t st);
 cudaError_t launch_set_epoch(int* tile_epoch, int tile, int value, cudaStream_t st);
+cudaError_t launch_gate(const uint32_t* flag_mapped, cudaStream_t st);
 
 }  // namespace bd
