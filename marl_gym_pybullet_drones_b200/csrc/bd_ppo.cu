@@ -176,11 +176,13 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
   float* sLs = sB3 + kNOut;    // [16]
   __shared__ __align__(8) uint64_t mbar[B_COUNT];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_red[11];   // CTA-wide sums of the tiles' statistics, flushed to P.stats once at the end
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool train = P.mode != MODE_FORWARD;
   for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
   if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd != nullptr ? W.logstd[tid] : 0.f; }
+  if (tid < 11) s_red[tid] = 0.f;
   if (tid == 0) {
     mbar_init(smem_u32(&mbar[B_W3]), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&mbar[B_XFULL + i]), kEpiThreads); mbar_init(smem_u32(&mbar[B_XEMPTY + i]), 1); }
@@ -469,6 +471,20 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       const long long samp = cur_sample;
       long long* const tr = (tr0 != nullptr && tile / gridDim.x < 16) ? tr0 + (tile / gridDim.x) * 16 : nullptr;
       if (tr) tr[0] = clock64();     // tile start
+      // the row's loss inputs (a gather by sample index) are requested now and used two epilogues later: read at the
+      // point of use they cost a DRAM latency on the tile's critical path (2 k of 35 k cycles in the phase trace)
+      float pre_a[4] = {0.f, 0.f, 0.f, 0.f}, pre_lpo = 0.f, pre_adv = 0.f;
+      if (train && grp == 0 && samp >= 0) {
+        if (P.mode == MODE_ACTOR_TRAIN) {
+          const size_t arow = (size_t)samp * P.M + (int)((tile * kRows + row) % rps);
+          for (int k = 0; k < W.out_dim; ++k) pre_a[k] = ldg_f1_pinned(P.act + arow * W.out_dim + k);
+          pre_lpo = ldg_f1_pinned(P.logp_old + arow);
+          pre_adv = ldg_f1_pinned(P.adv + samp);
+        } else {
+          pre_adv = ldg_f1_pinned(P.ret + samp);
+          if (P.use_clipped_value > 0.f && P.v_old != nullptr) pre_lpo = ldg_f1_pinned(P.v_old + samp);
+        }
+      }
       // ---- stage the input chunks (actor: one, critic: one per agent); the next chunk is already on its way
       for (int c = 0; c < C; ++c, ++xcnt) {
         const int xbuf = nxb == 2 ? (int)(xcnt & 1) : 0;
@@ -514,19 +530,18 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
             for (int k = 0; k < W.out_dim; ++k) P.out[(size_t)r * W.out_dim + k] = __uint_as_float(v[k]) + sB3[k];
           } else if (P.mode == MODE_ACTOR_TRAIN) {
             // agent.py:617-640 with torch.distributions.Normal.log_prob summed over the action dims
-            const int agent = (int)(r % rps);
-            const size_t arow = (size_t)samp * P.M + agent;
             float lp = 0.f, diff[4], ivar[4];
             for (int k = 0; k < W.out_dim; ++k) {
               const float mu = __uint_as_float(v[k]) + sB3[k];
               const float ls = sLs[k];
               ivar[k] = __expf(-2.0f * ls);
-              diff[k] = P.act[arow * W.out_dim + k] - mu;
+              diff[k] = pre_a[k] - mu;
               lp += -0.5f * diff[k] * diff[k] * ivar[k] - ls - 0.91893853320467f;
             }
-            const float lpo = P.logp_old[arow];
+            const float lpo = pre_lpo;
+            if (tr) tr[12] = clock64();   // loss inputs have arrived
             const float ratio = __expf(lp - lpo);
-            const float a = (P.adv[samp] - P.adv_stats[0]) * P.adv_stats[1];
+            const float a = (pre_adv - P.adv_stats[0]) * P.adv_stats[1];
             const float s1 = ratio * a;
             const float s2 = fminf(fmaxf(ratio, 1.0f - P.clip), 1.0f + P.clip) * a;
             loss = -fminf(s1, s2);
@@ -542,11 +557,11 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           } else {
             // agent.py:643-700, centralised critic: target = mean over agents of identical returns
             const float vv = __uint_as_float(v[0]) + sB3[0];
-            const float rt = P.ret[samp];
+            const float rt = pre_adv;            // prefetched P.ret[samp]
             float e = vv - rt;
             float l = e * e;
             if (P.use_clipped_value > 0.f) {
-              const float vo = P.v_old != nullptr ? P.v_old[samp] : 0.f;
+              const float vo = pre_lpo;          // prefetched P.v_old[samp] (0 without stored values)
               const float dvc = fminf(fmaxf(vv - vo, -P.clip), P.clip);
               const float ec = vo + dvc - rt;
               if (ec * ec > l) { l = ec * ec; e = (fabsf(vv - vo) <= P.clip) ? ec : 0.f; }
@@ -568,13 +583,16 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
           proxy_fence();
           tc_fence_before();
           mbar_arrive(bar(B_Z3));
-          // tile statistics: warp reduce, one atomic per value and warp
+          if (tr) tr[13] = clock64();     // dZ3 handed to the tensor core
+          // tile statistics: warp reduce, then one shared-memory atomic per value and warp; the CTA's sums go to global
+          // memory once, when the kernel ends (11 double atomics per warp and tile on the same 11 addresses from every
+          // CTA cost ~4 k of a tile's 35 k cycles: profiles/r2_ppo_tile_trace_actor.txt)
           float red[11] = {loss, kl, cntv, dls[0], dls[1], dls[2], dls[3], dz[0], dz[1], dz[2], dz[3]};
 #pragma unroll
           for (int i = 0; i < 11; ++i) {
             float x = red[i];
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0 && x != 0.f) atomicAdd(P.stats + i, (double)x);
+            if (lane == 0 && x != 0.f) atomicAdd(&s_red[i], x);
           }
         }
       }
@@ -601,6 +619,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
   }
   tc_fence_before();
   __syncthreads();
+  if (train && tid < 11 && s_red[tid] != 0.f) atomicAdd(P.stats + tid, (double)s_red[tid]);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 

@@ -58,6 +58,13 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16])
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// read-only global load that stays where it is written (asm volatile): the per-row loss inputs are requested at the start
+// of a tile and used two epilogues later; a plain __ldg may be sunk down to that use
+__device__ __forceinline__ float ldg_f1_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -48,12 +48,12 @@ torch.cuda.synchronize()
 net._lib.bd_ppo_set_trace(net._h, None)
 tr = trace.cpu().numpy()
 names = ["tile start", "inputs staged", "L1 complete", "H1 written", "L2 complete", "H2 written", "L3 complete", "loss done",
-         "dH2 complete", "dZ2 written", "dH1 complete", "dZ1 written"]
+         "dH2 complete", "dZ2 written", "dH1 complete", "dZ1 written", "(loss inputs in)", "(dZ3 handed over)"]
 rows = [j for j in range(16) if tr[j, 0] != 0]
 for j in rows[:3] + rows[-1:]:
     print(f"tile {j} of CTA 0 (cycles since the tile started, delta)")
     prev = tr[j, 0]
-    for k, nme in enumerate(names):
+    for k, nme in sorted(enumerate(names), key=lambda kn: tr[j, kn[0]]):
         if tr[j, k]:
             print(f"   {nme:14s} {tr[j, k] - tr[j, 0]:8d}  +{tr[j, k] - prev:6d}")
             prev = tr[j, k]
