@@ -16,7 +16,7 @@ Stated tolerances:
   fp64 : state (pos, quat, rpy, vel, ang_vel) and reward <= 1e-9 relative at every step of the free-running horizon,
          observations (float32 storage) <= 2.5e-7, terminated / truncated identical, for ALL envs.
   fp32 : per control step from the oracle's state (teacher-forced, every env, every step):
-         plain DYN (configs[1], fast tile kernel) <= 1e-5; all aero terms (configs[2], generic kernel) <= 5e-5
+         plain DYN (configs[1], fast tile kernel) <= 1e-5; all aero terms (configs[2], fast tile kernel, aero flavour) <= 5e-5
          of max(|x|, 1) on env-steps where no two drones are within 3 cm of the same height (the downwash term is
          singular there, see the test), <= 2e-2 otherwise; flags identical (configs[1]: all env-steps;
          configs[2]: the well-conditioned ones).
@@ -187,7 +187,7 @@ def test_cfg2_fp64_spiral_aero_full_horizon(auto_reset):
 
 
 def test_cfg2_fp32_per_step_spiral_aero():
-    """Generic float kernel with ground effect + drag + downwash, teacher-forced from the oracle's state.
+    """Fast tile kernel (aero flavour: ground effect + drag + downwash by warp shuffle), teacher-forced from the oracle's state.
 
     The downwash force on a drone is alpha exp(..), alpha = DW1 (r_prop / 4 dz)^2 (`BaseAviary.py:802`): its relative
     sensitivity to the height difference is 2/dz, so a float32 rounding of dz (6e-8 of |z| ~ 0.5) becomes a relative

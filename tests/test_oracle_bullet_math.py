@@ -56,6 +56,33 @@ def test_pose_roundtrip_normalises_and_canonicalises():
                 assert r[i] > 0           # pivot component is the positive square root
 
 
+def test_pose_roundtrip_vs_scipy_canonical_in_the_trace_nonpositive_region():
+    """rotations by more than 120 degrees (trace <= 0, where btMatrix3x3::getRotation pivots on the
+    largest diagonal element).  The round trip must be the same ROTATION as scipy's canonical (w >= 0) quaternion; the
+    SIGN is Bullet's own convention — pivot component positive — which differs from scipy's exactly when the w that
+    follows from it is negative.  Both facts are asserted, so a sign slip in the restatement cannot hide."""
+    n_neg_w = 0
+    for _ in range(2000):
+        axis = RNG.standard_normal(3)
+        axis /= np.linalg.norm(axis)
+        ang = RNG.uniform(2.2, np.pi)                       # > 120 degrees: trace = 1 + 2 cos(ang) <= 0 mostly
+        q = np.concatenate([axis * np.sin(ang / 2), [np.cos(ang / 2)]]) * RNG.choice([-1.0, 1.0])
+        m = np.array(bm.matrix_from_quaternion(q)).reshape(3, 3)
+        if np.trace(m) > 0:
+            continue
+        r = np.array(bm.pose_roundtrip(q))
+        canon = Rotation.from_matrix(m).as_quat(canonical=True)
+        assert np.allclose(Rotation.from_quat(r).as_matrix(), m, atol=1e-14)
+        i = int(np.argmax(np.diag(m)))
+        assert r[i] > 0
+        if r[3] >= 0:
+            assert np.allclose(r, canon, atol=1e-13)
+        else:
+            n_neg_w += 1
+            assert np.allclose(r, -canon, atol=1e-13)
+    assert n_neg_w > 100            # the region where Bullet's and scipy's conventions differ is really visited
+
+
 def test_integrate_q_is_body_frame_exponential():
     for q in random_quats(100):
         w = RNG.standard_normal(3) * RNG.choice([1e-3, 1.0, 30.0])
