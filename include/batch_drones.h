@@ -351,6 +351,9 @@ int bd_ppo_adv_stats(const double* acc3_dev, float* stats2_dev, void* stream);
 /* diagnostics: CTA 0 of the following forward / sample launches writes SM-clock stamps of its pipeline phases
  * ([tile pair][64] int64, see csrc/bd_ppo.cu); NULL switches tracing off */
 int bd_ppo_set_trace(bd_ppo_net* n, long long* trace_dev);
+/* which forward / loss / backward kernel bd_ppo_grad launches: 0 (default) one 128-row tile in flight per CTA, 1 two tiles in
+ * flight (one in-place activation buffer per tile, every weight slab serving both tiles); same results */
+int bd_ppo_set_train_mode(bd_ppo_net* n, int mode);
 int64_t bd_ppo_launch_count(const bd_ppo_net* n);
 const char* bd_ppo_last_error(void);
 

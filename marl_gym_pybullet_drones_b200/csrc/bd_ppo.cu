@@ -1011,6 +1011,475 @@ int fwd2_stages(int K1p) {
   return st;
 }
 
+// ---------------------------------------------------------------------------------------------
+//              forward + loss + backward with TWO tiles in flight per CTA (training, round 2)
+// ---------------------------------------------------------------------------------------------
+// mlp_tile_kernel takes one tile at a time through ten dependent phases (MMA, epilogue, MMA, ...): 34 k cycles per tile
+// of which the tensor pipe works 12 % (profiles/r2_ppo_tile_trace_actor.txt).  Two observations make a second tile fit:
+//   * H1 is an MMA operand only for layer 2; the backward pass needs it element-wise (dZ1 = dH1 (1 - H1^2)), and the
+//     thread that needs an element is the thread that wrote it to the H1 tile in global memory (for the weight-gradient
+//     kernel) — so H2 can overwrite H1 in shared memory (after layer 2 has completed) and H1 is re-read from global;
+//   * dZ1 is never an MMA operand here (only in dw_kernel): it goes to global memory and nowhere else.
+// A tile therefore needs ONE 64 KB activation buffer (H1 -> H2 -> dZ2, all in place), its input buffer and a 4 KB dZ3
+// tile, and one 256-column accumulator when the next MMA phase starts only after the previous epilogue has finished —
+// which costs nothing once a second tile keeps both units busy: the tensor core runs phase k of tile B while the 512
+// epilogue threads finish phase k of tile A.  Same roles, ring and barrier style as mlp_fwd2_kernel.
+// Phases per slot t:  L1 -> H1 | L2 -> H2 | L3 -> loss (-> dZ3) | D2 (dH2) -> dZ2 | D1 (dH1) -> dZ1.
+enum { T_W3 = 0, T_XFULL, T_XEMPTY = T_XFULL + 2, T_L1 = T_XEMPTY + 2, T_L2 = T_L1 + 2, T_L3 = T_L2 + 2, T_D2 = T_L3 + 2,
+       T_D1 = T_D2 + 2, T_H1 = T_D1 + 2, T_H2 = T_H1 + 2, T_Z3 = T_H2 + 2, T_Z2 = T_Z3 + 2, T_OUT = T_Z2 + 2, T_FULL = T_OUT + 2,
+       T_EMPTY = T_FULL + kMaxStages, T_COUNT = T_EMPTY + kMaxStages };
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_train2_kernel(const __grid_constant__ TileArgs P) {
+  extern __shared__ __align__(128) unsigned char smem_t2[];
+  const NetDev& W = P.net;
+  const int K1p = W.K1p, C = W.C, D = W.D, stages = P.stages;
+  bf16* const bufT0 = reinterpret_cast<bf16*>(smem_t2);                      // 2 x 64 KB: H1 -> H2 -> dZ2
+  bf16* const bufX0 = bufT0 + 2 * (size_t)kRows * HID;                       // 2 x [128 x K1p]
+  const uint32_t xbytes = (uint32_t)kRows * (uint32_t)K1p * 2u;
+  bf16* const bufZ0 = bufX0 + 2 * (size_t)kRows * K1p;                       // 2 x [128 x 16]
+  bf16* sW3 = bufZ0 + 2 * (size_t)kRows * kNOut;
+  unsigned char* ring = reinterpret_cast<unsigned char*>(sW3 + (size_t)kNOut * HID);
+  float* sB1 = reinterpret_cast<float*>(ring + (size_t)stages * kSlabBytes);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;
+  float* sLs = sB3 + kNOut;
+  float* s_red = sLs + kNOut;                                                // [16] CTA-wide statistics
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_red + 16);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(mbar + T_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd != nullptr ? W.logstd[tid] : 0.f; s_red[tid] = 0.f; }
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[T_W3]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&mbar[T_XFULL + i]), kEpiThreads); mbar_init(smem_u32(&mbar[T_XEMPTY + i]), 1);
+      mbar_init(smem_u32(&mbar[T_L1 + i]), 1); mbar_init(smem_u32(&mbar[T_L2 + i]), 1); mbar_init(smem_u32(&mbar[T_L3 + i]), 1);
+      mbar_init(smem_u32(&mbar[T_D2 + i]), 1); mbar_init(smem_u32(&mbar[T_D1 + i]), 1);
+      mbar_init(smem_u32(&mbar[T_H1 + i]), kEpiThreads); mbar_init(smem_u32(&mbar[T_H2 + i]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[T_Z3 + i]), kRows); mbar_init(smem_u32(&mbar[T_Z2 + i]), kEpiThreads);
+      mbar_init(smem_u32(&mbar[T_OUT + i]), kEpiThreads);
+    }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(smem_u32(&mbar[T_FULL + i]), 1); mbar_init(smem_u32(&mbar[T_EMPTY + i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t aT0 = smem_u32(bufT0), aX0 = smem_u32(bufX0), aZ0 = smem_u32(bufZ0), aW3 = smem_u32(sW3), aRing = smem_u32(ring);
+  const uint32_t tbytes = (uint32_t)kRows * HID * 2u, zbytes = (uint32_t)kRows * kNOut * 2u;
+  const long long n_tiles = (P.rows + kRows - 1) / kRows;
+  const long long my_tiles = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int k1_steps = K1p / 16;
+
+  if (warp == kEpiThreads / 32 + 1) {
+    // ===================================== TMA producer ===========================================
+    if (lane == 0) {
+      mbar_expect_tx(bar(T_W3), (uint32_t)(kNOut * HID * 2));
+      bulk_g2s(aW3, W.w3f, (uint32_t)(kNOut * HID * 2), bar(T_W3));
+      uint32_t st = 0, epar = 1, lap0 = 1;
+      const uint64_t keep = l2_policy_evict_last();
+      auto push = [&](const bf16* src) {
+        if (!lap0) mbar_wait(bar(T_EMPTY + (int)st), epar);
+        mbar_expect_tx(bar(T_FULL + (int)st), kSlabBytes);
+        bulk_g2s_hint(aRing + st * kSlabBytes, src, kSlabBytes, bar(T_FULL + (int)st), keep);
+        if (++st == (uint32_t)stages) { st = 0; epar ^= 1; lap0 = 0; }
+      };
+      const int n1 = C * k1_steps;
+      for (long long p = 0; p < my_tiles; p += 2) {            // ONE set of slabs per pair: every slab serves both tiles
+        for (int q = 0; q < n1; ++q) push(W.w1_slabs + (size_t)q * (kSlabBytes / 2));
+        for (int q = 0; q < 16; ++q) push(W.w2f_slabs + (size_t)q * (kSlabBytes / 2));
+        push(W.w3b_slab);
+        for (int q = 0; q < 16; ++q) push(W.w2b_slabs + (size_t)q * (kSlabBytes / 2));
+      }
+    }
+  } else if (warp == kEpiThreads / 32) {
+    // ===================================== MMA issuer =============================================
+    if (lane == 0) {
+      uint32_t st = 0, fpar = 0;
+      uint32_t xpar = 0;                 // bit t: parity of slot t's next XFULL completion
+      const uint32_t sboX = (uint32_t)(K1p / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      const uint64_t dX = umma_desc(aX0, 128, sboX), dT = umma_desc(aT0, 128, sboH), dW3 = umma_desc(aW3, 128, sboH),
+                     dZ = umma_desc(aZ0, 128, 256), dRing = umma_desc(aRing, 128, 256);
+      const uint64_t xstep = (uint64_t)(xbytes >> 4), tstep = (uint64_t)(tbytes >> 4), zstep = (uint64_t)(zbytes >> 4);
+      constexpr uint32_t kIdH = umma_idesc(HID), kIdO = umma_idesc(kNOut);
+      // one streamed K-step for BOTH slots: wait for the slab, issue one MMA per tile of the pair on it, hand the stage
+      // back.  The slab stream is what bounds this kernel (an 8 KB slab arrives every 300-800 cycles with the 5 stages
+      // that fit, profiles/r2_ppo_train2_trace.txt), so a fetch has to feed as many rows as possible.
+      auto ring_mma2 = [&](int nt, uint64_t adescA, uint64_t adescB, uint32_t accumulate) {
+        mbar_wait(bar(T_FULL + (int)st), fpar);
+        const uint64_t b = dRing + (uint64_t)(st * (kSlabBytes >> 4));
+        umma_bf16(tmem_base, adescA, b, kIdH, accumulate);
+        if (nt > 1) umma_bf16(tmem_base + (uint32_t)HID, adescB, b, kIdH, accumulate);
+        umma_commit(bar(T_EMPTY + (int)st));
+        if (++st == (uint32_t)stages) { st = 0; fpar ^= 1; }
+      };
+      mbar_wait(bar(T_W3), 0);
+      uint32_t ppar = 0;
+      for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+        const int nt = (p + 1 < my_tiles) ? 2 : 1;
+        // ---- layer 1 of both tiles
+        if (p > 0)
+          for (int t = 0; t < nt; ++t) { mbar_wait(bar(T_OUT + t), ppar ^ 1); }   // the slots' previous tiles are through
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+          for (int t = 0; t < nt; ++t) { mbar_wait(bar(T_XFULL + t), (xpar >> t) & 1u); xpar ^= 1u << t; }
+          tc_fence_after();
+          for (int s = 0; s < k1_steps; ++s) ring_mma2(nt, dX + (uint64_t)(16 * s), dX + xstep + (uint64_t)(16 * s), (uint32_t)((c | s) != 0));
+          for (int t = 0; t < nt; ++t) umma_commit(bar(T_XEMPTY + t));
+        }
+        for (int t = 0; t < nt; ++t) umma_commit(bar(T_L1 + t));
+        // ---- layer 2: H1 W2^T
+        for (int t = 0; t < nt; ++t) mbar_wait(bar(T_H1 + t), ppar);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t o = (uint64_t)(16 * (4 * (i & 3) + (i >> 2)));
+          ring_mma2(nt, dT + o, dT + tstep + o, (uint32_t)(i != 0));
+        }
+        for (int t = 0; t < nt; ++t) umma_commit(bar(T_L2 + t));
+        // ---- layer 3: H2 W3^T (resident), N = 16, per slot as its H2 arrives
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait(bar(T_H2 + t), ppar);
+          tc_fence_after();
+          const uint64_t dTt = dT + tstep * (uint64_t)t;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) umma_bf16(acc, dTt + (uint64_t)(16 * s), dW3 + (uint64_t)(16 * s), kIdO, (uint32_t)(s != 0));
+          umma_commit(bar(T_L3 + t));
+        }
+        // ---- dH2 = dZ3 W3: one K = 16 step over the W3^T slab
+        for (int t = 0; t < nt; ++t) mbar_wait(bar(T_Z3 + t), ppar);
+        tc_fence_after();
+        ring_mma2(nt, dZ, dZ + zstep, 0u);
+        for (int t = 0; t < nt; ++t) umma_commit(bar(T_D2 + t));
+        // ---- dH1 = dZ2 W2 over the 16 W2^T slabs
+        for (int t = 0; t < nt; ++t) mbar_wait(bar(T_Z2 + t), ppar);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t o = (uint64_t)(16 * (4 * (i & 3) + (i >> 2)));
+          ring_mma2(nt, dT + o, dT + tstep + o, (uint32_t)(i != 0));
+        }
+        for (int t = 0; t < nt; ++t) umma_commit(bar(T_D1 + t));
+      }
+    }
+  } else {
+    // ================================ staging + epilogue threads ==================================
+    const int row = tid & (kRows - 1), grp = tid >> 7;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int rps = (P.mode == MODE_CRITIC_TRAIN) ? 1 : P.M;
+    const int n_pieces = K1p / 8;
+    const bool vec4 = (D & 3) == 0;
+    float4 xa[kMaxPieces], xb4[kMaxPieces];
+    uint32_t xe = 0, xused = 0;
+
+    auto tile_of = [&](long long pos) { return (long long)blockIdx.x + pos * gridDim.x; };
+    auto sample_of = [&](long long tile) -> long long {
+      const long long r = tile * kRows + row;
+      if (r >= P.rows) return -1;
+      const long long s = r / rps;
+      return P.idx != nullptr ? P.idx[s] : s;
+    };
+    auto load_x = [&](long long tile, int c, long long sm) {
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      const float* src = P.obs + ((size_t)(sm < 0 ? 0 : sm) * P.M + agent) * D;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int k0 = (grp + i * 4) * 8;
+        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < D && sm >= 0) {
+          if (vec4 && k0 + 8 <= D) {
+            xa[i] = __ldg(reinterpret_cast<const float4*>(src + k0));
+            xb4[i] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (k0 + j < D) ? __ldg(src + k0 + j) : 0.0f;
+            xa[i] = make_float4(x[0], x[1], x[2], x[3]);
+            xb4[i] = make_float4(x[4], x[5], x[6], x[7]);
+          }
+        }
+      }
+    };
+    // registers -> (normalise) -> bf16 canonical tile of slot t (+ the global copy dw_kernel reads)
+    auto stage_x = [&](int t, long long tile, int c, long long sm) {
+      const long long r = tile * kRows + row;
+      const int agent = (rps == 1) ? c : (int)(r % rps);
+      if ((xused >> t) & 1u) { mbar_wait(bar(T_XEMPTY + t), (xe >> t) & 1u); xe ^= 1u << t; }
+      xused |= 1u << t;
+      bf16* dst = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(bufX0) + (size_t)t * xbytes);
+      bf16* gdst = P.Xt + ((size_t)tile * C + c) * (size_t)kRows * K1p;
+      const bool norm = P.nmean != nullptr && sm >= 0;
+      const size_t nb = norm ? ((size_t)(sm / P.N) * P.M + agent) * D : 0;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int pc = grp + i * 4;
+        if (pc < n_pieces) {
+          float x[8] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w, xb4[i].x, xb4[i].y, xb4[i].z, xb4[i].w};
+          if (norm) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = pc * 8 + j;
+              if (k < D) {
+                const float v = (x[j] - __ldg(P.nmean + nb + k)) * __ldg(P.nrstd + nb + k);
+                x[j] = fminf(fmaxf(v, -P.nclip), P.nclip);
+              }
+            }
+          }
+          const uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+          const size_t off = canon_off(row, pc * 8, K1p);
+          *reinterpret_cast<uint4*>(dst + off) = pk;
+          __stcs(reinterpret_cast<uint4*>(gdst + off), pk);
+        }
+      }
+      proxy_fence();
+      mbar_arrive(bar(T_XFULL + t));
+    };
+    // forward epilogue: acc row -> +bias, tanh -> bf16 -> the slot's activation tile and its global copy
+    auto epi_forward = [&](uint32_t acc, const float* bias, bf16* sH, bf16* gH, int done_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float z[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = __uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e];
+          const uint4 pk = make_uint4(tanh2_bf16(z[0], z[1]), tanh2_bf16(z[2], z[3]), tanh2_bf16(z[4], z[5]), tanh2_bf16(z[6], z[7]));
+          const size_t off = canon_off(row, c0 + q * 8, HID);
+          *reinterpret_cast<uint4*>(sH + off) = pk;
+          __stcs(reinterpret_cast<uint4*>(gH + off), pk);
+        }
+        tmem_wait_ld();
+      }
+      proxy_fence();
+      tc_fence_before();
+      mbar_arrive(bar(done_bar));
+    };
+    // backward epilogue: dZ = dH (1 - H^2) with H from `hsrc` (shared: H2, in place; global: my own H1 copy);
+    // dZ -> `sdst` (shared, may be null) and the global tile `gZ`
+    auto epi_backward = [&](uint32_t acc, const bf16* hsrc, bf16* sdst, bf16* gZ, int done_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const size_t off = canon_off(row, c0 + q * 8, HID);
+          const uint4 hv = *reinterpret_cast<const uint4*>(hsrc + off);
+          const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float h0, h1;
+            unpack_bf16(hw[e], h0, h1);
+            const float d0 = __uint_as_float(cur[q * 8 + 2 * e]) * fmaf(-h0, h0, 1.0f);
+            const float d1 = __uint_as_float(cur[q * 8 + 2 * e + 1]) * fmaf(-h1, h1, 1.0f);
+            o[e] = pack_bf16(d0, d1);
+          }
+          const uint4 pk = make_uint4(o[0], o[1], o[2], o[3]);
+          if (sdst != nullptr) *reinterpret_cast<uint4*>(sdst + off) = pk;
+          __stcs(reinterpret_cast<uint4*>(gZ + off), pk);
+        }
+        tmem_wait_ld();
+      }
+      if (sdst != nullptr) proxy_fence();
+      tc_fence_before();
+      mbar_arrive(bar(done_bar));
+    };
+
+    // prologue: chunk 0 of both slots' first tiles
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t)
+      if (t < my_tiles) {
+        const long long tile = tile_of(t), sm = sample_of(tile);
+        load_x(tile, 0, sm);
+        stage_x(t, tile, 0, sm);
+      }
+    uint32_t ppar = 0;
+    long long* const tr0 = (P.trace != nullptr && blockIdx.x == 0 && tid == 0) ? P.trace : nullptr;
+    for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+      const int nt = (p + 1 < my_tiles) ? 2 : 1;
+      long long* const tr = (tr0 != nullptr && p < 32) ? tr0 + (p >> 1) * 16 : nullptr;   // [pair][16] stamps of thread 0
+      if (tr) tr[0] = clock64();
+      if (C > 1) {     // centralised critic: the remaining input chunks of the current tiles, one by one
+        // (chunk by chunk over BOTH slots: the tensor core consumes chunk c of the two tiles together)
+#pragma unroll 1
+        for (int c = 1; c < C; ++c)
+#pragma unroll 1
+          for (int t = 0; t < nt; ++t) {
+            const long long tile = tile_of(p + t), sm = sample_of(tile);
+            load_x(tile, c, sm);
+            stage_x(t, tile, c, sm);
+          }
+      }
+      // ---- hidden layers: H1 of A while the tensor core runs layer 1 of B, H1 of B during layer 2 of A, ...
+#pragma unroll 1
+      for (int lt = 0; lt < 4; ++lt) {
+        const int layer = lt >> 1, t = lt & 1;
+        if (t >= nt) continue;
+        const long long tile = tile_of(p + t);
+        const bool has_next = layer == 0 && p + t + 2 < my_tiles;
+        const long long ntile = tile_of(p + t + 2);
+        long long nsm = -1;
+        if (has_next) { nsm = sample_of(ntile); load_x(ntile, 0, nsm); }   // in flight during the epilogue below
+        mbar_wait(bar(T_L1 + 2 * layer + t), ppar);
+        tc_fence_after();
+        epi_forward(tmem_base + (uint32_t)t * HID, layer ? sB2 : sB1, bufT0 + (size_t)t * kRows * HID,
+                    (layer ? P.H2t : P.H1t) + (size_t)tile * kRows * HID, T_H1 + 2 * layer + t);
+        if (has_next) stage_x(t, ntile, 0, nsm);           // layer 1 of this tile is complete: its input buffer is free
+        if (tr) tr[1 + lt] = clock64();                    // H1(A), H1(B), H2(A), H2(B) done
+      }
+      // ---- output layer, loss, gradient at the output (column group 0 owns the rows)
+      if (grp == 0) {
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {
+          const long long tile = tile_of(p + t);
+          const long long r = tile * kRows + row;
+          const long long samp = sample_of(tile);
+          float pre_a[4] = {0.f, 0.f, 0.f, 0.f}, pre_lpo = 0.f, pre_adv = 0.f;
+          if (samp >= 0) {                                 // requested before the wait for layer 3
+            if (P.mode == MODE_ACTOR_TRAIN) {
+              const size_t arow = (size_t)samp * P.M + (int)(r % rps);
+              for (int k = 0; k < W.out_dim; ++k) pre_a[k] = __ldg(P.act + arow * W.out_dim + k);
+              pre_lpo = __ldg(P.logp_old + arow);
+              pre_adv = __ldg(P.adv + samp);
+            } else {
+              pre_adv = __ldg(P.ret + samp);
+              if (P.use_clipped_value > 0.f && P.v_old != nullptr) pre_lpo = __ldg(P.v_old + samp);
+            }
+          }
+          mbar_wait(bar(T_L3 + t), ppar);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16_nowait(tmem_base + (uint32_t)t * HID + lane_off, v);
+          tmem_wait_ld();
+          float dz[4] = {0.f, 0.f, 0.f, 0.f};
+          float loss = 0.f, kl = 0.f, dls[4] = {0.f, 0.f, 0.f, 0.f}, cntv = 0.f;
+          if (samp >= 0) {
+            cntv = 1.f;
+            if (P.mode == MODE_ACTOR_TRAIN) {
+              // agent.py:617-640 with torch.distributions.Normal.log_prob summed over the action dims
+              float lp = 0.f, diff[4], ivar[4];
+              for (int k = 0; k < W.out_dim; ++k) {
+                const float mu = __uint_as_float(v[k]) + sB3[k];
+                const float ls = sLs[k];
+                ivar[k] = __expf(-2.0f * ls);
+                diff[k] = pre_a[k] - mu;
+                lp += -0.5f * diff[k] * diff[k] * ivar[k] - ls - 0.91893853320467f;
+              }
+              const float lpo = pre_lpo;
+              const float ratio = __expf(lp - lpo);
+              const float a = (pre_adv - P.adv_stats[0]) * P.adv_stats[1];
+              const float s1 = ratio * a;
+              const float s2 = fminf(fmaxf(ratio, 1.0f - P.clip), 1.0f + P.clip) * a;
+              loss = -fminf(s1, s2);
+              kl = lpo - lp;
+              const bool inside = ratio >= 1.0f - P.clip && ratio <= 1.0f + P.clip;
+              const float g = (inside || s1 < s2) ? -a * ratio : 0.f;
+              for (int k = 0; k < W.out_dim; ++k) {
+                dz[k] = g * diff[k] * ivar[k];
+                dls[k] = g * (diff[k] * diff[k] * ivar[k] - 1.0f);
+              }
+            } else {
+              // agent.py:643-700, centralised critic: target = mean over agents of identical returns
+              const float vv = __uint_as_float(v[0]) + sB3[0];
+              const float rt = pre_adv;
+              float e = vv - rt;
+              float l = e * e;
+              if (P.use_clipped_value > 0.f) {
+                const float vo = pre_lpo;
+                const float dvc = fminf(fmaxf(vv - vo, -P.clip), P.clip);
+                const float ec = vo + dvc - rt;
+                if (ec * ec > l) { l = ec * ec; e = (fabsf(vv - vo) <= P.clip) ? ec : 0.f; }
+              }
+              loss = 0.5f * l;
+              dz[0] = e;
+            }
+          }
+          // dZ3 tile [128 x 16] bf16, K-major (K = 16): my row's 16 entries = two core-matrix rows
+          const uint4 lo = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+          const size_t off = canon_off(row, 0, kNOut);
+          bf16* z3 = bufZ0 + (size_t)t * kRows * kNOut;
+          *reinterpret_cast<uint4*>(z3 + off) = lo;
+          *reinterpret_cast<uint4*>(z3 + off + 64) = zero;
+          bf16* g3 = P.dZ3t + (size_t)tile * kRows * kNOut;
+          *reinterpret_cast<uint4*>(g3 + off) = lo;
+          *reinterpret_cast<uint4*>(g3 + off + 64) = zero;
+          proxy_fence();
+          tc_fence_before();
+          mbar_arrive(bar(T_Z3 + t));
+          float red[11] = {loss, kl, cntv, dls[0], dls[1], dls[2], dls[3], dz[0], dz[1], dz[2], dz[3]};
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            float x = red[i];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0 && x != 0.f) atomicAdd(&s_red[i], x);
+          }
+          if (tr) tr[5 + t] = clock64();                   // loss(A), loss(B) done
+        }
+      }
+      // ---- dZ2 = dH2 (1 - H2^2), in place over H2: the A operand of the dH1 MMAs
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const long long tile = tile_of(p + t);
+        mbar_wait(bar(T_D2 + t), ppar);
+        tc_fence_after();
+        bf16* sH = bufT0 + (size_t)t * kRows * HID;
+        epi_backward(tmem_base + (uint32_t)t * HID, sH, sH, P.dZ2t + (size_t)tile * kRows * HID, T_Z2 + t);
+        if (tr) tr[7 + t] = clock64();                     // dZ2(A), dZ2(B) done
+      }
+      // ---- dZ1 = dH1 (1 - H1^2): H1 from my own global copy, dZ1 to global only
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const long long tile = tile_of(p + t);
+        mbar_wait(bar(T_D1 + t), ppar);
+        tc_fence_after();
+        epi_backward(tmem_base + (uint32_t)t * HID, P.H1t + (size_t)tile * kRows * HID, nullptr,
+                     P.dZ1t + (size_t)tile * kRows * HID, T_OUT + t);
+        if (tr) tr[9 + t] = clock64();                     // dZ1(A), dZ1(B) done
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 11 && s_red[tid] != 0.f) atomicAdd(P.stats + tid, (double)s_red[tid]);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+size_t train2_kernel_smem(int K1p, int stages) {
+  return (size_t)2 * kRows * HID * 2 + (size_t)2 * kRows * K1p * 2 + (size_t)2 * kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
+         (size_t)stages * kSlabBytes + (size_t)(2 * HID + 2 * kNOut + 16) * 4 + (size_t)T_COUNT * 8 + 16;
+}
+int train2_stages(int K1p) {
+  int st = kMaxStages;
+  while (st > 2 && train2_kernel_smem(K1p, st) > (size_t)227 * 1024) --st;
+  return st;
+}
+
 // dynamic shared memory of mlp_tile_kernel for a net with C input chunks of K1p columns and `stages` ring stages
 size_t tile_kernel_smem(int C, int K1p, int stages) {
   return (size_t)2 * kRows * HID * 2 + (size_t)(C > 1 ? 2 : 1) * kRows * K1p * 2 + (size_t)kRows * kNOut * 2 + (size_t)kNOut * HID * 2 +
@@ -1433,6 +1902,7 @@ struct bd_ppo_net {
   int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
   double* stats = nullptr;       // [kStatSlots]
   long long* trace = nullptr;    // diagnostics (bd_ppo_set_trace)
+  int train_mode = 0;            // bd_ppo_set_train_mode: 0 = one tile in flight (mlp_tile_kernel), 1 = two (mlp_train2_kernel)
   int64_t launches = 0;
 };
 
@@ -1503,6 +1973,7 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   alloc((void**)&n->stats, kStatSlots * sizeof(double));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2SmemBudget);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_train2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwStages * kDwStageBytes);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -1524,6 +1995,11 @@ void bd_ppo_net_destroy(bd_ppo_net* n) {
 int bd_ppo_set_trace(bd_ppo_net* n, long long* trace_dev) {
   if (!n) return pfail(BD_EINVAL, "bd_ppo_set_trace: null net");
   n->trace = trace_dev;
+  return BD_OK;
+}
+int bd_ppo_set_train_mode(bd_ppo_net* n, int mode) {
+  if (!n || mode < 0 || mode > 1) return pfail(BD_EINVAL, "bd_ppo_set_train_mode: mode must be 0 or 1");
+  n->train_mode = mode;
   return BD_OK;
 }
 int64_t bd_ppo_net_param_count(const bd_ppo_net* n) { return n ? n->s.count() : 0; }
@@ -1652,9 +2128,19 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   a.stats = n->stats;
   const long long tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(tiles < n->sm_count ? tiles : n->sm_count);
-  a.stages = tile_stages(n->s.C, n->s.K1p);
-  a.trace = n->trace;
-  mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(n->s.C, n->s.K1p, a.stages), st>>>(a);
+  // BD_PPO_TRAIN=2tile (or bd_ppo_set_train_mode(n, 1)): the two-tiles-in-flight kernel.  It reproduces the one-tile
+  // kernel's results and its time (profiles/r2_ppo_train2_trace.txt), so the simpler kernel stays the default.
+  static const bool env_two = [] { const char* e = getenv("BD_PPO_TRAIN"); return e && strcmp(e, "2tile") == 0; }();
+  if ((env_two || n->train_mode == 1) && train2_stages(n->s.K1p) >= 3) {
+    a.stages = train2_stages(n->s.K1p);
+    a.trace = n->trace;
+    const int grid2 = (int)(tiles < 2LL * n->sm_count ? (tiles + 1) / 2 : n->sm_count);
+    mlp_train2_kernel<<<grid2 < 1 ? 1 : grid2, kThreads, train2_kernel_smem(n->s.K1p, a.stages), st>>>(a);
+  } else {
+    a.stages = tile_stages(n->s.C, n->s.K1p);
+    a.trace = n->trace;
+    mlp_tile_kernel<<<grid, kThreads, tile_kernel_smem(n->s.C, n->s.K1p, a.stages), st>>>(a);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (tile kernel): %s", cudaGetErrorString(e));
   // ---- weight gradients

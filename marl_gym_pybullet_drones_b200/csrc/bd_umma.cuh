@@ -124,6 +124,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// the same with an L2 evict-last hint: weight slabs that every CTA re-reads for every tile must survive the streaming
+// writes of the activation tiles
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(sdst),
+               "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }

@@ -28,6 +28,7 @@ else:
     net = PpoNet(D, 1, A, True, samples * M)
     net.pack(t._flat([torch.full((A,), -0.5, device="cuda")] + list(t._mlp(D, A, 6).parameters())))
 gr = torch.zeros(net.param_count, device="cuda")
+net.set_train_mode("--two" in sys.argv)
 
 
 def one():
@@ -47,15 +48,18 @@ one()
 torch.cuda.synchronize()
 net._lib.bd_ppo_set_trace(net._h, None)
 tr = trace.cpu().numpy()
-names = ["tile start", "inputs staged", "L1 complete", "H1 written", "L2 complete", "H2 written", "L3 complete", "loss done",
+two = "--two" in sys.argv
+names = ["pair start", "H1(A) done", "H1(B) done", "H2(A) done", "H2(B) done", "loss(A) done", "loss(B) done", "dZ2(A) done",
+         "dZ2(B) done", "dZ1(A) done", "dZ1(B) done"] if two else ["tile start", "inputs staged", "L1 complete", "H1 written", "L2 complete", "H2 written", "L3 complete", "loss done",
          "dH2 complete", "dZ2 written", "dH1 complete", "dZ1 written", "(loss inputs in)", "(dZ3 handed over)"]
 rows = [j for j in range(16) if tr[j, 0] != 0]
 for j in rows[:3] + rows[-1:]:
-    print(f"tile {j} of CTA 0 (cycles since the tile started, delta)")
+    print(f"{'pair' if two else 'tile'} {j} of CTA 0 (cycles since it started, delta)")
     prev = tr[j, 0]
     for k, nme in sorted(enumerate(names), key=lambda kn: tr[j, kn[0]]):
         if tr[j, k]:
             print(f"   {nme:14s} {tr[j, k] - tr[j, 0]:8d}  +{tr[j, k] - prev:6d}")
             prev = tr[j, k]
 if len(rows) > 2:
-    print("cycles per tile (steady):", (tr[rows[-1], 0] - tr[rows[1], 0]) / (len(rows) - 2))
+    per = (tr[rows[-1], 0] - tr[rows[1], 0]) / (len(rows) - 2)
+    print("cycles per tile (steady):", per / 2 if two else per)

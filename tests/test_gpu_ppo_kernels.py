@@ -199,11 +199,12 @@ def _actor_reference(mlp, logstd, obs, act, logp_old, adv_n, idx, T, N, M, D, A,
     return policy_loss, entropy_loss, kl
 
 
-@pytest.mark.parametrize("M,samples", [(4, 1024), (2, 333), (1, 128)])
-def test_actor_gradient_matches_autograd(M, samples):
+@pytest.mark.parametrize("two_tiles", [False, True])
+@pytest.mark.parametrize("M,samples", [(4, 1024), (2, 333), (1, 128), (4, 128 * 148 * 3 // 4 + 5)])
+def test_actor_gradient_matches_autograd(M, samples, two_tiles):
     from marl_gym_pybullet_drones_b200 import ppo_native
     from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
-    T, N, D, A = 8, 200, 72, 4
+    T, N, D, A = 8, (200 if samples <= 1600 else 2000), 72, 4
     obs, act, g = _rollout(T, N, M, D, A, 5)
     mlp = _mlp(D, A, 6)
     logstd = torch.nn.Parameter(torch.tensor([-0.5, -0.3, -0.7, -0.5], device="cuda"))
@@ -224,6 +225,7 @@ def test_actor_gradient_matches_autograd(M, samples):
     params = [logstd] + list(mlp.parameters())
     want = torch.autograd.grad(pl + ent * el, params)
     net = PpoNet(D, 1, A, True, samples * M)
+    net.set_train_mode(two_tiles)       # both forward / loss / backward kernels: one tile in flight (default), two tiles
     net.pack(_flat(params))
     grad = torch.zeros(net.param_count, device="cuda")
     net.grad(grad, obs, N, M, idx, samples, critic=False, act=act, logp_old=logp_old, adv=adv, adv_stats=stats2, clip=clip,
@@ -244,8 +246,9 @@ def test_actor_gradient_matches_autograd(M, samples):
     net.close()
 
 
+@pytest.mark.parametrize("two_tiles", [False, True])
 @pytest.mark.parametrize("M,samples,clipped", [(4, 700, False), (2, 256, True), (16, 150, False), (1, 130, False)])
-def test_critic_gradient_matches_autograd(M, samples, clipped):
+def test_critic_gradient_matches_autograd(M, samples, clipped, two_tiles):
     from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
     T, N, D = 8, 100, 72
     obs, _, g = _rollout(T, N, M, D, 4, 9)
@@ -265,6 +268,7 @@ def test_critic_gradient_matches_autograd(M, samples, clipped):
     params = list(mlp.parameters())
     want = torch.autograd.grad(loss, params)
     net = PpoNet(D, M, 1, False, samples)
+    net.set_train_mode(two_tiles)
     net.pack(_flat(params))
     grad = torch.zeros(net.param_count, device="cuda")
     net.grad(grad, obs, N, M, idx, samples, critic=True, ret=ret, v_old=v_old, clip=0.2, use_clipped_value=clipped)
