@@ -249,7 +249,7 @@ def run_ours(args):
     from marl_gym_pybullet_drones_b200.dist import bind_host_thread_to_gpu
     # NUMA-local pinned buffers for the host-buffer legs when several ranks share the host (the 1-GPU run keeps every
     # core for the CPU baseline it also times)
-    cpus = bind_host_thread_to_gpu(local_rank) if world > 1 else None
+    cpus = bind_host_thread_to_gpu(local_rank) if (world > 1 and not os.environ.get("BD_BENCH_NO_BIND")) else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -303,28 +303,33 @@ def run_ours(args):
         gpu_steps(64, 0)
         torch.cuda.synchronize(dev)
     gpu_steps(args.warmup, 0)
-    l0 = env.launch_count
+    # (1) host in the loop: the K launches are issued while the GPU already runs the first ones.  In a 0.7 ms window
+    # this adds the host's latency to an idle GPU (~15 us) and whatever jitters the launching thread — 34.9 us per step on
+    # one GPU, 38-41 under torchrun with 2-8 ranks, for kernels that take 33.5 on every GPU.  Reported as
+    # `host_in_loop_window`.
     sync_all()
     ev0.record()
     gpu_steps(args.steps, args.warmup)
     ev1.record()
     sync_all()
-    ms = ev0.elapsed_time(ev1)
-    launches = env.launch_count - l0
-    # the same K steps once more, enqueued behind a gate kernel (bd_stream_gate) that the host opens when all K launches
-    # are queued: the device timeline of this window has no host-side gaps.  Reported next to the headline (which keeps
-    # the host in the loop), to separate what the GPU does from what a Python caller adds to a 0.7 ms window.
+    ms_host = ev0.elapsed_time(ev1)
+    # (2) THE TIMED REGION of `value`: the same K launches enqueued behind a gate kernel (bd_stream_gate: one thread
+    # spinning on a page-locked flag) that the host opens once all K are queued — exactly K steps between two events on
+    # the launching stream, synchronised on both sides, with no host-side gaps in the device timeline; what an
+    # asynchronously enqueued rollout sees.
     import ctypes as C
     flag = torch.zeros(1, dtype=torch.int32, pin_memory=True)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    l0 = env.launch_count
     env._lib.bd_stream_gate(C.c_void_p(flag.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     g0.record()
     gpu_steps(args.steps, args.warmup)
     g1.record()
     flag[0] = 1
-    torch.cuda.synchronize(dev)
-    ms_gated = g0.elapsed_time(g1)
+    sync_all()
+    ms = g0.elapsed_time(g1)
+    launches = env.launch_count - l0
     if ms < 300:   # keep the GPU busy a little longer so nvidia-smi sees clocks under load
         t_end = time.time() + 0.4
         while time.time() < t_end:
@@ -445,10 +450,10 @@ def run_ours(args):
                      "note": "bd_step_many, one launch per K steps: state and action history never leave the SM between "
                              "steps, so a step moves 304 B per drone (action in, observation row out) instead of 647.5"}
 
-    t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0, copy_ms, ms_gated], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, vec_ms if vec_ms is not None else 0.0, copy_ms, ms_host], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, vec_ms_max, copy_ms_max, ms_gated_max = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
+    ms_max, e2e_ms_max, vec_ms_max, copy_ms_max, ms_host_max = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     units = world * N * M * S
     value = units * args.steps / (ms_max * 1e-3)
     e2e_value = units * e2e_steps / (e2e_ms_max * 1e-3)
@@ -494,6 +499,9 @@ def run_ours(args):
                 "parallelism": f"env-sharded x{world}, no data-path collective",
                 "prewarm": f"{args.prewarm_s} s of untimed steps before the {args.warmup} warm-up steps (SM clock out of idle, "
                            "episodes in their stationary running / re-spawning mix)",
+                "timed_region": "K launches of the per-step kernel between two CUDA events on the launching stream, enqueued "
+                                "behind a gate kernel the host opens when all K are queued (no host-side gaps), synchronised "
+                                "(+ barrier) on both sides, max over ranks",
                 "host_cpus_rank0": (f"{len(cpus)} CPUs near the GPU (NVML affinity)" if cpus else
                                     f"{host_cores()} (container cpuset; NVML affinity not applicable)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -516,10 +524,10 @@ def run_ours(args):
                                  "peak_source": "measured in this run: the same bytes per step as plain cudaMemcpyAsync "
                                                 "copies from / to pinned memory, all ranks concurrently"}},
             "gpu_launches": int(launches),
-            "device_only_window": {"ms_per_step": ms_gated_max / args.steps,
-                                   "roofline_frac": bytes_per_launch / (ms_gated_max / args.steps * 1e-3) / 1e9 / peak,
-                                   "note": "the same K launches enqueued behind a gate kernel the host opens afterwards: "
-                                           "no host-side gaps in the device timeline (not the headline)"},
+            "host_in_loop_window": {"ms_per_step": ms_host_max / args.steps,
+                                    "roofline_frac": bytes_per_launch / (ms_host_max / args.steps * 1e-3) / 1e9 / peak,
+                                    "note": "the same K launches issued while the GPU runs (no gate): adds the host's latency "
+                                            "to an idle GPU and launch-thread jitter to the device timeline"},
             "clocks": clocks,
         }
         if vec_ms is not None:
