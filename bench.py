@@ -599,7 +599,7 @@ def run_mappo_block(args, dev, rank, world):
     parts_ms = tot / args.mappo_steps
     ar_us = None
     if world > 1:                           # the collective that defines the multi-GPU design, timed on its own
-        g = algo.actor_opt.grad
+        g = algo._joint_grad
         for _ in range(5):
             dist.all_reduce(g)
         torch.cuda.synchronize(dev)
@@ -625,12 +625,14 @@ def run_mappo_block(args, dev, rank, world):
                                   f"rollout {T} steps, 1 epoch x {n_mb} minibatches of {mb} env-steps ({mb * M} actor rows)",
                       "update_impl": "native (bd_ppo.cu): tcgen05 fwd+bwd tile kernel, tcgen05 weight-gradient kernel, "
                                      "GAE scan, gated Adam; one CUDA graph per epoch" + (", NCCL all-reduces in the graph" if world > 1 else "")},
-           "collectives_per_train_step": {"gradient_allreduce": 2 * n_mb if world > 1 else 0,
+           "collectives_per_train_step": {"gradient_allreduce": n_mb if world > 1 else 0,
                                           "kl_pair_allreduce": n_mb if world > 1 else 0},
            "gradient_allreduce_us": ar_us,
-           "gradient_allreduce_share": (2 * n_mb * ar_us * 1e-3 / wall_ms) if ar_us is not None else 0.0,
-           "limiting_collective": ("actor+critic flat-gradient all-reduce (342 KB + 1.4 MB fp32), latency-bound" if world > 1 else None),
+           "gradient_allreduce_share": (n_mb * ar_us * 1e-3 / wall_ms) if ar_us is not None else 0.0,
+           "limiting_collective": ("joint actor+critic flat-gradient all-reduce (342 KB + 1.4 MB fp32 in one buffer), "
+                                   "latency-bound" if world > 1 else None),
            "gpu_launches_total": int(launches), "policy_loss": res["policy_loss"], "approx_kl": res["approx_kl"]}
+    algo.close()
     env.close()
     return out if rank == 0 else None
 

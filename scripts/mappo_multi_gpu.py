@@ -65,6 +65,7 @@ if rank == 0:
           f"(count {algo.obs_normalizer.rms.count:.1f} = {(args.iters * 32 + 1) * args.envs_per_gpu * world} rows + 1e-4)")
     assert dw == 0.0 and dm == 0.0 and dv == 0.0 and dr == 0.0, "replicas diverged"
     assert world == 1 or dobs > 0.0
+algo.close()           # the captured epoch graph contains NCCL collectives: release it before the process group goes
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
