@@ -146,6 +146,46 @@ def test_step_many_one_launch_equals_k_launches_all_flavours(cfg, M, N, physics,
         e.close()
 
 
+def test_step_many_one_launch_in_a_cuda_graph():
+    """The K-step kernel captured into a CUDA graph: replays read the ring head from the device-resident counter and the
+    last CTA out advances it by K; eager single steps before, between and after keep working on the same handle."""
+    M, N, K = 4, 3000, 6
+    cfg = _mh(M)
+    eager = batch_from_cfg(cfg, GRID, None, num_envs=N, precision="fp32", auto_reset=True, reset_mode="jitter_philox", seed=3)
+    graphed = batch_from_cfg(cfg, GRID, None, num_envs=N, precision="fp32", auto_reset=True, reset_mode="jitter_philox", seed=3)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    acts = (torch.rand((K, N, M, 4), generator=gen, device="cuda") * 2 - 1.3).contiguous()
+    obs = torch.empty((K, N, M, 72), device="cuda")
+    rew = torch.empty((K, N), device="cuda")
+    term = torch.empty((K, N), dtype=torch.bool, device="cuda")
+    trunc = torch.empty((K, N), dtype=torch.bool, device="cuda")
+    assert torch.equal(eager.reset_device(), graphed.reset_device())
+    for k in range(2):
+        assert torch.equal(eager.step_device(acts[k]).obs, graphed.step_device(acts[k]).obs)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            graphed.step_many(acts, obs, rew, term, trunc)
+    torch.cuda.synchronize()
+    for rep in range(4):          # 24 steps: more than one trip around the 15-slot ring
+        g.replay()
+        torch.cuda.synchronize()
+        for k in range(K):
+            r = eager.step_device(acts[k])
+            assert torch.equal(r.obs, obs[k]), (rep, k)
+            assert torch.equal(r.reward, rew[k]) and torch.equal(r.terminated, term[k]) and torch.equal(r.truncated, trunc[k])
+    ra, rb = eager.step_device(acts[0]), graphed.step_device(acts[0])     # eager step on the captured handle
+    assert torch.equal(ra.obs, rb.obs)
+    g.replay()
+    torch.cuda.synchronize()
+    for k in range(K):
+        assert torch.equal(eager.step_device(acts[k]).obs, obs[k]), k
+    eager.close()
+    graphed.close()
+
+
 def test_rng_state_roundtrip_continues_the_respawn_stream():
     """A fresh handle that is given the state of a running one draws the SAME re-spawn positions from then on;
     without it, it would replay the stream from the start."""
