@@ -128,6 +128,9 @@ struct NetDev {
   const bf16* w3b_slab;    // [256 j x 16 o] = W3[o][j]
   const float *b1, *b2, *b3, *logstd;   // b3 / logstd padded to 16
   int C, D, K1p, out_dim;
+  // CTA-pair kernel (actor nets, C == 1): per cluster rank r the N-half of every weight, resident in that CTA's shared
+  // memory: w1c [2][128 n x K1p], w2c [2][128 n x 256], w3c [2][8 n x 256], canonical K-major
+  const bf16 *w1c, *w2c, *w3c;
 };
 
 
@@ -1012,6 +1015,327 @@ int fwd2_stages(int K1p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+//          forward only on a CTA PAIR with resident weights (cta_group::2; actor nets, C == 1)
+// ---------------------------------------------------------------------------------------------
+// What bounds mlp_fwd2_kernel is the weight stream (a slab per ~340 cycles against the 128 an MMA needs).  A pair of CTAs
+// on the two SMs of a TPC executes M = 256 MMAs together: each CTA contributes its 128 rows of A and HALF of B (N / 2
+// rows of the weight matrix) from its own shared memory — so half of W1 / W2 / W3 (88 KB) fits next to two 64 KB
+// activation buffers and nothing is streamed.  Two cluster tiles (2 x 256 rows) are in flight, in alternation as in
+// mlp_fwd2_kernel; the inputs of a slot's next tile are staged into its activation buffer once its last layer has read
+// it.  Only the leader CTA's MMA thread issues; "operand ready" barriers live in the leader's shared memory and collect
+// the arrivals of BOTH CTAs' epilogue threads (remote arrive through mapa), "MMA done" commits are multicast to both.
+enum { C_W = 0, C_XFULL, C_L1 = C_XFULL + 2, C_L2 = C_L1 + 2, C_L3 = C_L2 + 2, C_H1 = C_L3 + 2, C_H2 = C_H1 + 2, C_COUNT = C_H2 + 2 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar_local), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t mbar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mlp_fwd2c_kernel(const __grid_constant__ Fwd2Args P) {
+  extern __shared__ __align__(128) unsigned char smem_c2[];
+  const NetDev& W = P.net;
+  const int K1p = W.K1p, D = W.D;
+  bf16* const bufT0 = reinterpret_cast<bf16*>(smem_c2);                      // 2 x 64 KB: X -> H1 -> H2 per slot
+  bf16* const sW2 = bufT0 + 2 * (size_t)kRows * HID;                         // [128 n x 256] my half of W2
+  bf16* const sW1 = sW2 + (size_t)kRows * HID;                               // [128 n x K1p]
+  bf16* const sW3 = sW1 + (size_t)kRows * K1p;                               // [8 n x 256]
+  float* sB1 = reinterpret_cast<float*>(sW3 + (size_t)8 * HID);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;
+  float* sLs = sB3 + kNOut;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLs + kNOut);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(mbar + C_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  for (int i = tid; i < HID; i += kThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd != nullptr ? W.logstd[tid] : 0.f; }
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[C_W]), 1);
+    for (int i = 0; i < 2; ++i) {
+      // operand-ready barriers: used in the leader only, both CTAs' 512 epilogue threads arrive
+      mbar_init(smem_u32(&mbar[C_XFULL + i]), 2 * kEpiThreads);
+      mbar_init(smem_u32(&mbar[C_H1 + i]), 2 * kEpiThreads);
+      mbar_init(smem_u32(&mbar[C_H2 + i]), 2 * kEpiThreads);
+      // MMA-done barriers: one multicast commit each, in both CTAs
+      mbar_init(smem_u32(&mbar[C_L1 + i]), 1); mbar_init(smem_u32(&mbar[C_L2 + i]), 1); mbar_init(smem_u32(&mbar[C_L3 + i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers exist before anybody arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t aT0 = smem_u32(bufT0), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  const uint32_t tbytes = (uint32_t)kRows * HID * 2u;
+  // cluster tiles of 256 rows: CTA `rank` owns rows [256 ct + 128 rank, + 128); cluster c takes ct = c, c + n_clusters, ...
+  const long long n_ct = (P.rows + 2 * kRows - 1) / (2 * kRows);
+  const long long cid = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
+  const long long my_tiles = n_ct > cid ? (n_ct - cid + n_cl - 1) / n_cl : 0;
+  const int k1_steps = K1p / 16;
+
+  if (warp == kEpiThreads / 32) {
+    // ============================ weights (every CTA its half) + MMA issuer (leader) =============================
+    if (lane == 0) {
+      const uint32_t w1b = (uint32_t)(kRows * K1p * 2), w2b = (uint32_t)(kRows * HID * 2), w3b = (uint32_t)(8 * HID * 2);
+      mbar_expect_tx(bar(C_W), w1b + w2b + w3b);
+      bulk_g2s(aW1, W.w1c + (size_t)rank * kRows * K1p, w1b, bar(C_W));
+      bulk_g2s(aW2, W.w2c + (size_t)rank * kRows * HID, w2b, bar(C_W));
+      bulk_g2s(aW3, W.w3c + (size_t)rank * 8 * HID, w3b, bar(C_W));
+      mbar_wait(bar(C_W), 0);
+    }
+    __syncwarp();
+    // the leader may only issue once the PEER's weights have landed too
+    cluster_sync_all();
+    if (leader && lane == 0) {
+      const uint32_t sboX = (uint32_t)(K1p / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      const uint64_t dX = umma_desc(aT0, 128, sboX), dT = umma_desc(aT0, 128, sboH), dW1 = umma_desc(aW1, 128, sboX),
+                     dW2 = umma_desc(aW2, 128, sboH), dW3 = umma_desc(aW3, 128, sboH);
+      const uint64_t tstep = (uint64_t)(tbytes >> 4);
+      constexpr uint32_t kIdH = umma_idesc_m256(HID), kIdO = umma_idesc_m256(kNOut);
+      uint32_t ppar = 0;
+      for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+        const int nt = (p + 1 < my_tiles) ? 2 : 1;
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 1
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait_cluster(bar(C_XFULL + t), ppar);
+          tc_fence_after();
+          const uint64_t a = dX + tstep * (uint64_t)t;
+          for (int s = 0; s < k1_steps; ++s) umma_bf16_2cta(acc, a + (uint64_t)(16 * s), dW1 + (uint64_t)(16 * s), kIdH, (uint32_t)(s != 0));
+          umma_commit_2cta(bar(C_L1 + t));
+        }
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 2
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait_cluster(bar(C_H1 + t), ppar);
+          tc_fence_after();
+          const uint64_t a = dT + tstep * (uint64_t)t;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) umma_bf16_2cta(acc, a + (uint64_t)(16 * s), dW2 + (uint64_t)(16 * s), kIdH, (uint32_t)(s != 0));
+          umma_commit_2cta(bar(C_L2 + t));
+        }
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t) {                     // layer 3, N = 16
+          const uint32_t acc = tmem_base + (uint32_t)t * HID;
+          mbar_wait_cluster(bar(C_H2 + t), ppar);
+          tc_fence_after();
+          const uint64_t a = dT + tstep * (uint64_t)t;
+#pragma unroll
+          for (int s = 0; s < 16; ++s) umma_bf16_2cta(acc, a + (uint64_t)(16 * s), dW3 + (uint64_t)(16 * s), kIdO, (uint32_t)(s != 0));
+          umma_commit_2cta(bar(C_L3 + t));
+        }
+      }
+    }
+  } else if (warp < kEpiThreads / 32) {
+    // ================================ staging + epilogue threads ==================================
+    const int row = tid & (kRows - 1), grp = tid >> 7;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int rps = P.rows_per_sample;
+    const int n_pieces = K1p / 8;
+    const bool vec4 = (D & 3) == 0;
+    float4 xa[kMaxPieces], xb4[kMaxPieces];
+    cluster_sync_all();          // matches the MMA warp's second cluster barrier (weights landed everywhere)
+
+    auto ctile_of = [&](long long pos) { return cid + pos * n_cl; };
+    auto row_of = [&](long long ct) { return ct * (2 * kRows) + (long long)rank * kRows + row; };
+    auto sample_of = [&](long long ct) -> long long {
+      const long long r = row_of(ct);
+      if (r >= P.rows) return -1;
+      const long long smp = r / rps;
+      return P.idx != nullptr ? P.idx[smp] : smp;
+    };
+    auto load_x = [&](long long ct, long long sm) {
+      const long long r = row_of(ct);
+      const int agent = (int)(r % rps);
+      const float* src = P.obs + ((size_t)(sm < 0 ? 0 : sm) * P.M + agent) * D;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int k0 = (grp + i * 4) * 8;
+        xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 < D && sm >= 0) {
+          if (vec4 && k0 + 8 <= D) {
+            xa[i] = __ldg(reinterpret_cast<const float4*>(src + k0));
+            xb4[i] = __ldg(reinterpret_cast<const float4*>(src + k0 + 4));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (k0 + j < D) ? __ldg(src + k0 + j) : 0.0f;
+            xa[i] = make_float4(x[0], x[1], x[2], x[3]);
+            xb4[i] = make_float4(x[4], x[5], x[6], x[7]);
+          }
+        }
+      }
+    };
+    // registers -> (normalise) -> bf16 canonical [128 x K1p] at the start of slot t's activation buffer
+    auto stage_x = [&](int t, long long ct, long long sm) {
+      const long long r = row_of(ct);
+      const int agent = (int)(r % rps);
+      bf16* dst = bufT0 + (size_t)t * kRows * HID;
+      const bool norm = P.nmean != nullptr && sm >= 0;
+      const size_t nb = norm ? ((size_t)(sm / P.N) * P.M + agent) * D : 0;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        const int pc = grp + i * 4;
+        if (pc < n_pieces) {
+          float x[8] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w, xb4[i].x, xb4[i].y, xb4[i].z, xb4[i].w};
+          if (norm) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = pc * 8 + j;
+              if (k < D) {
+                const float v = (x[j] - __ldg(P.nmean + nb + k)) * __ldg(P.nrstd + nb + k);
+                x[j] = fminf(fmaxf(v, -P.nclip), P.nclip);
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + canon_off(row, pc * 8, K1p)) =
+              make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        }
+      }
+      proxy_fence();
+      tc_fence_before();
+      mbar_arrive_cluster(bar(C_XFULL + t), 0);
+    };
+    auto epi_hidden = [&](uint32_t acc, const float* bias, bf16* sH, int done_bar) {
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(acc + lane_off + (uint32_t)(grp * 64), va);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c0 = grp * 64 + j * 16;
+        uint32_t* cur = (j & 1) ? vb : va;
+        uint32_t* nxt = (j & 1) ? va : vb;
+        if (j < 3) tmem_ld16_nowait(acc + lane_off + (uint32_t)(c0 + 16), nxt);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float z[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = __uint_as_float(cur[q * 8 + e]) + bias[c0 + q * 8 + e];
+          *reinterpret_cast<uint4*>(sH + canon_off(row, c0 + q * 8, HID)) =
+              make_uint4(tanh2_bf16(z[0], z[1]), tanh2_bf16(z[2], z[3]), tanh2_bf16(z[4], z[5]), tanh2_bf16(z[6], z[7]));
+        }
+        tmem_wait_ld();
+      }
+      proxy_fence();
+      tc_fence_before();
+      mbar_arrive_cluster(bar(done_bar), 0);
+    };
+    auto finish_row = [&](long long r, const uint32_t (&v)[16]) {
+      if (!P.sample) {
+        for (int k = 0; k < W.out_dim; ++k) P.out[(size_t)r * W.out_dim + k] = __uint_as_float(v[k]) + sB3[k];
+        return;
+      }
+      float eps[4] = {0.f, 0.f, 0.f, 0.f};
+      if (P.noise != nullptr) {
+        for (int k = 0; k < W.out_dim; ++k) eps[k] = P.noise[(size_t)r * W.out_dim + k];
+      } else {
+        uint32_t c[4] = {(uint32_t)r, (uint32_t)((unsigned long long)r >> 32), (uint32_t)P.offset, (uint32_t)(P.offset >> 32)};
+        philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+        const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+        float s0, c0, s1, c1;
+        __sincosf(6.28318530718f * u1, &s0, &c0);
+        __sincosf(6.28318530718f * u3, &s1, &c1);
+        eps[0] = r0 * c0; eps[1] = r0 * s0; eps[2] = r1 * c1; eps[3] = r1 * s1;
+      }
+      float lp = 0.f;
+      for (int k = 0; k < W.out_dim; ++k) {
+        const float m = __uint_as_float(v[k]) + sB3[k];
+        const float ls = sLs[k];
+        P.out[(size_t)r * W.out_dim + k] = fmaf(__expf(ls), eps[k], m);
+        if (P.mean_out != nullptr) P.mean_out[(size_t)r * W.out_dim + k] = m;
+        lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+      }
+      P.logp[r] = lp;
+    };
+
+    // prologue: both slots' first tiles
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t)
+      if (t < my_tiles) {
+        const long long ct = ctile_of(t), sm = sample_of(ct);
+        load_x(ct, sm);
+        stage_x(t, ct, sm);
+      }
+    uint32_t ppar = 0;
+    long long* const tr0 = (P.trace != nullptr && blockIdx.x == 0 && tid == 0) ? P.trace : nullptr;
+    for (long long p = 0; p < my_tiles; p += 2, ppar ^= 1) {
+      const int nt = (p + 1 < my_tiles) ? 2 : 1;
+      long long* const tr = (tr0 != nullptr && p < 64) ? tr0 + (p >> 1) * 64 : nullptr;
+      if (tr) tr[0] = clock64();
+#pragma unroll 1
+      for (int lt = 0; lt < 4; ++lt) {                     // H1(A), H1(B), H2(A), H2(B)
+        const int layer = lt >> 1, t = lt & 1;
+        if (t >= nt) continue;
+        mbar_wait(bar(C_L1 + 2 * layer + t), ppar);
+        tc_fence_after();
+        if (tr) tr[1 + 2 * lt] = clock64();                // accumulator ready
+        epi_hidden(tmem_base + (uint32_t)t * HID, layer ? sB2 : sB1, bufT0 + (size_t)t * kRows * HID, C_H1 + 2 * layer + t);
+        if (tr) tr[2 + 2 * lt] = clock64();                // epilogue done
+      }
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {                       // outputs; then the slot's next inputs into its (now free) buffer
+        const bool has_next = p + t + 2 < my_tiles;
+        const long long nct = ctile_of(p + t + 2);
+        long long nsm = -1;
+        if (has_next) { nsm = sample_of(nct); load_x(nct, nsm); }
+        mbar_wait(bar(C_L3 + t), ppar);
+        tc_fence_after();
+        if (tr) tr[9 + 3 * t] = clock64();                 // output accumulator ready
+        uint32_t v[16];
+        if (grp == 0) { tmem_ld16_nowait(tmem_base + (uint32_t)t * HID + lane_off, v); tmem_wait_ld(); }
+        if (has_next) stage_x(t, nct, nsm);               // (arrives after my read of the accumulator)
+        if (tr) tr[10 + 3 * t] = clock64();                // next inputs staged
+        const long long r = row_of(ctile_of(p + t));
+        if (grp == 0 && r < P.rows) finish_row(r, v);
+        if (tr) tr[11 + 3 * t] = clock64();                // rows written
+      }
+    }
+  } else {
+    cluster_sync_all();          // the spare warp only takes part in the cluster barriers
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // nobody leaves (and frees tensor memory the pair shares) before the peer is done
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+size_t fwd2c_kernel_smem(int K1p) {
+  return (size_t)2 * kRows * HID * 2 + (size_t)kRows * HID * 2 + (size_t)kRows * K1p * 2 + (size_t)8 * HID * 2 +
+         (size_t)(2 * HID + 2 * kNOut) * 4 + (size_t)C_COUNT * 8 + 16;
+}
+
+// ---------------------------------------------------------------------------------------------
 //              forward + loss + backward with TWO tiles in flight per CTA (training, round 2)
 // ---------------------------------------------------------------------------------------------
 // mlp_tile_kernel takes one tile at a time through ten dependent phases (MMA, epilogue, MMA, ...): 34 k cycles per tile
@@ -1840,6 +2164,7 @@ struct PackArgs {
   const float* param;
   bf16 *w1_slabs, *w2f_slabs, *w2b_slabs, *w3f, *w3b_slab;
   float *b1, *b2, *b3, *logstd;
+  bf16 *w1c, *w2c, *w3c;     // cluster halves (C == 1 nets), may be null
 };
 __global__ void pack_kernel(const __grid_constant__ PackArgs P) {
   const NetShape& s = P.s;
@@ -1853,6 +2178,7 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs P) {
     const int col = ks * 16 + kk;
     const float v = col < s.D ? P.param[s.off_w1() + (long long)n * s.din() + c * s.D + col] : 0.f;
     P.w1_slabs[slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(v);
+    if (P.w1c != nullptr) P.w1c[(size_t)(n >> 7) * 128 * s.K1p + canon_off(n & 127, col, s.K1p)] = __float2bfloat16(v);
     return;
   }
   long long k = i - n_w1;
@@ -1860,6 +2186,8 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs P) {
     const int slab = (int)(k / 4096), e = (int)(k % 4096), n = e / 16, kk = e % 16;
     const int ks = 4 * (slab & 3) + (slab >> 2);
     P.w2f_slabs[(size_t)slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(P.param[s.off_w2() + (long long)n * HID + ks * 16 + kk]);
+    if (P.w2c != nullptr)
+      P.w2c[(size_t)(n >> 7) * 128 * HID + canon_off(n & 127, ks * 16 + kk, HID)] = __float2bfloat16(P.param[s.off_w2() + (long long)n * HID + ks * 16 + kk]);
     // backward slab, same issue order over j: element (i = n, jj = kk) = W2[ks*16 + kk][n]
     P.w2b_slabs[(size_t)slab * 4096 + canon_off(n, kk, 16)] = __float2bfloat16(P.param[s.off_w2() + (long long)(ks * 16 + kk) * HID + n]);
     return;
@@ -1870,6 +2198,7 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs P) {
     const float v = o < s.out_dim ? P.param[s.off_w3() + (long long)o * HID + j] : 0.f;
     P.w3f[canon_off(o, j, HID)] = __float2bfloat16(v);
     P.w3b_slab[canon_off(j, o, 16)] = __float2bfloat16(v);
+    if (P.w3c != nullptr) P.w3c[(size_t)(o >> 3) * 8 * HID + canon_off(o & 7, j, HID)] = __float2bfloat16(v);
     return;
   }
   k -= n_w3;
@@ -1893,6 +2222,7 @@ struct bd_ppo_net {
   long long max_rows, max_tiles;
   // packed weights
   bf16 *w1_slabs = nullptr, *w2f_slabs = nullptr, *w2b_slabs = nullptr, *w3f = nullptr, *w3b_slab = nullptr;
+  bf16 *w1c = nullptr, *w2c = nullptr, *w3c = nullptr;   // cluster halves (C == 1)
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *logstd = nullptr;
   // tile scratch
   bf16 *Xt = nullptr, *H1t = nullptr, *H2t = nullptr, *dZ2t = nullptr, *dZ1t = nullptr, *dZ3t = nullptr;
@@ -1902,6 +2232,7 @@ struct bd_ppo_net {
   int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
   double* stats = nullptr;       // [kStatSlots]
   long long* trace = nullptr;    // diagnostics (bd_ppo_set_trace)
+  int fwd_mode = 0;              // bd_ppo_set_forward_mode: 0 = streamed two-tile kernel, 1 = CTA-pair kernel (actor nets)
   int train_mode = 0;            // bd_ppo_set_train_mode: 0 = one tile in flight (mlp_tile_kernel), 1 = two (mlp_train2_kernel)
   int64_t launches = 0;
 };
@@ -1909,6 +2240,7 @@ struct bd_ppo_net {
 namespace {
 void free_net(bd_ppo_net* n) {
   cudaFree(n->w1_slabs); cudaFree(n->w2f_slabs); cudaFree(n->w2b_slabs); cudaFree(n->w3f); cudaFree(n->w3b_slab);
+  cudaFree(n->w1c); cudaFree(n->w2c); cudaFree(n->w3c);
   cudaFree(n->b1); cudaFree(n->b2); cudaFree(n->b3); cudaFree(n->logstd);
   cudaFree(n->Xt); cudaFree(n->H1t); cudaFree(n->H2t); cudaFree(n->dZ2t); cudaFree(n->dZ1t); cudaFree(n->dZ3t);
   cudaFree(n->pw1); cudaFree(n->pw2); cudaFree(n->pw3); cudaFree(n->pb1); cudaFree(n->pb2); cudaFree(n->stats);
@@ -1917,6 +2249,7 @@ NetDev net_dev(const bd_ppo_net* n) {
   NetDev d;
   d.w1_slabs = n->w1_slabs; d.w2f_slabs = n->w2f_slabs; d.w2b_slabs = n->w2b_slabs; d.w3f = n->w3f; d.w3b_slab = n->w3b_slab;
   d.b1 = n->b1; d.b2 = n->b2; d.b3 = n->b3; d.logstd = n->s.has_logstd ? n->logstd : nullptr;
+  d.w1c = n->w1c; d.w2c = n->w2c; d.w3c = n->w3c;
   d.C = n->s.C; d.D = n->s.D; d.K1p = n->s.K1p; d.out_dim = n->s.out_dim;
   return d;
 }
@@ -1960,6 +2293,9 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   alloc((void**)&n->w1_slabs, (size_t)chunks * k1s * kSlabBytes);
   alloc((void**)&n->w2f_slabs, 16 * (size_t)kSlabBytes); alloc((void**)&n->w2b_slabs, 16 * (size_t)kSlabBytes);
   alloc((void**)&n->w3f, (size_t)kNOut * HID * 2); alloc((void**)&n->w3b_slab, kSlabBytes);
+  if (chunks == 1) {
+    alloc((void**)&n->w1c, (size_t)HID * n->s.K1p * 2); alloc((void**)&n->w2c, (size_t)HID * HID * 2); alloc((void**)&n->w3c, (size_t)kNOut * HID * 2);
+  }
   alloc((void**)&n->b1, HID * 4); alloc((void**)&n->b2, HID * 4); alloc((void**)&n->b3, kNOut * 4); alloc((void**)&n->logstd, kNOut * 4);
   const size_t T = (size_t)n->max_tiles;
   alloc((void**)&n->Xt, T * chunks * kRows * n->s.K1p * 2);
@@ -1974,6 +2310,7 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF2SmemBudget);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_train2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwStages * kDwStageBytes);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -1997,6 +2334,11 @@ int bd_ppo_set_trace(bd_ppo_net* n, long long* trace_dev) {
   n->trace = trace_dev;
   return BD_OK;
 }
+int bd_ppo_set_forward_mode(bd_ppo_net* n, int mode) {
+  if (!n || mode < 0 || mode > 1) return pfail(BD_EINVAL, "bd_ppo_set_forward_mode: mode must be 0 or 1");
+  n->fwd_mode = mode;
+  return BD_OK;
+}
 int bd_ppo_set_train_mode(bd_ppo_net* n, int mode) {
   if (!n || mode < 0 || mode > 1) return pfail(BD_EINVAL, "bd_ppo_set_train_mode: mode must be 0 or 1");
   n->train_mode = mode;
@@ -2013,6 +2355,7 @@ int bd_ppo_net_pack(bd_ppo_net* n, const float* flat_params_dev, void* stream) {
   a.s = n->s; a.param = flat_params_dev;
   a.w1_slabs = n->w1_slabs; a.w2f_slabs = n->w2f_slabs; a.w2b_slabs = n->w2b_slabs; a.w3f = n->w3f; a.w3b_slab = n->w3b_slab;
   a.b1 = n->b1; a.b2 = n->b2; a.b3 = n->b3; a.logstd = n->logstd;
+  a.w1c = n->w1c; a.w2c = n->w2c; a.w3c = n->w3c;
   const long long t = pack_threads(n->s);
   pack_kernel<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   n->launches++;
@@ -2027,8 +2370,28 @@ bool fwd_single_tile() {
   static const int v = [] { const char* e = getenv("BD_PPO_FWD"); return (e && strcmp(e, "1tile") == 0) ? 1 : 0; }();
   return v != 0;
 }
+// 0: cluster-pair kernel with resident weights (actor nets with K1p <= 80; bd_ppo_set_forward_mode(n, 1) or
+// BD_PPO_FWD=pair), 1: streamed-weight two-tile kernel (default)
+int fwd_variant(const bd_ppo_net* n) {
+  static const int env_pair = [] { const char* e = getenv("BD_PPO_FWD"); return (e && strcmp(e, "pair") == 0) ? 1 : 0; }();
+  const bool want = env_pair || n->fwd_mode == 1;
+  return (want && n->s.C == 1 && n->w1c != nullptr && fwd2c_kernel_smem(n->s.K1p) <= (size_t)227 * 1024) ? 0 : 1;
+}
 int launch_fwd2(bd_ppo_net* n, Fwd2Args& a, void* stream, const char* who) {
   a.net = net_dev(n);
+  if (fwd_variant(n) == 0) {
+    const long long ctiles = (a.rows + 2 * kRows - 1) / (2 * kRows);
+    long long clusters = n->sm_count / 2;
+    if (ctiles < 2 * clusters) clusters = (ctiles + 1) / 2;
+    if (clusters < 1) clusters = 1;
+    a.stages = 0;
+    a.trace = n->trace;
+    mlp_fwd2c_kernel<<<(unsigned)(2 * clusters), kThreads, fwd2c_kernel_smem(n->s.K1p), (cudaStream_t)stream>>>(a);
+    n->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pfail(BD_ECUDA, "%s (pair kernel): %s", who, cudaGetErrorString(e));
+    return BD_OK;
+  }
   const long long tiles = (a.rows + kRows - 1) / kRows;
   // one CTA per SM, every CTA an even number of tiles where possible (a CTA works on pairs)
   long long grid = tiles < n->sm_count ? tiles : n->sm_count;

@@ -79,9 +79,10 @@ def test_gae_kernel_matches_reference_scan(T, N):
         assert abs(float(st[1]) - 1.0 / (want_adv.std() + 1e-8)) <= 1e-4 / (want_adv.std() + 1e-8)   # np.std: ddof = 0
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("M,D,A,samples,critic", [(4, 72, 4, 300, False), (2, 72, 4, 1000, False), (4, 72, 4, 517, True),
                                                   (2, 27, 1, 260, False), (1, 72, 4, 129, True), (16, 72, 4, 200, True)])
-def test_forward_matches_torch(M, D, A, samples, critic):
+def test_forward_matches_torch(M, D, A, samples, critic, pair):
     from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
     T, N = 6, 64
     obs, act, g = _rollout(T, N, M, D, A, 1)
@@ -97,6 +98,7 @@ def test_forward_matches_torch(M, D, A, samples, critic):
         rows = samples * M
         x = obs[:T].reshape(T * N, M, D)[idx].reshape(rows, D)
     params = ([torch.full((A,), -0.5, device="cuda")] if not critic else []) + list(mlp.parameters())
+    net.set_forward_mode(pair)          # actor nets: the CTA-pair kernel (cta_group::2); critic nets ignore it
     net.pack(_flat(params))
     out = net.forward(obs, N, M, rows, idx=idx)
     want = mlp(x)
@@ -112,7 +114,8 @@ def test_forward_matches_torch(M, D, A, samples, critic):
     net.close()
 
 
-def test_forward_many_tiles_per_cta():
+@pytest.mark.parametrize("pair", [False, True])
+def test_forward_many_tiles_per_cta(pair):
     """More tiles than 2 x SMs, odd count, ragged last tile: every CTA of the two-tiles-in-flight kernel runs several
     pairs plus a single; actor rows and critic rows (M input chunks)."""
     from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
@@ -122,6 +125,7 @@ def test_forward_many_tiles_per_cta():
     idx = torch.randint(0, T * N, (samples,), device="cuda", generator=g)
     mlp = _mlp(D, A, 4)
     net = PpoNet(D, 1, A, True, samples * M)
+    net.set_forward_mode(pair)
     net.pack(_flat([torch.full((A,), -0.5, device="cuda")] + list(mlp.parameters())))
     out = net.forward(obs, N, M, samples * M, idx=idx)
     with torch.no_grad():
@@ -138,8 +142,9 @@ def test_forward_many_tiles_per_cta():
     cnet.close()
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("N,M,D,A", [(700, 4, 72, 4), (50, 2, 27, 1), (40000, 4, 72, 4), (3, 16, 72, 4)])
-def test_sample_matches_torch(N, M, D, A):
+def test_sample_matches_torch(N, M, D, A, pair):
     """`MAPPOActorCritic.step` (agent.py:389-415): act = mean + exp(logstd) eps, logp = summed Normal log-density;
     mean within the forward tolerance, act / logp exact given the mean and the noise (fp32, <= 1e-5)."""
     from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
@@ -148,6 +153,7 @@ def test_sample_matches_torch(N, M, D, A):
     mlp = _mlp(D, A, 8)
     logstd = torch.linspace(-0.7, -0.2, A, device="cuda")
     net = PpoNet(D, 1, A, True, 128)
+    net.set_forward_mode(pair)
     net.pack(_flat([logstd] + list(mlp.parameters())))
     noise = torch.randn((N, M, A), device="cuda", generator=g)
     act, logp, mean = (torch.empty((N, M, A), device="cuda"), torch.empty((N, M, 1), device="cuda"),
