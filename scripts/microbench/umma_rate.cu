@@ -90,6 +90,41 @@ __global__ void __launch_bounds__(kThreads, 1) rate_kernel(int mode, int n, int 
     // activation-like store traffic: 64 KB per ~2000 cycles is what the real epilogue writes; here as fast as it goes
     uint4* dst = reinterpret_cast<uint4*>(scratch);
     for (int it = 0; it < layers * 8; ++it) dst[(tid + it * 512) & 2047] = make_uint4(it, it, it, it);
+  } else if (warp < 16 && mode >= 3) {
+    // what an epilogue does while the tensor core works on the OTHER accumulator (columns 256..511 here, the MMAs write
+    // 0..255): mode 3 = TMEM loads only, 4 = tanh (MUFU) only, 5 = canonical-layout 16-byte shared-memory stores only,
+    // 6 = all three, i.e. the real epilogue loop
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int grp = warp >> 2, row = tid & 127;
+    float acc = 0.f;
+    __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(scratch);   // 32 KB: a quarter of a real activation tile (wraps)
+    for (int it = 0; it < layers * 2; ++it) {
+      uint32_t v[16];
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        if (mode == 3 || mode == 6) {
+          tmem_ld16_nowait(tmem + 256u + lane_off + (uint32_t)(grp * 64 + j * 16), v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(acc + (float)e);
+        }
+        float z[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = (mode == 4 || mode == 6) ? tanh_fast(__uint_as_float(v[e]) + 0.1f) : __uint_as_float(v[e]);
+        if (mode == 5 || mode == 6) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            *reinterpret_cast<uint4*>(sH + (canon_off(row, (grp * 64 + j * 16 + q * 8) & 127, 128))) =
+                make_uint4(pack_bf16(z[q * 8], z[q * 8 + 1]), pack_bf16(z[q * 8 + 2], z[q * 8 + 3]), pack_bf16(z[q * 8 + 4], z[q * 8 + 5]),
+                           pack_bf16(z[q * 8 + 6], z[q * 8 + 7]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc += z[e];
+        }
+      }
+    }
+    if (acc == 123.456f) out[2] = 1;   // keep the work alive
   }
   tc_fence_before();
   __syncthreads();
@@ -106,7 +141,8 @@ int main() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int smem = 65536 + 131072 + 32768;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const char* names[3] = {"resident", "resident+stores", "streamed (6 x 8 KB ring)"};
+  const char* names[7] = {"resident", "resident+stores", "streamed (6 x 8 KB ring)", "resident + TMEM loads", "resident + tanh",
+                          "resident + canonical stores", "resident + full epilogue loop"};
   // operand layouts: A K-major [128 x 256]: lbo = distance between the two core matrices of a K-step, sbo = between 8-row
   // groups.  "4096" = dense canonical tile; "4224" = row groups padded by 128 B; "kblock" = K-step-major blocks
   // [16 K-steps][16 row groups][2][128 B] (lbo 128, sbo 256, K-step stride 4096).  B resident: slab per K-step (sbo 256,
@@ -121,9 +157,9 @@ int main() {
     for (int n : {256, 128, 64}) {
       if (c.sbo_a != 4096 || c.sbo_b != 256) { if (chains > 1) continue; }
       if (n * chains > 512) continue;
-      for (int mode = 0; mode < 3; ++mode) {
+      for (int mode = 0; mode < 7; ++mode) {
         if (mode == 2 && c.sbo_b != 256) continue;
-        if (mode == 1 && n != 256) continue;
+        if ((mode == 1 || mode >= 3) && (n != 256 || chains != 1 || c.sbo_a != 4096 || c.sbo_b != 256)) continue;
         if (c.sbo_b == 4224 && n == 256) continue;   // 256 rows x 4224 B does not fit next to A
         const int grid = sms;
         rate_kernel<<<grid, kThreads, smem>>>(mode, n, 64, slabs, out, c.sbo_a, c.lbo_a, c.sbo_b, c.kstep_b, chains);
