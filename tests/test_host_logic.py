@@ -25,6 +25,17 @@ def test_batch_aviary_fails_loudly_without_cuda():
         BatchAviary(task="multihover", num_envs=2, num_drones=2)
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_trainer_kernels_fail_loudly_without_cuda():
+    """The PPO-update front end and the fused actor have no CPU path either: they raise, they do not fall back."""
+    from marl_gym_pybullet_drones_b200.ppo_native import PpoNet
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PpoNet(72, 1, 4, True, 128)
+    from marl_gym_pybullet_drones_b200.actor import FusedActor
+    with pytest.raises(Exception):
+        FusedActor(72, 256, 4)
+
+
 def test_unsupported_modes_raise_before_touching_the_device():
     from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
     with pytest.raises(ValueError, match="pyb_freq is not divisible"):
