@@ -231,3 +231,53 @@ def test_cfg2_fp32_per_step_spiral_aero():
     print(f"cfg2 fp32 per step: worst {worst_good:.2e} over {n_good} well-conditioned env-steps, {worst_all:.2e} over all {n_all}")
     assert n_good > 0.5 * n_all
     env.close()
+
+
+# ------------------------------------------------------------------------------------------- configs[4]
+def test_cfg4_full_size_shape_properties_and_env_sharding():
+    """BASELINE configs[4]'s per-GPU shape at FULL size — 131 072 envs x 16 drones, DYN + downwash, fp32 — through the
+    properties that do not need an oracle: (1) env sharding is exact: the batch stepped as one handle equals
+    the same envs stepped as two half-size handles (what `--gpus N` relies on: no data-path collective, downwash couples
+    drones only inside an env); (2) the observation's action-history columns shift by one slot per step and end in the
+    action just applied; (3) quaternions stay unit, everything stays finite; (4) the K-steps-in-one-launch kernel
+    reproduces the per-step launches at this size."""
+    from marl_gym_pybullet_drones_b200.batch_aviary import BatchAviary
+    N, M, T = 131072, 16, 4
+    side = 4
+    xyz = np.array([[float(i % side) - 1.5, float(i // side) - 1.5, 0.5 + 0.07 * (i % 5)] for i in range(M)])
+    mk = lambda n: BatchAviary(task="multihover", num_envs=n, num_drones=M, initial_xyzs=xyz, physics="dyn_dw",   # noqa: E731
+                               precision="fp32", auto_reset=True, reset_mode="fixed", seed=1)
+    whole, lo, hi, many = mk(N), mk(N // 2), mk(N // 2), mk(N)
+    for e in (whole, lo, hi, many):
+        e.reset_device()
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    acts = (torch.rand((T, N, M, 4), generator=gen, device="cuda") * 2 - 1.2).contiguous()
+    prev = None
+    outs = []
+    for t in range(T):
+        r = whole.step_device(acts[t])
+        a, b = lo.step_device(acts[t, :N // 2].contiguous()), hi.step_device(acts[t, N // 2:].contiguous())
+        assert torch.equal(r.obs[:N // 2], a.obs) and torch.equal(r.obs[N // 2:], b.obs), t
+        assert torch.equal(r.reward[:N // 2], a.reward) and torch.equal(r.reward[N // 2:], b.reward), t
+        assert torch.equal(r.terminated[N // 2:], b.terminated) and torch.equal(r.truncated[:N // 2], a.truncated), t
+        assert bool(torch.isfinite(r.obs).all()) and bool(torch.isfinite(r.reward).all())
+        assert torch.equal(r.obs[..., -4:], acts[t])
+        if prev is not None:
+            keep = ~(r.terminated | r.truncated)          # (a reset keeps the ring too, BaseRLAviary.py:153-154; all rows hold)
+            assert torch.equal(r.obs[:, :, 12:12 + 56], prev[:, :, 16:16 + 56]) and bool(keep.any())
+        prev = r.obs.clone()
+        outs.append((prev, r.reward.clone(), r.terminated.clone(), r.truncated.clone()))
+    st = whole.get_state()
+    assert float((torch.linalg.vector_norm(st[:, :, 3:7], dim=-1) - 1).abs().max()) <= 3e-7
+    obs = torch.empty((T, N, M, 72), device="cuda")
+    rew = torch.empty((T, N), device="cuda")
+    term = torch.empty((T, N), dtype=torch.bool, device="cuda")
+    trunc = torch.empty((T, N), dtype=torch.bool, device="cuda")
+    l0 = many.launch_count
+    many.step_many(acts, obs, rew, term, trunc)
+    assert many.launch_count - l0 == 1
+    for t in range(T):
+        assert torch.equal(obs[t], outs[t][0]) and torch.equal(rew[t], outs[t][1]), t
+        assert torch.equal(term[t], outs[t][2]) and torch.equal(trunc[t], outs[t][3]), t
+    for e in (whole, lo, hi, many):
+        e.close()
