@@ -378,6 +378,12 @@ namespace bd {
 //       (1 + u_k)(1 + c_k) = 1 + u_k + e_k with e_k = (1 + u_k) c_k: thrust/m gains (g/4) sum e_k, the roll / pitch
 //       mixes see u_k + e_k, the yaw torque (KM rpm^2) is unchanged; gated by |roll|, |pitch| < pi/2
 //   drag (:773-774): F_world += k (.) v, k = -DRAG sum_k 2 pi rpm_k / 60, v = velocity at the start of the substep
+// Single-instruction approximations for the pair terms of the fast flavour: `__fdividef` / `__expf` wrap MUFU.RCP / MUFU.EX2
+// in denormal-range rescaling (a compare, two predicated multiplies and a select each) because this library is not built
+// with flush-to-zero; in the O(M^2) downwash loop that is a fifth of the instructions.  Forces below 1e-38 N may flush.
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 template <int MODE>
 __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<float>& d, const float onep[4],
                                               float& avx, float& avy, float& avz, int group_base = 0, int drone = 0,
@@ -423,7 +429,7 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
         for (int k = 0; k < 4; ++k) {
           float h = d.pz + fmaf(r20, P.prop_x[k], r21 * P.prop_y[k]);
           h = fmaxf(h, P.gnd_h_clip);
-          const float ratio = __fdividef(P.prop_radius, 4.0f * h);
+          const float ratio = P.prop_radius * rcp_ftz(4.0f * h);
           // products that feed sums — and the sum 1 + u, whose u is itself a product — are rounded on their own (the _rn
           // intrinsics are never contracted): whether a multiply is fused into a following add depends on the surrounding kernel, and the one-launch K-step kernel must
           // reproduce the per-step kernel bit for bit
@@ -469,11 +475,11 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
           const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
           const float adz = fabsf(dz);
           const float dxy2 = fmaf(dx, dx, dy * dy);
-          const float ratio = __fdividef(P.prop_radius, 4.0f * adz);
+          const float ratio = P.prop_radius * rcp_ftz(4.0f * adz);
           const float alpha = P.dw1 * ratio * ratio;
           const float beta = fmaf(P.dw2, adz, P.dw3);
-          const float q2 = __fdividef(dxy2, beta * beta);
-          float f = -alpha * __expf(-0.5f * q2);
+          const float q2 = dxy2 * rcp_ftz(beta * beta);
+          float f = -alpha * ex2_ftz(-0.72134752044448f * q2);          // exp(-q2 / 2) = 2^(-q2 log2(e) / 2)
           const bool mine_to_count = (2 * o != M) || (drone < half);     // the doubly visited offset: one owner
           if (!(adz > 0.f && dxy2 < 100.f && mine_to_count)) f = 0.f;       // :801 (delta_xy < 10)
           const float theirs = dz < 0.f ? f : 0.f;                          // the partner is below me
