@@ -146,6 +146,45 @@ def test_step_many_one_launch_equals_k_launches_all_flavours(cfg, M, N, physics,
         e.close()
 
 
+@pytest.mark.parametrize("task,M,physics,act", [
+    ("multihover", 1, "dyn", "rpm"), ("multihover", 3, "dyn_dw", "rpm"), ("multihover", 6, "dyn_gnd_drag_dw", "rpm"),
+    ("multihover", 7, "dyn", "one_d_rpm"), ("multihover", 8, "dyn_drag", "rpm"), ("multihover", 32, "dyn_dw", "rpm"),
+    ("hover", 1, "dyn_gnd", "one_d_rpm"), ("spiral", 4, "dyn", "rpm"), ("spiral", 3, "dyn_dw", "rpm"),
+    ("meetup", 4, "dyn", "rpm"), ("meetup", 3, "dyn", "rpm"), ("leaderfollower", 2, "dyn", "rpm"), ("leaderfollower", 5, "dyn", "rpm"),
+    ("flock", 8, "dyn", "rpm"), ("flock", 16, "dyn_dw", "rpm"),
+])
+def test_step_many_equals_k_steps_across_team_sizes_tasks_and_physics(task, M, physics, act):
+    """Differential sweep: `step_many` (one launch where the fast kernel applies, K launches where the generic kernel has
+    to run — e.g. swarm tasks whose team size is not a power of two) against K `step_device` calls, bit for bit, with a
+    ragged number of envs and re-spawns inside the window."""
+    if task == "hover" and M != 1:
+        pytest.skip("hover is single-drone")
+    N, K = 517, 23
+    cfg = dict(task=task, drone_model="cf2x", num_drones=M, pyb_freq=240, ctrl_freq=30 if task != "spiral" else 48, act=act)
+    side = int(np.ceil(np.sqrt(M)))
+    xyz = np.array([[0.7 * (i % side), 0.7 * (i // side), 0.25 + 0.04 * (i % 7)] for i in range(M)])
+    envs = [batch_from_cfg(cfg, xyz, None, num_envs=N, precision="fp32", physics=physics, auto_reset=True,
+                           reset_mode="jitter_philox" if task == "multihover" else "fixed", seed=2) for _ in range(2)]
+    for e in envs:
+        e.reset_device()
+    A = envs[0].ACTION_DIM
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + len(task))
+    acts = (torch.rand((K, N, M, A), device="cuda", generator=gen) * 2 - 1.25).contiguous()
+    D = envs[0].OBS_DIM
+    obs = torch.empty((K, N, M, D), device="cuda")
+    rew = torch.empty((K, N), device="cuda")
+    term = torch.empty((K, N), device="cuda", dtype=torch.bool)
+    trunc = torch.empty((K, N), device="cuda", dtype=torch.bool)
+    for rep in range(2):
+        envs[0].step_many(acts, obs, rew, term, trunc)
+        for k in range(K):
+            r = envs[1].step_device(acts[k])
+            assert torch.equal(r.obs, obs[k]), (rep, k, float((r.obs - obs[k]).abs().max()))
+            assert torch.equal(r.reward, rew[k]) and torch.equal(r.terminated, term[k]) and torch.equal(r.truncated, trunc[k]), (rep, k)
+    for e in envs:
+        e.close()
+
+
 def test_step_many_one_launch_in_a_cuda_graph():
     """The K-step kernel captured into a CUDA graph: replays read the ring head from the device-resident counter and the
     last CTA out advances it by K; eager single steps before, between and after keep working on the same handle."""
