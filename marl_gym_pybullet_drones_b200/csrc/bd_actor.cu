@@ -505,6 +505,348 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
 }
 
+// =================================================================================================
+// TMEM-resident variant (hidden = 256): the hidden activations never leave tensor memory.
+//
+// The epilogue threads turn an accumulator row into the next layer's A operand IN PLACE: 16 fp32
+// columns come out with tcgen05.ld, go through +bias / tanh, and are written back as 8 columns of packed
+// bf16 pairs (tcgen05.st) at the start of the thread's own 64-column group, where the next layer's
+// tcgen05.mma reads them as a TMEM A operand (K-major, column c = elements 2c | 2c+1).  Shared memory
+// then holds only operands that never change (W1, W2, W3: 176 KB) plus the staged observation tiles,
+// so W1 is no longer re-fetched per tile, and the accumulator of layer 1 is free as soon as layer 2
+// has consumed it: the MMA thread runs layer 1 of tile t+1 while the epilogue threads are still in
+// tile t's second epilogue.  Loading / converting the observations and sampling / writing the finished
+// rows are taken off the epilogue threads' critical path by four auxiliary warps (one thread per row).
+//   per tile:  E:   wait L1 | epilogue 1 (acc0 -> H1 in acc0) | wait L2 | epilogue 2 (acc1 -> H2 in acc1)
+//              MMA: L2(t) chunk by chunk behind epilogue 1 | L1(t+1) | L3(t) -> acc1[32..48) once H2 is complete
+//              AUX: stage X(t+NX) | noise for tile t | wait L3 | read 16 columns | sample, write rows
+// TMEM: acc0 = columns [0,256), acc1 = [256,512).
+constexpr int kTEpi = 512, kTAux = 128, kTThreads = kTEpi + 32 + kTAux;
+enum { TB_W = 0, TB_L1, TB_L2, TB_L3, TB_ACC1FREE, TB_XFULL, TB_XFREE = TB_XFULL + 2, TB_H1 = TB_XFREE + 2, TB_H2 = TB_H1 + 4,
+       TB_COUNT = TB_H2 + 4 };
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+      "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&p)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(p[0]), "r"(p[1]), "r"(p[2]),
+               "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16 accumulator columns -> +bias, tanh -> 8 columns of bf16 pairs, in place
+__device__ __forceinline__ void hidden_chunk_tmem(const uint32_t (&v)[16], const float* __restrict__ bias16, uint32_t dst) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias16);
+  uint32_t p[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = b4[q];
+    p[2 * q] = pack_bf16(tanh_fast(__uint_as_float(v[4 * q]) + b.x), tanh_fast(__uint_as_float(v[4 * q + 1]) + b.y));
+    p[2 * q + 1] = pack_bf16(tanh_fast(__uint_as_float(v[4 * q + 2]) + b.z), tanh_fast(__uint_as_float(v[4 * q + 3]) + b.w));
+  }
+  tmem_st8(dst, p);
+}
+
+// one hidden epilogue of a thread: its 64 columns [64 g, 64 g + 64) of the accumulator row, four chunks
+// of 16, each published (mbarrier) as soon as it is back in tensor memory
+__device__ __forceinline__ void epilogue_tmem(uint32_t grp_base, const float* __restrict__ bias64, uint32_t chunk_bar0) {
+  uint32_t va[16], vb[16];
+  tmem_ld16_nowait(grp_base, va);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 4; j += 2) {
+    tmem_ld16_nowait(grp_base + 16u * (uint32_t)(j + 1), vb);
+    hidden_chunk_tmem(va, bias64 + 16 * j, grp_base + 8u * (uint32_t)j);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(chunk_bar0 + 8u * (uint32_t)j);
+    tmem_wait_ld();
+    if (j + 2 < 4) tmem_ld16_nowait(grp_base + 16u * (uint32_t)(j + 2), va);
+    hidden_chunk_tmem(vb, bias64 + 16 * (j + 1), grp_base + 8u * (uint32_t)(j + 1));
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(chunk_bar0 + 8u * (uint32_t)(j + 1));
+    if (j + 2 < 4) tmem_wait_ld();
+  }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(kTThreads, 1)
+actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
+                  unsigned long long seed, unsigned long long offset, float* __restrict__ act, float* __restrict__ logp,
+                  float* __restrict__ mean_out) {
+  constexpr int HID = 256;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int K1 = W.K1;
+  __nv_bfloat16* sW1 = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sW2 = sW1 + (size_t)HID * K1;
+  __nv_bfloat16* sW3 = sW2 + (size_t)HID * HID;
+  __nv_bfloat16* sX = sW3 + (size_t)kNOut * HID;               // NX tiles of [128 x K1]
+  float* sB1 = reinterpret_cast<float*>(sX + (size_t)NX * kRows * K1);
+  float* sB2 = sB1 + HID;
+  float* sB3 = sB2 + HID;
+  float* sLs = sB3 + kNOut;
+  __shared__ __align__(8) uint64_t mbar[TB_COUNT];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < HID; i += kTThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
+  if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd[tid]; }
+  {   // padded columns [obs_dim, K1) of the observation tiles stay zero for the kernel's lifetime
+    uint4* z = reinterpret_cast<uint4*>(sX);
+    const int n16 = NX * kRows * K1 / 8;
+    for (int i = tid; i < n16; i += kTThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    proxy_fence();
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar[TB_W]), 1);
+    mbar_init(smem_u32(&mbar[TB_L1]), 1);
+    mbar_init(smem_u32(&mbar[TB_L2]), 1);
+    mbar_init(smem_u32(&mbar[TB_L3]), 1);
+    mbar_init(smem_u32(&mbar[TB_ACC1FREE]), kTAux);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&mbar[TB_XFULL + b]), kTAux);
+      mbar_init(smem_u32(&mbar[TB_XFREE + b]), 1);
+    }
+    for (int j = 0; j < 4; ++j) {
+      mbar_init(smem_u32(&mbar[TB_H1 + j]), kTEpi);
+      mbar_init(smem_u32(&mbar[TB_H2 + j]), kTEpi);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u, out3 = acc1 + 32u;
+  const uint32_t bar0 = smem_u32(&mbar[0]);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const long long n_tiles = (rows + kRows - 1) / kRows;
+  const int n_local = (long long)blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  long long* const trace = (W.trace != nullptr && blockIdx.x == 0) ? W.trace : nullptr;
+
+  if (warp == kTEpi / 32) {
+    // =============================== MMA issuer (one thread) =====================================
+    if (lane == 0 && n_local > 0) {
+      const uint32_t sbo1 = (uint32_t)(K1 / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
+      mbar_expect_tx(bar(TB_W), (uint32_t)((HID * K1 + (HID + kNOut) * HID) * 2));
+      bulk_g2s(smem_u32(sW1), W.w1, (uint32_t)(HID * K1 * 2), bar(TB_W));
+      bulk_g2s(smem_u32(sW2), W.w2, (uint32_t)(HID * HID * 2), bar(TB_W));
+      bulk_g2s(smem_u32(sW3), W.w3, (uint32_t)(kNOut * HID * 2), bar(TB_W));
+      const uint64_t dW1 = umma_desc(smem_u32(sW1), 128, sbo1), dW2 = umma_desc(smem_u32(sW2), 128, sboH);
+      const uint64_t dW3 = umma_desc(smem_u32(sW3), 128, sboH);
+      const uint64_t dX0 = umma_desc(smem_u32(sX), 128, sbo1);
+      const uint64_t x_stride = (uint64_t)((kRows * K1 * 2) >> 4);   // one observation tile, in descriptor address units
+      constexpr uint32_t idH = umma_idesc(HID), idO = umma_idesc(kNOut);
+      const int k1_steps = K1 / 16;
+      auto layer1 = [&](int i) {   // acc0 = X(i) W1^T; the commit also hands the observation buffer back
+        const int b = i % NX;
+        mbar_wait_guarded(bar(TB_XFULL + b), (uint32_t)(i / NX) & 1u);
+        tc_fence_after();
+        const uint64_t dX = dX0 + (uint64_t)b * x_stride;
+        for (int s = 0; s < k1_steps; ++s) umma_bf16(acc0, dX + (uint64_t)(s * 16), dW1 + (uint64_t)(s * 16), idH, s > 0);
+        umma_commit(bar(TB_L1));
+        umma_commit(bar(TB_XFREE + b));
+      };
+      mbar_wait_guarded(bar(TB_W), 0);
+      layer1(0);
+      for (int i = 0; i < n_local; ++i) {
+        const uint32_t p = (uint32_t)i & 1u;
+        long long* tr = trace ? trace + (size_t)i * 16 : nullptr;
+        // layer 2: acc1 = H1 W2^T, the K-steps follow the layer-1 epilogue chunk by chunk
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait_guarded(bar(TB_H1 + j), p);
+          if (j == 0 && i > 0) mbar_wait_guarded(bar(TB_ACC1FREE), p ^ 1u);   // tile i-1's outputs have been read
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            umma_bf16_ts(acc1, acc0 + (uint32_t)(64 * g + 8 * j), dW2 + (uint64_t)((4 * g + j) * 16), idH, (j | g) != 0);
+        }
+        umma_commit(bar(TB_L2));
+        if (tr) tr[10] = clock64();
+        // layer 1 of the next tile: acc0 is free (layer 2 above read it in issue order)
+        if (i + 1 < n_local) layer1(i + 1);
+        if (tr) tr[9] = clock64();
+        // layer 3: out = H2 W3^T as FOUR independent partial sums, one per 64-column group g, accumulated in
+        // acc1[64 g + 32, 64 g + 48) — group g's third fp32 chunk, which every thread has in registers once chunk 2 of the
+        // layer-2 epilogue is published.  An N = 16 MMA is latency-bound on its accumulator (one chain of sixteen took
+        // ~120 cycles per K-step); four chains overlap, twelve K-steps run while the last chunk is still in the SFU
+        // and four follow it.  The auxiliary warps add the four partial rows.
+        mbar_wait_guarded(bar(TB_H2 + 2), p);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            umma_bf16_ts(acc1 + (uint32_t)(64 * g + 32), acc1 + (uint32_t)(64 * g + 8 * j), dW3 + (uint64_t)((4 * g + j) * 16), idO, j != 0);
+        mbar_wait_guarded(bar(TB_H2 + 3), p);
+        tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          umma_bf16_ts(acc1 + (uint32_t)(64 * g + 32), acc1 + (uint32_t)(64 * g + 24), dW3 + (uint64_t)((4 * g + 3) * 16), idO, 1);
+        umma_commit(bar(TB_L3));
+        if (tr) tr[11] = clock64();
+      }
+    }
+  } else if (warp < kTEpi / 32) {
+    // =============================== epilogue warps ==============================================
+    const int grp = warp >> 2;                                                   // my 64-column group
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;                 // my warp's 32 TMEM lanes
+    const uint32_t g0 = acc0 + lane_off + 64u * (uint32_t)grp, g1 = acc1 + lane_off + 64u * (uint32_t)grp;
+    for (int i = 0; i < n_local; ++i) {
+      const uint32_t p = (uint32_t)i & 1u;
+      long long* tr = (trace && tid == 0) ? trace + (size_t)i * 16 : nullptr;
+      if (tr) tr[0] = clock64();
+      mbar_wait_guarded(bar(TB_L1), p);
+      tc_fence_after();
+      if (tr) tr[1] = clock64();
+      epilogue_tmem(g0, sB1 + 64 * grp, bar(TB_H1));
+      if (tr) tr[2] = clock64();
+      mbar_wait_guarded(bar(TB_L2), p);
+      tc_fence_after();
+      if (tr) tr[3] = clock64();
+      epilogue_tmem(g1, sB2 + 64 * grp, bar(TB_H2));
+      if (tr) tr[4] = clock64();
+    }
+  } else {
+    // =============================== auxiliary warps: observations in, finished rows out ==========
+    const int q = warp & 3;                       // my warp's TMEM lane quadrant = its 32 rows of the tile
+    const int row = q * 32 + lane;
+    const int od = W.obs_dim;
+    const bool vec4 = (od & 3) == 0;
+    auto stage = [&](long long tile, int b) {     // fp32 rows -> (normalised) bf16, canonical K-major tile b
+      __nv_bfloat16* dst = sX + (size_t)b * kRows * K1;
+      const long long r0 = tile * kRows + q * 32;                 // the warp's 32 rows are contiguous in memory
+      const bool norm = W.nmean != nullptr;
+      const float cl = W.nclip;
+      if (vec4) {
+        const int q4 = od >> 2, n4 = 32 * q4;
+        const float4* src = reinterpret_cast<const float4*>(obs + (size_t)r0 * od);
+        constexpr int U = 4;
+        for (int f0 = lane; f0 < n4; f0 += 32 * U) {
+          float4 x[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int f = f0 + 32 * u;
+            const int r = f / q4;
+            x[u] = (f < n4 && r0 + r < rows) ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int f = f0 + 32 * u;
+            if (f < n4) {
+              const int r = f / q4, c = (f - r * q4) * 4;
+              float4 v = x[u];
+              if (norm && r0 + r < rows) {
+                const size_t sidx = (size_t)((r0 + r) % W.nperiod) * od + c;
+                const float4 m = __ldg(reinterpret_cast<const float4*>(W.nmean + sidx));
+                const float4 s = __ldg(reinterpret_cast<const float4*>(W.nrstd + sidx));
+                v.x = fminf(fmaxf((v.x - m.x) * s.x, -cl), cl); v.y = fminf(fmaxf((v.y - m.y) * s.y, -cl), cl);
+                v.z = fminf(fmaxf((v.z - m.z) * s.z, -cl), cl); v.w = fminf(fmaxf((v.w - m.w) * s.w, -cl), cl);
+              }
+              *reinterpret_cast<uint2*>(dst + canon_off(q * 32 + r, c, K1)) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            }
+          }
+        }
+      } else {
+        const int n = 32 * od;
+        const float* src = obs + (size_t)r0 * od;
+        for (int e = lane; e < n; e += 32) {
+          const int r = e / od, c = e - r * od;
+          float v = 0.f;
+          if (r0 + r < rows) {
+            v = __ldg(src + e);
+            if (norm) {
+              const size_t sidx = (size_t)((r0 + r) % W.nperiod) * od + c;
+              v = fminf(fmaxf((v - __ldg(W.nmean + sidx)) * __ldg(W.nrstd + sidx), -cl), cl);
+            }
+          }
+          dst[canon_off(q * 32 + r, c, K1)] = __float2bfloat16(v);
+        }
+      }
+      proxy_fence();               // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bar(TB_XFULL + b));
+    };
+    for (int k = 0; k < NX && k < n_local; ++k) stage((long long)blockIdx.x + (long long)k * gridDim.x, k);
+    for (int i = 0; i < n_local; ++i) {
+      const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+      long long* tr = (trace && tid == kTEpi + 32) ? trace + (size_t)i * 16 : nullptr;
+      if (i + NX < n_local) {      // the buffer of tile i is free once its layer-1 MMAs have completed
+        mbar_wait_guarded(bar(TB_XFREE + i % NX), (uint32_t)(i / NX) & 1u);
+        stage(tile + (long long)NX * gridDim.x, i % NX);
+      }
+      if (tr) tr[6] = clock64();
+      // the row's Gaussian noise does not depend on the network: drawn while the tile is still in flight
+      const long long row_g = tile * kRows + row;
+      const bool live = row_g < rows;
+      float eps[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        if (noise != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < W.act_dim) eps[k] = __ldg(noise + (size_t)row_g * W.act_dim + k);
+        } else {   // Philox4x32-10 keyed by the seed, counter = (row, call offset) -> 4 normals (Box-Muller)
+          uint32_t c[4] = {(uint32_t)row_g, (uint32_t)((unsigned long long)row_g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+          philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+          const float u0 = ((c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (c[1] >> 8) * (1.0f / 16777216.0f);
+          const float u2 = ((c[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (c[3] >> 8) * (1.0f / 16777216.0f);
+          const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
+          float s0, c0, s1, c1;
+          __sincosf(6.28318530718f * u1, &s0, &c0);
+          __sincosf(6.28318530718f * u3, &s1, &c1);
+          eps[0] = ra * c0; eps[1] = ra * s0; eps[2] = rb * c1; eps[3] = rb * s1;
+        }
+      }
+      mbar_wait_guarded(bar(TB_L3), (uint32_t)i & 1u);
+      tc_fence_after();
+      if (tr) tr[5] = clock64();
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        uint32_t w[4][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld4_nowait(out3 + 64u * (uint32_t)g + ((uint32_t)(q * 32) << 16), w[g]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          v[k] = (__uint_as_float(w[0][k]) + __uint_as_float(w[1][k])) + (__uint_as_float(w[2][k]) + __uint_as_float(w[3][k]));
+      }
+      tc_fence_before();
+      mbar_arrive(bar(TB_ACC1FREE));        // acc1 may be overwritten by the next tile's layer 2
+      if (live) {
+        float lp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < W.act_dim) {
+            const float m = v[k] + sB3[k];
+            const float ls = sLs[k];
+            act[(size_t)row_g * W.act_dim + k] = fmaf(__expf(ls), eps[k], m);
+            if (mean_out != nullptr) mean_out[(size_t)row_g * W.act_dim + k] = m;
+            lp += -0.5f * eps[k] * eps[k] - ls - 0.91893853320467f;
+          }
+        }
+        logp[row_g] = lp;
+      }
+      if (tr) tr[7] = clock64();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
 // fp32 [n x k] row-major (torch nn.Linear weight) -> bf16 canonical K-major [n_pad x k_pad], zero padded
 __global__ void pack_weight_kernel(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,6 +875,8 @@ struct bd_actor {
   __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *logstd = nullptr;
   size_t smem = 0;
+  int impl = 0;          // 0: activations through shared memory (actor_forward_kernel); 1 / 2: TMEM-resident activations
+  size_t smem_t = 0;     //    (actor_tmem_kernel) with that many observation buffers
   int64_t launches = 0;
   long long* trace = nullptr;
   const float *nmean = nullptr, *nrstd = nullptr;
@@ -570,7 +914,16 @@ int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor**
   alloc((void**)&a->w3, (size_t)kNOut * hidden * 2);
   alloc((void**)&a->b1, hidden * 4); alloc((void**)&a->b2, hidden * 4);
   alloc((void**)&a->b3, kNOut * 4); alloc((void**)&a->logstd, kNOut * 4);
-  if (a->smem > prop.sharedMemPerBlockOptin) {
+  if (hidden == 256) {   // TMEM-resident variant: W1 / W2 / W3 resident + one or two observation tiles (BD_ACTOR_IMPL=smem opts out)
+    const size_t fixed = (size_t)(hidden * K1 + (hidden + kNOut) * hidden) * 2 + (size_t)(2 * hidden + 2 * kNOut) * 4;
+    const size_t xb = (size_t)kRows * K1 * 2, room = prop.sharedMemPerBlockOptin - 1024;   // static shared memory: barriers
+    const char* im = getenv("BD_ACTOR_IMPL");
+    if (!(im && im[0] == 's')) {
+      if (fixed + 2 * xb <= room) { a->impl = 2; a->smem_t = fixed + 2 * xb; }
+      else if (fixed + xb <= room) { a->impl = 1; a->smem_t = fixed + xb; }
+    }
+  }
+  if (a->impl == 0 && a->smem > prop.sharedMemPerBlockOptin) {
     cudaFree(a->w1); cudaFree(a->w2); cudaFree(a->w3); cudaFree(a->b1); cudaFree(a->b2); cudaFree(a->b3); cudaFree(a->logstd);
     const size_t need = a->smem;
     delete a;
@@ -581,7 +934,11 @@ int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor**
   if (e == cudaSuccess) {
     const char* g = getenv("BD_ACTOR_GROUPS");
     if (g && g[0] == '2') a->groups = 2;
-    e = cudaFuncSetAttribute(actor_kernel(hidden, a->groups), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+    if (a->impl == 0)
+      e = cudaFuncSetAttribute(actor_kernel(hidden, a->groups), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a->smem);
+    else
+      e = cudaFuncSetAttribute(a->impl == 2 ? actor_tmem_kernel<2> : actor_tmem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)a->smem_t);
   }
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) {
@@ -627,9 +984,14 @@ int bd_actor_forward(bd_actor* a, const float* obs_dev, int64_t rows, const floa
   const long long n_tiles = (rows + kRows - 1) / kRows;
   const int grid = (int)(n_tiles < a->sm_count ? n_tiles : a->sm_count);   // persistent: one CTA per SM
   cudaStream_t st = (cudaStream_t)stream;
-  const int threads = a->groups == 2 ? ActorShape<2>::kThreads : ActorShape<4>::kThreads;
-  actor_kernel(a->hidden, a->groups)<<<grid, threads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev,
-                                                                    mean_dev);
+  if (a->impl != 0) {
+    (a->impl == 2 ? actor_tmem_kernel<2> : actor_tmem_kernel<1>)<<<grid, kTThreads, a->smem_t, st>>>(W, obs_dev, rows, noise_dev, seed,
+                                                                                                   offset, act_dev, logp_dev, mean_dev);
+  } else {
+    const int threads = a->groups == 2 ? ActorShape<2>::kThreads : ActorShape<4>::kThreads;
+    actor_kernel(a->hidden, a->groups)<<<grid, threads, a->smem, st>>>(W, obs_dev, rows, noise_dev, seed, offset, act_dev, logp_dev,
+                                                                      mean_dev);
+  }
   a->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(BD_ECUDA, "bd_actor_forward: %s", cudaGetErrorString(e));
