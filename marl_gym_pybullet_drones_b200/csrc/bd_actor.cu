@@ -512,18 +512,32 @@ actor_forward_kernel(ActorDev W, const float* __restrict__ obs, long long rows, 
 // columns come out with tcgen05.ld, go through +bias / tanh, and are written back as 8 columns of packed
 // bf16 pairs (tcgen05.st) at the start of the thread's own 64-column group, where the next layer's
 // tcgen05.mma reads them as a TMEM A operand (K-major, column c = elements 2c | 2c+1).  Shared memory
-// then holds only operands that never change (W1, W2, W3: 176 KB) plus the staged observation tiles,
+// then holds only operands that never change (W1, W2: 168 KB) plus the staged observation tiles,
 // so W1 is no longer re-fetched per tile, and the accumulator of layer 1 is free as soon as layer 2
 // has consumed it: the MMA thread runs layer 1 of tile t+1 while the epilogue threads are still in
 // tile t's second epilogue.  Loading / converting the observations and sampling / writing the finished
 // rows are taken off the epilogue threads' critical path by four auxiliary warps (one thread per row).
-//   per tile:  E:   wait L1 | epilogue 1 (acc0 -> H1 in acc0) | wait L2 | epilogue 2 (acc1 -> H2 in acc1)
-//              MMA: L2(t) chunk by chunk behind epilogue 1 | L1(t+1) | L3(t) -> acc1[32..48) once H2 is complete
-//              AUX: stage X(t+NX) | noise for tile t | wait L3 | read 16 columns | sample, write rows
-// TMEM: acc0 = columns [0,256), acc1 = [256,512).
-constexpr int kTEpi = 512, kTAux = 128, kTThreads = kTEpi + 32 + kTAux;
-enum { TB_W = 0, TB_L1, TB_L2, TB_L3, TB_ACC1FREE, TB_XFULL, TB_XFREE = TB_XFULL + 2, TB_H1 = TB_XFREE + 2, TB_H2 = TB_H1 + 4,
-       TB_COUNT = TB_H2 + 4 };
+//
+// Layer 3 (hidden -> act_dim <= 4) does NOT go through the tensor pipe.  With a TMEM A operand an M = 128 instruction
+// takes ~128 cycles whatever N is, so sixteen N = 16 MMAs cost as much pipe time as layer 2, and they kept accumulator 1
+// occupied until the whole second epilogue had finished: layer 2 of the next tile could not run under that tile's first
+// epilogue (tile period 3.9 us, 1.4 us of it epilogue threads waiting for layer 2).  Here the second epilogue keeps its
+// tanh outputs in fp32 registers and multiplies them with W3 on the FMA pipe (epilogue_out below): H2 is never rounded
+// to bf16 and never written anywhere; accumulator 1 is free as soon as every epilogue thread has loaded its last chunk.
+//   per tile:  E (16 warps):    wait L1 | epilogue 1 (acc0 -> H1 in acc0) | wait L2 | epilogue 2 (acc1 -> tanh -> x W3 -> partials)
+//              MMA (1 thread):  L2(t) chunk by chunk behind epilogue 1 | L1(t+1)
+//              loader (4 warps):  X(t+NX): global fp32 -> (normalised) bf16 -> canonical tile in shared memory
+//              sampler (3 warps): noise for tile t | wait partials | sum, + b3, sample, write rows
+// TMEM: acc0 = columns [0,256), acc1 = [256,512).  Measured (262 144 rows, obs 72): 69 us (the layer-3-on-MMA version
+// of this kernel 70, the shared-memory kernel above 83); tile period 3.6 us against an SFU floor of 2.1 us (2 x 128 x 256
+// MUFU.TANH at 16 / clock / SM) — profiles/r2_actor_tmem_ncu.txt, r2_actor_tmem_trace.txt.
+// epilogue | MMA | loader warps | sampler warps: 24 warps = 80 registers per thread (ptxas sizes the allocation for
+// whole groups of four warps: 25 warps got 72 registers and spilled)
+constexpr int kTEpi = 512, kTAux = 128, kTSamp = 96, kTThreads = kTEpi + 32 + kTAux + kTSamp;
+// warp roles: the loader warps come first (lowest warp ids)
+constexpr int kWLoad0 = 0, kWEpi0 = kTAux / 32, kWMma = kWEpi0 + kTEpi / 32, kWSamp0 = kWMma + 1;
+enum { TB_W = 0, TB_L1, TB_L2, TB_OUT, TB_PFREE, TB_ACC1FREE, TB_XFULL, TB_XFREE = TB_XFULL + 2, TB_H1 = TB_XFREE + 2,
+       TB_COUNT = TB_H1 + 4 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -536,9 +550,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&p)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(p[0]), "r"(p[1]), "r"(p[2]),
                "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7])
                : "memory");
-}
-__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -578,6 +589,83 @@ __device__ __forceinline__ void epilogue_tmem(uint32_t grp_base, const float* __
   }
 }
 
+// Second epilogue: accumulator 1 -> +bias, tanh (fp32, never rounded) -> layer 3 on the FMA pipe.
+// The accumulator is read with the 16x256b shape (the m16n8 fragment layout: thread t of a warp holds rows t/4 and
+// t/4 + 8 of a 16-lane half, columns 8 j + 2 (t % 4) + {0, 1} of every 8-column block), so a thread's 64 elements are
+// 4 rows x 16 columns instead of 1 row x 64 columns: one float4 of W3 (column c, outputs 0..3) then serves four rows.
+// With one row per thread every tanh needed its own broadcast LDS.128, and a broadcast still returns 16 B to each of
+// the 32 lanes — 2.1 us per tile on the 128 B / clock return path, twice the SFU time (measured; the constant bank was
+// worse: ptxas turns the operands into LDCU.128, 3.1 us).  The four lanes that share rows exchange partial sums by
+// shuffle (12 per tile) and each writes one finished row-partial over the warp group's 64 columns.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+// 16 columns [c0, c0 + 16) of the warp's 32 lanes: va = lanes 0..15, vb = lanes 16..31; o[r][k]: r = 2 * half + rowsel
+__device__ __forceinline__ void out_chunk4(const uint32_t (&va)[8], const uint32_t (&vb)[8], const float* __restrict__ bias_c,
+                                           const float4* __restrict__ w_c, float (&o)[4][4]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {      // 8-column block j: my columns 8 j + {0, 1} (+ 2 (t % 4), folded into the pointers)
+    const float2 b = *reinterpret_cast<const float2*>(bias_c + 8 * j);
+    const float4 w0 = w_c[8 * j], w1 = w_c[8 * j + 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t* v = (r < 2) ? va : vb;
+      const float h0 = tanh_fast(__uint_as_float(v[4 * j + 2 * (r & 1)]) + b.x);
+      const float h1 = tanh_fast(__uint_as_float(v[4 * j + 2 * (r & 1) + 1]) + b.y);
+      o[r][0] = fmaf(h0, w0.x, o[r][0]); o[r][1] = fmaf(h0, w0.y, o[r][1]); o[r][2] = fmaf(h0, w0.z, o[r][2]); o[r][3] = fmaf(h0, w0.w, o[r][3]);
+      o[r][0] = fmaf(h1, w1.x, o[r][0]); o[r][1] = fmaf(h1, w1.y, o[r][1]); o[r][2] = fmaf(h1, w1.z, o[r][2]); o[r][3] = fmaf(h1, w1.w, o[r][3]);
+    }
+  }
+}
+// grp_base: accumulator 1 at the warp's lane quadrant and 64-column group; bias_t / w_t already offset by the group's
+// first column + 2 (t % 4).  Returns the partial sums of row 8 m + t / 4 of the quadrant, m = 2 (t & 1) + ((t >> 1) & 1).
+__device__ __forceinline__ float4 epilogue_out(uint32_t grp_base, const float* __restrict__ bias_t, const float4* __restrict__ w_t,
+                                               uint32_t acc_free, int lane) {
+  float o[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[r][k] = 0.f;
+  uint32_t va[8], vb[8], vc[8], vd[8];
+  const uint32_t hi = grp_base + (16u << 16);
+  tmem_ld_16x256b_x2(grp_base, va);
+  tmem_ld_16x256b_x2(hi, vb);
+  tmem_wait_ld();
+  tmem_ld_16x256b_x2(grp_base + 16u, vc);
+  tmem_ld_16x256b_x2(hi + 16u, vd);
+  out_chunk4(va, vb, bias_t, w_t, o);
+  tmem_wait_ld();
+  tmem_ld_16x256b_x2(grp_base + 32u, va);
+  tmem_ld_16x256b_x2(hi + 32u, vb);
+  out_chunk4(vc, vd, bias_t + 16, w_t + 16, o);
+  tmem_wait_ld();
+  tmem_ld_16x256b_x2(grp_base + 48u, vc);
+  tmem_ld_16x256b_x2(hi + 48u, vd);
+  out_chunk4(va, vb, bias_t + 32, w_t + 32, o);
+  tmem_wait_ld();
+  tc_fence_before();
+  mbar_arrive(acc_free);
+  out_chunk4(vc, vd, bias_t + 48, w_t + 48, o);
+  // rows are shared by the four lanes of a quad: halve the row set twice
+  const bool odd = (lane & 1) != 0, up = (lane & 2) != 0;
+  float a[2][4], b[4];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float recv = __shfl_xor_sync(0xffffffffu, odd ? o[rr][k] : o[rr + 2][k], 1);
+      a[rr][k] = (odd ? o[rr + 2][k] : o[rr][k]) + recv;
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? a[0][k] : a[1][k], 2);
+    b[k] = (up ? a[1][k] : a[0][k]) + recv;
+  }
+  return make_float4(b[0], b[1], b[2], b[3]);
+}
+
 template <int NX>
 __global__ void __launch_bounds__(kTThreads, 1)
 actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, const float* __restrict__ noise,
@@ -588,18 +676,22 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
   const int K1 = W.K1;
   __nv_bfloat16* sW1 = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sW2 = sW1 + (size_t)HID * K1;
-  __nv_bfloat16* sW3 = sW2 + (size_t)HID * HID;
-  __nv_bfloat16* sX = sW3 + (size_t)kNOut * HID;               // NX tiles of [128 x K1]
+  __nv_bfloat16* sX = sW2 + (size_t)HID * HID;                 // NX tiles of [128 x K1]
   float* sB1 = reinterpret_cast<float*>(sX + (size_t)NX * kRows * K1);
   float* sB2 = sB1 + HID;
   float* sB3 = sB2 + HID;
   float* sLs = sB3 + kNOut;
+  float4* sW3f = reinterpret_cast<float4*>(sLs + kNOut);       // [HID] columns x 4 outputs, fp32 values of the packed bf16 W3
+  float4* sPart = sW3f + HID;                                  // [4 column groups][128 rows] partial layer-3 sums
   __shared__ __align__(8) uint64_t mbar[TB_COUNT];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < HID; i += kTThreads) { sB1[i] = W.b1[i]; sB2[i] = W.b2[i]; }
   if (tid < kNOut) { sB3[tid] = W.b3[tid]; sLs[tid] = W.logstd[tid]; }
+  for (int c = tid; c < HID; c += kTThreads)     // rows >= act_dim of the packed W3 are zero
+    sW3f[c] = make_float4(__bfloat162float(W.w3[canon_off(0, c, HID)]), __bfloat162float(W.w3[canon_off(1, c, HID)]),
+                          __bfloat162float(W.w3[canon_off(2, c, HID)]), __bfloat162float(W.w3[canon_off(3, c, HID)]));
   {   // padded columns [obs_dim, K1) of the observation tiles stay zero for the kernel's lifetime
     uint4* z = reinterpret_cast<uint4*>(sX);
     const int n16 = NX * kRows * K1 / 8;
@@ -610,15 +702,15 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
     mbar_init(smem_u32(&mbar[TB_W]), 1);
     mbar_init(smem_u32(&mbar[TB_L1]), 1);
     mbar_init(smem_u32(&mbar[TB_L2]), 1);
-    mbar_init(smem_u32(&mbar[TB_L3]), 1);
-    mbar_init(smem_u32(&mbar[TB_ACC1FREE]), kTAux);
+    mbar_init(smem_u32(&mbar[TB_OUT]), kTEpi);
+    mbar_init(smem_u32(&mbar[TB_PFREE]), kTSamp);
+    mbar_init(smem_u32(&mbar[TB_ACC1FREE]), kTEpi);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&mbar[TB_XFULL + b]), kTAux);
       mbar_init(smem_u32(&mbar[TB_XFREE + b]), 1);
     }
     for (int j = 0; j < 4; ++j) {
       mbar_init(smem_u32(&mbar[TB_H1 + j]), kTEpi);
-      mbar_init(smem_u32(&mbar[TB_H2 + j]), kTEpi);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -630,26 +722,24 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u, out3 = acc1 + 32u;
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u;
   const uint32_t bar0 = smem_u32(&mbar[0]);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const long long n_tiles = (rows + kRows - 1) / kRows;
   const int n_local = (long long)blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
   long long* const trace = (W.trace != nullptr && blockIdx.x == 0) ? W.trace : nullptr;
 
-  if (warp == kTEpi / 32) {
+  if (warp == kWMma) {
     // =============================== MMA issuer (one thread) =====================================
     if (lane == 0 && n_local > 0) {
       const uint32_t sbo1 = (uint32_t)(K1 / 8) * 128u, sboH = (uint32_t)(HID / 8) * 128u;
-      mbar_expect_tx(bar(TB_W), (uint32_t)((HID * K1 + (HID + kNOut) * HID) * 2));
+      mbar_expect_tx(bar(TB_W), (uint32_t)((HID * K1 + HID * HID) * 2));
       bulk_g2s(smem_u32(sW1), W.w1, (uint32_t)(HID * K1 * 2), bar(TB_W));
       bulk_g2s(smem_u32(sW2), W.w2, (uint32_t)(HID * HID * 2), bar(TB_W));
-      bulk_g2s(smem_u32(sW3), W.w3, (uint32_t)(kNOut * HID * 2), bar(TB_W));
       const uint64_t dW1 = umma_desc(smem_u32(sW1), 128, sbo1), dW2 = umma_desc(smem_u32(sW2), 128, sboH);
-      const uint64_t dW3 = umma_desc(smem_u32(sW3), 128, sboH);
       const uint64_t dX0 = umma_desc(smem_u32(sX), 128, sbo1);
       const uint64_t x_stride = (uint64_t)((kRows * K1 * 2) >> 4);   // one observation tile, in descriptor address units
-      constexpr uint32_t idH = umma_idesc(HID), idO = umma_idesc(kNOut);
+      constexpr uint32_t idH = umma_idesc(HID);
       const int k1_steps = K1 / 16;
       auto layer1 = [&](int i) {   // acc0 = X(i) W1^T; the commit also hands the observation buffer back
         const int b = i % NX;
@@ -669,7 +759,7 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           mbar_wait_guarded(bar(TB_H1 + j), p);
-          if (j == 0 && i > 0) mbar_wait_guarded(bar(TB_ACC1FREE), p ^ 1u);   // tile i-1's outputs have been read
+          if (j == 0 && i > 0) mbar_wait_guarded(bar(TB_ACC1FREE), p ^ 1u);   // tile i-1's second epilogue has loaded its last chunk
           tc_fence_after();
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -680,35 +770,16 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
         // layer 1 of the next tile: acc0 is free (layer 2 above read it in issue order)
         if (i + 1 < n_local) layer1(i + 1);
         if (tr) tr[9] = clock64();
-        // layer 3: out = H2 W3^T as FOUR independent partial sums, one per 64-column group g, accumulated in
-        // acc1[64 g + 32, 64 g + 48) — group g's third fp32 chunk, which every thread has in registers once chunk 2 of the
-        // layer-2 epilogue is published.  An N = 16 MMA is latency-bound on its accumulator (one chain of sixteen took
-        // ~120 cycles per K-step); four chains overlap, twelve K-steps run while the last chunk is still in the SFU
-        // and four follow it.  The auxiliary warps add the four partial rows.
-        mbar_wait_guarded(bar(TB_H2 + 2), p);
-        tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            umma_bf16_ts(acc1 + (uint32_t)(64 * g + 32), acc1 + (uint32_t)(64 * g + 8 * j), dW3 + (uint64_t)((4 * g + j) * 16), idO, j != 0);
-        mbar_wait_guarded(bar(TB_H2 + 3), p);
-        tc_fence_after();
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          umma_bf16_ts(acc1 + (uint32_t)(64 * g + 32), acc1 + (uint32_t)(64 * g + 24), dW3 + (uint64_t)((4 * g + 3) * 16), idO, 1);
-        umma_commit(bar(TB_L3));
-        if (tr) tr[11] = clock64();
       }
     }
-  } else if (warp < kTEpi / 32) {
+  } else if (warp >= kWEpi0 && warp < kWMma) {
     // =============================== epilogue warps ==============================================
-    const int grp = warp >> 2;                                                   // my 64-column group
+    const int grp = (warp - kWEpi0) >> 2;                                        // my 64-column group
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;                 // my warp's 32 TMEM lanes
     const uint32_t g0 = acc0 + lane_off + 64u * (uint32_t)grp, g1 = acc1 + lane_off + 64u * (uint32_t)grp;
     for (int i = 0; i < n_local; ++i) {
       const uint32_t p = (uint32_t)i & 1u;
-      long long* tr = (trace && tid == 0) ? trace + (size_t)i * 16 : nullptr;
+      long long* tr = (trace && tid == kWEpi0 * 32) ? trace + (size_t)i * 16 : nullptr;
       if (tr) tr[0] = clock64();
       mbar_wait_guarded(bar(TB_L1), p);
       tc_fence_after();
@@ -718,21 +789,87 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
       mbar_wait_guarded(bar(TB_L2), p);
       tc_fence_after();
       if (tr) tr[3] = clock64();
-      epilogue_tmem(g1, sB2 + 64 * grp, bar(TB_H2));
+      const float4 part = epilogue_out(g1, sB2 + 64 * grp + 2 * (lane & 3), sW3f + 64 * grp + 2 * (lane & 3), bar(TB_ACC1FREE), lane);
+      if (i > 0) mbar_wait_guarded(bar(TB_PFREE), p ^ 1u);     // tile i-1's partial sums have been consumed (long ago)
+      sPart[grp * kRows + (warp & 3) * 32 + 8 * (2 * (lane & 1) + ((lane >> 1) & 1)) + (lane >> 2)] = part;
+      mbar_arrive(bar(TB_OUT));
       if (tr) tr[4] = clock64();
     }
-  } else {
-    // =============================== auxiliary warps: observations in, finished rows out ==========
-    const int q = warp & 3;                       // my warp's TMEM lane quadrant = its 32 rows of the tile
-    const int row = q * 32 + lane;
+  } else if (warp < kWEpi0) {
+    // =============================== loader warps: observation tiles in ==========================
+    // On their own (nothing else in their loop) so that a tile's global loads are in flight while the previous one is
+    // still being converted; the loads of a tile are issued BEFORE the wait for its shared-memory buffer.
+    const int q = warp & 3;                       // my warp's 32 rows of the tile
     const int od = W.obs_dim;
     const bool vec4 = (od & 3) == 0;
-    auto stage = [&](long long tile, int b) {     // fp32 rows -> (normalised) bf16, canonical K-major tile b
+    // Fast path (obs_dim a multiple of 8, <= 80): lane = row.  A lane reads its row 32 bytes at a time (two LDG.128 at
+    // immediate offsets) and writes one 16-byte core-matrix row per 8 columns (STS.128 at immediate offsets; eight
+    // consecutive lanes fill one 128-byte core matrix, no bank conflicts): 27 memory instructions per lane and tile and
+    // no index arithmetic.  Every LDG / STS / LDL of a loader warp queues behind the epilogue warps' MUFU.TANH in the
+    // sub-partition's memory-IO queue (~100 cycles each while the epilogues run), so their NUMBER is what a tile costs
+    // the loader: the first version (float4 units, offsets through two divisions, 4-byte-granular stores) took 3.8 us
+    // per tile and was the slowest role of the kernel.
+    constexpr int kMaxU = 10, kHalfU = 5;
+    const int n8 = od >> 3;
+    const bool fast = (od & 7) == 0 && n8 <= kMaxU;
+    auto stage = [&](long long tile, int b, int wait_parity, long long* ltr) {     // fp32 rows -> (normalised) bf16, canonical K-major tile b
       __nv_bfloat16* dst = sX + (size_t)b * kRows * K1;
+      bool waited = wait_parity < 0;
       const long long r0 = tile * kRows + q * 32;                 // the warp's 32 rows are contiguous in memory
       const bool norm = W.nmean != nullptr;
       const float cl = W.nclip;
-      if (vec4) {
+      if (fast) {
+        const long long rg = r0 + lane;
+        const bool live = rg < rows;
+        const float4* src = reinterpret_cast<const float4*>(obs + (size_t)rg * od);
+        const uint32_t dst_l = smem_u32(dst) + (uint32_t)canon_off(q * 32 + lane, 0, K1) * 2u;
+        {   // the tile this warp stages next: into L2 now (one 128-byte line per lane and step)
+          const long long nt = tile + gridDim.x;
+          if ((nt + 1) * kRows <= rows) {
+            const char* nx = reinterpret_cast<const char*>(obs + (size_t)(nt * kRows + q * 32) * od);
+            for (int o = lane * 128; o < 32 * od * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+          }
+        }
+        const float4 *nm = nullptr, *ns = nullptr;
+        if (norm && live) {
+          const size_t sidx = (size_t)(rg % W.nperiod) * od;
+          nm = reinterpret_cast<const float4*>(W.nmean + sidx);
+          ns = reinterpret_cast<const float4*>(W.nrstd + sidx);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 x[kHalfU][2];
+          if (ltr) ltr[12 + 2 * h] = clock64();
+#pragma unroll
+          for (int u = 0; u < kHalfU; ++u) {
+            const int uu = h * kHalfU + u;
+            if (uu < n8) {
+              x[u][0] = live ? __ldg(src + 2 * uu) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[u][1] = live ? __ldg(src + 2 * uu + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (!waited) { mbar_wait_guarded(bar(TB_XFREE + b), (uint32_t)wait_parity); waited = true; }
+          if (ltr) ltr[13 + 2 * h] = clock64() + (__float_as_uint(x[0][0].x) & 1u);   // after the wait and the first load's arrival
+#pragma unroll
+          for (int u = 0; u < kHalfU; ++u) {
+            const int uu = h * kHalfU + u;
+            if (uu < n8) {
+              float4 v0 = x[u][0], v1 = x[u][1];
+              if (nm != nullptr) {
+                const float4 m0 = __ldg(nm + 2 * uu), m1 = __ldg(nm + 2 * uu + 1), s0 = __ldg(ns + 2 * uu), s1 = __ldg(ns + 2 * uu + 1);
+                v0.x = fminf(fmaxf((v0.x - m0.x) * s0.x, -cl), cl); v0.y = fminf(fmaxf((v0.y - m0.y) * s0.y, -cl), cl);
+                v0.z = fminf(fmaxf((v0.z - m0.z) * s0.z, -cl), cl); v0.w = fminf(fmaxf((v0.w - m0.w) * s0.w, -cl), cl);
+                v1.x = fminf(fmaxf((v1.x - m1.x) * s1.x, -cl), cl); v1.y = fminf(fmaxf((v1.y - m1.y) * s1.y, -cl), cl);
+                v1.z = fminf(fmaxf((v1.z - m1.z) * s1.z, -cl), cl); v1.w = fminf(fmaxf((v1.w - m1.w) * s1.w, -cl), cl);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_l + 128u * (uint32_t)uu), "r"(pack_bf16(v0.x, v0.y)),
+                           "r"(pack_bf16(v0.z, v0.w)), "r"(pack_bf16(v1.x, v1.y)), "r"(pack_bf16(v1.z, v1.w))
+                           : "memory");
+            }
+          }
+        }
+      } else if (vec4) {
+        if (!waited) { mbar_wait_guarded(bar(TB_XFREE + b), (uint32_t)wait_parity); waited = true; }
         const int q4 = od >> 2, n4 = 32 * q4;
         const float4* src = reinterpret_cast<const float4*>(obs + (size_t)r0 * od);
         constexpr int U = 4;
@@ -762,6 +899,7 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
           }
         }
       } else {
+        if (!waited) mbar_wait_guarded(bar(TB_XFREE + b), (uint32_t)wait_parity);
         const int n = 32 * od;
         const float* src = obs + (size_t)r0 * od;
         for (int e = lane; e < n; e += 32) {
@@ -780,15 +918,19 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
       proxy_fence();               // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bar(TB_XFULL + b));
     };
-    for (int k = 0; k < NX && k < n_local; ++k) stage((long long)blockIdx.x + (long long)k * gridDim.x, k);
+    for (int j = 0; j < n_local; ++j) {     // tile j goes into the buffer of tile j - NX, free once that tile's layer-1 MMAs have completed
+      stage((long long)blockIdx.x + (long long)j * gridDim.x, j % NX, j >= NX ? ((j - NX) / NX) & 1 : -1,
+            (trace && tid == 0 && j >= NX) ? trace + (size_t)(j - NX) * 16 : nullptr);
+      if (trace && tid == 0 && j >= NX) trace[(size_t)(j - NX) * 16 + 6] = clock64();
+    }
+  } else {
+    // =============================== sampler warps: finished rows out =============================
+    // 96 threads for 128 rows: the first warp takes rows 96..127 in a second pass
+    const int ts = tid - kWSamp0 * 32;
     for (int i = 0; i < n_local; ++i) {
-      const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
-      long long* tr = (trace && tid == kTEpi + 32) ? trace + (size_t)i * 16 : nullptr;
-      if (i + NX < n_local) {      // the buffer of tile i is free once its layer-1 MMAs have completed
-        mbar_wait_guarded(bar(TB_XFREE + i % NX), (uint32_t)(i / NX) & 1u);
-        stage(tile + (long long)NX * gridDim.x, i % NX);
-      }
-      if (tr) tr[6] = clock64();
+     const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+     long long* tr = (trace && ts == 0) ? trace + (size_t)i * 16 : nullptr;
+     for (int row = ts; row < kRows; row += kTSamp) {
       // the row's Gaussian noise does not depend on the network: drawn while the tile is still in flight
       const long long row_g = tile * kRows + row;
       const bool live = row_g < rows;
@@ -810,21 +952,15 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
           eps[0] = ra * c0; eps[1] = ra * s0; eps[2] = rb * c1; eps[3] = rb * s1;
         }
       }
-      mbar_wait_guarded(bar(TB_L3), (uint32_t)i & 1u);
-      tc_fence_after();
-      if (tr) tr[5] = clock64();
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row == ts) mbar_wait_guarded(bar(TB_OUT), (uint32_t)i & 1u);
+      if (tr && row == ts) tr[5] = clock64();
+      float v[4];
       {
-        uint32_t w[4][4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld4_nowait(out3 + 64u * (uint32_t)g + ((uint32_t)(q * 32) << 16), w[g]);
-        tmem_wait_ld();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          v[k] = (__uint_as_float(w[0][k]) + __uint_as_float(w[1][k])) + (__uint_as_float(w[2][k]) + __uint_as_float(w[3][k]));
+        const float4 p0 = sPart[row], p1 = sPart[kRows + row], p2 = sPart[2 * kRows + row], p3 = sPart[3 * kRows + row];
+        v[0] = (p0.x + p1.x) + (p2.x + p3.x); v[1] = (p0.y + p1.y) + (p2.y + p3.y);
+        v[2] = (p0.z + p1.z) + (p2.z + p3.z); v[3] = (p0.w + p1.w) + (p2.w + p3.w);
       }
-      tc_fence_before();
-      mbar_arrive(bar(TB_ACC1FREE));        // acc1 may be overwritten by the next tile's layer 2
+      if (row + kTSamp >= kRows) mbar_arrive(bar(TB_PFREE));   // the partial-sum rows may be overwritten by the next tile
       if (live) {
         float lp = 0.f;
 #pragma unroll
@@ -839,7 +975,8 @@ actor_tmem_kernel(ActorDev W, const float* __restrict__ obs, long long rows, con
         }
         logp[row_g] = lp;
       }
-      if (tr) tr[7] = clock64();
+     }
+     if (tr) tr[7] = clock64();
     }
   }
   tc_fence_before();
@@ -915,7 +1052,7 @@ int bd_actor_create(int obs_dim, int hidden, int act_dim, int device, bd_actor**
   alloc((void**)&a->b1, hidden * 4); alloc((void**)&a->b2, hidden * 4);
   alloc((void**)&a->b3, kNOut * 4); alloc((void**)&a->logstd, kNOut * 4);
   if (hidden == 256) {   // TMEM-resident variant: W1 / W2 / W3 resident + one or two observation tiles (BD_ACTOR_IMPL=smem opts out)
-    const size_t fixed = (size_t)(hidden * K1 + (hidden + kNOut) * hidden) * 2 + (size_t)(2 * hidden + 2 * kNOut) * 4;
+    const size_t fixed = (size_t)(hidden * K1 + hidden * hidden) * 2 + (size_t)(2 * hidden + 2 * kNOut) * 4 + (size_t)(hidden + 4 * kRows) * 16;
     const size_t xb = (size_t)kRows * K1 * 2, room = prop.sharedMemPerBlockOptin - 1024;   // static shared memory: barriers
     const char* im = getenv("BD_ACTOR_IMPL");
     if (!(im && im[0] == 's')) {

@@ -27,11 +27,11 @@ fa._lib.bd_actor_set_trace(fa._h, None)
 t = buf.cpu().numpy().astype(np.float64)
 t0 = t[0, 0]
 names = ["E wait L1", "E L1 ready", "E epi1 done", "E L2 ready", "E epi2 done", "A L3 ready", "A staged X(t+2)", "A rows written",
-         "M staged+W1", "M L1(t+1) issued", "M L2 issued", "M L3 issued"]
+         "M staged+W1", "M L1(t+1) issued", "M L2 issued", "M L3 issued", "Ld A issue", "Ld A here+free", "Ld B issue", "Ld B here"]
 ghz = 1.965
 print("stamps in us relative to the first one (CTA 0, thread 0 = E, MMA thread = M, first auxiliary thread = A)")
 for k in range(min(tiles, 6)):
-    order = [i for i in np.argsort(t[k, :12]) if t[k, i] != 0]
+    order = [i for i in np.argsort(t[k, :16]) if t[k, i] != 0]
     print(f"tile {k}: " + "  ".join(f"{names[i]}={(t[k, i] - t0) / ghz / 1e3:.2f}" for i in order))
 d = np.diff(t[:, 1]) / ghz / 1e3
 print("tile period (us):", np.round(d, 2))

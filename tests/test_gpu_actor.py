@@ -18,7 +18,12 @@ def _ref(mlp, logstd, obs, noise):
 
 
 @pytest.mark.parametrize("obs_dim,hidden,act_dim,rows", [(72, 256, 4, 128), (72, 256, 4, 100000), (27, 256, 1, 777),
-                                                         (119, 128, 4, 5000), (72, 128, 4, 3000), (72, 64, 4, 3000)])
+                                                         (119, 128, 4, 5000), (72, 128, 4, 3000), (72, 64, 4, 3000),
+                                                         # hidden 256 = the TMEM-resident kernel: loader fast path (obs_dim % 8 == 0,
+                                                         # <= 80) at its limits, the float4 and scalar loader paths, a grid with
+                                                         # more tiles than SMs x 2 and a ragged last tile, act_dim 2 and 3
+                                                         (80, 256, 4, 1000), (64, 256, 2, 333), (8, 256, 4, 129), (76, 256, 4, 500),
+                                                         (57, 256, 3, 40001)])
 def test_fused_actor_matches_torch_fp32(obs_dim, hidden, act_dim, rows):
     from marl_gym_pybullet_drones_b200.actor import FusedActor
     from marl_gym_pybullet_drones_b200.mappo import MLP
