@@ -597,19 +597,26 @@ def run_mappo_block(args, dev, rank, world):
         tot += parts
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.mappo_steps
     parts_ms = tot / args.mappo_steps
-    ar_us = None
+    ar_us = nccl_us = None
+    peer = getattr(algo, "_peer", None)
     if world > 1:                           # the collective that defines the multi-GPU design, timed on its own
+        def timed(fn):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / 50 * 1e3
         g = algo._joint_grad
-        for _ in range(5):
-            dist.all_reduce(g)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(50):
-            dist.all_reduce(g)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ar_us = e0.elapsed_time(e1) / 50 * 1e3
+        kl = algo.actor_net.stats[1:3]
+        g2 = torch.zeros_like(g)            # NCCL on the same sizes (what the peer kernel replaces): gradients + KL pair
+        nccl_us = timed(lambda: (dist.all_reduce(g2), dist.all_reduce(kl)))
+        ar_us = timed(lambda: peer.all_reduce(extra=kl)) if peer is not None else nccl_us
     t = torch.tensor([wall_ms, parts_ms[0], parts_ms[1], parts_ms[2]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -624,10 +631,15 @@ def run_mappo_block(args, dev, rank, world):
            "config": {"workload": f"BASELINE configs[4] per-GPU shape: MultiHover M={M} + downwash, {N} envs per GPU x {world}, "
                                   f"rollout {T} steps, 1 epoch x {n_mb} minibatches of {mb} env-steps ({mb * M} actor rows)",
                       "update_impl": "native (bd_ppo.cu): tcgen05 fwd+bwd tile kernel, tcgen05 weight-gradient kernel, "
-                                     "GAE scan, gated Adam; one CUDA graph per epoch" + (", NCCL all-reduces in the graph" if world > 1 else "")},
+                                     "GAE scan, gated Adam; one CUDA graph per epoch" +
+                                     ((", gradient + KL all-reduce as one NVLink peer-memory kernel per minibatch in the graph (bd_peer.cu)"
+                                       if peer is not None else ", NCCL all-reduces in the graph") if world > 1 else "")},
            "collectives_per_train_step": {"gradient_allreduce": n_mb if world > 1 else 0,
-                                          "kl_pair_allreduce": n_mb if world > 1 else 0},
+                                          "kl_pair_allreduce": (0 if peer is not None else n_mb) if world > 1 else 0},
+           "gradient_allreduce_impl": (("peer-memory kernel (bd_peer_allreduce), gradients + KL pair in one launch" if peer is not None
+                                        else "NCCL, two calls") if world > 1 else None),
            "gradient_allreduce_us": ar_us,
+           "nccl_same_sizes_us": nccl_us,
            "gradient_allreduce_share": (n_mb * ar_us * 1e-3 / wall_ms) if ar_us is not None else 0.0,
            "limiting_collective": ("joint actor+critic flat-gradient all-reduce (342 KB + 1.4 MB fp32 in one buffer), "
                                    "latency-bound" if world > 1 else None),

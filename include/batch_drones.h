@@ -360,6 +360,28 @@ int bd_ppo_set_forward_mode(bd_ppo_net* n, int mode);
 int64_t bd_ppo_launch_count(const bd_ppo_net* n);
 const char* bd_ppo_last_error(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient all-reduce of the data-parallel trainer over NVLink peer memory (csrc/bd_peer.cu).
+ * The reference's MAPPOAgent.update (mappo/agent.py:702-772) runs in one process; with the envs sharded
+ * over one process per GPU every minibatch needs the sum of the ranks' flat gradients and of the KL pair
+ * of the gate (agent.py:731) before the optimiser step.  A bd_peer is one rank's block of device memory,
+ * mapped by all ranks of the node through CUDA IPC; bd_peer_allreduce is ONE kernel launch per rank that
+ * sums the first `floats` floats of every rank's data region IN PLACE (rank r reduces slice r from all
+ * peers and writes it back to all of them: identical bits on every rank) and `n_extra` doubles that live
+ * outside the block.  Stream ordered, no host synchronisation, capturable in a CUDA graph; all ranks
+ * must make the same sequence of calls.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bd_peer bd_peer;
+int bd_peer_create(int device, int rank, int world, int64_t floats, bd_peer** out);   /* 2 <= world <= 16, one node */
+void bd_peer_destroy(bd_peer* p);
+int bd_peer_handle_size(void);                           /* bytes of an exported handle (cudaIpcMemHandle_t) */
+int bd_peer_get_handle(bd_peer* p, void* handle_out);    /* to be all-gathered by the caller (any transport) */
+int bd_peer_open(bd_peer* p, const void* handles, int count);   /* count = world handles in rank order */
+float* bd_peer_data(bd_peer* p);                         /* the rank's data region: gradient kernels write here */
+int bd_peer_allreduce(bd_peer* p, int64_t floats, double* extra_dev, int n_extra, void* stream);
+int64_t bd_peer_launch_count(const bd_peer* p);
+const char* bd_peer_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,8 @@ EXPORTS = (
     "bd_rms_launch_count", "bd_rms_last_error",
     "bd_ppo_net_create", "bd_ppo_net_destroy", "bd_ppo_net_param_count", "bd_ppo_net_stats", "bd_ppo_net_pack", "bd_ppo_forward", "bd_ppo_sample", "bd_ppo_set_trace", "bd_ppo_set_train_mode", "bd_ppo_set_forward_mode",
     "bd_ppo_grad", "bd_ppo_adam_step", "bd_ppo_gae", "bd_ppo_adv_stats", "bd_ppo_launch_count", "bd_ppo_last_error",
+    "bd_peer_create", "bd_peer_destroy", "bd_peer_handle_size", "bd_peer_get_handle", "bd_peer_open", "bd_peer_data", "bd_peer_allreduce",
+    "bd_peer_launch_count", "bd_peer_last_error",
 )
 
 
@@ -198,6 +200,24 @@ def load():
     lib.bd_ppo_launch_count.restype = C.c_int64
     lib.bd_ppo_last_error.argtypes = []
     lib.bd_ppo_last_error.restype = C.c_char_p
+    lib.bd_peer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(vp)]
+    lib.bd_peer_create.restype = C.c_int
+    lib.bd_peer_destroy.argtypes = [vp]
+    lib.bd_peer_destroy.restype = None
+    lib.bd_peer_handle_size.argtypes = []
+    lib.bd_peer_handle_size.restype = C.c_int
+    lib.bd_peer_get_handle.argtypes = [vp, vp]
+    lib.bd_peer_get_handle.restype = C.c_int
+    lib.bd_peer_open.argtypes = [vp, vp, C.c_int]
+    lib.bd_peer_open.restype = C.c_int
+    lib.bd_peer_data.argtypes = [vp]
+    lib.bd_peer_data.restype = vp
+    lib.bd_peer_allreduce.argtypes = [vp, C.c_int64, vp, C.c_int, vp]
+    lib.bd_peer_allreduce.restype = C.c_int
+    lib.bd_peer_launch_count.argtypes = [vp]
+    lib.bd_peer_launch_count.restype = C.c_int64
+    lib.bd_peer_last_error.argtypes = []
+    lib.bd_peer_last_error.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -15,7 +15,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = [os.path.join(CSRC, "bd_kernels.cu"), os.path.join(CSRC, "bd_tile_launch.cu"), os.path.join(CSRC, "bd_api.cu"), os.path.join(CSRC, "bd_actor.cu"),
-           os.path.join(CSRC, "bd_norm.cu"), os.path.join(CSRC, "bd_ppo.cu")]
+           os.path.join(CSRC, "bd_norm.cu"), os.path.join(CSRC, "bd_ppo.cu"), os.path.join(CSRC, "bd_peer.cu")]
 HEADERS = [os.path.join(CSRC, "bd_params.h"), os.path.join(CSRC, "bd_device.cuh"), os.path.join(CSRC, "bd_step_tile.cuh"),
            os.path.join(CSRC, "bd_umma.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "batch_drones.h")]

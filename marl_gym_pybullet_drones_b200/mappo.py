@@ -64,7 +64,9 @@ MAPPO_CONFIG = {   # reference mappo/config.py:3-48 with the learn_mappo.py:179-
     "rollout_values": "zeros",    # reference behaviour; "critic" = textbook GAE
     "use_clipped_value": False,
     "fused_actor": True,          # rollout-time actor forward + sampling as one tcgen05 kernel (actor.py)
-    "graph_update": True,         # replay the update as a CUDA graph (native: one graph per epoch, NCCL included)
+    "graph_update": True,         # replay the update as a CUDA graph (native: one graph per epoch, collectives included)
+    "peer_allreduce": True,       # several ranks on one node: gradient + KL all-reduce as ONE kernel over NVLink peer memory
+                                  # (peer.py / csrc/bd_peer.cu) instead of two NCCL calls per minibatch; falls back to NCCL
     "update_impl": "auto",        # "native": hand-written kernels (bd_ppo.cu); "torch": autograd + library GEMMs;
                                   # "auto": native where the kernels cover the shape, else torch
     "matmul_precision": "tf32",   # PPO-update GEMMs: "tf32" (tensor cores, fp32 storage / accumulation), "fp32" (CUDA
@@ -157,6 +159,7 @@ class DeviceMAPPO:
         self.critic_opt = GatedAdam(self.ac.critic.parameters(), lr=self.cfg["critic_lr"])
         self._graph = None
         self._world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self._peer = None
         impl = str(self.cfg["update_impl"])
         if impl not in ("auto", "native", "torch"):
             raise ValueError("update_impl must be 'auto', 'native' or 'torch'")
@@ -200,7 +203,13 @@ class DeviceMAPPO:
                 # both networks' flat gradients live in ONE buffer: one NCCL all-reduce per minibatch instead of two (the
                 # collectives are latency-bound: ~30 us each at 8 GPUs whatever their size up to a few MB)
                 na, nc = self.actor_opt.grad.numel(), self.critic_opt.grad.numel()
-                self._joint_grad = torch.zeros(na + nc, device=dev)
+                self._peer = None
+                if self.cfg["peer_allreduce"]:
+                    # ... and that buffer is this rank's block of peer-mapped memory: the gradient kernels write where the
+                    # all-reduce kernel reads, and the collective (gradients + the KL pair of the gate) is one launch
+                    from .peer import PeerAllReduce
+                    self._peer = PeerAllReduce.create(na + nc, dev)
+                self._joint_grad = self._peer.data if self._peer is not None else torch.zeros(na + nc, device=dev)
                 self.actor_opt.grad = self._joint_grad[:na]
                 self.critic_opt.grad = self._joint_grad[na:]
         # episode statistics (VecRecordEpisodeStatistics semantics, record_episode_statistics.py:144-171)
@@ -453,8 +462,11 @@ class DeviceMAPPO:
         c.grad(co.grad, self.obs, N, M, idx, mb, critic=True, ret=self.ret, v_old=self.val, clip=cfg["clip_param"],
                use_clipped_value=bool(cfg["use_clipped_value"]), rows_global=mb * W, run_acc=self._run_critic, **norm)
         if W > 1:   # every rank must see the same gradients and take the same gate decision
-            torch.distributed.all_reduce(self._joint_grad)
-            torch.distributed.all_reduce(a.stats[1:3])
+            if self._peer is not None:
+                self._peer.all_reduce(extra=a.stats[1:3])
+            else:
+                torch.distributed.all_reduce(self._joint_grad)
+                torch.distributed.all_reduce(a.stats[1:3])
         a.adam_step(ao.flat, ao.exp_avg, ao.exp_avg_sq, ao.grad, ao.step_t, ao.lr, ao.betas, ao.eps,
                     kl_sum=a.stats[1:2], kl_rows=a.stats[2:3], target_kl=float(cfg["target_kl"]), gate_count=self._gates)
         c.adam_step(co.flat, co.exp_avg, co.exp_avg_sq, co.grad, co.step_t, co.lr, co.betas, co.eps)
@@ -648,6 +660,10 @@ class DeviceMAPPO:
             if net is not None:
                 net.close()
         self.actor_net = self.critic_net = None
+        if getattr(self, "_peer", None) is not None:
+            self.actor_opt.grad = self.critic_opt.grad = self._joint_grad = None
+            self._peer.close()
+            self._peer = None
 
     def save(self, path):
         torch.save(self.state_dict(), path)
