@@ -413,6 +413,9 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
   // drag factors dt k / m per axis: previous step's rpm in the first substep, this step's afterwards
   const float kd = -6.28318530717958647692f / 60.0f * P.hover_rpm * dt * P.inv_m;
   const float cur_sum = (onep[0] + onep[1]) + (onep[2] + onep[3]);
+  // downwash constants of the power-of-two pair loop (see there)
+  const float dwa = -0.0625f * P.dw1 * (P.prop_radius * P.prop_radius);
+  const float dw2s = 1.17741002251547469101f * P.dw2, dw3s = 1.17741002251547469101f * P.dw3;   // / sqrt(log2(e) / 2)
 #pragma unroll 1
   for (int s = 0; s < P.S; ++s) {
     const float x = d.qx, y = d.qy, z = d.qz, w = d.qw;   // unit up to rounding
@@ -463,28 +466,56 @@ __device__ __forceinline__ void fast_substeps(const Params<float>& P, Drone<floa
         const int M = P.M;
         float fdw = 0.f;
         const int half = M >> 1;
+        if ((M & (M - 1)) == 0) {
+          // Power-of-two teams (the tile kernel's M = 2 .. 32; configs[4]: 16): the loop was 46 instructions per pair (now 31.5), a
+          // quarter of them lane arithmetic — an env is an aligned group of M lanes, so the shuffle's `width` does the
+          // modulo (source lane drone + o, hand-back lane drone - o + M, no compare / select / add per index).  Constants
+          // are folded (alpha = dw1 (R / 4 dz)^2 = c_a / dz^2; exp(-(dxy / beta)^2 / 2) = 2^-(dxy / beta')^2 with beta' =
+          // beta / sqrt(log2(e) / 2), its two coefficients computed once per step) and the three conditions are three
+          // chained predicates: "within 10 m" (and, for the doubly visited offset M / 2, "I own this pair"), "partner
+          // above me" and "partner below me".
+          const bool owner = drone < half;
+          auto pair = [&](int o, bool last) {
+            const float oz = __shfl_sync(0xffffffffu, d.pz, drone + o, M), ox = __shfl_sync(0xffffffffu, d.px, drone + o, M),
+                        oy = __shfl_sync(0xffffffffu, d.py, drone + o, M);
+            const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
+            const float adz = fabsf(dz);
+            const float dxy2 = fmaf(dx, dx, dy * dy);
+            const float r = rcp_ftz(adz);
+            const float rb = rcp_ftz(fmaf(dw2s, adz, dw3s));
+            const float f = ((r * r) * dwa) * ex2_ftz(-dxy2 * (rb * rb));      // < 0; inf / nan when dz == 0: never selected
+            const bool near = (dxy2 < 100.f) && (!last || owner);                // :801 (delta_xy < 10)
+            const float mine = (near && dz > 0.f) ? f : 0.f;                     // the partner is above me
+            const float theirs = (near && dz < 0.f) ? f : 0.f;                   // the partner is below me: its force
+            fdw += mine + __shfl_sync(0xffffffffu, theirs, drone - o + M, M);
+          };
 #pragma unroll 2
-        for (int o = 1; o <= half; ++o) {
-          int t = drone + o;
-          t -= (t >= M) ? M : 0;
-          int b = drone - o;
-          b += (b < 0) ? M : 0;
-          const int src = group_base + t;
-          const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
-                      oz = __shfl_sync(0xffffffffu, d.pz, src);
-          const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
-          const float adz = fabsf(dz);
-          const float dxy2 = fmaf(dx, dx, dy * dy);
-          const float ratio = P.prop_radius * rcp_ftz(4.0f * adz);
-          const float alpha = P.dw1 * ratio * ratio;
-          const float beta = fmaf(P.dw2, adz, P.dw3);
-          const float q2 = dxy2 * rcp_ftz(beta * beta);
-          float f = -alpha * ex2_ftz(-0.72134752044448f * q2);          // exp(-q2 / 2) = 2^(-q2 log2(e) / 2)
-          const bool mine_to_count = (2 * o != M) || (drone < half);     // the doubly visited offset: one owner
-          if (!(adz > 0.f && dxy2 < 100.f && mine_to_count)) f = 0.f;       // :801 (delta_xy < 10)
-          const float theirs = dz < 0.f ? f : 0.f;                          // the partner is below me
-          const float recv = __shfl_sync(0xffffffffu, theirs, group_base + b);
-          fdw += (dz > 0.f ? f : 0.f) + recv;
+          for (int o = 1; o < half; ++o) pair(o, false);      // (four pairs in flight, one unified loop: 437 vs 431 us, 80 registers)
+          if (half >= 1) pair(half, true);
+        } else {
+#pragma unroll 2
+          for (int o = 1; o <= half; ++o) {
+            int t = drone + o;
+            t -= (t >= M) ? M : 0;
+            int b = drone - o;
+            b += (b < 0) ? M : 0;
+            const int src = group_base + t;
+            const float ox = __shfl_sync(0xffffffffu, d.px, src), oy = __shfl_sync(0xffffffffu, d.py, src),
+                        oz = __shfl_sync(0xffffffffu, d.pz, src);
+            const float dz = oz - d.pz, dx = ox - d.px, dy = oy - d.py;
+            const float adz = fabsf(dz);
+            const float dxy2 = fmaf(dx, dx, dy * dy);
+            const float ratio = P.prop_radius * rcp_ftz(4.0f * adz);
+            const float alpha = P.dw1 * ratio * ratio;
+            const float beta = fmaf(P.dw2, adz, P.dw3);
+            const float q2 = dxy2 * rcp_ftz(beta * beta);
+            float f = -alpha * ex2_ftz(-0.72134752044448f * q2);          // exp(-q2 / 2) = 2^(-q2 log2(e) / 2)
+            const bool mine_to_count = (2 * o != M) || (drone < half);     // the doubly visited offset: one owner
+            if (!(adz > 0.f && dxy2 < 100.f && mine_to_count)) f = 0.f;       // :801 (delta_xy < 10)
+            const float theirs = dz < 0.f ? f : 0.f;                          // the partner is below me
+            const float recv = __shfl_sync(0xffffffffu, theirs, group_base + b);
+            fdw += (dz > 0.f ? f : 0.f) + recv;
+          }
         }
         const float k = dt * P.inv_m * fdw;                       // dt F / m along R[:,2]
         c1s += k;
