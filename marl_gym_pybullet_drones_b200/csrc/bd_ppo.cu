@@ -470,10 +470,18 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
     }
     long long* const tr0 = (P.trace != nullptr && blockIdx.x == 0 && tid == 0) ? P.trace : nullptr;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long next = tile + gridDim.x;
+      const long long next = tile + gridDim.x, next2 = next + gridDim.x;
       const long long samp = cur_sample;
       long long* const tr = (tr0 != nullptr && tile / gridDim.x < 16) ? tr0 + (tile / gridDim.x) * 16 : nullptr;
       if (tr) tr[0] = clock64();     // tile start
+      // The minibatch index of the NEXT tile's row is requested here and used after this tile's inputs are staged, and
+      // the one of the tile after that is used in the middle of this tile to pull its observation row into L2: read at
+      // the point of use, index -> row is a dependent pair of latencies inside the staging phase (update 140.7 -> 138.4
+      // ms at configs[4]'s shape).  Reading the row at the start of its own tile instead of holding it in 24 registers
+      // across the previous one was slower (141.5 ms): the staging phase is long (5-8 k cycles) because its loads queue
+      // behind the previous epilogue's 64 KB of activation stores, not because of the gather's own latency.
+      const long long nsamp = next < n_tiles ? sample_of(next) : -1;
+      const long long n2samp = next2 < n_tiles ? sample_of(next2) : -1;
       // the row's loss inputs (a gather by sample index) are requested now and used two epilogues later: read at the
       // point of use they cost a DRAM latency on the tile's critical path (2 k of 35 k cycles in the phase trace)
       float pre_a[4] = {0.f, 0.f, 0.f, 0.f}, pre_lpo = 0.f, pre_adv = 0.f;
@@ -498,7 +506,7 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
         proxy_fence();
         mbar_arrive(bar(B_XFULL + xbuf));
         if (c + 1 < C) load_x(tile, c + 1, samp);
-        else if (next < n_tiles) { cur_sample = sample_of(next); load_x(next, 0, cur_sample); }
+        else if (next < n_tiles) { cur_sample = nsamp; load_x(next, 0, cur_sample); }
       }
       const size_t tbase = (size_t)tile * kRows * HID;
       // ---- H1
@@ -509,6 +517,13 @@ mlp_tile_kernel(const __grid_constant__ TileArgs P) {
       epi_forward(acc0, sB1, bufH1, train ? P.H1t + tbase : nullptr, B_H1C);
       tc_fence_before();
       if (tr) tr[3] = clock64();     // H1 written
+      if (n2samp >= 0) {             // the row (actor) / the sample's M rows (critic) of the tile after the next one -> L2
+        const int agent0 = (rps == 1) ? 0 : (int)((next2 * kRows + row) % rps);
+        const char* b0 = reinterpret_cast<const char*>(P.obs + ((size_t)n2samp * P.M + agent0) * D);
+        const char* b1 = b0 + (size_t)(rps == 1 ? P.M : 1) * D * 4;
+        for (const char* a = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b0) & ~(uintptr_t)127) + grp * 128; a < b1; a += 4 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
       // ---- H2
       mbar_wait(bar(B_L2), tpar);
       tc_fence_after();
