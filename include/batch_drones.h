@@ -379,6 +379,8 @@ int bd_peer_get_handle(bd_peer* p, void* handle_out);    /* to be all-gathered b
 int bd_peer_open(bd_peer* p, const void* handles, int count);   /* count = world handles in rank order */
 float* bd_peer_data(bd_peer* p);                         /* the rank's data region: gradient kernels write here */
 int bd_peer_allreduce(bd_peer* p, int64_t floats, double* extra_dev, int n_extra, void* stream);
+/* shutdown: every rank bd_peer_unmap, barrier (caller's transport), every rank bd_peer_destroy */
+int bd_peer_unmap(bd_peer* p);
 int64_t bd_peer_launch_count(const bd_peer* p);
 const char* bd_peer_last_error(void);
 

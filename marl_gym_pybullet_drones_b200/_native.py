@@ -32,7 +32,7 @@ EXPORTS = (
     "bd_ppo_net_create", "bd_ppo_net_destroy", "bd_ppo_net_param_count", "bd_ppo_net_stats", "bd_ppo_net_pack", "bd_ppo_forward", "bd_ppo_sample", "bd_ppo_set_trace", "bd_ppo_set_train_mode", "bd_ppo_set_forward_mode",
     "bd_ppo_grad", "bd_ppo_adam_step", "bd_ppo_gae", "bd_ppo_adv_stats", "bd_ppo_launch_count", "bd_ppo_last_error",
     "bd_peer_create", "bd_peer_destroy", "bd_peer_handle_size", "bd_peer_get_handle", "bd_peer_open", "bd_peer_data", "bd_peer_allreduce",
-    "bd_peer_launch_count", "bd_peer_last_error",
+    "bd_peer_unmap", "bd_peer_launch_count", "bd_peer_last_error",
 )
 
 
@@ -216,6 +216,8 @@ def load():
     lib.bd_peer_allreduce.restype = C.c_int
     lib.bd_peer_launch_count.argtypes = [vp]
     lib.bd_peer_launch_count.restype = C.c_int64
+    lib.bd_peer_unmap.argtypes = [vp]
+    lib.bd_peer_unmap.restype = C.c_int
     lib.bd_peer_last_error.argtypes = []
     lib.bd_peer_last_error.restype = C.c_char_p
     _lib = lib

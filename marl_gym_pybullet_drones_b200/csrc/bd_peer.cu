@@ -22,7 +22,7 @@
 //           peer's flag_out[rank], and waits for all peers' flag_out: when the kernel ends, every slice
 //           has arrived and no peer still reads this rank's data — the next kernel may overwrite it.
 // The sequence number lives in device memory and is advanced by the kernel, so the launch can be
-// captured in a CUDA graph and replayed.  Spins are bounded (trap after ~4 s): a lost peer fails the
+// captured in a CUDA graph and replayed.  Spins are bounded (trap after ~20 s): a lost peer fails the
 // launch instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -91,7 +91,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - seq) < 0) {
     __nanosleep(64);
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > 40000000000LL) __trap();      // ~20 s of SM clocks
   }
 }
 
@@ -256,6 +256,21 @@ int bd_peer_allreduce(bd_peer* p, int64_t floats, double* extra_dev, int n_extra
 }
 
 int64_t bd_peer_launch_count(const bd_peer* p) { return p ? p->launches : 0; }
+
+/* Close the mappings of the peers' blocks (the own block stays).  Shutdown order: every rank unmaps, the ranks meet at a
+ * barrier of the caller's transport, then every rank destroys — an exporter must not free a block a peer still maps. */
+int bd_peer_unmap(bd_peer* p) {
+  if (!p) return pfail(BD_EINVAL, "bd_peer_unmap: null handle");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < p->world; ++r)
+    if (p->mapped[r]) { cudaIpcCloseMemHandle(p->mapped[r]); p->mapped[r] = nullptr; }
+  p->opened = false;
+  if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
+  return BD_OK;
+}
 
 void bd_peer_destroy(bd_peer* p) {
   if (!p) return;

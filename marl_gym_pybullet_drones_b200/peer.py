@@ -90,7 +90,13 @@ class PeerAllReduce:
         return int(self._lib.bd_peer_launch_count(self._h))
 
     def close(self):
+        """Collective: every rank unmaps its peers' blocks, the ranks meet, then every rank frees its own block (an
+        exporter must not free memory a peer still maps)."""
         if self._h:
             self.data = None
+            self._lib.bd_peer_unmap(self._h)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()
             self._lib.bd_peer_destroy(self._h)
             self._h = None
