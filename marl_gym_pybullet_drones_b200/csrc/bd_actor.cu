@@ -597,6 +597,8 @@ __device__ __forceinline__ void epilogue_tmem(uint32_t grp_base, const float* __
 // the 32 lanes — 2.1 us per tile on the 128 B / clock return path, twice the SFU time (measured; the constant bank was
 // worse: ptxas turns the operands into LDCU.128, 3.1 us).  The four lanes that share rows exchange partial sums by
 // shuffle (12 per tile) and each writes one finished row-partial over the warp group's 64 columns.
+// (Packed fp32 pairs — fma.rn.f32x2 / FFMA2 over the two rows of a 16-lane half, W3 stored pre-duplicated — halve the
+// FMA instructions but took 2.7 us per tile instead of 1.6: measured, reverted.)
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
