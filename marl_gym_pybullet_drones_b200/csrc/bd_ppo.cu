@@ -2066,10 +2066,10 @@ struct ReduceArgs {
   NetShape s;
   const float* pw1[16];   // per input chunk: partials [n1][256][K1p]
   const float* pw2;       // [n2][256][256]
-  const float* pw3;       // [n1][256][16]   (dW3 transposed)
+  const float* pw3;       // [n3][256][16]   (dW3 transposed)
   const float* pb1;       // [n1][256]
   const float* pb2;       // [n2][256]
-  int n1, n2;
+  int n1, n2, n3;
   const double* stats;    // tile-kernel statistics (rows at [2], dlogstd sums at [3..6], db3 sums at [7..10])
   double* run_acc;        // optional running statistics over minibatches: [0] += mean loss, [1] += mean kl, [2] += 1, [3] += entropy loss
   const float* logstd;    // packed logstd (entropy statistic)
@@ -2123,7 +2123,7 @@ __global__ void reduce_kernel(const __grid_constant__ ReduceArgs P) {
     const long long k = i - s.off_w3();
     const int o = (int)(k / HID), j = (int)(k % HID);
     const float* p = P.pw3 + (size_t)j * kNOut + o;
-    for (int n = 0; n < P.n1; ++n) g += p[(size_t)n * HID * kNOut];
+    for (int n = 0; n < P.n3; ++n) g += p[(size_t)n * HID * kNOut];
     g *= scale;
   } else {
     g = (float)P.stats[7 + (i - s.off_b3())] * scale;
@@ -2244,6 +2244,7 @@ struct bd_ppo_net {
   // gradient partials
   float *pw1 = nullptr, *pw2 = nullptr, *pw3 = nullptr, *pb1 = nullptr, *pb2 = nullptr;
   int n1 = 0, n2 = 0;            // CTAs of the two weight-gradient roles
+  int n3 = 0;                    // CTAs of the separate dW3 launch
   int n1_jobs = 1;               // input chunks are spread over this many role-1 jobs (TMEM: 512 columns)
   double* stats = nullptr;       // [kStatSlots]
   long long* trace = nullptr;    // diagnostics (bd_ppo_set_trace)
@@ -2302,6 +2303,9 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   n2 = sms - n1 * n->n1_jobs;
   if (n2 < 1) n2 = 1;
   n->n1 = n1; n->n2 = n2;
+  // dW3^T = H2^T dZ3 streams the whole H2 tile array through a 256 x 16 accumulator: bandwidth-bound, so it runs on every SM
+  // (it used the role-1 CTA count: 82 CTAs for the actor, 13 for the 16-agent critic = 23 us for 17 MB)
+  n->n3 = sms;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); };
   const size_t k1s = n->s.K1p / 16;
@@ -2319,7 +2323,7 @@ int bd_ppo_net_create(int in_dim, int chunks, int out_dim, int has_logstd, int64
   alloc((void**)&n->dZ3t, T * kRows * kNOut * 2);
   alloc((void**)&n->pw1, (size_t)chunks * n1 * HID * n->s.K1p * 4);
   alloc((void**)&n->pw2, (size_t)n2 * HID * HID * 4);
-  alloc((void**)&n->pw3, (size_t)n1 * HID * kNOut * 4);
+  alloc((void**)&n->pw3, (size_t)n->n3 * HID * kNOut * 4);
   alloc((void**)&n->pb1, (size_t)n1 * HID * 4); alloc((void**)&n->pb2, (size_t)n2 * HID * 4);
   alloc((void**)&n->stats, kStatSlots * sizeof(double));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBudget);
@@ -2551,16 +2555,16 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   dw_kernel<<<cta, kDwThreads, kDwStages * kDwStageBytes, st>>>(d);
   e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (dw kernel): %s", cudaGetErrorString(e));
-  // dW3^T = H2^T dZ3: a second, small launch of the same kernel (A = H2) over the role-1 CTA count
+  // dW3^T = H2^T dZ3: a second, small launch of the same kernel (A = H2) on every SM
   DwArgs d3;
   memset(&d3, 0, sizeof(d3));
   d3.tiles = tiles; d3.n_jobs = 1;
   {
     DwJob& J = d3.jobs[0];
     J.A = n->H2t; J.n_b = 1; J.B[0] = n->dZ3t; J.b_stride[0] = (long long)kRows * kNOut * 2; J.nB[0] = kNOut; J.out[0] = n->pw3;
-    J.bias_out = nullptr; J.cta0 = 0; J.n_cta = n->n1;
+    J.bias_out = nullptr; J.cta0 = 0; J.n_cta = n->n3;
   }
-  dw_kernel<<<n->n1, kDwThreads, kDwStages * kDwStageBytes, st>>>(d3);
+  dw_kernel<<<n->n3, kDwThreads, kDwStages * kDwStageBytes, st>>>(d3);
   e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(BD_ECUDA, "bd_ppo_grad (dw3 kernel): %s", cudaGetErrorString(e));
   // ---- flat gradient
@@ -2568,7 +2572,7 @@ int bd_ppo_grad(bd_ppo_net* n, int critic, const float* obs_dev, int n_envs, int
   memset(&r, 0, sizeof(r));
   r.s = n->s;
   for (int c = 0; c < C; ++c) r.pw1[c] = n->pw1 + (size_t)c * n->n1 * HID * K1p;
-  r.pw2 = n->pw2; r.pw3 = n->pw3; r.pb1 = n->pb1; r.pb2 = n->pb2; r.n1 = n->n1; r.n2 = n->n2;
+  r.pw2 = n->pw2; r.pw3 = n->pw3; r.pb1 = n->pb1; r.pb2 = n->pb2; r.n1 = n->n1; r.n2 = n->n2; r.n3 = n->n3;
   r.stats = n->stats; r.entropy_coef = critic ? 0.f : entropy_coef; r.rows_global = rows_global; r.grad = grad_dev;
   r.run_acc = run_acc_dev; r.logstd = n->logstd;
   const long long np = n->s.count();
