@@ -129,3 +129,32 @@ def test_two_rank_gated_adam_and_reward_normaliser_match_single_process():
     for t in range(6):
         o(rew[t].reshape(-1), done[t].reshape(-1))
     assert res[0][3] == res[1][3] and abs(res[0][3] - float(o.rms.var)) <= 1e-12 * float(o.rms.var)
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from marl_gym_pybullet_drones_b200.dist import init_distributed
+    from marl_gym_pybullet_drones_b200.peer import PeerAllReduce
+    init_distributed("gloo")
+    # no GPU here: bd_peer_create fails on every rank, the handle exchange still runs (over gloo, host tensors) and every rank
+    # takes the same decision — None, i.e. the trainer keeps NCCL — instead of one rank waiting for the other
+    p = PeerAllReduce.create(1000, torch.device("cuda", 0))
+    q.put((rank, p is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.skipif(torch.cuda.is_available(), reason="the CPU-only decision path (GPU boxes run tests/test_gpu_peer_allreduce.py)")
+def test_peer_allreduce_setup_falls_back_consistently_without_gpus():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(0, True), (1, True)]
