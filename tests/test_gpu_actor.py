@@ -23,7 +23,9 @@ def _ref(mlp, logstd, obs, noise):
                                                          # <= 80) at its limits, the float4 and scalar loader paths, a grid with
                                                          # more tiles than SMs x 2 and a ragged last tile, act_dim 2 and 3
                                                          (80, 256, 4, 1000), (64, 256, 2, 333), (8, 256, 4, 129), (76, 256, 4, 500),
-                                                         (57, 256, 3, 40001)])
+                                                         (57, 256, 3, 40001),
+                                                         # one observation buffer instead of two (K1 = 96), float4 loader path
+                                                         (88, 256, 4, 20000), (96, 256, 4, 1000)])
 def test_fused_actor_matches_torch_fp32(obs_dim, hidden, act_dim, rows):
     from marl_gym_pybullet_drones_b200.actor import FusedActor
     from marl_gym_pybullet_drones_b200.mappo import MLP
