@@ -25,6 +25,7 @@ class PeerAllReduce:
         self._lib = _native.load()
         self._h = handle
         self.floats, self.device, self.rank, self.world = int(floats), device, int(rank), int(world)
+        self._group = None
         ptr = self._lib.bd_peer_data(self._h)
 
         class _Arr:
@@ -69,7 +70,9 @@ class PeerAllReduce:
             if h:
                 lib.bd_peer_destroy(h)
             return None
-        return cls(h, floats, device, rank, world)
+        obj = cls(h, floats, device, rank, world)
+        obj._group = group
+        return obj
 
     def all_reduce(self, floats: Optional[int] = None, extra: Optional[torch.Tensor] = None):
         """Sum `.data[:floats]` over the ranks in place, and `extra` (a contiguous float64 device tensor of <= 16
@@ -97,6 +100,6 @@ class PeerAllReduce:
             self._lib.bd_peer_unmap(self._h)
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
-                dist.barrier()
+                dist.barrier(group=self._group)
             self._lib.bd_peer_destroy(self._h)
             self._h = None
